@@ -1,0 +1,271 @@
+// extern "C" surface of libfaststyle_b200 (see include/faststyle_b200.h).
+#include "../../include/faststyle_b200.h"
+#include "engine.cuh"
+#include <stdarg.h>
+#include <new>
+
+namespace fs {
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+}  // namespace fs
+
+using namespace fs;
+
+struct fs_engine { Engine e; };
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static int to_lc(const fs_loss_config* c, LossConfig& lc) {
+    FS_CHECK(c != nullptr, "loss config is NULL");
+    FS_CHECK(c->n_content >= 0 && c->n_content <= V_NCONV && c->n_style >= 0 && c->n_style <= V_NCONV,
+             "loss config: bad layer counts");
+    lc.n_content = c->n_content; lc.n_style = c->n_style; lc.beta = c->beta;
+    for (int i = 0; i < V_NCONV; ++i) {
+        lc.content_layer[i] = c->content_layer[i]; lc.content_w[i] = c->content_w[i];
+        lc.style_layer[i] = c->style_layer[i]; lc.style_w[i] = c->style_w[i];
+    }
+    return 0;
+}
+
+extern "C" {
+
+const char* fs_last_error(void) { return get_error(); }
+int fs_version(void) { return FS_VERSION; }
+
+long long fs_transform_param_count(void) { return T_NPARAMS; }
+
+int fs_transform_param_slot(int conv_index, int which, long long* offset, long long* count) {
+    FS_CHECK(conv_index >= 0 && conv_index < T_NCONV && which >= 0 && which <= 2, "bad slot query");
+    TConv tc[T_NCONV];
+    transform_param_table(tc);
+    const TConv& c = tc[conv_index];
+    if (which == 0) { *offset = c.offW; *count = (long long)c.k * c.k * c.cin * c.cout; }
+    else { *offset = which == 1 ? c.offG : c.offB; *count = c.cout; }
+    return 0;
+}
+
+long long fs_vgg_flat_floats(void) { return vgg_flat_floats(); }
+long long fs_vgg_packed_floats(void) { return vgg_packed_floats(); }
+int fs_vgg_pack(const float* flat, float* packed, void* stream) { return vgg_pack(flat, packed, S(stream)); }
+
+int fs_engine_create(int N, int H, int W, int flags, unsigned content_mask, unsigned style_mask,
+                     fs_engine** out) {
+    FS_CHECK(out != nullptr, "fs_engine_create: out is NULL");
+    FS_CHECK(flags != 0 && (flags & ~15) == 0, "fs_engine_create: bad flags 0x%x", flags);
+    FS_CHECK(!(flags & ENG_TRANSFORM_BWD) || (flags & ENG_TRANSFORM), "TRANSFORM_BWD needs TRANSFORM");
+    FS_CHECK(!(flags & ENG_VGG_BWD) || (flags & ENG_VGG), "VGG_BWD needs VGG");
+    FS_CHECK((content_mask >> V_NCONV) == 0 && (style_mask >> V_NCONV) == 0, "loss masks address layers > conv4_3");
+    fs_engine* h = new (std::nothrow) fs_engine();
+    FS_CHECK(h != nullptr, "out of host memory");
+    h->e.N = N; h->e.H = H; h->e.W = W; h->e.flags = flags;
+    h->e.content_mask = content_mask; h->e.style_mask = style_mask;
+    int r = h->e.plan();
+    if (r != 0) { delete h; return r; }
+    Arena a;
+    h->e.layout(a);
+    h->e.ws_bytes = a.off;
+    *out = h;
+    return 0;
+}
+
+int fs_engine_destroy(fs_engine* e) { delete e; return 0; }
+size_t fs_engine_workspace_bytes(const fs_engine* e) { return e ? e->e.ws_bytes : 0; }
+int fs_engine_bind(fs_engine* e, void* workspace, size_t bytes) {
+    FS_CHECK(e && workspace, "fs_engine_bind: NULL argument");
+    return e->e.bind(workspace, bytes);
+}
+int fs_engine_output_dims(const fs_engine* e, int* OH, int* OW) {
+    FS_CHECK(e, "NULL engine");
+    *OH = e->e.VH; *OW = e->e.VW;
+    return 0;
+}
+int fs_engine_vgg_activation(const fs_engine* e, int layer, const float** ptr, int* H, int* W, int* C) {
+    FS_CHECK(e && e->e.bound && (e->e.flags & ENG_VGG), "engine has no bound VGG plan");
+    FS_CHECK(layer >= 0 && layer < V_NCONV, "bad VGG layer %d", layer);
+    *ptr = e->e.vact[layer]; *H = e->e.vc[layer].H; *W = e->e.vc[layer].W; *C = e->e.vc[layer].cout;
+    return 0;
+}
+int fs_engine_transform_activation(const fs_engine* e, int conv_index, int stage, const float** ptr,
+                                   int* H, int* W, int* C) {
+    FS_CHECK(e && e->e.bound && (e->e.flags & ENG_TRANSFORM), "engine has no bound transform plan");
+    FS_CHECK(conv_index >= 0 && conv_index < T_NCONV && (stage == 0 || stage == 1), "bad activation query");
+    const TConv& c = e->e.tc[conv_index];
+    *ptr = stage == 0 ? e->e.tb[conv_index].raw : e->e.tb[conv_index].act;
+    FS_CHECK(*ptr != nullptr, "activation not stored (the last layer's output is y3)");
+    *H = c.outH; *W = c.outW; *C = c.cout_s;
+    return 0;
+}
+
+int fs_transform_forward(fs_engine* e, const float* params, const float* x3, float* y3, void* stream) {
+    FS_CHECK(e && params && x3 && y3, "fs_transform_forward: NULL argument");
+    FS_TRY(e->e.prep_transform_weights(params, false, S(stream)));
+    return e->e.transform_forward(params, x3, y3, S(stream));
+}
+
+int fs_vgg_forward(fs_engine* e, const float* packed, const float* img3, int upto, void* stream) {
+    FS_CHECK(e && packed && img3, "fs_vgg_forward: NULL argument");
+    return e->e.vgg_forward(packed, img3, upto, nullptr, S(stream));
+}
+
+int fs_vgg_grams(fs_engine* e, const float* packed, const float* img3, int n_layers, const int* layers,
+                 float* const* out_grams, void* stream) {
+    FS_CHECK(e && packed && img3 && layers && out_grams, "fs_vgg_grams: NULL argument");
+    FS_CHECK(n_layers >= 1 && n_layers <= V_NCONV, "fs_vgg_grams: bad layer count");
+    Engine& E = e->e;
+    int top = 0;
+    for (int i = 0; i < n_layers; ++i) {
+        FS_CHECK(layers[i] >= 0 && layers[i] < V_NCONV, "fs_vgg_grams: bad layer %d", layers[i]);
+        top = layers[i] > top ? layers[i] : top;
+    }
+    FS_TRY(E.vgg_forward(packed, img3, top, nullptr, S(stream)));
+    for (int i = 0; i < n_layers; ++i) {
+        const VConv& v = E.vc[layers[i]];
+        WGradArgs wa;
+        memset(&wa, 0, sizeof(wa));
+        wa.in = E.vact[layers[i]]; wa.dy = wa.in; wa.out = out_grams[i];
+        wa.partial = E.wg_partial; wa.partial_cap = E.wg_partial_cap;
+        wa.H = v.H; wa.W = v.W; wa.C = v.cout; wa.in_bs = (long long)v.H * v.W * v.cout;
+        wa.KH = wa.KW = 1; wa.stride = 1; wa.OH = v.H; wa.OW = v.W; wa.OC = v.cout; wa.dy_bs = wa.in_bs;
+        wa.N = E.N; wa.per_sample = 1; wa.scale = (float)(1.0 / ((double)v.H * v.W * v.cout));
+        FS_TRY(launch_wgrad(wa, S(stream)));
+    }
+    return 0;
+}
+
+int fs_vgg_set_content_targets(fs_engine* e, const float* packed, const float* img3,
+                               const fs_loss_config* cfg, void* stream) {
+    FS_CHECK(e && packed && img3, "fs_vgg_set_content_targets: NULL argument");
+    LossConfig lc;
+    FS_TRY(to_lc(cfg, lc));
+    return e->e.vgg_content_targets(packed, img3, lc, S(stream));
+}
+
+int fs_perceptual_loss(fs_engine* e, const float* packed, const float* img3, const fs_loss_config* cfg,
+                       const float* const* target_grams, float* losses4, float* grad3, void* stream) {
+    FS_CHECK(e && packed && img3 && losses4, "fs_perceptual_loss: NULL argument");
+    LossConfig lc;
+    FS_TRY(to_lc(cfg, lc));
+    Engine& E = e->e;
+    FS_CHECK(E.bound && (E.flags & ENG_VGG), "engine has no bound VGG plan");
+    cudaStream_t st = S(stream);
+    FS_TRY(fill_zero(E.loss_acc, 4 * sizeof(double), st));
+    FS_TRY(E.vgg_loss_backward(packed, img3, lc, target_grams, grad3 != nullptr, st));
+    if (lc.beta != 0.f) FS_TRY(tv_loss_grad(img3, grad3 ? E.dY4 : nullptr, E.N, E.VH, E.VW, lc.beta, E.loss_acc + 2, st));
+    if (grad3) FS_TRY(unpad_taps(E.dY4, grad3, E.N * E.VH * E.VW, 1, 3, 1, 4, st));
+    return finalize_losses(E.loss_acc, losses4, st);
+}
+
+int fs_train_fwd_bwd(fs_engine* e, const float* params, const float* packed, const float* x3,
+                     const fs_loss_config* cfg, const float* const* target_grams, float* grads,
+                     float* losses4, float* y3, void* stream) {
+    FS_CHECK(e && params && packed && x3 && grads && losses4, "fs_train_fwd_bwd: NULL argument");
+    LossConfig lc;
+    FS_TRY(to_lc(cfg, lc));
+    return e->e.train_fwd_bwd(params, packed, x3, lc, target_grams, grads, losses4, y3, S(stream));
+}
+
+int fs_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr,
+                 float beta1, float beta2, float eps, int* step_counter, void* stream) {
+    FS_CHECK(params && grads && m && v && step_counter && n > 0, "fs_adam_step: bad argument");
+    return adam_step(params, grads, m, v, n, lr, beta1, beta2, eps, step_counter, S(stream));
+}
+
+// ------------------------------------------------------------------ single ops
+static int conv_geom(int H, int W, int KH, int KW, int stride, int same, int* OH, int* OW, int* pt, int* pl) {
+    FS_CHECK(stride >= 1 && KH >= 1 && KW >= 1, "conv: bad geometry");
+    if (same) { tf_same(H, KH, stride, OH, pt); tf_same(W, KW, stride, OW, pl); }
+    else { *OH = (H - KH) / stride + 1; *OW = (W - KW) / stride + 1; *pt = *pl = 0; }
+    FS_CHECK(*OH > 0 && *OW > 0, "conv: empty output (%dx%d input, %dx%d kernel)", H, W, KH, KW);
+    return 0;
+}
+
+int fs_conv2d_forward(const float* x, const float* w, const float* bias, float* y, int N, int H, int W,
+                      int C, int KH, int KW, int OC, int stride, int padding_same, int relu, void* stream) {
+    FS_CHECK(x && w && y, "fs_conv2d_forward: NULL argument");
+    IGemmArgs a;
+    memset(&a, 0, sizeof(a));
+    FS_TRY(conv_geom(H, W, KH, KW, stride, padding_same, &a.OH, &a.OW, &a.pad_t, &a.pad_l));
+    a.in = x; a.w = w; a.out = y; a.N = N; a.H = H; a.W = W; a.C = C; a.in_bs = (long long)H * W * C;
+    a.KH = KH; a.KW = KW; a.stride = stride; a.OC = OC; a.out_bs = (long long)a.OH * a.OW * OC;
+    a.bias = bias; a.relu = relu;
+    return launch_igemm(a, S(stream));
+}
+
+int fs_conv2d_dgrad(const float* dy, const float* w, float* dx, float* wt_scratch, int N, int H, int W,
+                    int C, int KH, int KW, int OC, int stride, int padding_same, void* stream) {
+    FS_CHECK(dy && w && dx && wt_scratch, "fs_conv2d_dgrad: NULL argument");
+    IGemmArgs a;
+    memset(&a, 0, sizeof(a));
+    int OH, OW;
+    FS_TRY(conv_geom(H, W, KH, KW, stride, padding_same, &OH, &OW, &a.pad_t, &a.pad_l));
+    FS_TRY(transpose_taps(w, wt_scratch, KH * KW, C, OC, S(stream)));
+    a.in = dy; a.w = wt_scratch; a.out = dx; a.N = N; a.gather = 1;
+    a.H = OH; a.W = OW; a.C = OC; a.in_bs = (long long)OH * OW * OC;
+    a.KH = KH; a.KW = KW; a.stride = stride;
+    a.OH = H; a.OW = W; a.OC = C; a.out_bs = (long long)H * W * C;
+    return launch_igemm(a, S(stream));
+}
+
+long long fs_conv2d_wgrad_scratch_floats(int C, int KH, int KW, int OC) {
+    return wgrad_partial_floats(KH * KW * C, OC, 1);
+}
+
+int fs_conv2d_wgrad(const float* x, const float* dy, float* dw, float* scratch, long long scratch_floats,
+                    int N, int H, int W, int C, int KH, int KW, int OC, int stride, int padding_same,
+                    void* stream) {
+    FS_CHECK(x && dy && dw && scratch, "fs_conv2d_wgrad: NULL argument");
+    WGradArgs wa;
+    memset(&wa, 0, sizeof(wa));
+    FS_TRY(conv_geom(H, W, KH, KW, stride, padding_same, &wa.OH, &wa.OW, &wa.pad_t, &wa.pad_l));
+    wa.in = x; wa.dy = dy; wa.out = dw; wa.partial = scratch; wa.partial_cap = scratch_floats;
+    wa.H = H; wa.W = W; wa.C = C; wa.in_bs = (long long)H * W * C;
+    wa.KH = KH; wa.KW = KW; wa.stride = stride; wa.OC = OC; wa.dy_bs = (long long)wa.OH * wa.OW * OC;
+    wa.N = N; wa.per_sample = 0; wa.scale = 1.f;
+    return launch_wgrad(wa, S(stream));
+}
+
+int fs_upconv2d_forward(const float* x, const float* w, float* y, float* wc_scratch, int N, int H, int W,
+                        int C, int OC, void* stream) {
+    FS_CHECK(x && w && y && wc_scratch, "fs_upconv2d_forward: NULL argument");
+    FS_TRY(upconv_collapse(w, wc_scratch, C, OC, S(stream)));
+    IGemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = x; a.w = wc_scratch; a.out = y; a.N = N; a.H = H; a.W = W; a.C = C; a.in_bs = (long long)H * W * C;
+    a.KH = a.KW = 2; a.stride = 1; a.OH = H; a.OW = W; a.OC = 4 * OC; a.out_mode = 1;
+    a.out_bs = 4LL * H * W * OC;
+    return launch_igemm(a, S(stream));
+}
+
+int fs_instnorm_forward(const float* x, const float* scale, const float* shift, float* y, float* stats,
+                        double* scratch, int N, int H, int W, int C, float eps, int act, void* stream) {
+    FS_CHECK(x && scale && shift && y && stats && scratch, "fs_instnorm_forward: NULL argument");
+    FS_TRY(instnorm_stats(x, stats, stats + (long long)N * C, N, H * W, C, eps, scratch, S(stream)));
+    return instnorm_apply(x, stats, stats + (long long)N * C, scale, shift, nullptr, y, N, H, W, C, act, 0, S(stream));
+}
+
+int fs_maxpool2x2(const float* x, float* y, int N, int H, int W, int C, void* stream) {
+    FS_CHECK(x && y, "fs_maxpool2x2: NULL argument");
+    return maxpool2x2_fwd(x, y, N, H, W, C, S(stream));
+}
+
+long long fs_gram_scratch_floats(int N, int C) { return wgrad_partial_floats(C, C, N); }
+
+int fs_gram_forward(const float* f, float* g, float* scratch, long long scratch_floats, int N, int H, int W,
+                    int C, void* stream) {
+    FS_CHECK(f && g && scratch, "fs_gram_forward: NULL argument");
+    WGradArgs wa;
+    memset(&wa, 0, sizeof(wa));
+    wa.in = f; wa.dy = f; wa.out = g; wa.partial = scratch; wa.partial_cap = scratch_floats;
+    wa.H = H; wa.W = W; wa.C = C; wa.in_bs = (long long)H * W * C;
+    wa.KH = wa.KW = 1; wa.stride = 1; wa.OH = H; wa.OW = W; wa.OC = C; wa.dy_bs = wa.in_bs;
+    wa.N = N; wa.per_sample = 1; wa.scale = (float)(1.0 / ((double)H * W * C));
+    return launch_wgrad(wa, S(stream));
+}
+
+}  // extern "C"

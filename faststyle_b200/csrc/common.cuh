@@ -1,0 +1,94 @@
+// Shared declarations for libfaststyle_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace fs {
+
+// ---------------------------------------------------------------- errors
+// Every C-ABI entry point returns 0 on success or a negative code and records
+// a message retrievable through fs_last_error() (thread-local).
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define FS_CHECK(cond, ...)                                   \
+    do {                                                      \
+        if (!(cond)) { fs::set_error(__VA_ARGS__); return -1; } \
+    } while (0)
+
+#define FS_CUDA(expr)                                                          \
+    do {                                                                       \
+        cudaError_t _e = (expr);                                               \
+        if (_e != cudaSuccess) {                                               \
+            fs::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                          __FILE__, __LINE__);                                 \
+            return -2;                                                         \
+        }                                                                      \
+    } while (0)
+
+#define FS_LAUNCH_CHECK() FS_CUDA(cudaGetLastError())
+
+#define FS_TRY(expr)                   \
+    do {                               \
+        int _r = (expr);               \
+        if (_r != 0) return _r;        \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// TF 'SAME' padding rule: out = ceil(n/s),
+// total = max((out-1)*s + k - n, 0), before = total/2.
+static inline void tf_same(int n, int k, int s, int* out, int* before) {
+    int o = (n + s - 1) / s;
+    int total = (o - 1) * s + k - n;
+    if (total < 0) total = 0;
+    *out = o;
+    *before = total / 2;
+}
+
+// ---------------------------------------------------------------- implicit GEMM
+// One descriptor drives the FFMA implicit-GEMM kernels (forward conv, data
+// gradient, fused resize-conv, Gram backward).  GEMM view per sample n:
+//   out[m, j] = sum_k A[m, k] * Wm[k, j],   m = oy*OW+ox,  k = (kh*KW+kw)*C + c
+// A is gathered on the fly from the NHWC input.
+struct IGemmArgs {
+    const float* in;  const float* w;  float* out;
+    int H, W, C;                 // gathered tensor: logical spatial dims, channels per tap (C%4==0)
+    int in_mode;                 // 0: plain NHWC [H,W,C]; 1: space-to-depth view of [2H,2W,C/4]
+    long long in_bs;             // input batch stride (elements)
+    int KH, KW, stride, pad_t, pad_l;
+    int gather;                  // 0: iy = oy*stride - pad_t + kh      (forward)
+                                 // 1: iy = (oy + pad_t - kh)/stride if divisible (data gradient)
+    int OH, OW, OC;              // GEMM M = OH*OW, N = OC (OC%4==0)
+    int out_mode;                // 0: plain [OH,OW,OC]; 1: depth-to-space into [2OH,2OW,OC/4]
+    long long out_bs;            // output batch stride (elements)
+    long long w_bs;              // weight batch stride (0 = shared across the batch)
+    // epilogue: v += bias[j]; v += addend[...]; if relu v=max(v,0); if ref && ref<=0 v=0
+    const float* bias; const float* addend; const float* ref;
+    int relu;
+    int add_crop, addH, addW;    // addend is [N,addH,addW,OC]; pixel (y,x) reads (y-crop, x-crop)
+    long long add_bs;
+    int N;
+};
+int launch_igemm(const IGemmArgs& a, cudaStream_t st);
+
+// Reduction-over-pixels GEMM (weight gradient, Gram forward):
+//   out[g][k, j] = scale * sum_pix A[pix, k] * B[pix, j]
+struct WGradArgs {
+    const float* in;  const float* dy;  float* out;  float* partial;  // partial: workspace
+    long long partial_cap;       // capacity of partial in floats
+    int H, W, C; int in_mode; long long in_bs;      // gathered A side (as IGemmArgs)
+    int KH, KW, stride, pad_t, pad_l;
+    int OH, OW, OC;              // dy logical dims [OH,OW,OC]
+    int dy_mode;                 // 0 plain; 1 space-to-depth view of [2OH,2OW,OC/4]
+    long long dy_bs;
+    int N;
+    int per_sample;              // 1: separate output per sample (Gram), 0: reduce over batch
+    float scale;
+};
+int launch_wgrad(const WGradArgs& a, cudaStream_t st);
+long long wgrad_partial_floats(int K, int OC, int groups);
+
+}  // namespace fs

@@ -1,0 +1,540 @@
+// Whole-path composites: transform net forward/backward, VGG16 perceptual loss
+// forward/backward, and the fused train step.  Host-side orchestration only;
+// the arithmetic is in igemm_f32.cu / ops.cu / (tensor path) conv3x3_tc.cu.
+//
+// Reference call sites being replaced (one Session.run each in the reference):
+//   transform fwd      stylize_image.py:75, train.py:161
+//   train step         train.py:250-251 (content targets) + train.py:274-275
+//   slow_style step    slow_style.py:170-176
+#include "engine.cuh"
+#include <algorithm>
+
+namespace fs {
+
+static const float IN_EPS = 1e-3f;       // reference im_transf_net.py:218
+
+// ---------------------------------------------------------------- parameter table
+void transform_param_table(TConv* tc) {
+    auto set = [&](int i, int k, int s, int same, int cin, int cout, int up, int act) {
+        tc[i].k = k; tc[i].stride = s; tc[i].same = same; tc[i].cin = cin; tc[i].cout = cout;
+        tc[i].upconv = up; tc[i].act = act;
+        tc[i].cin_s = (cin + 3) & ~3; tc[i].cout_s = (cout + 3) & ~3;
+    };
+    set(0, 9, 1, 1, 3, 16, 0, ACT_RELU);
+    set(1, 3, 2, 1, 16, 32, 0, ACT_RELU);
+    set(2, 3, 2, 1, 32, 64, 0, ACT_RELU);
+    for (int r = 0; r < 5; ++r) {
+        set(3 + 2 * r, 3, 1, 0, 64, 64, 0, ACT_RELU);
+        set(4 + 2 * r, 3, 1, 0, 64, 64, 0, ACT_NONE);
+    }
+    set(13, 3, 2, 1, 64, 32, 1, ACT_RELU);
+    set(14, 3, 2, 1, 32, 16, 1, ACT_RELU);
+    set(15, 9, 1, 1, 16, 3, 0, ACT_TANH255);
+    // flat layout == byte-sorted checkpoint key order
+    long long off = 0;
+    auto wsz = [&](int i) { return (long long)tc[i].k * tc[i].k * tc[i].cin * tc[i].cout; };
+    for (int i = 0; i < 3; ++i) {
+        tc[i].offG = off; off += tc[i].cout;
+        tc[i].offB = off; off += tc[i].cout;
+        tc[i].offW = off; off += wsz(i);
+    }
+    for (int r = 0; r < 5; ++r) {
+        int a = 3 + 2 * r, b = 4 + 2 * r;
+        tc[a].offG = off; off += 64;      // INscale1
+        tc[b].offG = off; off += 64;      // INscale2
+        tc[a].offB = off; off += 64;      // INshift1
+        tc[b].offB = off; off += 64;      // INshift2
+        tc[a].offW = off; off += wsz(a);  // W1
+        tc[b].offW = off; off += wsz(b);  // W2
+    }
+    for (int i = 13; i < 16; ++i) {
+        tc[i].offG = off; off += tc[i].cout;
+        tc[i].offB = off; off += tc[i].cout;
+        tc[i].offW = off; off += wsz(i);
+    }
+}
+
+// ---------------------------------------------------------------- VGG tables
+static const int V_CIN[V_NCONV] = {3, 64, 64, 128, 128, 256, 256, 256, 512, 512};
+static const int V_COUT[V_NCONV] = {64, 64, 128, 128, 256, 256, 256, 512, 512, 512};
+static const int V_POOL[V_NCONV] = {0, 1, 0, 1, 0, 0, 1, 0, 0, 0};
+
+long long vgg_flat_floats() {
+    long long n = 0;
+    for (int l = 0; l < V_NCONV; ++l) n += 9LL * V_CIN[l] * V_COUT[l] + V_COUT[l];
+    return n;
+}
+static void vgg_offsets(VConv* vc) {
+    long long off = 0;
+    for (int l = 0; l < V_NCONV; ++l) {
+        vc[l].cin = V_CIN[l]; vc[l].cout = V_COUT[l]; vc[l].cin_s = (V_CIN[l] + 3) & ~3;
+        vc[l].pool_after = V_POOL[l];
+        vc[l].offW = off; off += 9LL * vc[l].cin_s * vc[l].cout;
+        vc[l].offB = off; off += vc[l].cout;
+        vc[l].offWT = off; off += 9LL * vc[l].cin_s * vc[l].cout;
+    }
+}
+long long vgg_packed_floats() {
+    VConv vc[V_NCONV];
+    vgg_offsets(vc);
+    return vc[V_NCONV - 1].offWT + 9LL * vc[V_NCONV - 1].cin_s * vc[V_NCONV - 1].cout;
+}
+
+int vgg_pack(const float* flat, float* packed, cudaStream_t st) {
+    VConv vc[V_NCONV];
+    vgg_offsets(vc);
+    long long src = 0;
+    for (int l = 0; l < V_NCONV; ++l) {
+        long long wn = 9LL * vc[l].cin * vc[l].cout;
+        if (vc[l].cin != vc[l].cin_s)
+            FS_TRY(pad_taps(flat + src, packed + vc[l].offW, 9, vc[l].cin, vc[l].cout, vc[l].cin_s, vc[l].cout, st));
+        else
+            FS_CUDA(cudaMemcpyAsync(packed + vc[l].offW, flat + src, wn * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        src += wn;
+        FS_CUDA(cudaMemcpyAsync(packed + vc[l].offB, flat + src, vc[l].cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        src += vc[l].cout;
+        FS_TRY(transpose_taps(packed + vc[l].offW, packed + vc[l].offWT, 9, vc[l].cin_s, vc[l].cout, st));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- planning
+int Engine::plan() {
+    FS_CHECK(N >= 1 && H >= 1 && W >= 1, "engine: bad dims N=%d H=%d W=%d", N, H, W);
+    transform_param_table(tc);
+    VH = H; VW = W;
+    if (flags & ENG_TRANSFORM) {
+        FS_CHECK(H > 40 && W > 40, "transform net needs H,W > 40 for the 40-px reflect pad (got %dx%d)", H, W);
+        Hp = H + 80; Wp = W + 80;
+        int h = Hp, w = Wp;
+        for (int l = 0; l < T_NCONV; ++l) {
+            TConv& c = tc[l];
+            c.inH = h; c.inW = w;
+            if (c.upconv) {
+                c.outH = 2 * h; c.outW = 2 * w; c.pad_t = c.pad_l = 0;
+            } else if (c.same) {
+                tf_same(h, c.k, c.stride, &c.outH, &c.pad_t);
+                tf_same(w, c.k, c.stride, &c.outW, &c.pad_l);
+            } else {
+                c.outH = h - c.k + 1; c.outW = w - c.k + 1; c.pad_t = c.pad_l = 0;
+            }
+            FS_CHECK(c.outH > 0 && c.outW > 0, "transform net: image too small (layer %d output %dx%d)", l, c.outH, c.outW);
+            h = c.outH; w = c.outW;
+        }
+        OH = h; OW = w;
+        VH = OH; VW = OW;
+    }
+    if (flags & ENG_VGG) {
+        vgg_offsets(vc);
+        int h = VH, w = VW;
+        for (int l = 0; l < V_NCONV; ++l) {
+            vc[l].H = h; vc[l].W = w;
+            if (vc[l].pool_after) { h = (h + 1) / 2; w = (w + 1) / 2; }
+        }
+    }
+    return 0;
+}
+
+static long long maxll(long long a, long long b) { return a > b ? a : b; }
+
+void Engine::layout(Arena& a) {
+    const bool tb_ = flags & ENG_TRANSFORM, tbw = flags & ENG_TRANSFORM_BWD;
+    const bool vg = flags & ENG_VGG, vgb = flags & ENG_VGG_BWD;
+    long long wgcap = 0;
+    if (tb_) {
+        xpad4 = a.take<float>((long long)N * Hp * Wp * 4);
+        long long maxact = 0;
+        for (int l = 0; l < T_NCONV; ++l) {
+            TConv& c = tc[l];
+            long long n = (long long)N * c.outH * c.outW * c.cout_s;
+            maxact = maxll(maxact, n);
+            tb[l].raw = a.take<float>(n);
+            tb[l].act = l == T_NCONV - 1 ? nullptr : a.take<float>(n);
+            tb[l].mean = a.take<float>((long long)N * c.cout_s);
+            tb[l].rstd = a.take<float>((long long)N * c.cout_s);
+            weff[l] = nullptr; wefft[l] = nullptr;
+            if (l == 0 || l == 15) weff[l] = a.take<float>((long long)c.k * c.k * c.cin_s * c.cout_s);
+            if (c.upconv) weff[l] = a.take<float>(16LL * c.cin * c.cout);
+            if (tbw && l > 0) {
+                long long n2 = c.upconv ? 16LL * c.cin * c.cout : (long long)c.k * c.k * c.cin_s * c.cout_s;
+                wefft[l] = a.take<float>(n2);
+                }
+            if (tbw) {
+                int K = c.upconv ? 4 * c.cin : c.k * c.k * c.cin_s;
+                int OC = c.upconv ? 4 * c.cout : c.cout_s;
+                wgcap = maxll(wgcap, wgrad_partial_floats(K, OC, 1));
+            }
+        }
+        y3 = a.take<float>((long long)N * OH * OW * 3);
+        in_partial = a.take<double>((long long)N * 64 * 64 * 2);
+        in15 = a.take<float>(8);
+        if (tbw) {
+            m12 = a.take<float>((long long)N * 64 * 2);
+            for (int i = 0; i < 3; ++i) tgrad[i] = a.take<float>(maxact);
+            wg_tmp = a.take<float>(81LL * 16 * 4 + 16LL * 64 * 32 + 1024);
+            gb_tmp = a.take<float>(8);
+        }
+    }
+    if (vg) {
+        v_in4 = a.take<float>((long long)N * VH * VW * 4);
+        long long maxact = 0;
+        for (int l = 0; l < V_NCONV; ++l) {
+            long long n = (long long)N * vc[l].H * vc[l].W * vc[l].cout;
+            maxact = maxll(maxact, n);
+            vact[l] = a.take<float>(n);
+            vpool[l] = vc[l].pool_after ? a.take<float>((long long)N * ((vc[l].H + 1) / 2) * ((vc[l].W + 1) / 2) * vc[l].cout) : nullptr;
+            bool st_ = (style_mask >> l) & 1, ct_ = (content_mask >> l) & 1;
+            gram[l] = st_ ? a.take<float>((long long)N * vc[l].cout * vc[l].cout) : nullptr;
+            gramS[l] = st_ ? a.take<float>((long long)N * vc[l].cout * vc[l].cout) : nullptr;
+            ctarget[l] = ct_ ? a.take<float>(n) : nullptr;
+            if (st_) wgcap = maxll(wgcap, wgrad_partial_floats(vc[l].cout, vc[l].cout, N));
+        }
+        loss_acc = a.take<double>(4);
+        if (vgb) {
+            vgrad_floats = maxact;
+            for (int i = 0; i < 4; ++i) vgrad[i] = a.take<float>(maxact);
+            dY4 = a.take<float>((long long)N * VH * VW * 4);
+        }
+    }
+    wg_partial_cap = wgcap;
+    wg_partial = wgcap ? a.take<float>(wgcap) : nullptr;
+}
+
+int Engine::bind(void* ws, size_t bytes) {
+    FS_CHECK(bytes >= ws_bytes, "engine: workspace too small (%zu < %zu bytes)", bytes, ws_bytes);
+    FS_CHECK(((uintptr_t)ws & 255) == 0, "engine: workspace must be 256-byte aligned");
+    Arena a; a.base = (char*)ws; a.cap = bytes;
+    layout(a);
+    bound = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------- transform net
+int Engine::prep_transform_weights(const float* params, bool need_bwd, cudaStream_t st) {
+    FS_CHECK(bound && (flags & ENG_TRANSFORM), "engine has no transform plan / workspace");
+    FS_TRY(pad_taps(params + tc[0].offW, weff[0], 81, 3, 16, 4, 16, st));
+    FS_TRY(pad_taps(params + tc[15].offW, weff[15], 81, 16, 3, 16, 4, st));
+    FS_TRY(upconv_collapse(params + tc[13].offW, weff[13], tc[13].cin, tc[13].cout, st));
+    FS_TRY(upconv_collapse(params + tc[14].offW, weff[14], tc[14].cin, tc[14].cout, st));
+    // 4-channel staging of the last layer's IN scale/shift (its flat slots are 3 floats, unaligned)
+    FS_TRY(fill_zero(in15, 8 * sizeof(float), st));
+    FS_CUDA(cudaMemcpyAsync(in15, params + tc[15].offG, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    FS_CUDA(cudaMemcpyAsync(in15 + 4, params + tc[15].offB, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (need_bwd) {
+        FS_CHECK(flags & ENG_TRANSFORM_BWD, "engine was not created with a backward plan");
+        for (int l = 1; l < T_NCONV; ++l) {
+            const TConv& c = tc[l];
+            const float* src = weff[l] ? weff[l] : params + c.offW;
+            if (c.upconv) FS_TRY(transpose_taps(src, wefft[l], 4, c.cin, 4 * c.cout, st));
+            else FS_TRY(transpose_taps(src, wefft[l], c.k * c.k, c.cin_s, c.cout_s, st));
+        }
+    }
+    return 0;
+}
+
+static void conv_fwd_args(const TConv& c, int N, const float* in, const float* w, float* out, IGemmArgs& a) {
+    memset(&a, 0, sizeof(a));
+    a.in = in; a.w = w; a.out = out; a.N = N;
+    a.H = c.inH; a.W = c.inW;
+    a.in_bs = (long long)c.inH * c.inW * c.cin_s;
+    if (c.upconv) {
+        a.C = c.cin; a.KH = a.KW = 2; a.stride = 1; a.pad_t = a.pad_l = 0;
+        a.OH = c.inH; a.OW = c.inW; a.OC = 4 * c.cout; a.out_mode = 1;
+        a.out_bs = (long long)c.outH * c.outW * c.cout;
+    } else {
+        a.C = c.cin_s; a.KH = a.KW = c.k; a.stride = c.stride; a.pad_t = c.pad_t; a.pad_l = c.pad_l;
+        a.OH = c.outH; a.OW = c.outW; a.OC = c.cout_s; a.out_mode = 0;
+        a.out_bs = (long long)c.outH * c.outW * c.cout_s;
+    }
+}
+
+int Engine::transform_forward(const float* params, const float* x3, float* y3_out, cudaStream_t st) {
+    FS_CHECK(bound && (flags & ENG_TRANSFORM), "engine has no transform plan / workspace");
+    FS_TRY(reflect_pad_c4(x3, xpad4, N, H, W, 40, st));
+    const float* cur = xpad4;
+    for (int l = 0; l < T_NCONV; ++l) {
+        const TConv& c = tc[l];
+        IGemmArgs a;
+        conv_fwd_args(c, N, cur, weff[l] ? weff[l] : params + c.offW, tb[l].raw, a);
+        FS_TRY(launch_igemm(a, st));
+        FS_TRY(instnorm_stats(tb[l].raw, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, in_partial, st));
+        const float* skip = nullptr;
+        if (l >= 4 && l <= 12 && (l & 1) == 0) skip = tb[l - 2].act;       // residual: block input
+        const bool last = l == T_NCONV - 1;
+        const float* g = last ? in15 : params + c.offG;
+        const float* b = last ? in15 + 4 : params + c.offB;
+        float* out = last ? (y3_out ? y3_out : y3) : tb[l].act;
+        FS_TRY(instnorm_apply(tb[l].raw, tb[l].mean, tb[l].rstd, g, b, skip, out, N, c.outH, c.outW,
+                              c.cout_s, c.act, last ? 1 : 0, st));
+        cur = tb[l].act;
+    }
+    return 0;
+}
+
+int Engine::transform_backward(const float* params, const float* dY4_in, float* grads, cudaStream_t st) {
+    FS_CHECK(bound && (flags & ENG_TRANSFORM_BWD), "engine has no transform backward plan");
+    // Three rotating gradient buffers.  cur = buffer holding dAct (gradient w.r.t. the layer's
+    // post-activation output; -1 while it is the caller's dY4), held = buffer holding the gradient
+    // of the enclosing residual block's output (needed again for the skip path).
+    auto pick2 = [](int a, int b) { for (int i = 0; i < 3; ++i) if (i != a && i != b) return i; return -1; };
+    const float* dAct = dY4_in;
+    int cur = -1, held = -1;
+    const float* resid_dOut = nullptr;
+    int resid_H = 0, resid_W = 0;
+    for (int l = T_NCONV - 1; l >= 0; --l) {
+        const TConv& c = tc[l];
+        const bool last = l == T_NCONV - 1;
+        const float* g = last ? in15 : params + c.offG;
+        const float* b = last ? in15 + 4 : params + c.offB;
+        float* dg = last ? gb_tmp : grads + c.offG;
+        float* db = last ? gb_tmp + 4 : grads + c.offB;
+        const bool second_of_block = (l >= 4 && l <= 12 && (l & 1) == 0);
+        if (second_of_block) { resid_dOut = dAct; resid_H = c.outH; resid_W = c.outW; held = cur; }
+        const int ri = pick2(cur, held);
+        float* dRaw = tgrad[ri];
+        FS_TRY(instnorm_bwd(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw, dg, db, N,
+                            c.outH * c.outW, c.cout_s, c.act, in_partial, m12, st));
+        if (last) {
+            FS_CUDA(cudaMemcpyAsync(grads + c.offG, gb_tmp, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            FS_CUDA(cudaMemcpyAsync(grads + c.offB, gb_tmp + 4, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+        // ---- weight gradient
+        const float* in_act = l == 0 ? xpad4 : tb[l - 1].act;
+        WGradArgs wa;
+        memset(&wa, 0, sizeof(wa));
+        wa.in = in_act; wa.dy = dRaw; wa.partial = wg_partial; wa.partial_cap = wg_partial_cap;
+        wa.H = c.inH; wa.W = c.inW; wa.in_bs = (long long)c.inH * c.inW * c.cin_s;
+        wa.N = N; wa.per_sample = 0; wa.scale = 1.f;
+        if (c.upconv) {
+            wa.C = c.cin; wa.KH = wa.KW = 2; wa.stride = 1;
+            wa.OH = c.inH; wa.OW = c.inW; wa.OC = 4 * c.cout; wa.dy_mode = 1;
+            wa.dy_bs = (long long)c.outH * c.outW * c.cout;
+            wa.out = wg_tmp;
+            FS_TRY(launch_wgrad(wa, st));
+            FS_TRY(upconv_collapse_grad(wg_tmp, grads + c.offW, c.cin, c.cout, st));
+        } else {
+            wa.C = c.cin_s; wa.KH = wa.KW = c.k; wa.stride = c.stride; wa.pad_t = c.pad_t; wa.pad_l = c.pad_l;
+            wa.OH = c.outH; wa.OW = c.outW; wa.OC = c.cout_s; wa.dy_mode = 0;
+            wa.dy_bs = (long long)c.outH * c.outW * c.cout_s;
+            const bool padded = (c.cin != c.cin_s) || (c.cout != c.cout_s);
+            wa.out = padded ? wg_tmp : grads + c.offW;
+            FS_TRY(launch_wgrad(wa, st));
+            if (padded) FS_TRY(unpad_taps(wg_tmp, grads + c.offW, c.k * c.k, c.cin, c.cout, c.cin_s, c.cout_s, st));
+        }
+        if (l == 0) break;                       // no gradient w.r.t. the input image (train.py:198-204)
+        // ---- data gradient -> gradient w.r.t. the previous layer's activation
+        const int pidx = pick2(ri, held);
+        float* dPrev = tgrad[pidx];
+        IGemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in = dRaw; a.w = wefft[l]; a.out = dPrev; a.N = N; a.gather = 1;
+        if (c.upconv) {
+            a.H = c.inH; a.W = c.inW; a.C = 4 * c.cout; a.in_mode = 1;
+            a.in_bs = (long long)c.outH * c.outW * c.cout;
+            a.KH = a.KW = 2; a.stride = 1; a.pad_t = a.pad_l = 0;
+        } else {
+            a.H = c.outH; a.W = c.outW; a.C = c.cout_s; a.in_mode = 0;
+            a.in_bs = (long long)c.outH * c.outW * c.cout_s;
+            a.KH = a.KW = c.k; a.stride = c.stride; a.pad_t = c.pad_t; a.pad_l = c.pad_l;
+        }
+        a.OH = c.inH; a.OW = c.inW; a.OC = c.cin_s;
+        a.out_bs = (long long)c.inH * c.inW * c.cin_s;
+        const bool first_of_block = (l >= 3 && l <= 11 && (l & 1) == 1);
+        if (first_of_block) {                    // add the skip-path gradient, zero-padded by 2 px
+            a.addend = resid_dOut; a.add_crop = 2; a.addH = resid_H; a.addW = resid_W;
+            a.add_bs = (long long)resid_H * resid_W * 64;
+        }
+        FS_TRY(launch_igemm(a, st));
+        dAct = dPrev; cur = pidx;
+        if (first_of_block) { held = -1; resid_dOut = nullptr; }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- VGG
+static void vgg_conv_args(const VConv& v, int N, const float* packed, const float* in, float* out, IGemmArgs& a) {
+    memset(&a, 0, sizeof(a));
+    a.in = in; a.w = packed + v.offW; a.out = out; a.N = N;
+    a.H = v.H; a.W = v.W; a.C = v.cin_s; a.in_bs = (long long)v.H * v.W * v.cin_s;
+    a.KH = a.KW = 3; a.stride = 1; a.pad_t = a.pad_l = 1;
+    a.OH = v.H; a.OW = v.W; a.OC = v.cout; a.out_bs = (long long)v.H * v.W * v.cout;
+    a.bias = packed + v.offB; a.relu = 1;
+}
+
+int Engine::vgg_forward(const float* packed, const float* img3, int upto, float* const* act_override,
+                        cudaStream_t st) {
+    FS_CHECK(bound && (flags & ENG_VGG), "engine has no VGG plan / workspace");
+    FS_CHECK(upto >= 0 && upto < V_NCONV, "vgg_forward: bad layer %d", upto);
+    FS_TRY(vgg_preprocess_c4(img3, v_in4, (long long)N * VH * VW, st));
+    const float* cur = v_in4;
+    for (int l = 0; l <= upto; ++l) {
+        float* out = (act_override && act_override[l]) ? act_override[l] : vact[l];
+        IGemmArgs a;
+        vgg_conv_args(vc[l], N, packed, cur, out, a);
+        FS_TRY(launch_igemm(a, st));
+        cur = out;
+        if (vc[l].pool_after && l < upto) {
+            FS_TRY(maxpool2x2_fwd(cur, vpool[l], N, vc[l].H, vc[l].W, vc[l].cout, st));
+            cur = vpool[l];
+        }
+    }
+    return 0;
+}
+
+int Engine::vgg_content_targets(const float* packed, const float* img3, const LossConfig& lc, cudaStream_t st) {
+    if (lc.n_content == 0) return 0;
+    float* ov[V_NCONV] = {nullptr};
+    int top = 0;
+    for (int i = 0; i < lc.n_content; ++i) {
+        int l = lc.content_layer[i];
+        FS_CHECK(l >= 0 && l < V_NCONV && ctarget[l], "content layer %d not planned in this engine", l);
+        ov[l] = ctarget[l];
+        top = std::max(top, l);
+    }
+    return vgg_forward(packed, img3, top, ov, st);
+}
+
+int Engine::vgg_loss_backward(const float* packed, const float* img3, const LossConfig& lc,
+                              const float* const* target_grams, bool need_grad, cudaStream_t st) {
+    FS_CHECK(bound && (flags & ENG_VGG), "engine has no VGG plan / workspace");
+    FS_CHECK(!need_grad || (flags & ENG_VGG_BWD), "engine has no VGG backward plan");
+    float sw[V_NCONV] = {0}, cw[V_NCONV] = {0};
+    const float* tg[V_NCONV] = {nullptr};
+    int top = -1;
+    for (int i = 0; i < lc.n_style; ++i) {
+        int l = lc.style_layer[i];
+        FS_CHECK(l >= 0 && l < V_NCONV && gram[l], "style layer %d not planned in this engine", l);
+        FS_CHECK(tg[l] == nullptr, "style layer %d listed twice", l);
+        sw[l] = lc.style_w[i]; tg[l] = target_grams[i]; top = std::max(top, l);
+    }
+    bool has_c[V_NCONV] = {false};
+    for (int i = 0; i < lc.n_content; ++i) {
+        int l = lc.content_layer[i];
+        FS_CHECK(l >= 0 && l < V_NCONV && ctarget[l], "content layer %d not planned in this engine", l);
+        FS_CHECK(!has_c[l], "content layer %d listed twice", l);
+        cw[l] = lc.content_w[i]; has_c[l] = true; top = std::max(top, l);
+    }
+    FS_CHECK(top >= 0, "no loss layers configured");
+    FS_TRY(vgg_forward(packed, img3, top, nullptr, st));
+
+    // ---- losses (+ the Gram-space gradient S = coef*(G-T))
+    for (int l = 0; l <= top; ++l) {
+        const VConv& v = vc[l];
+        const double hwc = (double)v.H * v.W * v.cout;
+        if (tg[l]) {
+            WGradArgs wa;
+            memset(&wa, 0, sizeof(wa));
+            wa.in = vact[l]; wa.dy = vact[l]; wa.out = gram[l]; wa.partial = wg_partial; wa.partial_cap = wg_partial_cap;
+            wa.H = v.H; wa.W = v.W; wa.C = v.cout; wa.in_bs = (long long)v.H * v.W * v.cout;
+            wa.KH = wa.KW = 1; wa.stride = 1;
+            wa.OH = v.H; wa.OW = v.W; wa.OC = v.cout; wa.dy_bs = wa.in_bs;
+            wa.N = N; wa.per_sample = 1; wa.scale = (float)(1.0 / hwc);
+            FS_TRY(launch_wgrad(wa, st));
+            const double cc = (double)v.cout * v.cout;
+            FS_TRY(style_loss_grad(gram[l], tg[l], gramS[l], N, v.cout * v.cout,
+                                   (float)(4.0 * sw[l] / (cc * hwc)), sw[l] / cc, loss_acc + 1, st));
+        }
+        if (has_c[l])
+            FS_TRY(sqdiff_sum(vact[l], ctarget[l], (long long)N * v.H * v.W * v.cout, cw[l] / hwc, loss_acc + 0, st));
+    }
+    if (!need_grad) return 0;
+
+    // ---- backward: P_l = dLoss/d(pre-activation of conv l), top-down
+    auto pick = [](int a, int b, int c) { for (int i = 0; i < 4; ++i) if (i != a && i != b && i != c) return i; return -1; };
+    auto dgrad = [&](int lsrc, const float* P, float* out, const float* addend, const float* ref) -> int {
+        const VConv& v = vc[lsrc];
+        IGemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in = P; a.w = packed + v.offWT; a.out = out; a.N = N; a.gather = 1;
+        a.H = v.H; a.W = v.W; a.C = v.cout; a.in_bs = (long long)v.H * v.W * v.cout;
+        a.KH = a.KW = 3; a.stride = 1; a.pad_t = a.pad_l = 1;
+        a.OH = v.H; a.OW = v.W; a.OC = v.cin_s; a.out_bs = (long long)v.H * v.W * v.cin_s;
+        a.addend = addend; a.addH = v.H; a.addW = v.W; a.add_bs = a.out_bs; a.ref = ref;
+        return launch_igemm(a, st);
+    };
+    auto gram_bwd = [&](int l, const float* addend, const float* ref, float* out) -> int {
+        const VConv& v = vc[l];
+        IGemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in = vact[l]; a.w = gramS[l]; a.w_bs = (long long)v.cout * v.cout; a.out = out; a.N = N;
+        a.H = v.H; a.W = v.W; a.C = v.cout; a.in_bs = (long long)v.H * v.W * v.cout;
+        a.KH = a.KW = 1; a.stride = 1;
+        a.OH = v.H; a.OW = v.W; a.OC = v.cout; a.out_bs = a.in_bs;
+        a.addend = addend; a.addH = v.H; a.addW = v.W; a.add_bs = a.in_bs; a.ref = ref;
+        return launch_igemm(a, st);
+    };
+    int pi = -1;
+    for (int l = top; l >= 0; --l) {
+        const VConv& v = vc[l];
+        const float* Pnext = pi >= 0 ? vgrad[pi] : nullptr;
+        const bool pool_follow = v.pool_after && l < top;
+        const float* ct = has_c[l] ? ctarget[l] : nullptr;
+        const float cw2 = (float)(2.0 * cw[l] / ((double)v.H * v.W * v.cout));
+        if (l == top || pool_follow) {
+            int gi = -1; const float* gp = nullptr;
+            if (pool_follow) {
+                gi = pick(pi, -1, -1);
+                FS_TRY(dgrad(l + 1, Pnext, vgrad[gi], nullptr, nullptr));
+                gp = vgrad[gi];
+            }
+            if (tg[l]) {
+                int ti = -1; const float* T = nullptr;
+                if (gp || ct) {
+                    ti = pick(gi, -1, -1);
+                    FS_TRY(pool_bwd_combine(vact[l], gp, ct, cw2, 0, vgrad[ti], N, v.H, v.W, v.cout, st));
+                    T = vgrad[ti];
+                }
+                int oi = pick(gi, ti, -1);
+                FS_TRY(gram_bwd(l, T, vact[l], vgrad[oi]));
+                pi = oi;
+            } else {
+                int oi = pick(gi, -1, -1);
+                FS_TRY(pool_bwd_combine(vact[l], gp, ct, cw2, 1, vgrad[oi], N, v.H, v.W, v.cout, st));
+                pi = oi;
+            }
+        } else {
+            int ai = -1; const float* A = nullptr;
+            if (tg[l]) {
+                int ti = -1; const float* T = nullptr;
+                if (ct) {
+                    ti = pick(pi, -1, -1);
+                    FS_TRY(pool_bwd_combine(vact[l], nullptr, ct, cw2, 0, vgrad[ti], N, v.H, v.W, v.cout, st));
+                    T = vgrad[ti];
+                }
+                ai = pick(pi, ti, -1);
+                FS_TRY(gram_bwd(l, T, nullptr, vgrad[ai]));
+                A = vgrad[ai];
+            } else if (ct) {
+                ai = pick(pi, -1, -1);
+                FS_TRY(pool_bwd_combine(vact[l], nullptr, ct, cw2, 0, vgrad[ai], N, v.H, v.W, v.cout, st));
+                A = vgrad[ai];
+            }
+            int oi = pick(pi, ai, -1);
+            FS_TRY(dgrad(l + 1, Pnext, vgrad[oi], A, vact[l]));
+            pi = oi;
+        }
+    }
+    FS_TRY(dgrad(0, vgrad[pi], dY4, nullptr, nullptr));
+    return 0;
+}
+
+int Engine::train_fwd_bwd(const float* params, const float* packed, const float* x3, const LossConfig& lc,
+                          const float* const* target_grams, float* grads, float* losses4, float* y3_out,
+                          cudaStream_t st) {
+    const int need = ENG_TRANSFORM | ENG_TRANSFORM_BWD | ENG_VGG | ENG_VGG_BWD;
+    FS_CHECK(bound && (flags & need) == need, "engine was not created for training");
+    FS_CHECK(OH == H && OW == W, "train step needs (H+80)%%4==0 and (W+80)%%4==0 so that the stylised "
+             "image matches the content targets (got %dx%d -> %dx%d)", H, W, OH, OW);
+    float* Y = y3_out ? y3_out : y3;
+    FS_TRY(prep_transform_weights(params, true, st));
+    FS_TRY(fill_zero(loss_acc, 4 * sizeof(double), st));
+    FS_TRY(vgg_content_targets(packed, x3, lc, st));                  // train.py:250-251
+    FS_TRY(transform_forward(params, x3, Y, st));                     // train.py:161
+    FS_TRY(vgg_loss_backward(packed, Y, lc, target_grams, true, st)); // train.py:165-184 + autodiff
+    if (lc.beta != 0.f) FS_TRY(tv_loss_grad(Y, dY4, N, VH, VW, lc.beta, loss_acc + 2, st));
+    FS_TRY(transform_backward(params, dY4, grads, st));
+    FS_TRY(finalize_losses(loss_acc, losses4, st));
+    return 0;
+}
+
+}  // namespace fs

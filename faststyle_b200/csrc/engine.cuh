@@ -1,0 +1,105 @@
+// Engine: plans (shapes + workspace layout) and whole-path composites.
+#pragma once
+#include "common.cuh"
+#include "ops.cuh"
+
+namespace fs {
+
+// ---------------------------------------------------------------- transform net
+constexpr int T_NCONV = 16;         // 3 init + 10 residual + 3 "upsample" convs
+constexpr long long T_NPARAMS = 424102;
+
+struct TConv {
+    int k, stride, same, cin, cout;     // reference geometry (im_transf_net.py:37-70)
+    int upconv;                         // 1: resize-conv (NN x4 + 3x3 s2 SAME), run collapsed
+    int act;                            // activation after InstanceNorm
+    long long offW, offG, offB;         // offsets into the flat parameter buffer (floats)
+    // runtime geometry for one plan
+    int inH, inW, outH, outW;           // conv input / output spatial dims
+    int cin_s, cout_s;                  // stored channel counts (3 -> 4)
+    int pad_t, pad_l;
+};
+
+struct TBuf { float *raw, *act, *mean, *rstd; };
+
+// ---------------------------------------------------------------- VGG16 (conv1_1..conv4_3)
+constexpr int V_NCONV = 10;
+struct VConv { int cin, cout, cin_s, pool_after; long long offW, offB, offWT; int H, W; };
+long long vgg_flat_floats();        // unpacked: W,b per layer in order (HWIO)
+long long vgg_packed_floats();      // packed: padded W, b, transposed W per layer
+
+struct LossConfig {
+    int n_content; int content_layer[V_NCONV]; float content_w[V_NCONV];
+    int n_style;   int style_layer[V_NCONV];   float style_w[V_NCONV];
+    float beta;
+};
+
+enum EngineFlags { ENG_TRANSFORM = 1, ENG_TRANSFORM_BWD = 2, ENG_VGG = 4, ENG_VGG_BWD = 8 };
+
+struct Arena {
+    char* base = nullptr; size_t off = 0; size_t cap = 0;
+    template <typename T> T* take(long long n) {
+        size_t bytes = ((size_t)n * sizeof(T) + 255) & ~(size_t)255;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += bytes;
+        return p;
+    }
+};
+
+struct Engine {
+    int N, H, W, flags;
+    int upsample_deconv = 0;
+    unsigned content_mask = 0, style_mask = 0;   // VGG conv indices with loss taps
+    // transform plan
+    TConv tc[T_NCONV];
+    int Hp, Wp, OH, OW;                  // padded-input dims, output dims
+    // vgg plan
+    VConv vc[V_NCONV];
+    int VH, VW;
+    // workspace
+    size_t ws_bytes = 0;
+    bool bound = false;
+    // --- device buffers (assigned by layout())
+    float* xpad4 = nullptr;              // [N,Hp,Wp,4]
+    TBuf tb[T_NCONV];
+    float* weff[T_NCONV];                // effective forward weights (null = use flat params)
+    float* wefft[T_NCONV];               // transposed weights for the data gradient
+    float* y3 = nullptr;                 // [N,OH,OW,3] when the caller does not supply an output
+    double* in_partial = nullptr;
+    float* in15 = nullptr;               // 4-channel staging of the last layer's IN scale/shift
+    float* gb_tmp = nullptr;
+    float* m12 = nullptr;
+    float* tgrad[3];                     // rotating gradient buffers (transform bwd)
+    float* wg_partial = nullptr; long long wg_partial_cap = 0;
+    float* wg_tmp = nullptr;             // padded / collapsed weight-gradient staging
+    // vgg
+    float* v_in4 = nullptr;              // [N,VH,VW,4]
+    float* vact[V_NCONV]; float* vpool[V_NCONV];
+    float* vgrad[4]; long long vgrad_floats = 0;
+    float* gram[V_NCONV]; float* gramS[V_NCONV];
+    float* ctarget[V_NCONV];
+    float* dY4 = nullptr;                // [N,VH,VW,4] gradient w.r.t. the VGG input image
+    double* loss_acc = nullptr;          // double[4]
+
+    int plan();                          // fill geometry; returns 0 / error
+    void layout(Arena& a);               // assign (or just size) workspace
+    int bind(void* ws, size_t bytes);
+
+    // composites (all asynchronous on st)
+    int prep_transform_weights(const float* params, bool need_bwd, cudaStream_t st);
+    int transform_forward(const float* params, const float* x3, float* y3_out, cudaStream_t st);
+    int transform_backward(const float* params, const float* dY4_in, float* grads, cudaStream_t st);
+    int vgg_forward(const float* packed, const float* img3, int upto, float* const* act_override,
+                    cudaStream_t st);
+    int vgg_content_targets(const float* packed, const float* img3, const LossConfig& lc, cudaStream_t st);
+    int vgg_loss_backward(const float* packed, const float* img3, const LossConfig& lc,
+                          const float* const* target_grams, bool need_grad, cudaStream_t st);
+    int train_fwd_bwd(const float* params, const float* packed, const float* x3, const LossConfig& lc,
+                      const float* const* target_grams, float* grads, float* losses4, float* y3_out,
+                      cudaStream_t st);
+};
+
+int vgg_pack(const float* flat, float* packed, cudaStream_t st);
+void transform_param_table(TConv* tc);        // fills reference geometry + offsets
+
+}  // namespace fs

@@ -1,0 +1,429 @@
+// FFMA (CUDA-core, exact fp32) implicit-GEMM kernels.
+//
+// These are the generic, any-shape convolution engines of the library: forward
+// conv, data gradient (incl. stride-2 "fractionally strided"), the collapsed
+// resize-conv (depth-to-space store / space-to-depth gather) and the per-sample
+// Gram backward GEMM all run through igemm_kernel; weight gradients and the Gram
+// forward (reductions over pixels) run through wgrad_kernel.  The tcgen05 path
+// (conv3x3_tc.cu) takes over the 64-channel-multiple 3x3 layers; the kernels here
+// remain the path for tiny-N / tiny-K layers (Cin=3, Cout=3) that cannot feed the
+// tensor pipe.
+//
+// Reference semantics reproduced: tf.nn.conv2d NHWC/HWIO with TF SAME/VALID
+// padding (reference im_transf_net.py:115-118, libs/vgg16.py:48-52).
+#include "common.cuh"
+
+namespace fs {
+
+namespace {
+
+constexpr int BK = 16;
+
+struct RowInfo { int oy, ox; bool ok; };
+
+__device__ __forceinline__ float4 ldg4(const float* p) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+// Gather one float4 (4 consecutive channels of one tap) of the implicit A matrix.
+__device__ __forceinline__ float4 gather_a(const IGemmArgs& a, const float* in_n, int oy, int ox,
+                                           bool row_ok, int kh, int kw, int c, bool k_ok) {
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!row_ok || !k_ok) return z;
+    int iy, ix;
+    if (a.gather == 0) {
+        iy = oy * a.stride - a.pad_t + kh;
+        ix = ox * a.stride - a.pad_l + kw;
+    } else {
+        int ny = oy + a.pad_t - kh, nx = ox + a.pad_l - kw;
+        if (ny < 0 || nx < 0) return z;
+        iy = ny / a.stride; ix = nx / a.stride;
+        if (iy * a.stride != ny || ix * a.stride != nx) return z;
+    }
+    if (iy < 0 || iy >= a.H || ix < 0 || ix >= a.W) return z;
+    long long off;
+    if (a.in_mode == 0) {
+        off = ((long long)iy * a.W + ix) * a.C + c;
+    } else {
+        int C0 = a.C >> 2;
+        int pq = c / C0, co = c - pq * C0;
+        off = ((long long)(2 * iy + (pq >> 1)) * (2 * a.W) + 2 * ix + (pq & 1)) * C0 + co;
+    }
+    return ldg4(in_n + off);
+}
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(256) igemm_kernel(const IGemmArgs a) {
+    constexpr int TXN = BN / TN;
+    constexpr int TYN = 256 / TXN;
+    static_assert(TYN * TM == BM, "tile/thread mismatch");
+    constexpr int A_F4 = (BM * BK / 4) / 256;
+    constexpr int B_TOT = BK * BN / 4;
+    constexpr int B_F4 = (B_TOT + 255) / 256;
+    constexpr int NG = TN / 4;               // float4 column groups per thread
+    constexpr int GSTRIDE = BN / NG;
+
+    __shared__ __align__(16) float As[2][BK][BM + 4];
+    __shared__ __align__(16) float Bs[2][BK][BN + 4];
+
+    const int t = threadIdx.x;
+    const int n = blockIdx.z;
+    const int m0 = blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int M = a.OH * a.OW;
+    const int Ktot = a.KH * a.KW * a.C;
+    const int C4 = a.C >> 2;
+    const int nk = (Ktot + BK - 1) / BK;
+    const float* in_n = a.in + (long long)n * a.in_bs;
+    const float* w_n = a.w + (long long)n * a.w_bs;
+
+    // rows this thread gathers
+    const int k4 = t & 3;
+    RowInfo rows[A_F4];
+#pragma unroll
+    for (int i = 0; i < A_F4; ++i) {
+        int m = m0 + (t >> 2) + i * 64;
+        rows[i].ok = m < M;
+        int mm = rows[i].ok ? m : 0;
+        rows[i].oy = mm / a.OW;
+        rows[i].ox = mm - rows[i].oy * a.OW;
+    }
+
+    float4 ra[A_F4];
+    float4 rb[B_F4];
+
+    auto load_tile = [&](int kt) {
+        int kg4 = kt * (BK / 4) + k4;
+        bool k_ok = kg4 * 4 < Ktot;
+        int tap = kg4 / C4;
+        int c = (kg4 - tap * C4) * 4;
+        int kh = tap / a.KW;
+        int kw = tap - kh * a.KW;
+#pragma unroll
+        for (int i = 0; i < A_F4; ++i)
+            ra[i] = gather_a(a, in_n, rows[i].oy, rows[i].ox, rows[i].ok, kh, kw, c, k_ok);
+#pragma unroll
+        for (int i = 0; i < B_F4; ++i) {
+            int f = t + i * 256;
+            rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (f < B_TOT) {
+                int bk = f / (BN / 4), bn4 = f - bk * (BN / 4);
+                int kg = kt * BK + bk, col = n0 + bn4 * 4;
+                if (kg < Ktot && col < a.OC) rb[i] = ldg4(w_n + (long long)kg * a.OC + col);
+            }
+        }
+    };
+    auto store_tile = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < A_F4; ++i) {
+            int r = (t >> 2) + i * 64;
+            As[buf][k4 * 4 + 0][r] = ra[i].x;
+            As[buf][k4 * 4 + 1][r] = ra[i].y;
+            As[buf][k4 * 4 + 2][r] = ra[i].z;
+            As[buf][k4 * 4 + 3][r] = ra[i].w;
+        }
+#pragma unroll
+        for (int i = 0; i < B_F4; ++i) {
+            int f = t + i * 256;
+            if (f < B_TOT) {
+                int bk = f / (BN / 4), bn4 = f - bk * (BN / 4);
+                *reinterpret_cast<float4*>(&Bs[buf][bk][bn4 * 4]) = rb[i];
+            }
+        }
+    };
+
+    const int tx = t % TXN, ty = t / TXN;
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    load_tile(0);
+    store_tile(0);
+    __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) load_tile(kt + 1);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float ar[TM], br[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) ar[i] = As[buf][kk][ty * TM + i];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                float4 v = *reinterpret_cast<const float4*>(&Bs[buf][kk][g * GSTRIDE + tx * 4]);
+                br[g * 4 + 0] = v.x; br[g * 4 + 1] = v.y; br[g * 4 + 2] = v.z; br[g * 4 + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) store_tile(buf ^ 1);
+        __syncthreads();
+    }
+
+    // ---------------------------------------------------------------- epilogue
+    float* out_n = a.out + (long long)n * a.out_bs;
+    const float* ref_n = a.ref ? a.ref + (long long)n * a.out_bs : nullptr;
+    const float* add_n = a.addend ? a.addend + (long long)n * a.add_bs : nullptr;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        int m = m0 + ty * TM + i;
+        if (m >= M) continue;
+        int oy = m / a.OW, ox = m - oy * a.OW;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            int col = n0 + g * GSTRIDE + tx * 4;
+            if (col >= a.OC) continue;
+            float4 v = make_float4(acc[i][g * 4 + 0], acc[i][g * 4 + 1], acc[i][g * 4 + 2],
+                                   acc[i][g * 4 + 3]);
+            if (a.bias) {
+                float4 b = ldg4(a.bias + col);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            if (add_n) {
+                int ay = oy - a.add_crop, ax = ox - a.add_crop;
+                if (ay >= 0 && ay < a.addH && ax >= 0 && ax < a.addW) {
+                    float4 d = *reinterpret_cast<const float4*>(
+                        add_n + ((long long)ay * a.addW + ax) * a.OC + col);
+                    v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
+                }
+            }
+            if (a.relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
+                v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            long long off;
+            if (a.out_mode == 0) {
+                off = (long long)m * a.OC + col;
+            } else {
+                int C0 = a.OC >> 2;
+                int pq = col / C0, co = col - pq * C0;
+                off = ((long long)(2 * oy + (pq >> 1)) * (2 * a.OW) + 2 * ox + (pq & 1)) * C0 + co;
+            }
+            if (ref_n) {
+                float4 r = *reinterpret_cast<const float4*>(ref_n + off);
+                v.x = r.x > 0.f ? v.x : 0.f; v.y = r.y > 0.f ? v.y : 0.f;
+                v.z = r.z > 0.f ? v.z : 0.f; v.w = r.w > 0.f ? v.w : 0.f;
+            }
+            *reinterpret_cast<float4*>(out_n + off) = v;
+        }
+    }
+}
+
+template <int BM, int BN, int TM, int TN>
+int launch_cfg(const IGemmArgs& a, cudaStream_t st) {
+    int M = a.OH * a.OW;
+    dim3 grid(cdiv(M, BM), cdiv(a.OC, BN), a.N);
+    igemm_kernel<BM, BN, TM, TN><<<grid, 256, 0, st>>>(a);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+int launch_igemm(const IGemmArgs& a, cudaStream_t st) {
+    FS_CHECK(a.C % 4 == 0 && a.OC % 4 == 0, "igemm: channel counts must be multiples of 4 (C=%d OC=%d)", a.C, a.OC);
+    FS_CHECK(a.in_mode == 0 || (a.C % 16 == 0), "igemm: s2d gather needs C%%16==0");
+    FS_CHECK(a.out_mode == 0 || (a.OC % 16 == 0), "igemm: d2s store needs OC%%16==0");
+    FS_CHECK(a.N > 0 && a.N <= 65535, "igemm: batch %d out of range", a.N);
+    FS_CHECK(a.stride >= 1, "igemm: bad stride");
+    if (a.OH <= 0 || a.OW <= 0) return 0;
+    if (a.OC >= 128) return launch_cfg<128, 128, 8, 8>(a, st);
+    if (a.OC > 32) return launch_cfg<128, 64, 8, 4>(a, st);
+    if (a.OC > 16) return launch_cfg<128, 32, 4, 4>(a, st);
+    if (a.OC > 4) return launch_cfg<128, 16, 2, 4>(a, st);
+    return launch_cfg<256, 4, 1, 4>(a, st);
+}
+
+// =====================================================================
+// Reduction-over-pixels GEMM: weight gradient / Gram forward
+//   out[g][k, j] = scale * sum_{pix} A[pix, k] * B[pix, j]
+// Deterministic: each split writes a partial tile, wgrad_reduce_kernel sums the
+// splits in a fixed order.
+// =====================================================================
+namespace {
+
+constexpr int WK = 64;    // k rows per tile
+constexpr int WN = 64;    // output channels per tile
+constexpr int WP = 16;    // pixels per smem step
+
+struct WGeom {
+    int M, Ktot, C4, groups, splits, pix_per_group, chunk;
+};
+
+__global__ void __launch_bounds__(128) wgrad_kernel(const WGradArgs a, const WGeom g) {
+    __shared__ __align__(16) float As[2][WP][WK + 4];
+    __shared__ __align__(16) float Bs[2][WP][WN + 4];
+    const int t = threadIdx.x;
+    const int k0 = blockIdx.x * WK, j0 = blockIdx.y * WN;
+    const int grp = blockIdx.z / g.splits, sp = blockIdx.z - grp * g.splits;
+    const int pbeg = sp * g.chunk;
+    const int pend = min(pbeg + g.chunk, g.pix_per_group);
+    const int nsteps = pend > pbeg ? (pend - pbeg + WP - 1) / WP : 0;
+    const int samples_per_group = g.pix_per_group / g.M;
+
+    // load mapping: 256 float4 per operand per step, 2 per thread
+    const int lk4 = t & 15;                 // float4 index along k / along j
+    const int lp = t >> 4;                  // pixel 0..7 (+8)
+    // decode this thread's k (fixed for the whole loop)
+    const int kg4 = (k0 >> 2) + lk4;
+    const bool k_ok = kg4 * 4 < g.Ktot;
+    const int tap = kg4 / g.C4;
+    const int c = (kg4 - tap * g.C4) * 4;
+    const int kh = tap / a.KW, kw = tap - kh * a.KW;
+    const int jcol = j0 + lk4 * 4;
+    const bool j_ok = jcol < a.OC;
+
+    float4 ra[2], rb[2];
+    auto load_step = [&](int s) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            int pix = pbeg + s * WP + lp + i * 8;
+            ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rb[i] = ra[i];
+            if (pix < pend) {
+                int ns = pix / g.M;
+                int m = pix - ns * g.M;
+                int n = grp * samples_per_group + ns;
+                int oy = m / a.OW, ox = m - oy * a.OW;
+                if (k_ok) {
+                    int iy = oy * a.stride - a.pad_t + kh, ix = ox * a.stride - a.pad_l + kw;
+                    if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
+                        long long off;
+                        if (a.in_mode == 0) off = ((long long)iy * a.W + ix) * a.C + c;
+                        else {
+                            int C0 = a.C >> 2; int pq = c / C0, co = c - pq * C0;
+                            off = ((long long)(2 * iy + (pq >> 1)) * (2 * a.W) + 2 * ix + (pq & 1)) * C0 + co;
+                        }
+                        ra[i] = ldg4(a.in + (long long)n * a.in_bs + off);
+                    }
+                }
+                if (j_ok) {
+                    long long off;
+                    if (a.dy_mode == 0) off = (long long)m * a.OC + jcol;
+                    else {
+                        int C0 = a.OC >> 2; int pq = jcol / C0, co = jcol - pq * C0;
+                        off = ((long long)(2 * oy + (pq >> 1)) * (2 * a.OW) + 2 * ox + (pq & 1)) * C0 + co;
+                    }
+                    rb[i] = ldg4(a.dy + (long long)n * a.dy_bs + off);
+                }
+            }
+        }
+    };
+    auto store_step = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            *reinterpret_cast<float4*>(&As[buf][lp + i * 8][lk4 * 4]) = ra[i];
+            *reinterpret_cast<float4*>(&Bs[buf][lp + i * 8][lk4 * 4]) = rb[i];
+        }
+    };
+
+    const int tx = t & 15, ty = t >> 4;     // ty 0..7 -> 8 k rows, tx -> 4 cols
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    if (nsteps > 0) {
+        load_step(0);
+        store_step(0);
+    }
+    __syncthreads();
+    for (int s = 0; s < nsteps; ++s) {
+        const int buf = s & 1;
+        if (s + 1 < nsteps) load_step(s + 1);
+#pragma unroll
+        for (int p = 0; p < WP; ++p) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[buf][p][ty * 8]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[buf][p][ty * 8 + 4]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[buf][p][tx * 4]);
+            float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+        if (s + 1 < nsteps) store_step(buf ^ 1);
+        __syncthreads();
+    }
+    // partial[z][k][j]
+    float* part = a.partial + (long long)blockIdx.z * g.Ktot * a.OC;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int k = k0 + ty * 8 + i;
+        int col = j0 + tx * 4;
+        if (k < g.Ktot && col < a.OC)
+            *reinterpret_cast<float4*>(part + (long long)k * a.OC + col) =
+                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                    long long tile_elems, int groups, int splits, float scale) {
+    long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long n4 = tile_elems / 4;
+    if (i4 >= n4 * groups) return;
+    long long grp = i4 / n4, e = i4 - grp * n4;
+    const float4* p = reinterpret_cast<const float4*>(partial) + grp * splits * n4 + e;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < splits; ++k) {
+        float4 v = p[(long long)k * n4];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    s.x *= scale; s.y *= scale; s.z *= scale; s.w *= scale;
+    reinterpret_cast<float4*>(out)[grp * n4 + e] = s;
+}
+
+int choose_splits(int tiles, int groups, int pix_per_group) {
+    const int target = 148 * 6;
+    int s = (target + tiles * groups - 1) / (tiles * groups);
+    int max_s = pix_per_group / (WP * 8);
+    if (max_s < 1) max_s = 1;
+    if (s > max_s) s = max_s;
+    if (s < 1) s = 1;
+    if (s > 256) s = 256;
+    return s;
+}
+
+}  // namespace
+
+long long wgrad_partial_floats(int K, int OC, int groups) {
+    // upper bound used by workspace planning: splits <= 256, but tiles*groups*splits ~ target
+    long long tiles = (long long)cdiv(K, WK) * cdiv(OC, WN);
+    long long s = (148 * 6 + tiles * groups - 1) / (tiles * groups);
+    if (s < 1) s = 1;
+    if (s > 256) s = 256;
+    return s * groups * (long long)K * OC;
+}
+
+int launch_wgrad(const WGradArgs& a, cudaStream_t st) {
+    FS_CHECK(a.C % 4 == 0 && a.OC % 4 == 0, "wgrad: channel counts must be multiples of 4");
+    WGeom g;
+    g.M = a.OH * a.OW;
+    g.Ktot = a.KH * a.KW * a.C;
+    g.C4 = a.C >> 2;
+    g.groups = a.per_sample ? a.N : 1;
+    g.pix_per_group = a.per_sample ? g.M : a.N * g.M;
+    int tiles = cdiv(g.Ktot, WK) * cdiv(a.OC, WN);
+    g.splits = choose_splits(tiles, g.groups, g.pix_per_group);
+    g.chunk = cdiv(cdiv(g.pix_per_group, g.splits), WP) * WP;
+    long long need = (long long)g.groups * g.splits * g.Ktot * a.OC;
+    FS_CHECK(need <= a.partial_cap, "wgrad: partial workspace too small (%lld > %lld floats)", need, a.partial_cap);
+    FS_CHECK((long long)g.groups * g.splits <= 65535, "wgrad: too many z blocks");
+    dim3 grid(cdiv(g.Ktot, WK), cdiv(a.OC, WN), g.groups * g.splits);
+    wgrad_kernel<<<grid, 128, 0, st>>>(a, g);
+    FS_LAUNCH_CHECK();
+    long long tile_elems = (long long)g.Ktot * a.OC;
+    long long tot4 = tile_elems / 4 * g.groups;
+    wgrad_reduce_kernel<<<cdiv(tot4, 256), 256, 0, st>>>(a.partial, a.out, tile_elems, g.groups,
+                                                       g.splits, a.scale);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace fs

@@ -1,0 +1,678 @@
+// HBM-bound kernels of the hot path: padding, InstanceNorm (fwd/bwd), pooling,
+// loss reductions + their gradients, TF-Adam, weight-layout helpers.
+// All tensors are fp32 NHWC with channel counts that are multiples of 4 (RGB
+// tensors are carried as 4 channels with a zero 4th channel inside the engine).
+#include "ops.cuh"
+
+namespace fs {
+
+namespace {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum of a double, result valid in thread 0
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double red[32];
+    v = warp_sum(v);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (w == 0) {
+        r = l < (int)((blockDim.x + 31) >> 5) ? red[l] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+__device__ __forceinline__ float in_affine(float x, float mean, float rstd, float g, float b) {
+    return __fmaf_rn((x - mean) * rstd, g, b);
+}
+
+// ------------------------------------------------------------------ padding
+__global__ void reflect_pad_c4_kernel(const float* __restrict__ x, float* __restrict__ out, int N,
+                                      int H, int W, int pad) {
+    int OH = H + 2 * pad, OW = W + 2 * pad;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)N * OH * OW) return;
+    int ox = (int)(i % OW);
+    long long r = i / OW;
+    int oy = (int)(r % OH);
+    int n = (int)(r / OH);
+    int sy = oy - pad, sx = ox - pad;
+    if (sy < 0) sy = -sy;
+    if (sy >= H) sy = 2 * (H - 1) - sy;
+    if (sx < 0) sx = -sx;
+    if (sx >= W) sx = 2 * (W - 1) - sx;
+    const float* s = x + (((long long)n * H + sy) * W + sx) * 3;
+    st4(out + i * 4, make_float4(s[0], s[1], s[2], 0.f));
+}
+
+__global__ void vgg_preprocess_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                      long long npix) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const float* s = x + i * 3;
+    st4(out + i * 4, make_float4(s[0] - 123.68f, s[1] - 116.779f, s[2] - 103.939f, 0.f));
+}
+
+// ------------------------------------------------------------------ InstanceNorm
+// MODE 0: sums of (x, x^2).   MODE 1: sums of (dz, dz*xhat) for the backward pass.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+in_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dY,
+                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                 const float* __restrict__ scale, const float* __restrict__ shift,
+                 double* __restrict__ partial, int HW, int C, int chunks, int act) {
+    extern __shared__ double sm[];            // [C][2]
+    const int t = threadIdx.x, n = blockIdx.y, chunk = blockIdx.x;
+    const int CL = C >> 2, rows = 256 / CL;
+    const int lane = t % CL, row = t / CL;
+    const int per = (HW + chunks - 1) / chunks;
+    const int beg = chunk * per, end = min(beg + per, HW);
+    for (int i = t; i < 2 * C; i += 256) sm[i] = 0.0;
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    float mu[4], rs[4], g[4], b[4];
+    if (MODE == 1) {
+        float4 v;
+        v = ld4(mean + (long long)n * C + lane * 4); mu[0] = v.x; mu[1] = v.y; mu[2] = v.z; mu[3] = v.w;
+        v = ld4(rstd + (long long)n * C + lane * 4); rs[0] = v.x; rs[1] = v.y; rs[2] = v.z; rs[3] = v.w;
+        v = ld4(scale + lane * 4); g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
+        v = ld4(shift + lane * 4); b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+    }
+    const float* xn = x + (long long)n * HW * C + lane * 4;
+    const float* dn = MODE == 1 ? dY + (long long)n * HW * C + lane * 4 : nullptr;
+    if (row < rows) {
+        for (int p = beg + row; p < end; p += rows) {
+            float4 v = ld4(xn + (long long)p * C);
+            float xv[4] = {v.x, v.y, v.z, v.w};
+            if (MODE == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    double d = (double)xv[j];
+                    s1[j] += d;
+                    s2[j] += d * d;
+                }
+            } else {
+                float4 dv = ld4(dn + (long long)p * C);
+                float dy[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float xh = (xv[j] - mu[j]) * rs[j];
+                    float dz = dy[j];
+                    if (act == ACT_RELU) {
+                        dz = __fmaf_rn(xh, g[j], b[j]) > 0.f ? dz : 0.f;
+                    } else if (act == ACT_TANH255) {
+                        float th = tanhf(__fmaf_rn(xh, g[j], b[j]));
+                        dz = dz * 127.5f * (1.f - th * th);
+                    }
+                    s1[j] += (double)dz;
+                    s2[j] += (double)dz * (double)xh;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (row < rows) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&sm[(lane * 4 + j) * 2 + 0], s1[j]);
+            atomicAdd(&sm[(lane * 4 + j) * 2 + 1], s2[j]);
+        }
+    }
+    __syncthreads();
+    double* dst = partial + ((long long)n * chunks + chunk) * 2 * C;
+    for (int i = t; i < 2 * C; i += 256) dst[i] = sm[i];
+}
+
+__global__ void in_stats_finalize_kernel(const double* __restrict__ partial, float* __restrict__ mean,
+                                         float* __restrict__ rstd, int N, int C, int chunks, int HW,
+                                         float eps) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * C) return;
+    int n = i / C, c = i - n * C;
+    double s1 = 0, s2 = 0;
+    for (int k = 0; k < chunks; ++k) {
+        const double* p = partial + ((long long)n * chunks + k) * 2 * C + c * 2;
+        s1 += p[0];
+        s2 += p[1];
+    }
+    double m = s1 / HW;
+    double var = s2 / HW - m * m;
+    if (var < 0) var = 0;
+    mean[i] = (float)m;
+    rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+__global__ void in_bwd_finalize_kernel(const double* __restrict__ partial, float* __restrict__ m12,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int N,
+                                       int C, int chunks, int HW) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double g = 0, b = 0;
+    for (int n = 0; n < N; ++n) {
+        double s1 = 0, s2 = 0;
+        for (int k = 0; k < chunks; ++k) {
+            const double* p = partial + ((long long)n * chunks + k) * 2 * C + c * 2;
+            s1 += p[0];
+            s2 += p[1];
+        }
+        m12[((long long)n * C + c) * 2 + 0] = (float)(s1 / HW);
+        m12[((long long)n * C + c) * 2 + 1] = (float)(s2 / HW);
+        b += s1;
+        g += s2;
+    }
+    if (dgamma) dgamma[c] = (float)g;
+    if (dbeta) dbeta[c] = (float)b;
+}
+
+__global__ void in_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                const float* __restrict__ rstd, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const float* __restrict__ skip,
+                                float* __restrict__ out, int N, int H, int W, int C, int act, int out3) {
+    const int C4 = C >> 2;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)N * H * W * C4;
+    if (i >= total) return;
+    int c = (int)(i % C4) * 4;
+    long long pix = i / C4;
+    int HW = H * W;
+    int n = (int)(pix / HW);
+    float4 v = ld4(x + i * 4);
+    float4 mu = ld4(mean + (long long)n * C + c), rs = ld4(rstd + (long long)n * C + c);
+    float4 g = ld4(scale + c), b = ld4(shift + c);
+    float r[4] = {in_affine(v.x, mu.x, rs.x, g.x, b.x), in_affine(v.y, mu.y, rs.y, g.y, b.y),
+                  in_affine(v.z, mu.z, rs.z, g.z, b.z), in_affine(v.w, mu.w, rs.w, g.w, b.w)};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (act == ACT_RELU) r[j] = fmaxf(r[j], 0.f);
+        else if (act == ACT_TANH255) r[j] = __fmaf_rn(127.5f, tanhf(r[j]), 127.5f);
+    }
+    if (skip) {
+        int p = (int)(pix - (long long)n * HW);
+        int y = p / W, xx = p - y * W;
+        float4 s = ld4(skip + (((long long)n * (H + 4) + y + 2) * (W + 4) + xx + 2) * C + c);
+        r[0] += s.x; r[1] += s.y; r[2] += s.z; r[3] += s.w;
+    }
+    if (out3) {
+        float* o = out + pix * 3;
+        o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
+    } else {
+        st4(out + i * 4, make_float4(r[0], r[1], r[2], r[3]));
+    }
+}
+
+__global__ void in_bwd_apply_kernel(const float* __restrict__ dY, const float* __restrict__ x,
+                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ m12, float* __restrict__ dx, int N,
+                                    int HW, int C, int act) {
+    const int C4 = C >> 2;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)N * HW * C4;
+    if (i >= total) return;
+    int c = (int)(i % C4) * 4;
+    long long pix = i / C4;
+    int n = (int)(pix / HW);
+    float4 xv4 = ld4(x + i * 4), dv4 = ld4(dY + i * 4);
+    float4 mu4 = ld4(mean + (long long)n * C + c), rs4 = ld4(rstd + (long long)n * C + c);
+    float4 g4 = ld4(scale + c), b4 = ld4(shift + c);
+    const float* mm = m12 + ((long long)n * C + c) * 2;
+    float4 ma = ld4(mm), mb = ld4(mm + 4);
+    float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w}, dy[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
+    float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
+    float g[4] = {g4.x, g4.y, g4.z, g4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+    float m1[4] = {ma.x, ma.z, mb.x, mb.z}, m2[4] = {ma.y, ma.w, mb.y, mb.w};
+    float r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float xh = (xv[j] - mu[j]) * rs[j];
+        float dz = dy[j];
+        if (act == ACT_RELU) {
+            dz = __fmaf_rn(xh, g[j], b[j]) > 0.f ? dz : 0.f;
+        } else if (act == ACT_TANH255) {
+            float th = tanhf(__fmaf_rn(xh, g[j], b[j]));
+            dz = dz * 127.5f * (1.f - th * th);
+        }
+        r[j] = g[j] * rs[j] * (dz - m1[j] - xh * m2[j]);
+    }
+    st4(dx + i * 4, make_float4(r[0], r[1], r[2], r[3]));
+}
+
+__global__ void add_padded_kernel(float* __restrict__ dst, const float* __restrict__ src, int N, int H,
+                                  int W, int C, int crop) {
+    const int C4 = C >> 2;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)N * H * W * C4;
+    if (i >= total) return;
+    int c = (int)(i % C4) * 4;
+    long long pix = i / C4;
+    int x = (int)(pix % W);
+    long long r = pix / W;
+    int y = (int)(r % H);
+    int n = (int)(r / H);
+    float* d = dst + (((long long)n * (H + 2 * crop) + y + crop) * (W + 2 * crop) + x + crop) * C + c;
+    float4 a = ld4(d), s = ld4(src + i * 4);
+    st4(d, make_float4(a.x + s.x, a.y + s.y, a.z + s.z, a.w + s.w));
+}
+
+// ------------------------------------------------------------------ pooling
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int H,
+                                   int W, int C) {
+    const int C4 = C >> 2, PH = (H + 1) >> 1, PW = (W + 1) >> 1;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)N * PH * PW * C4;
+    if (i >= total) return;
+    int c = (int)(i % C4) * 4;
+    long long pix = i / C4;
+    int px = (int)(pix % PW);
+    long long r = pix / PW;
+    int py = (int)(r % PH);
+    int n = (int)(r / PH);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            int y = 2 * py + dy, xx = 2 * px + dx;
+            if (y < H && xx < W) {
+                float4 v = ld4(x + (((long long)n * H + y) * W + xx) * C + c);
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y);
+                m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            }
+        }
+    st4(out + i * 4, m);
+}
+
+__global__ void pool_bwd_combine_kernel(const float* __restrict__ act, const float* __restrict__ gpool,
+                                        const float* __restrict__ ctarget, float cw2, int apply_mask,
+                                        float* __restrict__ out, int N, int H, int W, int C) {
+    const int C4 = C >> 2, PH = (H + 1) >> 1, PW = (W + 1) >> 1;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)N * H * W * C4;
+    if (i >= total) return;
+    int c = (int)(i % C4) * 4;
+    long long pix = i / C4;
+    int x = (int)(pix % W);
+    long long r = pix / W;
+    int y = (int)(r % H);
+    int n = (int)(r / H);
+    float4 a4 = ld4(act + i * 4);
+    float a[4] = {a4.x, a4.y, a4.z, a4.w};
+    float res[4] = {0.f, 0.f, 0.f, 0.f};
+    if (gpool) {
+        int py = y >> 1, px = x >> 1;
+        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int arg[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int yy = 2 * py + (k >> 1), xx = 2 * px + (k & 1);
+            if (yy < H && xx < W) {
+                float4 v4 = ld4(act + (((long long)n * H + yy) * W + xx) * C + c);
+                float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (v[j] > best[j]) { best[j] = v[j]; arg[j] = k; }
+            }
+        }
+        int me = ((y & 1) << 1) | (x & 1);
+        float4 g4 = ld4(gpool + (((long long)n * PH + py) * PW + px) * C + c);
+        float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) res[j] = arg[j] == me ? g[j] : 0.f;
+    }
+    if (ctarget) {
+        float4 t4 = ld4(ctarget + i * 4);
+        res[0] += cw2 * (a[0] - t4.x); res[1] += cw2 * (a[1] - t4.y);
+        res[2] += cw2 * (a[2] - t4.z); res[3] += cw2 * (a[3] - t4.w);
+    }
+    if (apply_mask) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) res[j] = a[j] > 0.f ? res[j] : 0.f;
+    }
+    st4(out + i * 4, make_float4(res[0], res[1], res[2], res[3]));
+}
+
+// ------------------------------------------------------------------ losses
+__global__ void sqdiff_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n4,
+                                  double scale, double* acc) {
+    double s = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (long long)gridDim.x * blockDim.x) {
+        float4 x = ld4(a + i * 4), y = ld4(b + i * 4);
+        float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+        s += (double)d0 * d0 + (double)d1 * d1 + (double)d2 * d2 + (double)d3 * d3;
+    }
+    s = block_sum(s);
+    if (threadIdx.x == 0) atomicAdd(acc, s * scale);
+}
+
+__global__ void style_loss_grad_kernel(const float* __restrict__ G, const float* __restrict__ T,
+                                       float* __restrict__ S, long long total, int CC, float coef,
+                                       double lscale, double* acc) {
+    double s = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        float d = G[i] - T[i % CC];
+        if (S) S[i] = coef * d;
+        s += (double)d * d;
+    }
+    s = block_sum(s);
+    if (threadIdx.x == 0) atomicAdd(acc, s * lscale);
+}
+
+__global__ void tv_kernel(const float* __restrict__ Y, float* __restrict__ dY4, int N, int H, int W,
+                          float beta, double* acc) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)N * H * W;
+    double s = 0;
+    if (i < total) {
+        int x = (int)(i % W);
+        long long r = i / W;
+        int y = (int)(r % H);
+        const float* p = Y + i * 3;
+        float g[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v = p[c];
+            if (y + 1 < H) { float d = v - p[c + (long long)W * 3]; s += (double)d * d; g[c] += 2.f * d; }
+            if (y > 0) { float d = p[c - (long long)W * 3] - v; g[c] -= 2.f * d; }
+            if (x + 1 < W) { float d = v - p[c + 3]; s += (double)d * d; g[c] += 2.f * d; }
+            if (x > 0) { float d = p[c - 3] - v; g[c] -= 2.f * d; }
+        }
+        if (dY4) {
+            float4 o = ld4(dY4 + i * 4);
+            o.x += beta * g[0]; o.y += beta * g[1]; o.z += beta * g[2];
+            st4(dY4 + i * 4, o);
+        }
+    }
+    s = block_sum(s);
+    if (threadIdx.x == 0 && s != 0.0) atomicAdd(acc, s * (double)beta);
+}
+
+__global__ void finalize_losses_kernel(const double* acc, float* out4) {
+    out4[0] = (float)acc[0];
+    out4[1] = (float)acc[1];
+    out4[2] = (float)acc[2];
+    out4[3] = (float)(acc[0] + acc[1] + acc[2]);
+}
+
+// ------------------------------------------------------------------ Adam
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                            const int* __restrict__ step) {
+    __shared__ float lr_t_s;
+    if (threadIdx.x == 0) {
+        int t = *step + 1;
+        double c = (double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t));
+        lr_t_s = (float)c;
+    }
+    __syncthreads();
+    const float lr_t = lr_t_s;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float gi = g[i];
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+}
+__global__ void incr_kernel(int* c) { *c += 1; }
+
+// ------------------------------------------------------------------ weight layouts
+__global__ void pad_taps_kernel(const float* __restrict__ src, float* __restrict__ dst, int T, int Ci,
+                                int Co, int Cip, int Cop, int unpad) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (!unpad) {
+        if (i >= (long long)T * Cip * Cop) return;
+        int o = (int)(i % Cop);
+        long long r = i / Cop;
+        int ci = (int)(r % Cip);
+        int t = (int)(r / Cip);
+        dst[i] = (ci < Ci && o < Co) ? src[((long long)t * Ci + ci) * Co + o] : 0.f;
+    } else {
+        if (i >= (long long)T * Ci * Co) return;
+        int o = (int)(i % Co);
+        long long r = i / Co;
+        int ci = (int)(r % Ci);
+        int t = (int)(r / Ci);
+        dst[i] = src[((long long)t * Cip + ci) * Cop + o];
+    }
+}
+
+__global__ void transpose_taps_kernel(const float* __restrict__ src, float* __restrict__ dst, int T,
+                                      int Ci, int Co) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)T * Ci * Co) return;
+    int ci = (int)(i % Ci);
+    long long r = i / Ci;
+    int o = (int)(r % Co);
+    int t = (int)(r / Co);
+    dst[i] = src[((long long)t * Ci + ci) * Co + o];     // dst[t][o][ci]
+}
+
+// R_0 = [[1,1,1],[0,0,0]],  R_1 = [[1,1,0],[0,0,1]]   (rows a, cols kh)
+__device__ __forceinline__ bool rsel(int p, int a, int k) {
+    return p == 0 ? (a == 0) : (a == 0 ? k < 2 : k == 2);
+}
+
+__global__ void upconv_collapse_kernel(const float* __restrict__ W, float* __restrict__ Wc, int Ci,
+                                       int Co) {
+    // Wc[a][b][ci][(p*2+q)*Co + co]
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = 4LL * Ci * 4 * Co;
+    if (i >= total) return;
+    int co = (int)(i % Co);
+    long long r = i / Co;
+    int pq = (int)(r % 4); r /= 4;
+    int ci = (int)(r % Ci); r /= Ci;
+    int b = (int)(r % 2), a = (int)(r / 2);
+    int p = pq >> 1, q = pq & 1;
+    float s = 0.f;
+    for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw)
+            if (rsel(p, a, kh) && rsel(q, b, kw)) s += W[(((long long)kh * 3 + kw) * Ci + ci) * Co + co];
+    Wc[i] = s;
+}
+
+__global__ void upconv_collapse_grad_kernel(const float* __restrict__ dWc, float* __restrict__ dW,
+                                            int Ci, int Co) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = 9LL * Ci * Co;
+    if (i >= total) return;
+    int co = (int)(i % Co);
+    long long r = i / Co;
+    int ci = (int)(r % Ci); r /= Ci;
+    int kw = (int)(r % 3), kh = (int)(r / 3);
+    float s = 0.f;
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b)
+            for (int p = 0; p < 2; ++p)
+                for (int q = 0; q < 2; ++q)
+                    if (rsel(p, a, kh) && rsel(q, b, kw))
+                        s += dWc[((((long long)a * 2 + b) * Ci + ci) * 4 + (p * 2 + q)) * Co + co];
+    dW[i] = s;
+}
+
+inline int grid1(long long n, int bs = 256) { return (int)((n + bs - 1) / bs); }
+
+}  // namespace
+
+// ==================================================================== launchers
+int reflect_pad_c4(const float* x, float* out, int N, int H, int W, int pad, cudaStream_t st) {
+    FS_CHECK(pad < H && pad < W, "reflect_pad: pad %d must be smaller than the image (%dx%d)", pad, H, W);
+    long long n = (long long)N * (H + 2 * pad) * (W + 2 * pad);
+    reflect_pad_c4_kernel<<<grid1(n), 256, 0, st>>>(x, out, N, H, W, pad);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int vgg_preprocess_c4(const float* x, float* out, long long npix, cudaStream_t st) {
+    vgg_preprocess_kernel<<<grid1(npix), 256, 0, st>>>(x, out, npix);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int in_chunks(int N, int HW) {
+    int c = (148 * 4 + N - 1) / N;
+    int maxc = HW / 1024;
+    if (maxc < 1) maxc = 1;
+    if (c > maxc) c = maxc;
+    if (c > 64) c = 64;
+    if (c < 1) c = 1;
+    return c;
+}
+
+static int check_in_c(int C) {
+    int CL = C / 4;
+    FS_CHECK(C % 4 == 0 && CL >= 1 && CL <= 64 && 256 % CL == 0,
+             "instnorm: unsupported channel count %d (need C/4 in {1,2,4,...,64})", C);
+    return 0;
+}
+
+int instnorm_stats(const float* x, float* mean, float* rstd, int N, int HW, int C, float eps,
+                   double* partial, cudaStream_t st) {
+    FS_TRY(check_in_c(C));
+    int chunks = in_chunks(N, HW);
+    in_reduce_kernel<0><<<dim3(chunks, N), 256, 2 * C * sizeof(double), st>>>(
+        x, nullptr, nullptr, nullptr, nullptr, nullptr, partial, HW, C, chunks, 0);
+    FS_LAUNCH_CHECK();
+    in_stats_finalize_kernel<<<grid1((long long)N * C, 128), 128, 0, st>>>(partial, mean, rstd, N, C,
+                                                                         chunks, HW, eps);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int instnorm_apply(const float* x, const float* mean, const float* rstd, const float* scale,
+                   const float* shift, const float* skip, float* out, int N, int H, int W, int C,
+                   int act, int out3, cudaStream_t st) {
+    FS_CHECK(C % 4 == 0, "instnorm_apply: C%%4 != 0");
+    FS_CHECK(!out3 || C == 4, "instnorm_apply: out3 needs C==4");
+    long long n = (long long)N * H * W * (C / 4);
+    in_apply_kernel<<<grid1(n), 256, 0, st>>>(x, mean, rstd, scale, shift, skip, out, N, H, W, C, act, out3);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int instnorm_bwd(const float* dY, const float* x, const float* mean, const float* rstd,
+                 const float* scale, const float* shift, float* dx, float* dgamma, float* dbeta,
+                 int N, int HW, int C, int act, double* partial, float* m12, cudaStream_t st) {
+    FS_TRY(check_in_c(C));
+    int chunks = in_chunks(N, HW);
+    in_reduce_kernel<1><<<dim3(chunks, N), 256, 2 * C * sizeof(double), st>>>(
+        x, dY, mean, rstd, scale, shift, partial, HW, C, chunks, act);
+    FS_LAUNCH_CHECK();
+    in_bwd_finalize_kernel<<<grid1(C, 64), 64, 0, st>>>(partial, m12, dgamma, dbeta, N, C, chunks, HW);
+    FS_LAUNCH_CHECK();
+    long long n = (long long)N * HW * (C / 4);
+    in_bwd_apply_kernel<<<grid1(n), 256, 0, st>>>(dY, x, mean, rstd, scale, shift, m12, dx, N, HW, C, act);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int add_padded(float* dst, const float* src, int N, int H, int W, int C, int crop, cudaStream_t st) {
+    long long n = (long long)N * H * W * (C / 4);
+    add_padded_kernel<<<grid1(n), 256, 0, st>>>(dst, src, N, H, W, C, crop);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int maxpool2x2_fwd(const float* x, float* out, int N, int H, int W, int C, cudaStream_t st) {
+    FS_CHECK(C % 4 == 0, "maxpool: C%%4 != 0");
+    long long n = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
+    maxpool_fwd_kernel<<<grid1(n), 256, 0, st>>>(x, out, N, H, W, C);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int pool_bwd_combine(const float* act, const float* gpool, const float* ctarget, float cw2,
+                     int apply_mask, float* out, int N, int H, int W, int C, cudaStream_t st) {
+    FS_CHECK(C % 4 == 0, "pool_bwd: C%%4 != 0");
+    long long n = (long long)N * H * W * (C / 4);
+    pool_bwd_combine_kernel<<<grid1(n), 256, 0, st>>>(act, gpool, ctarget, cw2, apply_mask, out, N, H, W, C);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int sqdiff_sum(const float* a, const float* b, long long n, double scale, double* acc, cudaStream_t st) {
+    FS_CHECK(n % 4 == 0, "sqdiff_sum: n%%4 != 0");
+    int blocks = grid1(n / 4);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    sqdiff_sum_kernel<<<blocks, 256, 0, st>>>(a, b, n / 4, scale, acc);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int style_loss_grad(const float* G, const float* T, float* S, int N, int CC, float coef, double lscale,
+                    double* acc, cudaStream_t st) {
+    long long total = (long long)N * CC;
+    int blocks = grid1(total);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    style_loss_grad_kernel<<<blocks, 256, 0, st>>>(G, T, S, total, CC, coef, lscale, acc);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int tv_loss_grad(const float* Y, float* dY4, int N, int H, int W, float beta, double* acc, cudaStream_t st) {
+    long long n = (long long)N * H * W;
+    tv_kernel<<<grid1(n), 256, 0, st>>>(Y, dY4, N, H, W, beta, acc);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int finalize_losses(const double* acc, float* out4, cudaStream_t st) {
+    finalize_losses_kernel<<<1, 1, 0, st>>>(acc, out4);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
+              float eps, int* step_counter, cudaStream_t st) {
+    adam_kernel<<<grid1(n), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, step_counter);
+    FS_LAUNCH_CHECK();
+    incr_kernel<<<1, 1, 0, st>>>(step_counter);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int pad_taps(const float* src, float* dst, int T, int Ci, int Co, int Cip, int Cop, cudaStream_t st) {
+    pad_taps_kernel<<<grid1((long long)T * Cip * Cop), 256, 0, st>>>(src, dst, T, Ci, Co, Cip, Cop, 0);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+int unpad_taps(const float* src, float* dst, int T, int Ci, int Co, int Cip, int Cop, cudaStream_t st) {
+    pad_taps_kernel<<<grid1((long long)T * Ci * Co), 256, 0, st>>>(src, dst, T, Ci, Co, Cip, Cop, 1);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+int transpose_taps(const float* src, float* dst, int T, int Ci, int Co, cudaStream_t st) {
+    transpose_taps_kernel<<<grid1((long long)T * Ci * Co), 256, 0, st>>>(src, dst, T, Ci, Co);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+int upconv_collapse(const float* W, float* Wc, int Ci, int Co, cudaStream_t st) {
+    upconv_collapse_kernel<<<grid1(16LL * Ci * Co), 256, 0, st>>>(W, Wc, Ci, Co);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+int upconv_collapse_grad(const float* dWc, float* dW, int Ci, int Co, cudaStream_t st) {
+    upconv_collapse_grad_kernel<<<grid1(9LL * Ci * Co), 256, 0, st>>>(dWc, dW, Ci, Co);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int fill_zero(void* p, size_t bytes, cudaStream_t st) {
+    FS_CUDA(cudaMemsetAsync(p, 0, bytes, st));
+    return 0;
+}
+
+}  // namespace fs

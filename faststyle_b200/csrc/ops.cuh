@@ -1,0 +1,60 @@
+// Launchers for the HBM-bound (non-GEMM) kernels of the hot path.
+#pragma once
+#include "common.cuh"
+
+namespace fs {
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH255 = 2 };
+
+// K1: tf.pad REFLECT + channel pad 3->4           (reference im_transf_net.py:78-88)
+int reflect_pad_c4(const float* x, float* out, int N, int H, int W, int pad, cudaStream_t st);
+// K9: x - VGG mean, channel pad 3->4             (reference libs/vgg16.py:41-42)
+int vgg_preprocess_c4(const float* x, float* out, long long npix, cudaStream_t st);
+
+// K3: InstanceNorm                               (reference im_transf_net.py:218-247)
+struct INWork { double* partial; int max_chunks; };       // partial: [N][chunks][C][2] doubles
+int in_chunks(int N, int HW);
+int instnorm_stats(const float* x, float* mean, float* rstd, int N, int HW, int C, float eps,
+                   double* partial, cudaStream_t st);
+int instnorm_apply(const float* x, const float* mean, const float* rstd, const float* scale,
+                   const float* shift, const float* skip, float* out, int N, int H, int W, int C,
+                   int act, int out3, cudaStream_t st);
+// backward: dz = dY*act'(z); dgamma[c] += sum dz*xhat; dbeta[c] += sum dz;
+// dx = scale*rstd*(dz - mean(dz) - xhat*mean(dz*xhat))
+int instnorm_bwd(const float* dY, const float* x, const float* mean, const float* rstd,
+                 const float* scale, const float* shift, float* dx, float* dgamma, float* dbeta,
+                 int N, int HW, int C, int act, double* partial, float* m12 /*[N][C][2]*/,
+                 cudaStream_t st);
+// zero-pad-add:  dst[n, y+crop, x+crop, c] += src[n,y,x,c]   (skip-connection gradient)
+int add_padded(float* dst, const float* src, int N, int H, int W, int C, int crop, cudaStream_t st);
+
+// K8: 2x2 s2 SAME max-pool                        (reference libs/vgg16.py:67-71)
+int maxpool2x2_fwd(const float* x, float* out, int N, int H, int W, int C, cudaStream_t st);
+// out = [mask(act>0)] * ( route(gpool) + cw2*(act - ctarget) )
+int pool_bwd_combine(const float* act, const float* gpool, const float* ctarget, float cw2,
+                     int apply_mask, float* out, int N, int H, int W, int C, cudaStream_t st);
+
+// K11/K12 losses. loss_acc: device double[4] = {content, style, tv, unused}
+int sqdiff_sum(const float* a, const float* b, long long n, double scale, double* acc, cudaStream_t st);
+// S[n] = coef*(G[n]-T); acc += lscale*sum (G-T)^2
+int style_loss_grad(const float* G, const float* T, float* S, int N, int CC, float coef,
+                    double lscale, double* acc, cudaStream_t st);
+// TV on Y [N,H,W,3]; acc += beta*tv; dY4 [N,H,W,4] += beta*dTV/dY  (dY4 may be null)
+int tv_loss_grad(const float* Y, float* dY4, int N, int H, int W, float beta, double* acc, cudaStream_t st);
+int finalize_losses(const double* acc, float* out4, cudaStream_t st);
+
+// K13: TF-Adam on a flat buffer                   (reference train.py:203)
+int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1,
+              float b2, float eps, int* step_counter, cudaStream_t st);
+
+// weight layout helpers
+int pad_taps(const float* src, float* dst, int T, int Ci, int Co, int Cip, int Cop, cudaStream_t st);
+int unpad_taps(const float* src, float* dst, int T, int Ci, int Co, int Cip, int Cop, cudaStream_t st);
+int transpose_taps(const float* src, float* dst, int T, int Ci, int Co, cudaStream_t st);
+// resize-conv collapse W[3,3,Ci,Co] -> W'[2,2,Ci,4Co] and its adjoint for gradients
+int upconv_collapse(const float* W, float* Wc, int Ci, int Co, cudaStream_t st);
+int upconv_collapse_grad(const float* dWc, float* dW, int Ci, int Co, cudaStream_t st);
+
+int fill_zero(void* p, size_t bytes, cudaStream_t st);
+
+}  // namespace fs

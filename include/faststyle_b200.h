@@ -1,0 +1,146 @@
+/* faststyle_b200 — C-ABI of the B200-native fast-style-transfer hot path.
+ *
+ * The reference (ghwatson/faststyle) has no FFI: its hot path is reached through
+ * Python functions that build TensorFlow-1 graphs and `tf.Session.run` calls.
+ * Each entry point below names the reference call site(s) whose device work it
+ * replaces.  Conventions:
+ *   - every function returns 0 on success, non-zero on failure;
+ *     fs_last_error() returns a thread-local message for the last failure;
+ *   - all tensor arguments are DEVICE pointers to fp32, NHWC activations and
+ *     HWIO weights, exactly the reference's layouts (im_transf_net.py:113,
+ *     libs/vgg16.py:46); the caller owns every buffer;
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it;
+ *   - no hidden allocation: composites run out of a caller-provided workspace
+ *     whose size is queried from the engine plan.
+ * The library has no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef FASTSTYLE_B200_H
+#define FASTSTYLE_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FS_VERSION 100
+
+const char* fs_last_error(void);
+int fs_version(void);
+
+/* ------------------------------------------------------------------ layouts
+ * Transform-net parameters live in ONE flat fp32 buffer whose order is the
+ * byte-sorted checkpoint key order of the reference's models/\*.ckpt
+ * (48 tensors, 424102 floats; reference train.py:198-199 `img_t_net` scope).
+ * conv index: 0-2 initconv_k, 3+2r / 4+2r resblock_r W1 / W2, 13-15 upsample_k. */
+#define FS_T_NCONV 16
+long long fs_transform_param_count(void);
+/* which: 0 = W, 1 = INscale, 2 = INshift */
+int fs_transform_param_slot(int conv_index, int which, long long* offset, long long* count);
+
+/* VGG16 conv1_1..conv4_3 (reference libs/vgg16.py:45-173, load_weights :257-266).
+ * flat   = conv1_1_W, conv1_1_b, conv1_2_W, ... conv4_3_b  (HWIO, RGB first layer)
+ * packed = engine-internal layout produced once by fs_vgg_pack. */
+#define FS_V_NCONV 10
+long long fs_vgg_flat_floats(void);
+long long fs_vgg_packed_floats(void);
+int fs_vgg_pack(const float* flat, float* packed, void* stream);
+
+/* ------------------------------------------------------------------ engine plan */
+typedef struct fs_engine fs_engine;
+enum { FS_ENG_TRANSFORM = 1, FS_ENG_TRANSFORM_BWD = 2, FS_ENG_VGG = 4, FS_ENG_VGG_BWD = 8 };
+
+/* Plan for batch N of HxW RGB images.  content_mask / style_mask: bit l set =
+ * VGG conv index l (0 = conv1_1 ... 9 = conv4_3) carries a content / style tap. */
+int fs_engine_create(int N, int H, int W, int flags, unsigned content_mask, unsigned style_mask,
+                     fs_engine** out);
+int fs_engine_destroy(fs_engine* e);
+size_t fs_engine_workspace_bytes(const fs_engine* e);
+int fs_engine_bind(fs_engine* e, void* workspace, size_t bytes);
+/* output dims of the transform net (== VGG input dims when both are planned) */
+int fs_engine_output_dims(const fs_engine* e, int* OH, int* OW);
+/* device pointer + dims of a saved VGG activation (post-ReLU conv output) */
+int fs_engine_vgg_activation(const fs_engine* e, int layer, const float** ptr, int* H, int* W, int* C);
+/* saved transform-net activation: stage 0 = raw conv output, 1 = post IN+activation */
+int fs_engine_transform_activation(const fs_engine* e, int conv_index, int stage, const float** ptr,
+                                   int* H, int* W, int* C);
+
+typedef struct {
+    int n_content; int content_layer[FS_V_NCONV]; float content_w[FS_V_NCONV];
+    int n_style;   int style_layer[FS_V_NCONV];   float style_w[FS_V_NCONV];
+    float beta;
+} fs_loss_config;
+
+/* ------------------------------------------------------------------ composites */
+/* create_net forward, upsample_method='resize' (reference im_transf_net.py:14-75;
+ * replaces sess.run(Y) at stylize_image.py:75).  x3 [N,H,W,3] 0..255 -> y3 [N,OH,OW,3]. */
+int fs_transform_forward(fs_engine* e, const float* params, const float* x3, float* y3, void* stream);
+
+/* VGG16 forward to conv index `upto`; activations stay in the workspace
+ * (reference libs/vgg16.py:36-173; replaces sess.run(content_layers) train.py:250). */
+int fs_vgg_forward(fs_engine* e, const float* packed, const float* img3, int upto, void* stream);
+
+/* Gram matrices G = F^T F / (h*w*c) of the listed layers of img3
+ * (reference utils.py:66-83; replaces sess.run(get_grams) train.py:150).
+ * out_grams[i] -> device [N, C_i, C_i]. */
+int fs_vgg_grams(fs_engine* e, const float* packed, const float* img3, int n_layers, const int* layers,
+                 float* const* out_grams, void* stream);
+
+/* Store VGG(content_img3) activations of cfg's content layers as the engine's
+ * content targets (reference slow_style.py:133-137). */
+int fs_vgg_set_content_targets(fs_engine* e, const float* packed, const float* img3,
+                               const fs_loss_config* cfg, void* stream);
+
+/* Perceptual loss of an image (+ gradient w.r.t. its pixels when grad3 != NULL):
+ * content + style + beta*TV (reference losses.py:12-97, slow_style.py:140-154).
+ * losses4 (device float[4]) = {content, style, beta*tv, total}. */
+int fs_perceptual_loss(fs_engine* e, const float* packed, const float* img3, const fs_loss_config* cfg,
+                       const float* const* target_grams, float* losses4, float* grad3, void* stream);
+
+/* One training step's forward + backward (reference train.py:250-255,274-275 up to
+ * the gradient): content targets from the raw batch, transform fwd, VGG fwd, losses,
+ * VGG data-gradient, transform backward.  grads: flat [424102] (sum over the local
+ * batch - the reference's losses sum over the batch, losses.py:32-37,63-64).
+ * y3 may be NULL. */
+int fs_train_fwd_bwd(fs_engine* e, const float* params, const float* packed, const float* x3,
+                     const fs_loss_config* cfg, const float* const* target_grams, float* grads,
+                     float* losses4, float* y3, void* stream);
+
+/* tf.train.AdamOptimizer update on a flat buffer (reference train.py:203,
+ * slow_style.py:153): epsilon outside the bias correction.  step_counter: device
+ * int holding the number of updates applied so far (incremented by the call). */
+int fs_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr,
+                 float beta1, float beta2, float eps, int* step_counter, void* stream);
+
+/* ------------------------------------------------------------------ single ops
+ * (exported for op-level parity tests and the Python op mirror) */
+/* tf.nn.conv2d NHWC/HWIO; padding_same: 1 = TF 'SAME', 0 = 'VALID'; C and OC must be
+ * multiples of 4 (reference im_transf_net.py:115, libs/vgg16.py:48-52). */
+int fs_conv2d_forward(const float* x, const float* w, const float* bias, float* y, int N, int H, int W,
+                      int C, int KH, int KW, int OC, int stride, int padding_same, int relu, void* stream);
+/* data gradient of the above; wt_scratch: KH*KW*C*OC floats */
+int fs_conv2d_dgrad(const float* dy, const float* w, float* dx, float* wt_scratch, int N, int H, int W,
+                    int C, int KH, int KW, int OC, int stride, int padding_same, void* stream);
+/* weight gradient; scratch: fs_conv2d_wgrad_scratch_floats() floats */
+long long fs_conv2d_wgrad_scratch_floats(int C, int KH, int KW, int OC);
+int fs_conv2d_wgrad(const float* x, const float* dy, float* dw, float* scratch, long long scratch_floats,
+                    int N, int H, int W, int C, int KH, int KW, int OC, int stride, int padding_same,
+                    void* stream);
+/* upconv2d = NN resize x4 + 3x3 stride-2 SAME conv, fused (reference im_transf_net.py:122-155);
+ * wc_scratch: 16*C*OC floats.  x [N,H,W,C] -> y [N,2H,2W,OC]. */
+int fs_upconv2d_forward(const float* x, const float* w, float* y, float* wc_scratch, int N, int H, int W,
+                        int C, int OC, void* stream);
+/* inst_norm + activation (0 none, 1 relu, 2 scaled tanh) (reference im_transf_net.py:193-247);
+ * scratch_doubles >= N*64*2*C doubles, stats: 2*N*C floats (mean, rstd) */
+int fs_instnorm_forward(const float* x, const float* scale, const float* shift, float* y, float* stats,
+                        double* scratch, int N, int H, int W, int C, float eps, int act, void* stream);
+int fs_maxpool2x2(const float* x, float* y, int N, int H, int W, int C, void* stream);
+/* G = F^T F/(h*w*c), F [N,H,W,C] -> G [N,C,C] (reference utils.py:76-81) */
+long long fs_gram_scratch_floats(int N, int C);
+int fs_gram_forward(const float* f, float* g, float* scratch, long long scratch_floats, int N, int H, int W,
+                    int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
