@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named by BASELINE.json: the 256x256 train step
+(transform fwd + VGG16 perceptual loss + backward + TF-Adam), data-parallel.
+
+    python bench.py --gpus N --steps K --warmup W           # our CUDA path
+    python bench.py --impl reference ...                    # CPU restatement of the reference
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); weak scaling with
+8 images per GPU (BASELINE.json configs[3] at N=8; configs[2]'s step at batch 8 for
+N=1).  Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for definitions.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+PER_GPU_BATCH = 8
+HW = 256
+STYLE_LAYERS = ["conv1_2", "conv2_2", "conv3_3", "conv4_3"]
+CONTENT_LAYERS = ["conv3_3"]
+# algorithmic work per image of one train step, SURVEY.md 8(d): 60.97 GMAC
+GFLOP_PER_IMAGE_TRAIN = 121.9
+GFLOP_PER_IMAGE_FWD = 7.069
+METRIC = "images/sec 256x256 train step (transform fwd + VGG16 perceptual loss + bwd + Adam)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d.get("hbm_gbs", 6650.0), bf16_tflops=d.get("bf16_tflops", 1590.0),
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", 1400.0), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"],
+                                 parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_batch(rank, n=PER_GPU_BATCH):
+    g = torch.Generator().manual_seed(100 + rank)
+    return torch.randint(0, 256, (n, HW, HW, 3), generator=g).float()
+
+
+def load_style_image():
+    import cv2
+    img = cv2.cvtColor(cv2.imread(os.path.join(GOLDEN, "starry_night_crop.jpg")), cv2.COLOR_BGR2RGB)
+    return img[None].astype(np.float32)
+
+
+# ----------------------------------------------------------------------------- CPU (oracle) arm
+def cpu_train_step_setup():
+    from oracle import ckpt as ockpt, restate as R
+    from faststyle_b200 import synth
+    params = ockpt.load(os.path.join(GOLDEN, "starry_final.ckpt"))
+    vggw = synth.synthetic_vgg_weights(7)
+    style = load_style_image()[:, :256, :256]          # bounded: a 256x256 crop of the style image
+    tg = R.style_target_grams(style, vggw, STYLE_LAYERS, torch.float32)
+    p = {k: torch.from_numpy(v).clone() for k, v in params.items()}
+    opt = R.TFAdam(p, 1e-3)
+
+    def step(x):
+        out = R.train_grads(x, p, vggw, tg, dtype=torch.float32, beta=0.0)
+        opt.step(p, out["grads"])
+        return float(out["loss"])
+    return step
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own TF1-CPU path cannot run here (TensorFlow
+    is absent), so this arm times the CPU restatement of the same graph (oracle/) on all
+    host threads.  Only rank 0 works."""
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_train_step_setup()
+    sample_b = 4
+    x = synthetic_batch(0, sample_b).numpy()
+    for _ in range(max(args.warmup, 1)):
+        step(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(x)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = sample_b / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "train.py step 256x256 (CPU sample: batch %d per step)" % sample_b,
+                   "per_gpu_batch": PER_GPU_BATCH, "parallelism": "cpu"},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": "torch-CPU restatement (not TF1), batch %d x %d steps" % (sample_b, args.steps)},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, local_rank, world):
+    import torch.distributed as dist
+    from faststyle_b200 import _lib, synth
+    from faststyle_b200.engine import Engine, TFAdam, make_loss_config, pack_vgg, params_to_device
+    from faststyle_b200.tf_bundle import read_checkpoint
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    params = params_to_device(read_checkpoint(os.path.join(GOLDEN, "starry_final.ckpt")), dev)
+    packed = pack_vgg(synth.synthetic_vgg_weights(7), dev)
+    cfg = make_loss_config(CONTENT_LAYERS, [1.0], STYLE_LAYERS, [5.0] * 4, 0.0)
+    style = load_style_image()
+    seng = Engine(1, style.shape[1], style.shape[2], vgg=True, style_layers=STYLE_LAYERS, device=dev)
+    tgrams = seng.vgg_grams(packed, style, STYLE_LAYERS)
+    torch.cuda.synchronize()
+    del seng
+    eng = Engine(PER_GPU_BATCH, HW, HW, transform_bwd=True, vgg_bwd=True, content_layers=CONTENT_LAYERS,
+                 style_layers=STYLE_LAYERS, device=dev)
+    opt = TFAdam(params, 1e-3)
+    grads = torch.empty_like(params)
+    losses = torch.empty(4, dtype=torch.float32, device=dev)
+    x_host = synthetic_batch(rank).pin_memory()
+    x_dev = x_host.to(dev)
+    loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
+
+    def step_device():
+        eng.train_fwd_bwd(params, packed, x_dev, cfg, tgrams, grads=grads, losses=losses)
+        if world > 1:
+            dist.all_reduce(grads, op=dist.ReduceOp.SUM)       # loss is a batch SUM (losses.py:32-37)
+        opt.step(grads)
+
+    def step_e2e():
+        x_dev.copy_(x_host, non_blocking=True)
+        step_device()
+        loss_host.copy_(losses, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, sample_clocks=False):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        barrier()
+        if sampler:
+            sampler.start()
+        n0 = lib.fs_launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        n1 = lib.fs_launch_count()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), n1 - n0, clocks
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step_e2e()
+    ms, launches, clocks = timed(step_device, args.steps, sample_clocks=True)
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    imgs = PER_GPU_BATCH * world * args.steps
+    value = imgs / (ms / 1e3)
+    e2e_value = imgs / (ms_e2e / 1e3)
+
+    # ---- extras (rank 0, N=1 semantics): forward-only throughput, roofline, CPU baseline
+    extra = {}
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        peaks = load_peaks()
+        # whole-step tensor-pipe view (algorithmic FLOPs of one step / step time)
+        step_tflops = GFLOP_PER_IMAGE_TRAIN * PER_GPU_BATCH / (ms / args.steps / 1e3) / 1e3
+        # dominant kernel live: VGG conv3x3 64->64 @256^2 (conv1_2 shape) through the op C-ABI
+        roof = dominant_kernel_roofline(dev, peaks)
+        roof["step_tflops"] = step_tflops
+        roof["step_frac_of_sustained"] = step_tflops / peaks["bf16_tflops_sustained"]
+        # transform forward only, batch 32 (BASELINE.json configs[1])
+        extra["transform_fwd_b32_images_per_s"] = bench_forward(dev, params)
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_base = cpu_baseline()
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "train.py step, per-GPU batch %d, %dx%d, starry ckpt weights, synthetic "
+                                   "VGG16 weights, style starry_night_crop.jpg" % (PER_GPU_BATCH, HW, HW),
+                       "global_batch": PER_GPU_BATCH * world, "parallelism": "dp%d" % world,
+                       "l2": "per-step working set ~1.3 GB >> 126 MB L2, no explicit flush",
+                       "precision": "fp32 operands, fp32 accumulate"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "images/s",
+                    "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": 16,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu_base,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(dev, peaks):
+    """The dominant kernel of the step is the 3x3 convolution of the VGG stack (80% of the
+    step's MACs).  Time its conv1_2-shaped launch (64->64, 256x256, batch 8) in isolation with
+    CUDA events on the launching stream."""
+    import ctypes as C
+    from faststyle_b200 import _lib
+    N, H, W, Ci, Co = PER_GPU_BATCH, HW, HW, 64, 64
+    x = torch.randn((N, H, W, Ci), device=dev)
+    w = torch.randn((3, 3, Ci, Co), device=dev) * 0.05
+    b = torch.zeros(Co, device=dev)
+    y = torch.empty((N, H, W, Co), device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def launch():
+        _lib.call("fs_conv2d_forward", C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()),
+                  C.c_void_p(b.data_ptr()), C.c_void_p(y.data_ptr()), N, H, W, Ci, 3, 3, Co, 1, 1, 1, st)
+    for _ in range(3):
+        launch()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * N * H * W * 9 * Ci * Co
+    achieved = flops / (ms / 1e3) / 1e12
+    return {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+            "kernel": "conv3x3 64->64 SAME +bias+relu, batch 8 @256x256 (VGG conv1_2 shape)",
+            "kernel_ms": ms, "precision": "fp32 FFMA path (tensor path not enabled)"}
+
+
+def bench_forward(dev, params):
+    from faststyle_b200.engine import Engine
+    B = 32
+    eng = Engine(B, HW, HW, transform=True, device=dev)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randint(0, 256, (B, HW, HW, 3), generator=g).float().to(dev)
+    for _ in range(3):
+        eng.transform_forward(params, x)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        eng.transform_forward(params, x)
+    e1.record()
+    torch.cuda.synchronize()
+    return B * reps / (e0.elapsed_time(e1) / 1e3)
+
+
+def cpu_baseline():
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_train_step_setup()
+    b = 4
+    x = synthetic_batch(0, b).numpy()
+    step(x)
+    n = 3
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step(x)
+    dt = (time.perf_counter() - t0) / n
+    return {"value": b / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "torch-CPU restatement of the train step (not TF1): batch %d, %d steps after 1 warm-up" % (b, n)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

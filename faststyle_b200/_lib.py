@@ -34,6 +34,7 @@ _PP = C.POINTER(C.c_void_p)
 SIGNATURES = {
     "fs_last_error": (C.c_char_p, []),
     "fs_version": (_I, []),
+    "fs_launch_count": (_LL, []),
     "fs_transform_param_count": (_LL, []),
     "fs_transform_param_slot": (_I, [_I, _I, C.POINTER(_LL), C.POINTER(_LL)]),
     "fs_vgg_flat_floats": (_LL, []),

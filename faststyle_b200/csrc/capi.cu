@@ -13,6 +13,7 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* get_error() { return g_err; }
+long long g_launches = 0;
 }  // namespace fs
 
 using namespace fs;
@@ -37,6 +38,7 @@ extern "C" {
 
 const char* fs_last_error(void) { return get_error(); }
 int fs_version(void) { return FS_VERSION; }
+long long fs_launch_count(void) { return g_launches; }
 
 long long fs_transform_param_count(void) { return T_NPARAMS; }
 

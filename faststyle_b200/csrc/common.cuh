@@ -28,7 +28,14 @@ const char* get_error();
         }                                                                      \
     } while (0)
 
-#define FS_LAUNCH_CHECK() FS_CUDA(cudaGetLastError())
+// every kernel launch of this library goes through FS_LAUNCH_CHECK: it also counts launches
+// (fs_launch_count) so that callers can report how many of OUR kernels ran in a timed region.
+extern long long g_launches;
+#define FS_LAUNCH_CHECK()                \
+    do {                                 \
+        ++fs::g_launches;                \
+        FS_CUDA(cudaGetLastError());     \
+    } while (0)
 
 #define FS_TRY(expr)                   \
     do {                               \

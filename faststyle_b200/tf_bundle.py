@@ -327,8 +327,10 @@ def read_checkpoint(prefix: str, verify=True) -> "OrderedDict[str, np.ndarray]":
 
 def serialize_checkpoint(tensors) -> "tuple[bytes, bytes]":
     """Return (index_bytes, data_bytes) for {name: ndarray}."""
-    items = sorted(((k.encode("utf-8"), np.ascontiguousarray(v)) for k, v in tensors.items()),
-                   key=lambda kv: kv[0])
+    def _c(v):                       # C-contiguous without promoting 0-d scalars to 1-d
+        a = np.asarray(v)
+        return a if a.flags.c_contiguous else np.ascontiguousarray(a)
+    items = sorted(((k.encode("utf-8"), _c(v)) for k, v in tensors.items()), key=lambda kv: kv[0])
     data = bytearray()
     kvs = [(b"", b"\x08\x01\x1a\x02\x08\x01")]   # BundleHeaderProto{num_shards=1, version{producer=1}}
     for key, arr in items:

@@ -27,6 +27,8 @@ extern "C" {
 
 const char* fs_last_error(void);
 int fs_version(void);
+/* number of kernels this library has launched so far in this process */
+long long fs_launch_count(void);
 
 /* ------------------------------------------------------------------ layouts
  * Transform-net parameters live in ONE flat fp32 buffer whose order is the

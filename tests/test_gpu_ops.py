@@ -61,7 +61,8 @@ def test_conv_forward_dgrad_wgrad(built_lib, case):
 
     xd, wd = _dev(x), _dev(w)
     y = torch.empty((N, OH, OW, Co), device="cuda")
-    _lib.call("fs_conv2d_forward", _ptr(xd), _ptr(wd), _ptr(_dev(b)) if br else None, _ptr(y),
+    bd = _dev(b) if br else None
+    _lib.call("fs_conv2d_forward", _ptr(xd), _ptr(wd), _ptr(bd) if br else None, _ptr(y),
               N, H, W, Ci, K, K, Co, s, same, br, _st())
     assert _relerr(y, R.nchw_to_nhwc(yo.detach())) < 2e-6
     if br:
@@ -91,7 +92,8 @@ def test_upconv_forward(built_lib, shape):
     yo = R.upconv2d(R.nhwc_to_nchw(torch.from_numpy(x).double()), torch.from_numpy(w).double(), 2)
     y = torch.empty((N, 2 * H, 2 * W, Co), device="cuda")
     sc = torch.empty(16 * Ci * Co, device="cuda")
-    _lib.call("fs_upconv2d_forward", _ptr(_dev(x)), _ptr(_dev(w)), _ptr(y), _ptr(sc), N, H, W, Ci, Co, _st())
+    xd, wd = _dev(x), _dev(w)          # keep the device tensors alive across the async launch
+    _lib.call("fs_upconv2d_forward", _ptr(xd), _ptr(wd), _ptr(y), _ptr(sc), N, H, W, Ci, Co, _st())
     assert tuple(yo.shape[2:]) == (2 * H, 2 * W)
     assert _relerr(y, R.nchw_to_nhwc(yo)) < 2e-6
 
@@ -110,7 +112,8 @@ def test_instnorm_forward(built_lib, C_, act):
     y = torch.empty((N, H, W, C_), device="cuda")
     stats = torch.empty(2 * N * C_, device="cuda")
     sc = torch.empty(N * 64 * 2 * C_, dtype=torch.float64, device="cuda")
-    _lib.call("fs_instnorm_forward", _ptr(_dev(x)), _ptr(_dev(g)), _ptr(_dev(b)), _ptr(y), _ptr(stats),
+    xd, gd, bd = _dev(x), _dev(g), _dev(b)
+    _lib.call("fs_instnorm_forward", _ptr(xd), _ptr(gd), _ptr(bd), _ptr(y), _ptr(stats),
               _ptr(sc), N, H, W, C_, C.c_float(1e-3), act, _st())
     assert _relerr(y, R.nchw_to_nhwc(yo)) < 5e-6
 
@@ -125,10 +128,11 @@ def test_gram_and_pool(built_lib, shape):
     g = torch.empty((N, C_, C_), device="cuda")
     nsc = _lib.load().fs_gram_scratch_floats(N, C_)
     sc = torch.empty(nsc, device="cuda")
-    _lib.call("fs_gram_forward", _ptr(_dev(f)), _ptr(g), _ptr(sc), C.c_longlong(nsc), N, H, W, C_, _st())
+    fd = _dev(f)
+    _lib.call("fs_gram_forward", _ptr(fd), _ptr(g), _ptr(sc), C.c_longlong(nsc), N, H, W, C_, _st())
     assert _relerr(g, R.gram(fo)) < 2e-6
     p = torch.empty((N, (H + 1) // 2, (W + 1) // 2, C_), device="cuda")
-    _lib.call("fs_maxpool2x2", _ptr(_dev(f)), _ptr(p), N, H, W, C_, _st())
+    _lib.call("fs_maxpool2x2", _ptr(fd), _ptr(p), N, H, W, C_, _st())
     assert torch.equal(p.cpu().double(), R.nchw_to_nhwc(R.max_pool_same(fo)))
 
 
