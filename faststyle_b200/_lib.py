@@ -63,6 +63,9 @@ SIGNATURES = {
     "fs_maxpool2x2": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "fs_gram_scratch_floats": (_LL, [_I, _I]),
     "fs_gram_forward": (_I, [_P, _P, _P, _LL, _I, _I, _I, _I, _P]),
+    "fs_conv3x3_tc_scratch_bytes": (_SZ, [_I, _I, _I, _I, _I]),
+    "fs_conv3x3_tc_forward": (_I, [_P, _P, _P, _P, _P, _SZ] + [_I] * 7 + [_P]),
+    "fs_conv3x3_tc_dgrad": (_I, [_P, _P, _P, _P, _SZ] + [_I] * 6 + [_P]),
 }
 
 _lib = None

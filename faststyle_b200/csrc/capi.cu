@@ -1,6 +1,7 @@
 // extern "C" surface of libfaststyle_b200 (see include/faststyle_b200.h).
 #include "../../include/faststyle_b200.h"
 #include "engine.cuh"
+#include "tc.cuh"
 #include <stdarg.h>
 #include <new>
 
@@ -268,6 +269,57 @@ int fs_gram_forward(const float* f, float* g, float* scratch, long long scratch_
     wa.KH = wa.KW = 1; wa.stride = 1; wa.OH = H; wa.OW = W; wa.OC = C; wa.dy_bs = wa.in_bs;
     wa.N = N; wa.per_sample = 1; wa.scale = (float)(1.0 / ((double)H * W * C));
     return launch_wgrad(wa, S(stream));
+}
+
+// ------------------------------------------------------------------ tensor-core path
+static size_t al1k(size_t b) { return (b + 1023) & ~(size_t)1023; }
+
+size_t fs_conv3x3_tc_scratch_bytes(int N, int H, int W, int C, int OC) {
+    size_t act = (size_t)N * H * W * (C > OC ? C : OC) * 2;      // one bf16 plane of the larger tensor
+    size_t wts = (size_t)9 * C * OC * 2;
+    return 2 * al1k(act) + 2 * al1k(wts) + 1024;
+}
+
+static int tc_scratch(void* scratch, size_t bytes, size_t act_elems, size_t w_elems, SplitPtr* xs, SplitPtr* ws) {
+    FS_CHECK(scratch && ((uintptr_t)scratch & 1023) == 0, "tc scratch must be 1024-byte aligned");
+    size_t a = al1k(act_elems * 2), w = al1k(w_elems * 2);
+    FS_CHECK(bytes >= 2 * a + 2 * w, "tc scratch too small");
+    char* p = (char*)scratch;
+    xs->hi = (__nv_bfloat16*)p; xs->lo = (__nv_bfloat16*)(p + a);
+    ws->hi = (__nv_bfloat16*)(p + 2 * a); ws->lo = (__nv_bfloat16*)(p + 2 * a + w);
+    return 0;
+}
+
+int fs_conv3x3_tc_forward(const float* x, const float* w, const float* bias, float* y, void* scratch,
+                          size_t scratch_bytes, int N, int H, int W, int C, int OC, int padding_same,
+                          int relu, void* stream) {
+    FS_CHECK(x && w && y, "fs_conv3x3_tc_forward: NULL argument");
+    Conv3x3TcArgs a;
+    memset(&a, 0, sizeof(a));
+    FS_TRY(tc_scratch(scratch, scratch_bytes, (size_t)N * H * W * C, (size_t)9 * C * OC, &a.x, &a.w));
+    FS_TRY(split_bf16(x, a.x, (long long)N * H * W * C, S(stream)));
+    FS_TRY(pack_w3x3_tc(w, a.w, C, OC, 0, S(stream)));
+    a.N = N; a.H = H; a.W = W; a.C = C; a.OC = OC;
+    a.pad = padding_same ? 1 : 0;
+    a.OH = padding_same ? H : H - 2; a.OW = padding_same ? W : W - 2;
+    a.bias = bias; a.relu = relu; a.out_f32 = y;
+    return launch_conv3x3_tc(a, S(stream));
+}
+
+int fs_conv3x3_tc_dgrad(const float* dy, const float* w, float* dx, void* scratch, size_t scratch_bytes,
+                        int N, int H, int W, int C, int OC, int padding_same, void* stream) {
+    FS_CHECK(dy && w && dx, "fs_conv3x3_tc_dgrad: NULL argument");
+    const int OH = padding_same ? H : H - 2, OW = padding_same ? W : W - 2;
+    Conv3x3TcArgs a;
+    memset(&a, 0, sizeof(a));
+    FS_TRY(tc_scratch(scratch, scratch_bytes, (size_t)N * OH * OW * OC, (size_t)9 * C * OC, &a.x, &a.w));
+    FS_TRY(split_bf16(dy, a.x, (long long)N * OH * OW * OC, S(stream)));
+    FS_TRY(pack_w3x3_tc(w, a.w, C, OC, 1, S(stream)));
+    a.N = N; a.H = OH; a.W = OW; a.C = OC;          // gathered tensor = dy
+    a.OH = H; a.OW = W; a.OC = C;                   // produces dx
+    a.pad = padding_same ? 1 : 2;                   // k-1-pad
+    a.out_f32 = dx;
+    return launch_conv3x3_tc(a, S(stream));
 }
 
 }  // extern "C"

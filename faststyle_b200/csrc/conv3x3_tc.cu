@@ -1,0 +1,534 @@
+// tcgen05 implicit-GEMM 3x3 stride-1 convolution (forward and data gradient) for NHWC
+// activations whose channel counts are multiples of 64.
+//
+//   GEMM view per output tile: D[128*NACC pixels, BN out-channels] += A[pixels, 64 ch] * B[64 ch, BN]
+//   summed over 9 taps x (C/64) channel blocks.
+//
+// Precision: operands are "split bf16" (x ~= hi + lo, 16 mantissa bits); each logical product is
+// three kind::f16 MMAs (hi*hi + hi*lo + lo*hi) accumulated in fp32 in TMEM.  That restores
+// fp32-class accuracy (~1e-5 on the unit pixel scale) at 3 MMA issues.
+//
+// Data movement: a persistent CTA per SM; a TMA producer thread streams
+//   * A "slabs": for every (channel block, kw) one box {64 ch, 16 px, TH+2 rows} of the hi and lo
+//     planes (128B-swizzled, zero-filled out of bounds = conv zero padding for free).  The three kh
+//     taps of that kw are the SAME slab at +kh*2048 B (16 px * 128 B), so the slab is read once from
+//     L2 and used by 3 taps: 3.4-3.75 slab loads per tile instead of 9.
+//   * B tiles: per tap one [BN x 64] box of the packed hi/lo weights.
+// One elected thread issues tcgen05.mma into double-buffered TMEM accumulators; four epilogue warps
+// drain TMEM (tcgen05.ld), apply bias/ReLU/addend/mask and store fp32 and/or split-bf16 NHWC while the
+// next tile's MMAs run.
+#include <cuda.h>
+#include "tc.cuh"
+
+namespace fs {
+
+namespace {
+
+constexpr int TW = 16;            // tile width in pixels (16 px * 128 B = 2048 B per slab row)
+constexpr int KB = 64;            // channels per K block (= one 128-byte swizzle row of bf16)
+constexpr int A_STAGES = 2;
+constexpr uint32_t SPIN_LIMIT_CYCLES = 2000000000u;   // ~1 s: trap instead of hanging the GPU
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if ((unsigned long long)(clock64() - t0) > SPIN_LIMIT_CYCLES) {
+            printf("conv3x3_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row (1024 B) swizzle atoms.
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);     // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset: 8 rows * 128 B
+    d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                       // layout: SWIZZLE_128B
+    return d;
+}
+
+template <int BN>
+__device__ __forceinline__ uint32_t make_idesc() {
+    return (1u << 4)                // D format: fp32
+         | (1u << 7)                // A format: bf16
+         | (1u << 10)               // B format: bf16
+         | ((uint32_t)(BN >> 3) << 17)      // N
+         | ((uint32_t)(128 >> 4) << 24);    // M = 128
+}
+
+struct TcParams {
+    int N, H, W, C, OH, OW, OC, pad;
+    int tilesX, tilesY, tilesN;
+    long long total_tiles;
+    const float* bias; const float* addend; const float* ref;
+    int relu, add_crop, addH, addW;
+    float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+};
+
+template <int TH, int BN>
+struct Cfg {
+    static constexpr int NACC = TH / 8;
+    static constexpr int B_STAGES = (BN == 64) ? 4 : 2;
+    static constexpr int SLAB_BYTES = (TH + 2) * TW * 128;        // one plane
+    static constexpr int A_STAGE_BYTES = 2 * SLAB_BYTES;          // hi + lo
+    static constexpr int BTILE_BYTES = BN * 128;                  // one plane
+    static constexpr int B_STAGE_BYTES = 2 * BTILE_BYTES;
+    static constexpr int TMEM_COLS = 2 * NACC * BN;               // double-buffered accumulators
+    static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int TH, int BN>
+__global__ void __launch_bounds__(256, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                  const TcParams p) {
+    using K = Cfg<TH, BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smemA = smem;
+    uint8_t* smemB = smem + A_STAGES * K::A_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + K::B_STAGES * K::B_STAGE_BYTES);
+    uint64_t* a_full = bars;                       // [A_STAGES]
+    uint64_t* a_empty = a_full + A_STAGES;         // [A_STAGES]
+    uint64_t* b_full = a_empty + A_STAGES;         // [B_STAGES]
+    uint64_t* b_empty = b_full + K::B_STAGES;      // [B_STAGES]
+    uint64_t* t_full = b_empty + K::B_STAGES;      // [2]
+    uint64_t* t_empty = t_full + 2;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int CB = p.C / KB;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < K::B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, K::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const int nt = (int)(t % p.tilesN);
+            long long r = t / p.tilesN;
+            const int tx = (int)(r % p.tilesX); r /= p.tilesX;
+            const int ty = (int)(r % p.tilesY);
+            const int n = (int)(r / p.tilesY);
+            const int y0 = ty * TH - p.pad, x0 = tx * TW - p.pad, n0 = nt * BN;
+            for (int cb = 0; cb < CB; ++cb) {
+                for (int kw = 0; kw < 3; ++kw) {
+                    mbar_wait(&a_empty[sa], pa ^ 1);
+                    uint8_t* dst = smemA + sa * K::A_STAGE_BYTES;
+                    mbar_expect_tx(&a_full[sa], K::A_STAGE_BYTES);
+                    tma_load_4d(dst, &tmA_hi, &a_full[sa], cb * KB, x0 + kw, y0, n);
+                    tma_load_4d(dst + K::SLAB_BYTES, &tmA_lo, &a_full[sa], cb * KB, x0 + kw, y0, n);
+                    if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
+                    for (int kh = 0; kh < 3; ++kh) {
+                        mbar_wait(&b_empty[sb], pb ^ 1);
+                        uint8_t* bd = smemB + sb * K::B_STAGE_BYTES;
+                        mbar_expect_tx(&b_full[sb], K::B_STAGE_BYTES);
+                        const int row = ((kh * 3 + kw) * CB + cb) * p.OC + n0;
+                        tma_load_2d(bd, &tmB_hi, &b_full[sb], 0, row);
+                        tma_load_2d(bd + K::BTILE_BYTES, &tmB_lo, &b_full[sb], 0, row);
+                        if (++sb == K::B_STAGES) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc<BN>();
+        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+        int as = 0; uint32_t pt = 0;
+        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            mbar_wait(&t_empty[as], pt ^ 1);
+            tc_fence_after();
+            const uint32_t acc_base = tmem_base + (uint32_t)(as * K::NACC * BN);
+            bool first = true;
+            for (int cb = 0; cb < CB; ++cb) {
+                for (int kw = 0; kw < 3; ++kw) {
+                    mbar_wait(&a_full[sa], pa);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smemA + sa * K::A_STAGE_BYTES);
+                    const uint32_t a_lo = a_hi + K::SLAB_BYTES;
+                    for (int kh = 0; kh < 3; ++kh) {
+                        mbar_wait(&b_full[sb], pb);
+                        tc_fence_after();
+                        const uint32_t b_hi = smem_u32(smemB + sb * K::B_STAGE_BYTES);
+                        const uint32_t b_lo = b_hi + K::BTILE_BYTES;
+#pragma unroll
+                        for (int acc = 0; acc < K::NACC; ++acc) {
+                            const uint32_t aoff = (uint32_t)((acc * 8 + kh) * TW * 128);
+                            const uint32_t d = acc_base + (uint32_t)(acc * BN);
+#pragma unroll
+                            for (int prod = 0; prod < 3; ++prod) {
+                                const uint32_t abase = (prod == 2 ? a_lo : a_hi) + aoff;
+                                const uint32_t bbase = (prod == 1 ? b_lo : b_hi);
+#pragma unroll
+                                for (int k4 = 0; k4 < 4; ++k4) {
+                                    tc_mma_bf16(d, make_sdesc(abase + k4 * 32), make_sdesc(bbase + k4 * 32), idesc,
+                                                (first && prod == 0 && k4 == 0) ? 0u : 1u);
+                                }
+                            }
+                        }
+                        first = false;
+                        tc_commit(&b_empty[sb]);
+                        if (++sb == K::B_STAGES) { sb = 0; pb ^= 1; }
+                    }
+                    tc_commit(&a_empty[sa]);
+                    if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
+                }
+            }
+            tc_commit(&t_full[as]);
+            if (++as == 2) { as = 0; pt ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+        const int ew = warp - 4;                       // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+        const int row = ew * 32 + lane;                // MMA row = pixel within the 8x16 sub-tile
+        const int prow = row >> 4, pcol = row & 15;
+        int as = 0; uint32_t pt = 0;
+        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const int nt = (int)(t % p.tilesN);
+            long long r = t / p.tilesN;
+            const int tx = (int)(r % p.tilesX); r /= p.tilesX;
+            const int ty = (int)(r % p.tilesY);
+            const int n = (int)(r / p.tilesY);
+            mbar_wait(&t_full[as], pt);
+            tc_fence_after();
+#pragma unroll 1
+            for (int acc = 0; acc < K::NACC; ++acc) {
+                const int oy = ty * TH + acc * 8 + prow, ox = tx * TW + pcol;
+                const bool ok = oy < p.OH && ox < p.OW;
+                const long long pix = ((long long)n * p.OH + oy) * p.OW + ox;
+                const float* addp = nullptr;
+                if (p.addend && ok) {
+                    int ay = oy - p.add_crop, ax = ox - p.add_crop;
+                    if (ay >= 0 && ay < p.addH && ax >= 0 && ax < p.addW)
+                        addp = p.addend + (((long long)n * p.addH + ay) * p.addW + ax) * p.OC;
+                }
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ++ch) {
+                    float v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) +
+                                           (uint32_t)(as * K::NACC * BN + acc * BN + ch * 32);
+                    tmem_ld32(taddr, v);                // warp-collective: executed by all lanes
+                    if (ok) {
+                        const int c0 = nt * BN + ch * 32;
+                        if (p.bias) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i));
+                                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                            }
+                        }
+                        if (addp) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                float4 b = *reinterpret_cast<const float4*>(addp + c0 + i);
+                                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                            }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                        }
+                        if (p.ref) {
+                            const float* rp = p.ref + pix * p.OC + c0;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                float4 b = *reinterpret_cast<const float4*>(rp + i);
+                                v[i] = b.x > 0.f ? v[i] : 0.f; v[i + 1] = b.y > 0.f ? v[i + 1] : 0.f;
+                                v[i + 2] = b.z > 0.f ? v[i + 2] : 0.f; v[i + 3] = b.w > 0.f ? v[i + 3] : 0.f;
+                            }
+                        }
+                        if (p.out_f32) {
+                            float* op = p.out_f32 + pix * p.OC + c0;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4)
+                                *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        }
+                        if (p.out_hi) {
+                            __nv_bfloat16* hp = p.out_hi + pix * p.OC + c0;
+                            __nv_bfloat16* lp = p.out_lo + pix * p.OC + c0;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                uint32_t hw[4], lw[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    __nv_bfloat16 h0 = __float2bfloat16_rn(v[i + 2 * j]);
+                                    __nv_bfloat16 h1 = __float2bfloat16_rn(v[i + 2 * j + 1]);
+                                    __nv_bfloat16 l0 = __float2bfloat16_rn(v[i + 2 * j] - __bfloat162float(h0));
+                                    __nv_bfloat16 l1 = __float2bfloat16_rn(v[i + 2 * j + 1] - __bfloat162float(h1));
+                                    hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                                    lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                                }
+                                *reinterpret_cast<uint4*>(hp + i) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                                *reinterpret_cast<uint4*>(lp + i) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[as]);
+            if (++as == 2) { as = 0; pt ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, K::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ helpers kernels
+__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, long long n4) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 v = *reinterpret_cast<const float4*>(x + i * 4);
+    float f[4] = {v.x, v.y, v.z, v.w};
+    uint32_t h[2], l[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * j]), h1 = __float2bfloat16_rn(f[2 * j + 1]);
+        __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * j] - __bfloat162float(h0));
+        __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * j + 1] - __bfloat162float(h1));
+        h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint2*>(hi + i * 4) = make_uint2(h[0], h[1]);
+    *reinterpret_cast<uint2*>(lo + i * 4) = make_uint2(l[0], l[1]);
+}
+
+__global__ void pack_w3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo, int Ci, int Co, int mode) {
+    // output index: (((tap*CB + cb)*Nn + n)*64 + k)
+    const int Kc = mode == 0 ? Ci : Co;        // reduction channels
+    const int Nn = mode == 0 ? Co : Ci;        // output channels
+    const int CB = Kc / 64;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = 9LL * Kc * Nn;
+    if (i >= total) return;
+    int k = (int)(i % 64);
+    long long r = i / 64;
+    int n = (int)(r % Nn); r /= Nn;
+    int cb = (int)(r % CB);
+    int tap = (int)(r / CB);
+    int kh = tap / 3, kw = tap % 3;
+    float v;
+    if (mode == 0) v = w[(((long long)kh * 3 + kw) * Ci + cb * 64 + k) * Co + n];
+    else v = w[(((long long)(2 - kh) * 3 + (2 - kw)) * Ci + n) * Co + cb * 64 + k];
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+int make_act_map(CUtensorMap* tm, const __nv_bfloat16* base, int N, int H, int W, int C, int box_h) {
+    EncodeTiledFn enc = get_encode_fn();
+    FS_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)KB, (cuuint32_t)TW, (cuuint32_t)box_h, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation %dx%dx%dx%d) failed: %d", N, H, W, C, (int)r);
+    return 0;
+}
+
+int make_w_map(CUtensorMap* tm, const __nv_bfloat16* base, long long rows, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    FS_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    cuuint64_t dims[2] = {(cuuint64_t)KB, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)KB * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights rows=%lld) failed: %d", rows, (int)r);
+    return 0;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int TH, int BN>
+int launch_cfg(const Conv3x3TcArgs& a, cudaStream_t st) {
+    using K = Cfg<TH, BN>;
+    CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+    FS_TRY(make_act_map(&tmA_hi, a.x.hi, a.N, a.H, a.W, a.C, TH + 2));
+    FS_TRY(make_act_map(&tmA_lo, a.x.lo, a.N, a.H, a.W, a.C, TH + 2));
+    const long long wrows = 9LL * (a.C / KB) * a.OC;
+    FS_TRY(make_w_map(&tmB_hi, a.w.hi, wrows, BN));
+    FS_TRY(make_w_map(&tmB_lo, a.w.lo, wrows, BN));
+    TcParams p;
+    p.N = a.N; p.H = a.H; p.W = a.W; p.C = a.C; p.OH = a.OH; p.OW = a.OW; p.OC = a.OC; p.pad = a.pad;
+    p.tilesX = cdiv(a.OW, TW); p.tilesY = cdiv(a.OH, TH); p.tilesN = a.OC / BN;
+    p.total_tiles = (long long)a.N * p.tilesX * p.tilesY * p.tilesN;
+    p.bias = a.bias; p.addend = a.addend; p.ref = a.ref; p.relu = a.relu;
+    p.add_crop = a.add_crop; p.addH = a.addH; p.addW = a.addW;
+    p.out_f32 = a.out_f32; p.out_hi = a.out_split.hi; p.out_lo = a.out_split.lo;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<TH, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+        attr_set = true;
+    }
+    int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
+    conv3x3_tc_kernel<TH, BN><<<grid, 256, K::SMEM_BYTES, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+bool conv3x3_tc_supported(int C, int OC, int W, int OW) {
+    return C % 64 == 0 && OC % 64 == 0 && C >= 64 && OC >= 64 && W >= 1 && OW >= 1;
+}
+
+int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st) {
+    FS_CHECK(conv3x3_tc_supported(a.C, a.OC, a.W, a.OW), "conv3x3_tc: needs C%%64==0 and OC%%64==0 (C=%d OC=%d)", a.C, a.OC);
+    FS_CHECK(a.x.hi && a.x.lo && a.w.hi && a.w.lo, "conv3x3_tc: NULL operand planes");
+    FS_CHECK(a.out_f32 || a.out_split.hi, "conv3x3_tc: no output requested");
+    FS_CHECK((a.out_split.hi == nullptr) == (a.out_split.lo == nullptr), "conv3x3_tc: split output needs both planes");
+    FS_CHECK(a.OH > 0 && a.OW > 0 && a.N > 0, "conv3x3_tc: empty output");
+    const bool tall = a.OH > 8;
+    if (a.OC % 128 == 0) return tall ? launch_cfg<16, 128>(a, st) : launch_cfg<8, 128>(a, st);
+    return tall ? launch_cfg<16, 64>(a, st) : launch_cfg<8, 64>(a, st);
+}
+
+int split_bf16(const float* x, SplitPtr out, long long n, cudaStream_t st) {
+    FS_CHECK(n % 4 == 0, "split_bf16: n %% 4 != 0");
+    long long n4 = n / 4;
+    split_bf16_kernel<<<cdiv(n4, 256), 256, 0, st>>>(x, out.hi, out.lo, n4);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int pack_w3x3_tc(const float* w, SplitPtr out, int Ci, int Co, int mode, cudaStream_t st) {
+    FS_CHECK(Ci % 64 == 0 && Co % 64 == 0, "pack_w3x3_tc: channels must be multiples of 64");
+    long long total = 9LL * Ci * Co;
+    pack_w3x3_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, out.hi, out.lo, Ci, Co, mode);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace fs

@@ -1,0 +1,37 @@
+// Tensor-core (tcgen05 / TMEM / TMA) path: 3x3 stride-1 implicit-GEMM convolution with
+// split-bf16 operands.  sm_100a only.
+#pragma once
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace fs {
+
+// A "split" fp32 tensor: x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi)  (16 mantissa bits).
+struct SplitPtr { __nv_bfloat16* hi; __nv_bfloat16* lo; };
+
+// fp32 [n] -> hi/lo bf16 planes (n % 4 == 0)
+int split_bf16(const float* x, SplitPtr out, long long n, cudaStream_t st);
+
+// Pack HWIO fp32 weights [3,3,Ci,Co] for the tensor path.
+//   mode 0 (forward):        B[tap=(kh,kw)][cb][n=co][k=ci%64]          = W[kh,kw,cb*64+k,n]
+//   mode 1 (data gradient):  B[tap=(2-kh,2-kw)][cb][n=ci][k=co%64]      = W[kh,kw,n,cb*64+k]
+// Output: hi/lo planes of 9*(K/64)*N*64 bf16 each (K = reduction channels, N = output channels).
+int pack_w3x3_tc(const float* w, SplitPtr out, int Ci, int Co, int mode, cudaStream_t st);
+
+struct Conv3x3TcArgs {
+    SplitPtr x;                // input  [N,H,W,C]  split bf16 planes (C % 64 == 0)
+    SplitPtr w;                // packed weights (pack_w3x3_tc), reduction channels = C, outputs = OC
+    int N, H, W, C;
+    int OH, OW, OC;            // output dims (OC % 64 == 0)
+    int pad;                   // zero padding on top/left (SAME: 1, VALID: 0, VALID data gradient: 2)
+    // epilogue: v = acc + bias[c] + addend[pix,c]; relu; mask by ref[pix,c] > 0
+    const float* bias; const float* addend; const float* ref;
+    int relu;
+    int add_crop, addH, addW;  // addend is [N,addH,addW,OC]; output pixel (y,x) reads (y-crop, x-crop)
+    float* out_f32;            // [N,OH,OW,OC] fp32 (may be null)
+    SplitPtr out_split;        // split planes of the same tensor (may be null)
+};
+int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st);
+bool conv3x3_tc_supported(int C, int OC, int W, int OW);
+
+}  // namespace fs

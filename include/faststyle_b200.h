@@ -142,6 +142,18 @@ long long fs_gram_scratch_floats(int N, int C);
 int fs_gram_forward(const float* f, float* g, float* scratch, long long scratch_floats, int N, int H, int W,
                     int C, void* stream);
 
+/* ------------------------------------------------------------------ tensor-core path
+ * 3x3 stride-1 convolution on the tcgen05 tensor pipe with split-bf16 operands
+ * (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM); C and OC multiples of 64.
+ * Same semantics as fs_conv2d_forward / fs_conv2d_dgrad with KH=KW=3, stride 1.
+ * scratch: fs_conv3x3_tc_scratch_bytes() bytes, 1024-byte aligned. */
+size_t fs_conv3x3_tc_scratch_bytes(int N, int H, int W, int C, int OC);
+int fs_conv3x3_tc_forward(const float* x, const float* w, const float* bias, float* y, void* scratch,
+                          size_t scratch_bytes, int N, int H, int W, int C, int OC, int padding_same,
+                          int relu, void* stream);
+int fs_conv3x3_tc_dgrad(const float* dy, const float* w, float* dx, void* scratch, size_t scratch_bytes,
+                        int N, int H, int W, int C, int OC, int padding_same, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,73 @@
+"""tcgen05 3x3 convolution (split-bf16 x3) against the fp64 oracle conv.
+Tolerance: 2e-5 relative to the output's max magnitude - bf16x3 drops only the lo*lo term
+(2^-16 relative per product, averaged over K >= 576)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import restate as R  # noqa: E402
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _relerr(got, want):
+    want = want.double()
+    return float((got.double().cpu() - want).abs().max() / max(want.abs().max().item(), 1e-30))
+
+
+CASES = [
+    # N, H, W, C, OC, same, relu
+    (1, 16, 16, 64, 64, 1, 0),       # single full tile
+    (2, 20, 18, 64, 64, 0, 0),       # residual-block VALID, ragged tiles
+    (1, 19, 23, 64, 128, 1, 1),      # VGG SAME + bias + relu, odd sizes
+    (2, 33, 40, 128, 256, 1, 1),     # two N tiles, two channel blocks, TH=16 path
+    (1, 8, 8, 256, 512, 1, 1),       # TH=8 path, deep K
+    (3, 64, 64, 64, 64, 1, 1),       # > 1 tile per CTA in flight (double-buffered TMEM)
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv3x3_tc_forward_and_dgrad(built_lib, case):
+    from faststyle_b200 import _lib
+    lib = _lib.load()
+    N, H, W, Ci, Co, same, relu = case
+    rng = np.random.RandomState(abs(hash(case)) % 2**31)
+    x = rng.standard_normal((N, H, W, Ci)).astype(np.float32)
+    w = (rng.standard_normal((3, 3, Ci, Co)) * 0.05).astype(np.float32)
+    b = rng.standard_normal(Co).astype(np.float32)
+    xt = R.nhwc_to_nchw(torch.from_numpy(x).double()).requires_grad_(True)
+    wt = torch.from_numpy(w).double()
+    yo = R.conv2d_tf(xt, wt, 1, "SAME" if same else "VALID")
+    ypre = yo
+    if relu:
+        yo = torch.relu(yo + torch.from_numpy(b).double().view(1, -1, 1, 1))
+    OH, OW = yo.shape[2], yo.shape[3]
+    xd, wd, bd = torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(), torch.from_numpy(b).cuda()
+    nb = lib.fs_conv3x3_tc_scratch_bytes(N, H, W, Ci, Co)
+    scratch = torch.empty(nb + 1024, dtype=torch.uint8, device="cuda")
+    off = (-scratch.data_ptr()) % 1024
+    sp = C.c_void_p(scratch.data_ptr() + off)
+    y = torch.full((N, OH, OW, Co), float("nan"), device="cuda")
+    _lib.call("fs_conv3x3_tc_forward", _ptr(xd), _ptr(wd), _ptr(bd) if relu else None, _ptr(y), sp,
+              C.c_size_t(nb), N, H, W, Ci, Co, same, relu, _st())
+    torch.cuda.synchronize()
+    assert _relerr(y, R.nchw_to_nhwc(yo.detach())) < 2e-5
+    # data gradient of the plain conv
+    dy = rng.standard_normal((N, OH, OW, Co)).astype(np.float32)
+    ypre.backward(R.nhwc_to_nchw(torch.from_numpy(dy).double()))
+    dyd = torch.from_numpy(dy).cuda()
+    dx = torch.full((N, H, W, Ci), float("nan"), device="cuda")
+    _lib.call("fs_conv3x3_tc_dgrad", _ptr(dyd), _ptr(wd), _ptr(dx), sp, C.c_size_t(nb), N, H, W, Ci, Co,
+              same, _st())
+    torch.cuda.synchronize()
+    assert _relerr(dx, R.nchw_to_nhwc(xt.grad)) < 2e-5
