@@ -42,6 +42,7 @@ SIGNATURES = {
     "fs_vgg_pack": (_I, [_P, _P, _P]),
     "fs_engine_create": (_I, [_I, _I, _I, _I, _U, _U, _PP]),
     "fs_engine_destroy": (_I, [_P]),
+    "fs_engine_set_tensor_path": (_I, [_P, _I]),
     "fs_engine_workspace_bytes": (_SZ, [_P]),
     "fs_engine_bind": (_I, [_P, _P, _SZ]),
     "fs_engine_output_dims": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),

@@ -3,6 +3,7 @@
 #include "engine.cuh"
 #include "tc.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <new>
 
 namespace fs {
@@ -68,6 +69,8 @@ int fs_engine_create(int N, int H, int W, int flags, unsigned content_mask, unsi
     FS_CHECK(h != nullptr, "out of host memory");
     h->e.N = N; h->e.H = H; h->e.W = W; h->e.flags = flags;
     h->e.content_mask = content_mask; h->e.style_mask = style_mask;
+    const char* env = getenv("FS_TENSOR_PATH");
+    h->e.use_tc = (env && env[0] == '0') ? 0 : 1;
     int r = h->e.plan();
     if (r != 0) { delete h; return r; }
     Arena a;
@@ -77,6 +80,11 @@ int fs_engine_create(int N, int H, int W, int flags, unsigned content_mask, unsi
     return 0;
 }
 
+int fs_engine_set_tensor_path(fs_engine* e, int enabled) {
+    FS_CHECK(e, "NULL engine");
+    e->e.use_tc = enabled ? 1 : 0;
+    return 0;
+}
 int fs_engine_destroy(fs_engine* e) { delete e; return 0; }
 size_t fs_engine_workspace_bytes(const fs_engine* e) { return e ? e->e.ws_bytes : 0; }
 int fs_engine_bind(fs_engine* e, void* workspace, size_t bytes) {

@@ -72,12 +72,25 @@ static void vgg_offsets(VConv* vc) {
         vc[l].offW = off; off += 9LL * vc[l].cin_s * vc[l].cout;
         vc[l].offB = off; off += vc[l].cout;
         vc[l].offWT = off; off += 9LL * vc[l].cin_s * vc[l].cout;
+        vc[l].offTcF = vc[l].offTcD = -1;
+        if (l >= 1) {       // two bf16 planes of 9*cin*cout elements = 9*cin*cout floats per packing
+            vc[l].offTcF = off; off += 9LL * vc[l].cin * vc[l].cout;
+            vc[l].offTcD = off; off += 9LL * vc[l].cin * vc[l].cout;
+        }
     }
+}
+
+static SplitPtr vgg_tc_w(const float* packed, const VConv& v, int mode) {
+    SplitPtr s;
+    s.hi = reinterpret_cast<__nv_bfloat16*>(const_cast<float*>(packed + (mode == 0 ? v.offTcF : v.offTcD)));
+    s.lo = s.hi + 9LL * v.cin * v.cout;
+    return s;
 }
 long long vgg_packed_floats() {
     VConv vc[V_NCONV];
     vgg_offsets(vc);
-    return vc[V_NCONV - 1].offWT + 9LL * vc[V_NCONV - 1].cin_s * vc[V_NCONV - 1].cout;
+    const VConv& v = vc[V_NCONV - 1];
+    return v.offTcD + 9LL * v.cin * v.cout;
 }
 
 int vgg_pack(const float* flat, float* packed, cudaStream_t st) {
@@ -94,6 +107,10 @@ int vgg_pack(const float* flat, float* packed, cudaStream_t st) {
         FS_CUDA(cudaMemcpyAsync(packed + vc[l].offB, flat + src, vc[l].cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
         src += vc[l].cout;
         FS_TRY(transpose_taps(packed + vc[l].offW, packed + vc[l].offWT, 9, vc[l].cin_s, vc[l].cout, st));
+        if (l >= 1) {
+            FS_TRY(pack_w3x3_tc(packed + vc[l].offW, vgg_tc_w(packed, vc[l], 0), vc[l].cin, vc[l].cout, 0, st));
+            FS_TRY(pack_w3x3_tc(packed + vc[l].offW, vgg_tc_w(packed, vc[l], 1), vc[l].cin, vc[l].cout, 1, st));
+        }
     }
     return 0;
 }
@@ -165,12 +182,25 @@ void Engine::layout(Arena& a) {
                 wgcap = maxll(wgcap, wgrad_partial_floats(K, OC, 1));
             }
         }
+        for (int l = 0; l < T_NCONV; ++l) {
+            tsplit[l].hi = tsplit[l].lo = nullptr; tw_f[l].hi = tw_f[l].lo = nullptr; tw_d[l].hi = tw_d[l].lo = nullptr;
+            if (l >= 3 && l <= 12) {
+                long long n = (long long)N * tc[l].inH * tc[l].inW * 64;
+                tsplit[l].hi = a.take<__nv_bfloat16>(n); tsplit[l].lo = a.take<__nv_bfloat16>(n);
+                tw_f[l].hi = a.take<__nv_bfloat16>(9 * 64 * 64); tw_f[l].lo = a.take<__nv_bfloat16>(9 * 64 * 64);
+                if (tbw) { tw_d[l].hi = a.take<__nv_bfloat16>(9 * 64 * 64); tw_d[l].lo = a.take<__nv_bfloat16>(9 * 64 * 64); }
+            }
+        }
         y3 = a.take<float>((long long)N * OH * OW * 3);
         in_partial = a.take<double>((long long)N * 64 * 64 * 2);
         in15 = a.take<float>(8);
         if (tbw) {
             m12 = a.take<float>((long long)N * 64 * 2);
             for (int i = 0; i < 3; ++i) tgrad[i] = a.take<float>(maxact);
+            {   // split companions only ever hold dRaw of residual convs (<= N*80*80*64 at 256^2)
+                long long nres = (long long)N * tc[3].outH * tc[3].outW * 64;
+                for (int i = 0; i < 3; ++i) { tgsplit[i].hi = a.take<__nv_bfloat16>(nres); tgsplit[i].lo = a.take<__nv_bfloat16>(nres); }
+            }
             wg_tmp = a.take<float>(81LL * 16 * 4 + 16LL * 64 * 32 + 1024);
             gb_tmp = a.take<float>(8);
         }
@@ -188,11 +218,19 @@ void Engine::layout(Arena& a) {
             gramS[l] = st_ ? a.take<float>((long long)N * vc[l].cout * vc[l].cout) : nullptr;
             ctarget[l] = ct_ ? a.take<float>(n) : nullptr;
             if (st_) wgcap = maxll(wgcap, wgrad_partial_floats(vc[l].cout, vc[l].cout, N));
+            vsplit[l].hi = vsplit[l].lo = nullptr;
+            if (l >= 1) {
+                long long nin = (long long)N * vc[l].H * vc[l].W * vc[l].cin;
+                vsplit[l].hi = a.take<__nv_bfloat16>(nin); vsplit[l].lo = a.take<__nv_bfloat16>(nin);
+            }
         }
         loss_acc = a.take<double>(4);
         if (vgb) {
             vgrad_floats = maxact;
-            for (int i = 0; i < 4; ++i) vgrad[i] = a.take<float>(maxact);
+            for (int i = 0; i < 4; ++i) {
+                vgrad[i] = a.take<float>(maxact);
+                vgsplit[i].hi = a.take<__nv_bfloat16>(maxact); vgsplit[i].lo = a.take<__nv_bfloat16>(maxact);
+            }
             dY4 = a.take<float>((long long)N * VH * VW * 4);
         }
     }
@@ -220,6 +258,12 @@ int Engine::prep_transform_weights(const float* params, bool need_bwd, cudaStrea
     FS_TRY(fill_zero(in15, 8 * sizeof(float), st));
     FS_CUDA(cudaMemcpyAsync(in15, params + tc[15].offG, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     FS_CUDA(cudaMemcpyAsync(in15 + 4, params + tc[15].offB, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (use_tc) {
+        for (int l = 3; l <= 12; ++l) {
+            FS_TRY(pack_w3x3_tc(params + tc[l].offW, tw_f[l], 64, 64, 0, st));
+            if (need_bwd) FS_TRY(pack_w3x3_tc(params + tc[l].offW, tw_d[l], 64, 64, 1, st));
+        }
+    }
     if (need_bwd) {
         FS_CHECK(flags & ENG_TRANSFORM_BWD, "engine was not created with a backward plan");
         for (int l = 1; l < T_NCONV; ++l) {
@@ -254,9 +298,19 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
     const float* cur = xpad4;
     for (int l = 0; l < T_NCONV; ++l) {
         const TConv& c = tc[l];
-        IGemmArgs a;
-        conv_fwd_args(c, N, cur, weff[l] ? weff[l] : params + c.offW, tb[l].raw, a);
-        FS_TRY(launch_igemm(a, st));
+        const bool tcl = use_tc && l >= 3 && l <= 12;
+        if (tcl) {
+            Conv3x3TcArgs ta;
+            memset(&ta, 0, sizeof(ta));
+            ta.x = tsplit[l]; ta.w = tw_f[l];
+            ta.N = N; ta.H = c.inH; ta.W = c.inW; ta.C = 64; ta.OH = c.outH; ta.OW = c.outW; ta.OC = 64; ta.pad = 0;
+            ta.out_f32 = tb[l].raw;
+            FS_TRY(launch_conv3x3_tc(ta, st));
+        } else {
+            IGemmArgs a;
+            conv_fwd_args(c, N, cur, weff[l] ? weff[l] : params + c.offW, tb[l].raw, a);
+            FS_TRY(launch_igemm(a, st));
+        }
         FS_TRY(instnorm_stats(tb[l].raw, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, in_partial, st));
         const float* skip = nullptr;
         if (l >= 4 && l <= 12 && (l & 1) == 0) skip = tb[l - 2].act;       // residual: block input
@@ -264,8 +318,10 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
         const float* g = last ? in15 : params + c.offG;
         const float* b = last ? in15 + 4 : params + c.offB;
         float* out = last ? (y3_out ? y3_out : y3) : tb[l].act;
+        const bool next_tc = use_tc && (l + 1) >= 3 && (l + 1) <= 12;      // next conv consumes split planes
         FS_TRY(instnorm_apply(tb[l].raw, tb[l].mean, tb[l].rstd, g, b, skip, out, N, c.outH, c.outW,
-                              c.cout_s, c.act, last ? 1 : 0, st));
+                              c.cout_s, c.act, last ? 1 : 0, st, next_tc ? tsplit[l + 1].hi : nullptr,
+                              next_tc ? tsplit[l + 1].lo : nullptr));
         cur = tb[l].act;
     }
     return 0;
@@ -292,8 +348,10 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         if (second_of_block) { resid_dOut = dAct; resid_H = c.outH; resid_W = c.outW; held = cur; }
         const int ri = pick2(cur, held);
         float* dRaw = tgrad[ri];
+        const bool tcl = use_tc && l >= 3 && l <= 12;
         FS_TRY(instnorm_bwd(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw, dg, db, N,
-                            c.outH * c.outW, c.cout_s, c.act, in_partial, m12, st));
+                            c.outH * c.outW, c.cout_s, c.act, in_partial, m12, st,
+                            tcl ? tgsplit[ri].hi : nullptr, tcl ? tgsplit[ri].lo : nullptr));
         if (last) {
             FS_CUDA(cudaMemcpyAsync(grads + c.offG, gb_tmp, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
             FS_CUDA(cudaMemcpyAsync(grads + c.offB, gb_tmp + 4, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -325,6 +383,20 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         // ---- data gradient -> gradient w.r.t. the previous layer's activation
         const int pidx = pick2(ri, held);
         float* dPrev = tgrad[pidx];
+        const bool first_of_block = (l >= 3 && l <= 11 && (l & 1) == 1);
+        if (tcl) {
+            Conv3x3TcArgs ta;
+            memset(&ta, 0, sizeof(ta));
+            ta.x = tgsplit[ri]; ta.w = tw_d[l];
+            ta.N = N; ta.H = c.outH; ta.W = c.outW; ta.C = 64; ta.OH = c.inH; ta.OW = c.inW; ta.OC = 64;
+            ta.pad = 2;                              // VALID conv: data gradient is the "full" correlation
+            if (first_of_block) { ta.addend = resid_dOut; ta.add_crop = 2; ta.addH = resid_H; ta.addW = resid_W; }
+            ta.out_f32 = dPrev;
+            FS_TRY(launch_conv3x3_tc(ta, st));
+            dAct = dPrev; cur = pidx;
+            if (first_of_block) { held = -1; resid_dOut = nullptr; }
+            continue;
+        }
         IGemmArgs a;
         memset(&a, 0, sizeof(a));
         a.in = dRaw; a.w = wefft[l]; a.out = dPrev; a.N = N; a.gather = 1;
@@ -339,7 +411,6 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         }
         a.OH = c.inH; a.OW = c.inW; a.OC = c.cin_s;
         a.out_bs = (long long)c.inH * c.inW * c.cin_s;
-        const bool first_of_block = (l >= 3 && l <= 11 && (l & 1) == 1);
         if (first_of_block) {                    // add the skip-path gradient, zero-padded by 2 px
             a.addend = resid_dOut; a.add_crop = 2; a.addH = resid_H; a.addW = resid_W;
             a.add_bs = (long long)resid_H * resid_W * 64;
@@ -369,12 +440,29 @@ int Engine::vgg_forward(const float* packed, const float* img3, int upto, float*
     const float* cur = v_in4;
     for (int l = 0; l <= upto; ++l) {
         float* out = (act_override && act_override[l]) ? act_override[l] : vact[l];
-        IGemmArgs a;
-        vgg_conv_args(vc[l], N, packed, cur, out, a);
-        FS_TRY(launch_igemm(a, st));
+        const bool pool_next = vc[l].pool_after && l < upto;
+        if (use_tc && l >= 1) {
+            Conv3x3TcArgs ta;
+            memset(&ta, 0, sizeof(ta));
+            ta.x = vsplit[l]; ta.w = vgg_tc_w(packed, vc[l], 0);
+            ta.N = N; ta.H = vc[l].H; ta.W = vc[l].W; ta.C = vc[l].cin;
+            ta.OH = vc[l].H; ta.OW = vc[l].W; ta.OC = vc[l].cout; ta.pad = 1;
+            ta.bias = packed + vc[l].offB; ta.relu = 1;
+            ta.out_f32 = out;
+            if (l < upto && !pool_next) ta.out_split = vsplit[l + 1];     // next conv reads split planes
+            FS_TRY(launch_conv3x3_tc(ta, st));
+        } else {
+            IGemmArgs a;
+            vgg_conv_args(vc[l], N, packed, cur, out, a);
+            FS_TRY(launch_igemm(a, st));
+            if (use_tc && l < upto && !pool_next)
+                FS_TRY(split_bf16(out, vsplit[l + 1], (long long)N * vc[l].H * vc[l].W * vc[l].cout, st));
+        }
         cur = out;
-        if (vc[l].pool_after && l < upto) {
-            FS_TRY(maxpool2x2_fwd(cur, vpool[l], N, vc[l].H, vc[l].W, vc[l].cout, st));
+        if (pool_next) {
+            const bool sp = use_tc != 0;
+            FS_TRY(maxpool2x2_fwd(cur, vpool[l], N, vc[l].H, vc[l].W, vc[l].cout, st,
+                                  sp ? vsplit[l + 1].hi : nullptr, sp ? vsplit[l + 1].lo : nullptr));
             cur = vpool[l];
         }
     }
@@ -441,8 +529,19 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
 
     // ---- backward: P_l = dLoss/d(pre-activation of conv l), top-down
     auto pick = [](int a, int b, int c) { for (int i = 0; i < 4; ++i) if (i != a && i != b && i != c) return i; return -1; };
-    auto dgrad = [&](int lsrc, const float* P, float* out, const float* addend, const float* ref) -> int {
+    // data gradient of VGG conv lsrc applied to the masked gradient held in vgrad[pidx]
+    auto dgrad = [&](int lsrc, int pidx, float* out, SplitPtr out_split, const float* addend, const float* ref) -> int {
         const VConv& v = vc[lsrc];
+        const float* P = vgrad[pidx];
+        if (use_tc && lsrc >= 1) {
+            Conv3x3TcArgs ta;
+            memset(&ta, 0, sizeof(ta));
+            ta.x = vgsplit[pidx]; ta.w = vgg_tc_w(packed, v, 1);
+            ta.N = N; ta.H = v.H; ta.W = v.W; ta.C = v.cout; ta.OH = v.H; ta.OW = v.W; ta.OC = v.cin; ta.pad = 1;
+            ta.addend = addend; ta.addH = v.H; ta.addW = v.W; ta.ref = ref;
+            ta.out_f32 = out; ta.out_split = out_split;
+            return launch_conv3x3_tc(ta, st);
+        }
         IGemmArgs a;
         memset(&a, 0, sizeof(a));
         a.in = P; a.w = packed + v.offWT; a.out = out; a.N = N; a.gather = 1;
@@ -451,6 +550,12 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
         a.OH = v.H; a.OW = v.W; a.OC = v.cin_s; a.out_bs = (long long)v.H * v.W * v.cin_s;
         a.addend = addend; a.addH = v.H; a.addW = v.W; a.add_bs = a.out_bs; a.ref = ref;
         return launch_igemm(a, st);
+    };
+    const SplitPtr no_split = {nullptr, nullptr};
+    // make the split planes of P_l (held in vgrad[idx]) valid when the consumer is a tensor-path conv
+    auto ensure_split = [&](int l, int idx) -> int {
+        if (!(use_tc && l >= 1)) return 0;
+        return split_bf16(vgrad[idx], vgsplit[idx], (long long)N * vc[l].H * vc[l].W * vc[l].cout, st);
     };
     auto gram_bwd = [&](int l, const float* addend, const float* ref, float* out) -> int {
         const VConv& v = vc[l];
@@ -466,7 +571,6 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
     int pi = -1;
     for (int l = top; l >= 0; --l) {
         const VConv& v = vc[l];
-        const float* Pnext = pi >= 0 ? vgrad[pi] : nullptr;
         const bool pool_follow = v.pool_after && l < top;
         const float* ct = has_c[l] ? ctarget[l] : nullptr;
         const float cw2 = (float)(2.0 * cw[l] / ((double)v.H * v.W * v.cout));
@@ -474,7 +578,7 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
             int gi = -1; const float* gp = nullptr;
             if (pool_follow) {
                 gi = pick(pi, -1, -1);
-                FS_TRY(dgrad(l + 1, Pnext, vgrad[gi], nullptr, nullptr));
+                FS_TRY(dgrad(l + 1, pi, vgrad[gi], no_split, nullptr, nullptr));
                 gp = vgrad[gi];
             }
             if (tg[l]) {
@@ -486,10 +590,12 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
                 }
                 int oi = pick(gi, ti, -1);
                 FS_TRY(gram_bwd(l, T, vact[l], vgrad[oi]));
+                FS_TRY(ensure_split(l, oi));
                 pi = oi;
             } else {
                 int oi = pick(gi, -1, -1);
                 FS_TRY(pool_bwd_combine(vact[l], gp, ct, cw2, 1, vgrad[oi], N, v.H, v.W, v.cout, st));
+                FS_TRY(ensure_split(l, oi));
                 pi = oi;
             }
         } else {
@@ -510,11 +616,11 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
                 A = vgrad[ai];
             }
             int oi = pick(pi, ai, -1);
-            FS_TRY(dgrad(l + 1, Pnext, vgrad[oi], A, vact[l]));
+            FS_TRY(dgrad(l + 1, pi, vgrad[oi], (use_tc && l >= 1) ? vgsplit[oi] : no_split, A, vact[l]));
             pi = oi;
         }
     }
-    FS_TRY(dgrad(0, vgrad[pi], dY4, nullptr, nullptr));
+    FS_TRY(dgrad(0, pi, dY4, no_split, nullptr, nullptr));
     return 0;
 }
 

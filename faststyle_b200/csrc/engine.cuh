@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "ops.cuh"
+#include "tc.cuh"
 
 namespace fs {
 
@@ -24,7 +25,13 @@ struct TBuf { float *raw, *act, *mean, *rstd; };
 
 // ---------------------------------------------------------------- VGG16 (conv1_1..conv4_3)
 constexpr int V_NCONV = 10;
-struct VConv { int cin, cout, cin_s, pool_after; long long offW, offB, offWT; int H, W; };
+struct VConv {
+    int cin, cout, cin_s, pool_after;
+    long long offW, offB, offWT;        // fp32: padded HWIO weights, bias, transposed weights
+    long long offTcF, offTcD;           // tensor path (layers >= 1): packed split-bf16 weights for the
+                                        // forward / data-gradient conv; hi plane, lo plane follows
+    int H, W;
+};
 long long vgg_flat_floats();        // unpacked: W,b per layer in order (HWIO)
 long long vgg_packed_floats();      // packed: padded W, b, transposed W per layer
 
@@ -80,6 +87,13 @@ struct Engine {
     float* ctarget[V_NCONV];
     float* dY4 = nullptr;                // [N,VH,VW,4] gradient w.r.t. the VGG input image
     double* loss_acc = nullptr;          // double[4]
+    // tensor-core path (tcgen05): split-bf16 companions of the tensors feeding 3x3 convs
+    int use_tc = 1;
+    SplitPtr vsplit[V_NCONV];            // input planes of VGG conv l (l >= 1)
+    SplitPtr vgsplit[4];                 // planes of vgrad[i]
+    SplitPtr tsplit[T_NCONV];            // input planes of residual conv l (3..12)
+    SplitPtr tgsplit[3];                 // planes of tgrad[i] (dRaw of residual convs)
+    SplitPtr tw_f[T_NCONV], tw_d[T_NCONV];   // packed residual-conv weights (forward / data gradient)
 
     int plan();                          // fill geometry; returns 0 / error
     void layout(Arena& a);               // assign (or just size) workspace

@@ -3,6 +3,7 @@
 // All tensors are fp32 NHWC with channel counts that are multiples of 4 (RGB
 // tensors are carried as 4 channels with a zero 4th channel inside the engine).
 #include "ops.cuh"
+#include <cuda_bf16.h>
 
 namespace fs {
 
@@ -31,6 +32,21 @@ __device__ __forceinline__ double block_sum(double v) {
         r = warp_sum(r);
     }
     return r;
+}
+
+// optional split-bf16 companion output (x ~= hi + lo) for the tensor-core convolutions
+__device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, long long idx, const float* r) {
+    uint32_t h[2], l[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        __nv_bfloat16 h0 = __float2bfloat16_rn(r[2 * j]), h1 = __float2bfloat16_rn(r[2 * j + 1]);
+        __nv_bfloat16 l0 = __float2bfloat16_rn(r[2 * j] - __bfloat162float(h0));
+        __nv_bfloat16 l1 = __float2bfloat16_rn(r[2 * j + 1] - __bfloat162float(h1));
+        h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint2*>(hi + idx) = make_uint2(h[0], h[1]);
+    *reinterpret_cast<uint2*>(lo + idx) = make_uint2(l[0], l[1]);
 }
 
 __device__ __forceinline__ float in_affine(float x, float mean, float rstd, float g, float b) {
@@ -177,7 +193,8 @@ __global__ void in_bwd_finalize_kernel(const double* __restrict__ partial, float
 __global__ void in_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                                 const float* __restrict__ rstd, const float* __restrict__ scale,
                                 const float* __restrict__ shift, const float* __restrict__ skip,
-                                float* __restrict__ out, int N, int H, int W, int C, int act, int out3) {
+                                float* __restrict__ out, int N, int H, int W, int C, int act, int out3,
+                                __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo) {
     const int C4 = C >> 2;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)N * H * W * C4;
@@ -207,6 +224,7 @@ __global__ void in_apply_kernel(const float* __restrict__ x, const float* __rest
         o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
     } else {
         st4(out + i * 4, make_float4(r[0], r[1], r[2], r[3]));
+        if (shi) store_split4(shi, slo, i * 4, r);
     }
 }
 
@@ -214,7 +232,8 @@ __global__ void in_bwd_apply_kernel(const float* __restrict__ dY, const float* _
                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ scale, const float* __restrict__ shift,
                                     const float* __restrict__ m12, float* __restrict__ dx, int N,
-                                    int HW, int C, int act) {
+                                    int HW, int C, int act, __nv_bfloat16* __restrict__ shi,
+                                    __nv_bfloat16* __restrict__ slo) {
     const int C4 = C >> 2;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)N * HW * C4;
@@ -245,6 +264,7 @@ __global__ void in_bwd_apply_kernel(const float* __restrict__ dY, const float* _
         r[j] = g[j] * rs[j] * (dz - m1[j] - xh * m2[j]);
     }
     st4(dx + i * 4, make_float4(r[0], r[1], r[2], r[3]));
+    if (shi) store_split4(shi, slo, i * 4, r);
 }
 
 __global__ void add_padded_kernel(float* __restrict__ dst, const float* __restrict__ src, int N, int H,
@@ -266,7 +286,8 @@ __global__ void add_padded_kernel(float* __restrict__ dst, const float* __restri
 
 // ------------------------------------------------------------------ pooling
 __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int H,
-                                   int W, int C) {
+                                   int W, int C, __nv_bfloat16* __restrict__ shi,
+                                   __nv_bfloat16* __restrict__ slo) {
     const int C4 = C >> 2, PH = (H + 1) >> 1, PW = (W + 1) >> 1;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)N * PH * PW * C4;
@@ -290,6 +311,10 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restric
             }
         }
     st4(out + i * 4, m);
+    if (shi) {
+        float r[4] = {m.x, m.y, m.z, m.w};
+        store_split4(shi, slo, i * 4, r);
+    }
 }
 
 __global__ void pool_bwd_combine_kernel(const float* __restrict__ act, const float* __restrict__ gpool,
@@ -554,18 +579,21 @@ int instnorm_stats(const float* x, float* mean, float* rstd, int N, int HW, int 
 
 int instnorm_apply(const float* x, const float* mean, const float* rstd, const float* scale,
                    const float* shift, const float* skip, float* out, int N, int H, int W, int C,
-                   int act, int out3, cudaStream_t st) {
+                   int act, int out3, cudaStream_t st, void* split_hi, void* split_lo) {
     FS_CHECK(C % 4 == 0, "instnorm_apply: C%%4 != 0");
+    FS_CHECK(!(split_hi && out3), "instnorm_apply: split output not available with out3");
     FS_CHECK(!out3 || C == 4, "instnorm_apply: out3 needs C==4");
     long long n = (long long)N * H * W * (C / 4);
-    in_apply_kernel<<<grid1(n), 256, 0, st>>>(x, mean, rstd, scale, shift, skip, out, N, H, W, C, act, out3);
+    in_apply_kernel<<<grid1(n), 256, 0, st>>>(x, mean, rstd, scale, shift, skip, out, N, H, W, C, act, out3,
+                                              (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo);
     FS_LAUNCH_CHECK();
     return 0;
 }
 
 int instnorm_bwd(const float* dY, const float* x, const float* mean, const float* rstd,
                  const float* scale, const float* shift, float* dx, float* dgamma, float* dbeta,
-                 int N, int HW, int C, int act, double* partial, float* m12, cudaStream_t st) {
+                 int N, int HW, int C, int act, double* partial, float* m12, cudaStream_t st,
+                 void* split_hi, void* split_lo) {
     FS_TRY(check_in_c(C));
     int chunks = in_chunks(N, HW);
     in_reduce_kernel<1><<<dim3(chunks, N), 256, 2 * C * sizeof(double), st>>>(
@@ -574,7 +602,8 @@ int instnorm_bwd(const float* dY, const float* x, const float* mean, const float
     in_bwd_finalize_kernel<<<grid1(C, 64), 64, 0, st>>>(partial, m12, dgamma, dbeta, N, C, chunks, HW);
     FS_LAUNCH_CHECK();
     long long n = (long long)N * HW * (C / 4);
-    in_bwd_apply_kernel<<<grid1(n), 256, 0, st>>>(dY, x, mean, rstd, scale, shift, m12, dx, N, HW, C, act);
+    in_bwd_apply_kernel<<<grid1(n), 256, 0, st>>>(dY, x, mean, rstd, scale, shift, m12, dx, N, HW, C, act,
+                                                  (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo);
     FS_LAUNCH_CHECK();
     return 0;
 }
@@ -586,10 +615,12 @@ int add_padded(float* dst, const float* src, int N, int H, int W, int C, int cro
     return 0;
 }
 
-int maxpool2x2_fwd(const float* x, float* out, int N, int H, int W, int C, cudaStream_t st) {
+int maxpool2x2_fwd(const float* x, float* out, int N, int H, int W, int C, cudaStream_t st,
+                   void* split_hi, void* split_lo) {
     FS_CHECK(C % 4 == 0, "maxpool: C%%4 != 0");
     long long n = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
-    maxpool_fwd_kernel<<<grid1(n), 256, 0, st>>>(x, out, N, H, W, C);
+    maxpool_fwd_kernel<<<grid1(n), 256, 0, st>>>(x, out, N, H, W, C, (__nv_bfloat16*)split_hi,
+                                                 (__nv_bfloat16*)split_lo);
     FS_LAUNCH_CHECK();
     return 0;
 }

@@ -18,18 +18,19 @@ int instnorm_stats(const float* x, float* mean, float* rstd, int N, int HW, int 
                    double* partial, cudaStream_t st);
 int instnorm_apply(const float* x, const float* mean, const float* rstd, const float* scale,
                    const float* shift, const float* skip, float* out, int N, int H, int W, int C,
-                   int act, int out3, cudaStream_t st);
+                   int act, int out3, cudaStream_t st, void* split_hi = nullptr, void* split_lo = nullptr);
 // backward: dz = dY*act'(z); dgamma[c] += sum dz*xhat; dbeta[c] += sum dz;
 // dx = scale*rstd*(dz - mean(dz) - xhat*mean(dz*xhat))
 int instnorm_bwd(const float* dY, const float* x, const float* mean, const float* rstd,
                  const float* scale, const float* shift, float* dx, float* dgamma, float* dbeta,
                  int N, int HW, int C, int act, double* partial, float* m12 /*[N][C][2]*/,
-                 cudaStream_t st);
+                 cudaStream_t st, void* split_hi = nullptr, void* split_lo = nullptr);
 // zero-pad-add:  dst[n, y+crop, x+crop, c] += src[n,y,x,c]   (skip-connection gradient)
 int add_padded(float* dst, const float* src, int N, int H, int W, int C, int crop, cudaStream_t st);
 
 // K8: 2x2 s2 SAME max-pool                        (reference libs/vgg16.py:67-71)
-int maxpool2x2_fwd(const float* x, float* out, int N, int H, int W, int C, cudaStream_t st);
+int maxpool2x2_fwd(const float* x, float* out, int N, int H, int W, int C, cudaStream_t st,
+                   void* split_hi = nullptr, void* split_lo = nullptr);
 // out = [mask(act>0)] * ( route(gpool) + cw2*(act - ctarget) )
 int pool_bwd_combine(const float* act, const float* gpool, const float* ctarget, float cw2,
                      int apply_mask, float* out, int N, int H, int W, int C, cudaStream_t st);

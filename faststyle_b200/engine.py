@@ -102,6 +102,11 @@ class Engine:
         _lib.call("fs_engine_output_dims", self._h, C.byref(oh), C.byref(ow))
         self.OH, self.OW = oh.value, ow.value
 
+    def set_tensor_path(self, enabled: bool):
+        """True (default): tcgen05 split-bf16 path for the 64-channel-multiple 3x3 convs;
+        False: exact-fp32 FFMA path everywhere."""
+        _lib.call("fs_engine_set_tensor_path", self._h, 1 if enabled else 0)
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h is not None and h.value:

@@ -59,6 +59,10 @@ int fs_engine_create(int N, int H, int W, int flags, unsigned content_mask, unsi
 int fs_engine_destroy(fs_engine* e);
 size_t fs_engine_workspace_bytes(const fs_engine* e);
 int fs_engine_bind(fs_engine* e, void* workspace, size_t bytes);
+/* 1 (default): 3x3 convolutions with 64-multiple channels run on the tcgen05 tensor path
+ * (split-bf16 x3); 0: every convolution on the exact-fp32 FFMA path.  Also settable
+ * through the environment variable FS_TENSOR_PATH=0 read at fs_engine_create. */
+int fs_engine_set_tensor_path(fs_engine* e, int enabled);
 /* output dims of the transform net (== VGG input dims when both are planned) */
 int fs_engine_output_dims(const fs_engine* e, int* OH, int* OW);
 /* device pointer + dims of a saved VGG activation (post-ReLU conv output) */
