@@ -212,7 +212,12 @@ def run_ours(args, rank, local_rank, world):
         sampler = ClockSampler(local_rank) if sample_clocks else None
         barrier()
         if sampler:
+            # nvidia-smi needs a few hundred ms to deliver its first sample: keep the GPU under the
+            # same load (untimed steps) until the sampler is running, then enter the timed region
             sampler.start()
+            for _ in range(40):          # fixed count: every rank must issue the same collectives
+                fn()
+            barrier()
         n0 = lib.fs_launch_count()
         e0.record()
         for _ in range(steps):
@@ -244,7 +249,8 @@ def run_ours(args, rank, local_rank, world):
         # whole-step tensor-pipe view (algorithmic FLOPs of one step / step time)
         step_tflops = GFLOP_PER_IMAGE_TRAIN * PER_GPU_BATCH / (ms / args.steps / 1e3) / 1e3
         # dominant kernel live: VGG conv3x3 64->64 @256^2 (conv1_2 shape) through the op C-ABI
-        roof = dominant_kernel_roofline(dev, peaks)
+        prof = live_kernel_profile(eng, step_device)
+        roof = dominant_kernel_roofline(prof, peaks, ms / args.steps)
         roof["step_tflops"] = step_tflops
         roof["step_frac_of_sustained"] = step_tflops / peaks["bf16_tflops_sustained"]
         # transform forward only, batch 32 (BASELINE.json configs[1])
@@ -263,7 +269,8 @@ def run_ours(args, rank, local_rank, world):
                                    "VGG16 weights, style starry_night_crop.jpg" % (PER_GPU_BATCH, HW, HW),
                        "global_batch": PER_GPU_BATCH * world, "parallelism": "dp%d" % world,
                        "l2": "per-step working set ~1.3 GB >> 126 MB L2, no explicit flush",
-                       "precision": "fp32 operands, fp32 accumulate"},
+                       "precision": "fp32 storage; 3x3 convs with 64-multiple channels: split-bf16 x3 on tcgen05 "
+                                    "(fp32-class, 16 mantissa bits), fp32 accumulate; everything else fp32 FFMA"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s",
                     "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": 16,
@@ -277,39 +284,54 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def dominant_kernel_roofline(dev, peaks):
-    """The dominant kernel of the step is the 3x3 convolution of the VGG stack (80% of the
-    step's MACs).  Time its conv1_2-shaped launch (64->64, 256x256, batch 8) in isolation with
-    CUDA events on the launching stream."""
+PROF_CATS = ["tc_vgg_conv_fwd", "tc_vgg_conv_dgrad", "tc_res_conv_fwd", "tc_res_conv_dgrad",
+             "ffma_conv", "wgrad", "gram_fwd", "gram_bwd"]
+
+
+def live_kernel_profile(eng, step_fn, steps=3):
+    """Per-kernel-class device time inside real train steps: CUDA events recorded by the engine
+    around every GEMM-class launch on the launching stream (fs_engine_profile)."""
     import ctypes as C
     from faststyle_b200 import _lib
-    N, H, W, Ci, Co = PER_GPU_BATCH, HW, HW, 64, 64
-    x = torch.randn((N, H, W, Ci), device=dev)
-    w = torch.randn((3, 3, Ci, Co), device=dev) * 0.05
-    b = torch.zeros(Co, device=dev)
-    y = torch.empty((N, H, W, Co), device=dev)
-    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    n = len(PROF_CATS)
+    _lib.call("fs_engine_profile", eng._h, 1)
+    for _ in range(steps):
+        step_fn()
+    torch.cuda.synchronize()
+    ms = (C.c_float * n)(); fl = (C.c_double * n)(); cnt = (C.c_int * n)()
+    _lib.call("fs_engine_profile_read", eng._h, n, ms, fl, cnt)
+    _lib.call("fs_engine_profile", eng._h, 0)
+    out = {}
+    for i, name in enumerate(PROF_CATS):
+        if cnt[i]:
+            out[name] = {"ms_per_step": ms[i] / steps, "launches_per_step": cnt[i] // steps,
+                         "tflops": fl[i] / (ms[i] / 1e3) / 1e12 if ms[i] > 0 else None,
+                         "gflop_per_step": fl[i] / steps / 1e9}
+    return out
 
-    def launch():
-        _lib.call("fs_conv2d_forward", C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()),
-                  C.c_void_p(b.data_ptr()), C.c_void_p(y.data_ptr()), N, H, W, Ci, 3, 3, Co, 1, 1, 1, st)
-    for _ in range(3):
-        launch()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    reps = 10
-    e0.record()
-    for _ in range(reps):
-        launch()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    flops = 2.0 * N * H * W * 9 * Ci * Co
-    achieved = flops / (ms / 1e3) / 1e12
-    return {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
-            "kernel": "conv3x3 64->64 SAME +bias+relu, batch 8 @256x256 (VGG conv1_2 shape)",
-            "kernel_ms": ms, "precision": "fp32 FFMA path (tensor path not enabled)"}
+
+def dominant_kernel_roofline(prof, peaks, step_ms):
+    """Dominant kernel = the tcgen05 3x3 convolution (VGG fwd + dgrad + residual convs):
+    achieved = algorithmic FLOPs of those launches (2*MACs; the three split-bf16 passes are NOT
+    multiplied in) / their summed event time."""
+    names = [k for k in ("tc_vgg_conv_fwd", "tc_vgg_conv_dgrad", "tc_res_conv_fwd", "tc_res_conv_dgrad") if k in prof]
+    if names:
+        ms = sum(prof[k]["ms_per_step"] for k in names)
+        gf = sum(prof[k]["gflop_per_step"] for k in names)
+        launches = sum(prof[k]["launches_per_step"] for k in names)
+        kernel, precision = "conv3x3_tc_kernel (tcgen05, TMA slabs, TMEM accumulators)", "split-bf16 x3 (hi*hi+hi*lo+lo*hi), fp32 accumulate"
+    else:
+        ms = prof["ffma_conv"]["ms_per_step"]; gf = prof["ffma_conv"]["gflop_per_step"]
+        launches = prof["ffma_conv"]["launches_per_step"]
+        kernel, precision = "igemm_kernel (FFMA)", "fp32"
+    achieved = gf / ms                      # GFLOP / ms == TFLOP/s
+    return {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] +
+            " cuBLAS bf16 sustained (kernel timed inside a long step)",
+            "kernel": kernel, "precision": precision, "kernel_ms_per_step": ms, "launches_per_step": launches,
+            "share_of_step": ms / step_ms,
+            "mma_issue_frac": 3.0 * achieved / peaks["bf16_tflops_sustained"] if names else None,
+            "by_kernel_class": prof}
 
 
 def bench_forward(dev, params):
@@ -349,7 +371,7 @@ def cpu_baseline():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")

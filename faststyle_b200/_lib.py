@@ -43,6 +43,8 @@ SIGNATURES = {
     "fs_engine_create": (_I, [_I, _I, _I, _I, _U, _U, _PP]),
     "fs_engine_destroy": (_I, [_P]),
     "fs_engine_set_tensor_path": (_I, [_P, _I]),
+    "fs_engine_profile": (_I, [_P, _I]),
+    "fs_engine_profile_read": (_I, [_P, _I, _P, _P, _P]),
     "fs_engine_workspace_bytes": (_SZ, [_P]),
     "fs_engine_bind": (_I, [_P, _P, _SZ]),
     "fs_engine_output_dims": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),
@@ -64,6 +66,9 @@ SIGNATURES = {
     "fs_maxpool2x2": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "fs_gram_scratch_floats": (_LL, [_I, _I]),
     "fs_gram_forward": (_I, [_P, _P, _P, _LL, _I, _I, _I, _I, _P]),
+    "fs_loss_sqdiff": (_I, [_P, _P, _LL, C.c_double, _P, _P, _P]),
+    "fs_loss_style": (_I, [_P, _P, _I, _I, C.c_double, _P, _P, _P]),
+    "fs_loss_tv": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "fs_conv3x3_tc_scratch_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "fs_conv3x3_tc_forward": (_I, [_P, _P, _P, _P, _P, _SZ] + [_I] * 7 + [_P]),
     "fs_conv3x3_tc_dgrad": (_I, [_P, _P, _P, _P, _SZ] + [_I] * 6 + [_P]),

@@ -85,6 +85,15 @@ int fs_engine_set_tensor_path(fs_engine* e, int enabled) {
     e->e.use_tc = enabled ? 1 : 0;
     return 0;
 }
+int fs_engine_profile(fs_engine* e, int enabled) {
+    FS_CHECK(e, "NULL engine");
+    e->e.prof_on = enabled != 0;
+    return 0;
+}
+int fs_engine_profile_read(fs_engine* e, int ncat, float* ms, double* flops, int* launches) {
+    FS_CHECK(e && ms && flops && launches && ncat >= 1 && ncat <= 64, "fs_engine_profile_read: bad argument");
+    return e->e.prof_read(ncat, ms, flops, launches);
+}
 int fs_engine_destroy(fs_engine* e) { delete e; return 0; }
 size_t fs_engine_workspace_bytes(const fs_engine* e) { return e ? e->e.ws_bytes : 0; }
 int fs_engine_bind(fs_engine* e, void* workspace, size_t bytes) {
@@ -277,6 +286,26 @@ int fs_gram_forward(const float* f, float* g, float* scratch, long long scratch_
     wa.KH = wa.KW = 1; wa.stride = 1; wa.OH = H; wa.OW = W; wa.OC = C; wa.dy_bs = wa.in_bs;
     wa.N = N; wa.per_sample = 1; wa.scale = (float)(1.0 / ((double)H * W * C));
     return launch_wgrad(wa, S(stream));
+}
+
+// loss single ops: acc is a device double (zeroed by the caller), out a device float
+int fs_loss_sqdiff(const float* a, const float* b, long long n, double scale, double* acc, float* out, void* stream) {
+    FS_CHECK(a && b && acc && out && n % 4 == 0, "fs_loss_sqdiff: bad argument (n must be a multiple of 4)");
+    FS_TRY(fill_zero(acc, 4 * sizeof(double), S(stream)));
+    FS_TRY(sqdiff_sum(a, b, n, scale, acc, S(stream)));
+    return finalize_losses(acc, out, S(stream));
+}
+int fs_loss_style(const float* G, const float* T, int N, int CC, double scale, double* acc, float* out, void* stream) {
+    FS_CHECK(G && T && acc && out, "fs_loss_style: NULL argument");
+    FS_TRY(fill_zero(acc, 4 * sizeof(double), S(stream)));
+    FS_TRY(style_loss_grad(G, T, nullptr, N, CC, 0.f, scale, acc, S(stream)));
+    return finalize_losses(acc, out, S(stream));
+}
+int fs_loss_tv(const float* Y3, int N, int H, int W, double* acc, float* out, void* stream) {
+    FS_CHECK(Y3 && acc && out, "fs_loss_tv: NULL argument");
+    FS_TRY(fill_zero(acc, 4 * sizeof(double), S(stream)));
+    FS_TRY(tv_loss_grad(Y3, nullptr, N, H, W, 1.f, acc, S(stream)));
+    return finalize_losses(acc, out, S(stream));
 }
 
 // ------------------------------------------------------------------ tensor-core path

@@ -13,6 +13,45 @@ namespace fs {
 
 static const float IN_EPS = 1e-3f;       // reference im_transf_net.py:218
 
+// ---------------------------------------------------------------- live per-kernel timing
+// Optional CUDA-event instrumentation of the GEMM-class launches of a step (bench.py roofline).
+int Engine::pbegin(int cat, double flops, cudaStream_t st) {
+    if (!prof_on) return 0;
+    cudaEvent_t a, b;
+    FS_CUDA(cudaEventCreate(&a));
+    FS_CUDA(cudaEventCreate(&b));
+    FS_CUDA(cudaEventRecord(a, st));
+    prof_ev.push_back(a); prof_ev.push_back(b); prof_cat.push_back(cat); prof_flops.push_back(flops);
+    return 0;
+}
+int Engine::pend(cudaStream_t st) {
+    if (!prof_on) return 0;
+    FS_CUDA(cudaEventRecord(prof_ev.back(), st));
+    return 0;
+}
+int Engine::prof_read(int ncat, float* ms, double* flops, int* launches) {
+    for (int i = 0; i < ncat; ++i) { ms[i] = 0.f; flops[i] = 0.0; launches[i] = 0; }
+    for (size_t i = 0; i < prof_cat.size(); ++i) {
+        float t = 0.f;
+        FS_CUDA(cudaEventSynchronize(prof_ev[2 * i + 1]));
+        FS_CUDA(cudaEventElapsedTime(&t, prof_ev[2 * i], prof_ev[2 * i + 1]));
+        int c = prof_cat[i];
+        if (c >= 0 && c < ncat) { ms[c] += t; flops[c] += prof_flops[i]; launches[c] += 1; }
+        cudaEventDestroy(prof_ev[2 * i]); cudaEventDestroy(prof_ev[2 * i + 1]);
+    }
+    prof_ev.clear(); prof_cat.clear(); prof_flops.clear();
+    return 0;
+}
+#define PROF(cat, flops, call)              \
+    do {                                    \
+        FS_TRY(pbegin((cat), (flops), st)); \
+        FS_TRY(call);                       \
+        FS_TRY(pend(st));                   \
+    } while (0)
+static double igemm_flops(const IGemmArgs& a) { return 2.0 * a.N * a.OH * a.OW * (double)a.OC * a.KH * a.KW * a.C; }
+static double tc_flops(const Conv3x3TcArgs& a) { return 2.0 * a.N * a.OH * a.OW * (double)a.OC * 9.0 * a.C; }
+static double wgrad_flops(const WGradArgs& a) { return 2.0 * a.N * a.OH * a.OW * (double)a.OC * a.KH * a.KW * a.C; }
+
 // ---------------------------------------------------------------- parameter table
 void transform_param_table(TConv* tc) {
     auto set = [&](int i, int k, int s, int same, int cin, int cout, int up, int act) {
@@ -305,11 +344,11 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
             ta.x = tsplit[l]; ta.w = tw_f[l];
             ta.N = N; ta.H = c.inH; ta.W = c.inW; ta.C = 64; ta.OH = c.outH; ta.OW = c.outW; ta.OC = 64; ta.pad = 0;
             ta.out_f32 = tb[l].raw;
-            FS_TRY(launch_conv3x3_tc(ta, st));
+            PROF(PC_TC_RES_FWD, tc_flops(ta), launch_conv3x3_tc(ta, st));
         } else {
             IGemmArgs a;
             conv_fwd_args(c, N, cur, weff[l] ? weff[l] : params + c.offW, tb[l].raw, a);
-            FS_TRY(launch_igemm(a, st));
+            PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
         }
         FS_TRY(instnorm_stats(tb[l].raw, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, in_partial, st));
         const float* skip = nullptr;
@@ -368,7 +407,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
             wa.OH = c.inH; wa.OW = c.inW; wa.OC = 4 * c.cout; wa.dy_mode = 1;
             wa.dy_bs = (long long)c.outH * c.outW * c.cout;
             wa.out = wg_tmp;
-            FS_TRY(launch_wgrad(wa, st));
+            PROF(PC_WGRAD, wgrad_flops(wa), launch_wgrad(wa, st));
             FS_TRY(upconv_collapse_grad(wg_tmp, grads + c.offW, c.cin, c.cout, st));
         } else {
             wa.C = c.cin_s; wa.KH = wa.KW = c.k; wa.stride = c.stride; wa.pad_t = c.pad_t; wa.pad_l = c.pad_l;
@@ -376,7 +415,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
             wa.dy_bs = (long long)c.outH * c.outW * c.cout_s;
             const bool padded = (c.cin != c.cin_s) || (c.cout != c.cout_s);
             wa.out = padded ? wg_tmp : grads + c.offW;
-            FS_TRY(launch_wgrad(wa, st));
+            PROF(PC_WGRAD, wgrad_flops(wa), launch_wgrad(wa, st));
             if (padded) FS_TRY(unpad_taps(wg_tmp, grads + c.offW, c.k * c.k, c.cin, c.cout, c.cin_s, c.cout_s, st));
         }
         if (l == 0) break;                       // no gradient w.r.t. the input image (train.py:198-204)
@@ -392,7 +431,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
             ta.pad = 2;                              // VALID conv: data gradient is the "full" correlation
             if (first_of_block) { ta.addend = resid_dOut; ta.add_crop = 2; ta.addH = resid_H; ta.addW = resid_W; }
             ta.out_f32 = dPrev;
-            FS_TRY(launch_conv3x3_tc(ta, st));
+            PROF(PC_TC_RES_DGRAD, tc_flops(ta), launch_conv3x3_tc(ta, st));
             dAct = dPrev; cur = pidx;
             if (first_of_block) { held = -1; resid_dOut = nullptr; }
             continue;
@@ -415,7 +454,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
             a.addend = resid_dOut; a.add_crop = 2; a.addH = resid_H; a.addW = resid_W;
             a.add_bs = (long long)resid_H * resid_W * 64;
         }
-        FS_TRY(launch_igemm(a, st));
+        PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
         dAct = dPrev; cur = pidx;
         if (first_of_block) { held = -1; resid_dOut = nullptr; }
     }
@@ -450,11 +489,11 @@ int Engine::vgg_forward(const float* packed, const float* img3, int upto, float*
             ta.bias = packed + vc[l].offB; ta.relu = 1;
             ta.out_f32 = out;
             if (l < upto && !pool_next) ta.out_split = vsplit[l + 1];     // next conv reads split planes
-            FS_TRY(launch_conv3x3_tc(ta, st));
+            PROF(PC_TC_VGG_FWD, tc_flops(ta), launch_conv3x3_tc(ta, st));
         } else {
             IGemmArgs a;
             vgg_conv_args(vc[l], N, packed, cur, out, a);
-            FS_TRY(launch_igemm(a, st));
+            PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
             if (use_tc && l < upto && !pool_next)
                 FS_TRY(split_bf16(out, vsplit[l + 1], (long long)N * vc[l].H * vc[l].W * vc[l].cout, st));
         }
@@ -517,7 +556,7 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
             wa.KH = wa.KW = 1; wa.stride = 1;
             wa.OH = v.H; wa.OW = v.W; wa.OC = v.cout; wa.dy_bs = wa.in_bs;
             wa.N = N; wa.per_sample = 1; wa.scale = (float)(1.0 / hwc);
-            FS_TRY(launch_wgrad(wa, st));
+            PROF(PC_GRAM_FWD, wgrad_flops(wa), launch_wgrad(wa, st));
             const double cc = (double)v.cout * v.cout;
             FS_TRY(style_loss_grad(gram[l], tg[l], gramS[l], N, v.cout * v.cout,
                                    (float)(4.0 * sw[l] / (cc * hwc)), sw[l] / cc, loss_acc + 1, st));
@@ -540,7 +579,8 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
             ta.N = N; ta.H = v.H; ta.W = v.W; ta.C = v.cout; ta.OH = v.H; ta.OW = v.W; ta.OC = v.cin; ta.pad = 1;
             ta.addend = addend; ta.addH = v.H; ta.addW = v.W; ta.ref = ref;
             ta.out_f32 = out; ta.out_split = out_split;
-            return launch_conv3x3_tc(ta, st);
+            PROF(PC_TC_VGG_DGRAD, tc_flops(ta), launch_conv3x3_tc(ta, st));
+            return 0;
         }
         IGemmArgs a;
         memset(&a, 0, sizeof(a));
@@ -549,7 +589,8 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
         a.KH = a.KW = 3; a.stride = 1; a.pad_t = a.pad_l = 1;
         a.OH = v.H; a.OW = v.W; a.OC = v.cin_s; a.out_bs = (long long)v.H * v.W * v.cin_s;
         a.addend = addend; a.addH = v.H; a.addW = v.W; a.add_bs = a.out_bs; a.ref = ref;
-        return launch_igemm(a, st);
+        PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
+        return 0;
     };
     const SplitPtr no_split = {nullptr, nullptr};
     // make the split planes of P_l (held in vgrad[idx]) valid when the consumer is a tensor-path conv
@@ -566,7 +607,8 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
         a.KH = a.KW = 1; a.stride = 1;
         a.OH = v.H; a.OW = v.W; a.OC = v.cout; a.out_bs = a.in_bs;
         a.addend = addend; a.addH = v.H; a.addW = v.W; a.add_bs = a.in_bs; a.ref = ref;
-        return launch_igemm(a, st);
+        PROF(PC_GRAM_BWD, igemm_flops(a), launch_igemm(a, st));
+        return 0;
     };
     int pi = -1;
     for (int l = top; l >= 0; --l) {

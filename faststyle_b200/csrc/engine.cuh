@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "ops.cuh"
 #include "tc.cuh"
+#include <vector>
 
 namespace fs {
 
@@ -41,6 +42,8 @@ struct LossConfig {
     float beta;
 };
 
+enum ProfCat { PC_TC_VGG_FWD = 0, PC_TC_VGG_DGRAD, PC_TC_RES_FWD, PC_TC_RES_DGRAD, PC_FFMA_CONV, PC_WGRAD,
+               PC_GRAM_FWD, PC_GRAM_BWD, PC_COUNT };
 enum EngineFlags { ENG_TRANSFORM = 1, ENG_TRANSFORM_BWD = 2, ENG_VGG = 4, ENG_VGG_BWD = 8 };
 
 struct Arena {
@@ -94,6 +97,13 @@ struct Engine {
     SplitPtr tsplit[T_NCONV];            // input planes of residual conv l (3..12)
     SplitPtr tgsplit[3];                 // planes of tgrad[i] (dRaw of residual convs)
     SplitPtr tw_f[T_NCONV], tw_d[T_NCONV];   // packed residual-conv weights (forward / data gradient)
+
+    // live per-kernel timing (bench.py roofline)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_cat; std::vector<double> prof_flops;
+    int pbegin(int cat, double flops, cudaStream_t st);
+    int pend(cudaStream_t st);
+    int prof_read(int ncat, float* ms, double* flops, int* launches);
 
     int plan();                          // fill geometry; returns 0 / error
     void layout(Arena& a);               // assign (or just size) workspace

@@ -6,8 +6,9 @@
 // Gram backward GEMM all run through igemm_kernel; weight gradients and the Gram
 // forward (reductions over pixels) run through wgrad_kernel.  The tcgen05 path
 // (conv3x3_tc.cu) takes over the 64-channel-multiple 3x3 layers; the kernels here
-// remain the path for tiny-N / tiny-K layers (Cin=3, Cout=3) that cannot feed the
-// tensor pipe.
+// remain the path for tiny-N / tiny-K layers (Cin=3, Cout=3..32) that cannot feed the
+// tensor pipe.  Tile shapes are picked per output-channel count so
+// that every thread keeps a >= 8x4 (or 8x8) register tile: 32 FMAs per 3 LDS.128.
 //
 // Reference semantics reproduced: tf.nn.conv2d NHWC/HWIO with TF SAME/VALID
 // padding (reference im_transf_net.py:115-118, libs/vgg16.py:48-52).
@@ -16,8 +17,6 @@
 namespace fs {
 
 namespace {
-
-constexpr int BK = 16;
 
 struct RowInfo { int oy, ox; bool ok; };
 
@@ -52,15 +51,20 @@ __device__ __forceinline__ float4 gather_a(const IGemmArgs& a, const float* in_n
     return ldg4(in_n + off);
 }
 
-template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__(256) igemm_kernel(const IGemmArgs a) {
+// BM x BN output tile, BK reduction slice, TM x TN register tile, NT threads.
+template <int BM, int BN, int TM, int TN, int NT, int BK>
+__global__ void __launch_bounds__(NT) igemm_kernel(const IGemmArgs a) {
     constexpr int TXN = BN / TN;
-    constexpr int TYN = 256 / TXN;
-    static_assert(TYN * TM == BM, "tile/thread mismatch");
-    constexpr int A_F4 = (BM * BK / 4) / 256;
+    constexpr int TYN = NT / TXN;
+    static_assert(TYN * TM == BM && TXN * TN == BN, "tile/thread mismatch");
+    constexpr int K4 = BK / 4;                        // float4 per A row slice
+    static_assert(NT % K4 == 0, "thread count must be a multiple of BK/4");
+    constexpr int RSTEP = NT / K4;                    // rows covered per load round
+    static_assert(BM % RSTEP == 0, "BM must be a multiple of NT/(BK/4)");
+    constexpr int A_F4 = BM / RSTEP;
     constexpr int B_TOT = BK * BN / 4;
-    constexpr int B_F4 = (B_TOT + 255) / 256;
-    constexpr int NG = TN / 4;               // float4 column groups per thread
+    constexpr int B_F4 = (B_TOT + NT - 1) / NT;
+    constexpr int NG = TN / 4;                        // float4 column groups per thread
     constexpr int GSTRIDE = BN / NG;
 
     __shared__ __align__(16) float As[2][BK][BM + 4];
@@ -77,12 +81,13 @@ __global__ void __launch_bounds__(256) igemm_kernel(const IGemmArgs a) {
     const float* in_n = a.in + (long long)n * a.in_bs;
     const float* w_n = a.w + (long long)n * a.w_bs;
 
-    // rows this thread gathers
-    const int k4 = t & 3;
+    // rows this thread gathers (its float4 column k4 is the same for all of them)
+    const int k4 = t % K4;
+    const int r0 = t / K4;
     RowInfo rows[A_F4];
 #pragma unroll
     for (int i = 0; i < A_F4; ++i) {
-        int m = m0 + (t >> 2) + i * 64;
+        int m = m0 + r0 + i * RSTEP;
         rows[i].ok = m < M;
         int mm = rows[i].ok ? m : 0;
         rows[i].oy = mm / a.OW;
@@ -93,7 +98,7 @@ __global__ void __launch_bounds__(256) igemm_kernel(const IGemmArgs a) {
     float4 rb[B_F4];
 
     auto load_tile = [&](int kt) {
-        int kg4 = kt * (BK / 4) + k4;
+        int kg4 = kt * K4 + k4;
         bool k_ok = kg4 * 4 < Ktot;
         int tap = kg4 / C4;
         int c = (kg4 - tap * C4) * 4;
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(256) igemm_kernel(const IGemmArgs a) {
             ra[i] = gather_a(a, in_n, rows[i].oy, rows[i].ox, rows[i].ok, kh, kw, c, k_ok);
 #pragma unroll
         for (int i = 0; i < B_F4; ++i) {
-            int f = t + i * 256;
+            int f = t + i * NT;
             rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (f < B_TOT) {
                 int bk = f / (BN / 4), bn4 = f - bk * (BN / 4);
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__(256) igemm_kernel(const IGemmArgs a) {
     auto store_tile = [&](int buf) {
 #pragma unroll
         for (int i = 0; i < A_F4; ++i) {
-            int r = (t >> 2) + i * 64;
+            int r = r0 + i * RSTEP;
             As[buf][k4 * 4 + 0][r] = ra[i].x;
             As[buf][k4 * 4 + 1][r] = ra[i].y;
             As[buf][k4 * 4 + 2][r] = ra[i].z;
@@ -124,7 +129,7 @@ __global__ void __launch_bounds__(256) igemm_kernel(const IGemmArgs a) {
         }
 #pragma unroll
         for (int i = 0; i < B_F4; ++i) {
-            int f = t + i * 256;
+            int f = t + i * NT;
             if (f < B_TOT) {
                 int bk = f / (BN / 4), bn4 = f - bk * (BN / 4);
                 *reinterpret_cast<float4*>(&Bs[buf][bk][bn4 * 4]) = rb[i];
@@ -213,11 +218,11 @@ __global__ void __launch_bounds__(256) igemm_kernel(const IGemmArgs a) {
     }
 }
 
-template <int BM, int BN, int TM, int TN>
+template <int BM, int BN, int TM, int TN, int NT, int BK>
 int launch_cfg(const IGemmArgs& a, cudaStream_t st) {
     int M = a.OH * a.OW;
     dim3 grid(cdiv(M, BM), cdiv(a.OC, BN), a.N);
-    igemm_kernel<BM, BN, TM, TN><<<grid, 256, 0, st>>>(a);
+    igemm_kernel<BM, BN, TM, TN, NT, BK><<<grid, NT, 0, st>>>(a);
     FS_LAUNCH_CHECK();
     return 0;
 }
@@ -231,11 +236,13 @@ int launch_igemm(const IGemmArgs& a, cudaStream_t st) {
     FS_CHECK(a.N > 0 && a.N <= 65535, "igemm: batch %d out of range", a.N);
     FS_CHECK(a.stride >= 1, "igemm: bad stride");
     if (a.OH <= 0 || a.OW <= 0) return 0;
-    if (a.OC >= 128) return launch_cfg<128, 128, 8, 8>(a, st);
-    if (a.OC > 32) return launch_cfg<128, 64, 8, 4>(a, st);
-    if (a.OC > 16) return launch_cfg<128, 32, 4, 4>(a, st);
-    if (a.OC > 4) return launch_cfg<128, 16, 2, 4>(a, st);
-    return launch_cfg<256, 4, 1, 4>(a, st);
+    if (a.OC >= 128) return launch_cfg<128, 128, 8, 8, 256, 16>(a, st);
+    if (a.OC > 32) return launch_cfg<128, 64, 8, 4, 256, 16>(a, st);
+    // small-N layers are bound by the im2col gather, not by FMA issue: many light threads
+    // (high occupancy to hide the gather latency) beat big register tiles here (measured).
+    if (a.OC > 16) return launch_cfg<128, 32, 4, 4, 256, 16>(a, st);
+    if (a.OC > 4) return launch_cfg<128, 16, 2, 4, 256, 16>(a, st);
+    return launch_cfg<256, 4, 1, 4, 256, 16>(a, st);
 }
 
 // =====================================================================
@@ -246,15 +253,24 @@ int launch_igemm(const IGemmArgs& a, cudaStream_t st) {
 // =====================================================================
 namespace {
 
-constexpr int WK = 64;    // k rows per tile
-constexpr int WN = 64;    // output channels per tile
-constexpr int WP = 16;    // pixels per smem step
-
 struct WGeom {
     int M, Ktot, C4, groups, splits, pix_per_group, chunk;
 };
 
-__global__ void __launch_bounds__(128) wgrad_kernel(const WGradArgs a, const WGeom g) {
+// WK x WN output tile (k rows x out channels), WP pixels per smem step, TK x 4 register tile.
+template <int WK, int WN, int TK, int WP, int NT>
+__global__ void __launch_bounds__(NT) wgrad_kernel(const WGradArgs a, const WGeom g) {
+    constexpr int TXN = WN / 4;
+    constexpr int TYN = NT / TXN;
+    static_assert(TYN * TK == WK, "tile/thread mismatch");
+    constexpr int K4 = WK / 4;                               // float4 per A row
+    constexpr int KPT = (K4 + NT - 1) / NT;                  // distinct k4 columns per thread
+    constexpr int PSTEP = NT >= K4 ? NT / K4 : 1;            // pixel rows covered per load round
+    static_assert(WP % PSTEP == 0, "WP must be a multiple of the pixel step");
+    constexpr int PPT = WP / PSTEP;                          // pixel rows per thread per k4 column
+    constexpr int B_TOT = WP * WN / 4;
+    constexpr int B_F4 = (B_TOT + NT - 1) / NT;
+
     __shared__ __align__(16) float As[2][WP][WK + 4];
     __shared__ __align__(16) float Bs[2][WP][WN + 4];
     const int t = threadIdx.x;
@@ -265,66 +281,92 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const WGradArgs a, const WGe
     const int nsteps = pend > pbeg ? (pend - pbeg + WP - 1) / WP : 0;
     const int samples_per_group = g.pix_per_group / g.M;
 
-    // load mapping: 256 float4 per operand per step, 2 per thread
-    const int lk4 = t & 15;                 // float4 index along k / along j
-    const int lp = t >> 4;                  // pixel 0..7 (+8)
-    // decode this thread's k (fixed for the whole loop)
-    const int kg4 = (k0 >> 2) + lk4;
-    const bool k_ok = kg4 * 4 < g.Ktot;
-    const int tap = kg4 / g.C4;
-    const int c = (kg4 - tap * g.C4) * 4;
-    const int kh = tap / a.KW, kw = tap - kh * a.KW;
-    const int jcol = j0 + lk4 * 4;
-    const bool j_ok = jcol < a.OC;
+    // this thread's k columns (fixed for the whole loop): decode (tap, channel) once
+    int kc[KPT], kkh[KPT], kkw[KPT]; bool kok[KPT];
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {
+        int kg4 = (k0 >> 2) + (t % K4) + j * NT;
+        bool in_tile = ((t % K4) + j * NT) < K4;
+        kok[j] = in_tile && kg4 * 4 < g.Ktot;
+        int tap = kg4 / g.C4;
+        kc[j] = (kg4 - tap * g.C4) * 4;
+        kkh[j] = tap / a.KW;
+        kkw[j] = tap - kkh[j] * a.KW;
+    }
+    const int p0 = NT >= K4 ? t / K4 : 0;
 
-    float4 ra[2], rb[2];
+    float4 ra[KPT][PPT], rb[B_F4];
     auto load_step = [&](int s) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            int pix = pbeg + s * WP + lp + i * 8;
-            ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            rb[i] = ra[i];
-            if (pix < pend) {
-                int ns = pix / g.M;
-                int m = pix - ns * g.M;
-                int n = grp * samples_per_group + ns;
-                int oy = m / a.OW, ox = m - oy * a.OW;
-                if (k_ok) {
-                    int iy = oy * a.stride - a.pad_t + kh, ix = ox * a.stride - a.pad_l + kw;
+        for (int i = 0; i < PPT; ++i) {
+            int pix = pbeg + s * WP + p0 + i * PSTEP;
+            bool pok = pix < pend;
+            int ns = 0, m = 0, oy = 0, ox = 0;
+            if (pok) { ns = pix / g.M; m = pix - ns * g.M; oy = m / a.OW; ox = m - oy * a.OW; }
+            const float* in_n = a.in + (long long)(grp * samples_per_group + ns) * a.in_bs;
+#pragma unroll
+            for (int j = 0; j < KPT; ++j) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pok && kok[j]) {
+                    int iy = oy * a.stride - a.pad_t + kkh[j], ix = ox * a.stride - a.pad_l + kkw[j];
                     if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
                         long long off;
-                        if (a.in_mode == 0) off = ((long long)iy * a.W + ix) * a.C + c;
+                        if (a.in_mode == 0) off = ((long long)iy * a.W + ix) * a.C + kc[j];
                         else {
-                            int C0 = a.C >> 2; int pq = c / C0, co = c - pq * C0;
+                            int C0 = a.C >> 2; int pq = kc[j] / C0, co = kc[j] - pq * C0;
                             off = ((long long)(2 * iy + (pq >> 1)) * (2 * a.W) + 2 * ix + (pq & 1)) * C0 + co;
                         }
-                        ra[i] = ldg4(a.in + (long long)n * a.in_bs + off);
+                        v = ldg4(in_n + off);
                     }
                 }
-                if (j_ok) {
+                ra[j][i] = v;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < B_F4; ++i) {
+            int f = t + i * NT;
+            rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (f < B_TOT) {
+                int p = f / (WN / 4), n4 = f - p * (WN / 4);
+                int pix = pbeg + s * WP + p;
+                int jcol = j0 + n4 * 4;
+                if (pix < pend && jcol < a.OC) {
+                    int ns = pix / g.M;
+                    int m = pix - ns * g.M;
                     long long off;
                     if (a.dy_mode == 0) off = (long long)m * a.OC + jcol;
                     else {
+                        int oy = m / a.OW, ox = m - oy * a.OW;
                         int C0 = a.OC >> 2; int pq = jcol / C0, co = jcol - pq * C0;
                         off = ((long long)(2 * oy + (pq >> 1)) * (2 * a.OW) + 2 * ox + (pq & 1)) * C0 + co;
                     }
-                    rb[i] = ldg4(a.dy + (long long)n * a.dy_bs + off);
+                    rb[i] = ldg4(a.dy + (long long)(grp * samples_per_group + ns) * a.dy_bs + off);
                 }
             }
         }
     };
     auto store_step = [&](int buf) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            *reinterpret_cast<float4*>(&As[buf][lp + i * 8][lk4 * 4]) = ra[i];
-            *reinterpret_cast<float4*>(&Bs[buf][lp + i * 8][lk4 * 4]) = rb[i];
+        for (int i = 0; i < PPT; ++i)
+#pragma unroll
+            for (int j = 0; j < KPT; ++j) {
+                int kq = (t % K4) + j * NT;
+                if (kq < K4) *reinterpret_cast<float4*>(&As[buf][p0 + i * PSTEP][kq * 4]) = ra[j][i];
+            }
+#pragma unroll
+        for (int i = 0; i < B_F4; ++i) {
+            int f = t + i * NT;
+            if (f < B_TOT) {
+                int p = f / (WN / 4), n4 = f - p * (WN / 4);
+                *reinterpret_cast<float4*>(&Bs[buf][p][n4 * 4]) = rb[i];
+            }
         }
     };
 
-    const int tx = t & 15, ty = t >> 4;     // ty 0..7 -> 8 k rows, tx -> 4 cols
-    float acc[8][4];
+    const int tx = t % TXN, ty = t / TXN;
+    float acc[TK][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < TK; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
@@ -338,13 +380,16 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const WGradArgs a, const WGe
         if (s + 1 < nsteps) load_step(s + 1);
 #pragma unroll
         for (int p = 0; p < WP; ++p) {
-            float4 a0 = *reinterpret_cast<const float4*>(&As[buf][p][ty * 8]);
-            float4 a1 = *reinterpret_cast<const float4*>(&As[buf][p][ty * 8 + 4]);
+            float ar[TK];
+#pragma unroll
+            for (int i = 0; i < TK; i += 4) {
+                float4 v = *reinterpret_cast<const float4*>(&As[buf][p][ty * TK + i]);
+                ar[i] = v.x; ar[i + 1] = v.y; ar[i + 2] = v.z; ar[i + 3] = v.w;
+            }
             float4 b = *reinterpret_cast<const float4*>(&Bs[buf][p][tx * 4]);
-            float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             float br[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < TK; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
         }
@@ -354,8 +399,8 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const WGradArgs a, const WGe
     // partial[z][k][j]
     float* part = a.partial + (long long)blockIdx.z * g.Ktot * a.OC;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        int k = k0 + ty * 8 + i;
+    for (int i = 0; i < TK; ++i) {
+        int k = k0 + ty * TK + i;
         int col = j0 + tx * 4;
         if (k < g.Ktot && col < a.OC)
             *reinterpret_cast<float4*>(part + (long long)k * a.OC + col) =
@@ -379,8 +424,15 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     reinterpret_cast<float4*>(out)[grp * n4 + e] = s;
 }
 
-int choose_splits(int tiles, int groups, int pix_per_group) {
-    const int target = 148 * 6;
+struct WCfg { int WK, WN, WP; };
+WCfg pick_wcfg(int OC) {
+    if (OC > 16) return {64, 64, 16};
+    if (OC > 4) return {256, 16, 16};
+    return {512, 4, 8};
+}
+
+int choose_splits(int tiles, int groups, int pix_per_group, int WP) {
+    const int target = 148 * 4;
     int s = (target + tiles * groups - 1) / (tiles * groups);
     int max_s = pix_per_group / (WP * 8);
     if (max_s < 1) max_s = 1;
@@ -393,9 +445,10 @@ int choose_splits(int tiles, int groups, int pix_per_group) {
 }  // namespace
 
 long long wgrad_partial_floats(int K, int OC, int groups) {
-    // upper bound used by workspace planning: splits <= 256, but tiles*groups*splits ~ target
-    long long tiles = (long long)cdiv(K, WK) * cdiv(OC, WN);
-    long long s = (148 * 6 + tiles * groups - 1) / (tiles * groups);
+    // upper bound used by workspace planning (choose_splits only ever lowers the split count)
+    WCfg c = pick_wcfg(OC);
+    long long tiles = (long long)cdiv(K, c.WK) * cdiv(OC, c.WN);
+    long long s = (148 * 4 + tiles * groups - 1) / (tiles * groups);
     if (s < 1) s = 1;
     if (s > 256) s = 256;
     return s * groups * (long long)K * OC;
@@ -403,20 +456,23 @@ long long wgrad_partial_floats(int K, int OC, int groups) {
 
 int launch_wgrad(const WGradArgs& a, cudaStream_t st) {
     FS_CHECK(a.C % 4 == 0 && a.OC % 4 == 0, "wgrad: channel counts must be multiples of 4");
+    WCfg c = pick_wcfg(a.OC);
     WGeom g;
     g.M = a.OH * a.OW;
     g.Ktot = a.KH * a.KW * a.C;
     g.C4 = a.C >> 2;
     g.groups = a.per_sample ? a.N : 1;
     g.pix_per_group = a.per_sample ? g.M : a.N * g.M;
-    int tiles = cdiv(g.Ktot, WK) * cdiv(a.OC, WN);
-    g.splits = choose_splits(tiles, g.groups, g.pix_per_group);
-    g.chunk = cdiv(cdiv(g.pix_per_group, g.splits), WP) * WP;
+    int tiles = cdiv(g.Ktot, c.WK) * cdiv(a.OC, c.WN);
+    g.splits = choose_splits(tiles, g.groups, g.pix_per_group, c.WP);
+    g.chunk = cdiv(cdiv(g.pix_per_group, g.splits), c.WP) * c.WP;
     long long need = (long long)g.groups * g.splits * g.Ktot * a.OC;
     FS_CHECK(need <= a.partial_cap, "wgrad: partial workspace too small (%lld > %lld floats)", need, a.partial_cap);
     FS_CHECK((long long)g.groups * g.splits <= 65535, "wgrad: too many z blocks");
-    dim3 grid(cdiv(g.Ktot, WK), cdiv(a.OC, WN), g.groups * g.splits);
-    wgrad_kernel<<<grid, 128, 0, st>>>(a, g);
+    dim3 grid(cdiv(g.Ktot, c.WK), cdiv(a.OC, c.WN), g.groups * g.splits);
+    if (c.WN == 64) wgrad_kernel<64, 64, 8, 16, 128><<<grid, 128, 0, st>>>(a, g);
+    else if (c.WN == 16) wgrad_kernel<256, 16, 8, 16, 128><<<grid, 128, 0, st>>>(a, g);
+    else wgrad_kernel<512, 4, 8, 8, 64><<<grid, 64, 0, st>>>(a, g);
     FS_LAUNCH_CHECK();
     long long tile_elems = (long long)g.Ktot * a.OC;
     long long tot4 = tile_elems / 4 * g.groups;

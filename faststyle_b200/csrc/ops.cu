@@ -171,23 +171,36 @@ __global__ void in_stats_finalize_kernel(const double* __restrict__ partial, flo
 __global__ void in_bwd_finalize_kernel(const double* __restrict__ partial, float* __restrict__ m12,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int N,
                                        int C, int chunks, int HW) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    // one block per channel; warp w handles samples w, w+8, ...; lanes split the chunks.
+    // Fixed reduction order (lane tree, then warps 0..7 in order) -> deterministic.
+    __shared__ double wsum[8][2];
+    const int c = blockIdx.x;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double g = 0, b = 0;
-    for (int n = 0; n < N; ++n) {
+    for (int n = w; n < N; n += 8) {
         double s1 = 0, s2 = 0;
-        for (int k = 0; k < chunks; ++k) {
+        for (int k = lane; k < chunks; k += 32) {
             const double* p = partial + ((long long)n * chunks + k) * 2 * C + c * 2;
             s1 += p[0];
             s2 += p[1];
         }
-        m12[((long long)n * C + c) * 2 + 0] = (float)(s1 / HW);
-        m12[((long long)n * C + c) * 2 + 1] = (float)(s2 / HW);
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+            m12[((long long)n * C + c) * 2 + 0] = (float)(s1 / HW);
+            m12[((long long)n * C + c) * 2 + 1] = (float)(s2 / HW);
+        }
         b += s1;
         g += s2;
     }
-    if (dgamma) dgamma[c] = (float)g;
-    if (dbeta) dbeta[c] = (float)b;
+    if (lane == 0) { wsum[w][0] = b; wsum[w][1] = g; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double bb = 0, gg = 0;
+        for (int i = 0; i < 8; ++i) { bb += wsum[i][0]; gg += wsum[i][1]; }
+        if (dgamma) dgamma[c] = (float)gg;
+        if (dbeta) dbeta[c] = (float)bb;
+    }
 }
 
 __global__ void in_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
@@ -599,7 +612,7 @@ int instnorm_bwd(const float* dY, const float* x, const float* mean, const float
     in_reduce_kernel<1><<<dim3(chunks, N), 256, 2 * C * sizeof(double), st>>>(
         x, dY, mean, rstd, scale, shift, partial, HW, C, chunks, act);
     FS_LAUNCH_CHECK();
-    in_bwd_finalize_kernel<<<grid1(C, 64), 64, 0, st>>>(partial, m12, dgamma, dbeta, N, C, chunks, HW);
+    in_bwd_finalize_kernel<<<C, 256, 0, st>>>(partial, m12, dgamma, dbeta, N, C, chunks, HW);
     FS_LAUNCH_CHECK();
     long long n = (long long)N * HW * (C / 4);
     in_bwd_apply_kernel<<<grid1(n), 256, 0, st>>>(dY, x, mean, rstd, scale, shift, m12, dx, N, HW, C, act,

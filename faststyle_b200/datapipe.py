@@ -1,0 +1,204 @@
+"""Input pipeline for train.py (reference datapipe.py:14-78), without TensorFlow.
+
+Sources, chosen from ``train_dir``:
+* TFRecord shards ``train-*`` written by the reference's tfrecords_writer.py (framing +
+  ``tf.Example`` with ``image/encoded`` JPEG bytes) - decoded with OpenCV;
+* a directory of image files (jpg/jpeg/png);
+* the literal ``synthetic`` or ``synthetic:<count>`` - seeded uniform-noise images
+  (no dataset is reachable from the build machine).
+Images are resized to ``resize_shape`` with a restatement of TF-1.0's legacy bicubic kernel
+(``tf.image.resize_images(method=2)``, datapipe.py:25) and shuffled through a buffer of
+``min_after_dequeue`` elements like ``tf.train.shuffle_batch`` (datapipe.py:71-77).
+The reference's TF queue threads are replaced by a plain Python iterator; exhausting
+``num_epochs`` raises ``OutOfRangeError`` like the queue does (train.py:281).
+"""
+from __future__ import annotations
+
+import glob
+import os
+import struct
+
+import numpy as np
+
+
+class OutOfRangeError(Exception):
+    """Stand-in for tf.errors.OutOfRangeError (train.py:281)."""
+
+
+# ------------------------------------------------------------------ TF-1.0 bicubic
+_TABLE = 1024
+_A = -0.75
+
+
+def _coeff_table():
+    x = np.arange(_TABLE + 1, dtype=np.float32) / _TABLE
+    t = np.empty((_TABLE + 1) * 2, np.float32)
+    t[0::2] = ((_A + 2) * x - (_A + 3)) * x * x + 1
+    x1 = x + 1
+    t[1::2] = ((_A * x1 - 5 * _A) * x1 + 8 * _A) * x1 - 4 * _A
+    return t
+
+
+_TAB = _coeff_table()
+
+
+def _weights_indices(in_size, out_size):
+    scale = np.float32(in_size) / np.float32(out_size)
+    out = np.arange(out_size)
+    pos = scale * out.astype(np.float32)
+    in_loc = np.floor(pos).astype(np.int64)
+    delta = pos - in_loc
+    off = np.rint(delta * _TABLE).astype(np.int64)
+    w = np.stack([_TAB[off * 2 + 1], _TAB[off * 2], _TAB[(_TABLE - off) * 2], _TAB[(_TABLE - off) * 2 + 1]], 1)
+    idx = np.stack([in_loc - 1, in_loc, in_loc + 1, in_loc + 2], 1).clip(0, in_size - 1)
+    return w.astype(np.float32), idx
+
+
+def resize_bicubic_tf1(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """TF-1.0 ResizeBicubic (align_corners=False, no half-pixel centres, A=-0.75, 1024-entry
+    coefficient table), HWC uint8/float -> HWC float32.  Unpinned restatement."""
+    img = np.asarray(img, np.float32)
+    wy, iy = _weights_indices(img.shape[0], out_h)
+    wx, ix = _weights_indices(img.shape[1], out_w)
+    rows = (img[iy] * wy[:, :, None, None]).sum(1)                  # [out_h, W, C]
+    out = (rows[:, ix] * wx[None, :, :, None]).sum(2)               # [out_h, out_w, C]
+    return out.astype(np.float32)
+
+
+# ------------------------------------------------------------------ TFRecord / tf.Example
+def _varint(b, p):
+    v = s = 0
+    while True:
+        c = b[p]; p += 1
+        v |= (c & 127) << s; s += 7
+        if c < 128:
+            return v, p
+
+
+def _fields(b):
+    p = 0
+    while p < len(b):
+        key, p = _varint(b, p)
+        f, wt = key >> 3, key & 7
+        if wt == 0:
+            v, p = _varint(b, p)
+        elif wt == 2:
+            n, p = _varint(b, p); v = b[p:p + n]; p += n
+        elif wt == 5:
+            v = b[p:p + 4]; p += 4
+        elif wt == 1:
+            v = b[p:p + 8]; p += 8
+        else:
+            raise ValueError("bad wire type")
+        yield f, v
+
+
+def iter_tfrecord(path):
+    """Yield raw records of a TFRecord file (length:u64, crc:u32, data, crc:u32)."""
+    with open(path, "rb") as f:
+        while True:
+            head = f.read(12)
+            if len(head) < 12:
+                return
+            n = struct.unpack("<Q", head[:8])[0]
+            data = f.read(n)
+            f.read(4)
+            if len(data) < n:
+                return
+            yield data
+
+
+def example_bytes_feature(record: bytes, key: str):
+    """Extract a bytes feature of a serialized tf.Example (features{feature{key,value}})."""
+    for f, v in _fields(record):
+        if f != 1:
+            continue
+        for f2, entry in _fields(v):              # map entries
+            if f2 != 1:
+                continue
+            k, val = None, None
+            for f3, v3 in _fields(entry):
+                if f3 == 1:
+                    k = bytes(v3).decode()
+                elif f3 == 2:
+                    val = v3
+            if k == key and val is not None:
+                for f4, v4 in _fields(val):        # Feature: 1 = bytes_list
+                    if f4 == 1:
+                        for f5, v5 in _fields(v4):
+                            if f5 == 1:
+                                return bytes(v5)
+    return None
+
+
+# ------------------------------------------------------------------ batcher
+def _image_stream(train_dir, num_epochs, rng):
+    import cv2
+    if train_dir.startswith("synthetic"):
+        count = int(train_dir.split(":")[1]) if ":" in train_dir else 1 << 30
+        per_epoch = count
+        for _ in range(num_epochs if num_epochs else 1 << 30):
+            for _ in range(per_epoch):
+                yield rng.randint(0, 256, (256, 256, 3)).astype(np.uint8)
+        return
+    shards = sorted(glob.glob(os.path.join(train_dir, "train-*")))
+    files = [p for p in sorted(glob.glob(os.path.join(train_dir, "*")))
+             if p.lower().endswith((".jpg", ".jpeg", ".png"))]
+    if not shards and not files:
+        raise IOError("no TFRecord shards (train-*) or image files found in %r" % train_dir)
+    for _ in range(num_epochs if num_epochs else 1 << 30):
+        if shards:
+            order = list(shards); rng.shuffle(order)               # string_input_producer(shuffle=True)
+            for s in order:
+                for rec in iter_tfrecord(s):
+                    enc = example_bytes_feature(rec, "image/encoded")
+                    if enc is None:
+                        continue
+                    img = cv2.imdecode(np.frombuffer(enc, np.uint8), cv2.IMREAD_COLOR)
+                    if img is not None:
+                        yield cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+        else:
+            order = list(files); rng.shuffle(order)
+            for p in order:
+                img = cv2.imread(p)
+                if img is not None:
+                    yield cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+
+
+def batcher(train_dir, batch_size, resize_shape=None, num_epochs=None, min_after_dequeue=4000, seed=0,
+            shard=(0, 1)):
+    """Iterator of float32 NHWC batches.  ``shard=(rank, world)`` keeps every world-th image for
+    data-parallel training.  Raises OutOfRangeError when the epochs are exhausted."""
+    rng = np.random.RandomState(seed)
+    stream = _image_stream(train_dir, num_epochs, rng)
+    buf = []
+
+    def prep(img):
+        if resize_shape is None:
+            return np.asarray(img, np.float32)
+        if tuple(img.shape[:2]) == tuple(resize_shape):
+            return np.asarray(img, np.float32)
+        return resize_bicubic_tf1(img, resize_shape[0], resize_shape[1])
+
+    def gen():
+        exhausted = False
+        i = 0
+        while True:
+            while not exhausted and len(buf) < min_after_dequeue + batch_size:
+                try:
+                    img = next(stream)
+                except StopIteration:
+                    exhausted = True
+                    break
+                if i % shard[1] == shard[0]:
+                    buf.append(prep(img))
+                i += 1
+            if len(buf) < batch_size:
+                raise OutOfRangeError("input pipeline exhausted")
+            out = []
+            for _ in range(batch_size):
+                j = rng.randint(len(buf))
+                buf[j], buf[-1] = buf[-1], buf[j]
+                out.append(buf.pop())
+            yield np.stack(out, 0)
+    return gen()

@@ -63,6 +63,14 @@ int fs_engine_bind(fs_engine* e, void* workspace, size_t bytes);
  * (split-bf16 x3); 0: every convolution on the exact-fp32 FFMA path.  Also settable
  * through the environment variable FS_TENSOR_PATH=0 read at fs_engine_create. */
 int fs_engine_set_tensor_path(fs_engine* e, int enabled);
+/* Live per-kernel timing: while enabled, the GEMM-class launches of every composite are
+ * bracketed by CUDA events on the launching stream.  fs_engine_profile_read synchronises, sums
+ * elapsed ms / algorithmic FLOPs / launch counts per category and resets.  Categories:
+ * 0 tc VGG conv fwd, 1 tc VGG dgrad, 2 tc residual conv fwd, 3 tc residual dgrad,
+ * 4 FFMA implicit-GEMM conv/dgrad, 5 weight gradients, 6 Gram forward, 7 Gram backward. */
+#define FS_PROF_NCAT 8
+int fs_engine_profile(fs_engine* e, int enabled);
+int fs_engine_profile_read(fs_engine* e, int ncat, float* ms, double* flops, int* launches);
 /* output dims of the transform net (== VGG input dims when both are planned) */
 int fs_engine_output_dims(const fs_engine* e, int* OH, int* OW);
 /* device pointer + dims of a saved VGG activation (post-ReLU conv output) */
@@ -145,6 +153,15 @@ int fs_maxpool2x2(const float* x, float* y, int N, int H, int W, int C, void* st
 long long fs_gram_scratch_floats(int N, int C);
 int fs_gram_forward(const float* f, float* g, float* scratch, long long scratch_floats, int N, int H, int W,
                     int C, void* stream);
+
+/* Loss single ops (reference losses.py): acc = device double[4] scratch, out = device float[4];
+ * the result is out[0] for sqdiff (content), out[1] for style, out[2] for tv.
+ *   fs_loss_sqdiff: scale * sum (a-b)^2             (content_loss term, losses.py:32-37)
+ *   fs_loss_style : scale * sum (G[n]-T)^2, T [CC] broadcast over N (style_loss term, :61-64)
+ *   fs_loss_tv    : sum of squared forward differences of Y3 [N,H,W,3]  (tv_loss, :86-95) */
+int fs_loss_sqdiff(const float* a, const float* b, long long n, double scale, double* acc, float* out, void* stream);
+int fs_loss_style(const float* G, const float* T, int N, int CC, double scale, double* acc, float* out, void* stream);
+int fs_loss_tv(const float* Y3, int N, int H, int W, double* acc, float* out, void* stream);
 
 /* ------------------------------------------------------------------ tensor-core path
  * 3x3 stride-1 convolution on the tcgen05 tensor pipe with split-bf16 operands
