@@ -298,13 +298,13 @@ int fs_loss_sqdiff(const float* a, const float* b, long long n, double scale, do
 int fs_loss_style(const float* G, const float* T, int N, int CC, double scale, double* acc, float* out, void* stream) {
     FS_CHECK(G && T && acc && out, "fs_loss_style: NULL argument");
     FS_TRY(fill_zero(acc, 4 * sizeof(double), S(stream)));
-    FS_TRY(style_loss_grad(G, T, nullptr, N, CC, 0.f, scale, acc, S(stream)));
+    FS_TRY(style_loss_grad(G, T, nullptr, N, CC, 0.f, scale, acc + 1, S(stream)));
     return finalize_losses(acc, out, S(stream));
 }
 int fs_loss_tv(const float* Y3, int N, int H, int W, double* acc, float* out, void* stream) {
     FS_CHECK(Y3 && acc && out, "fs_loss_tv: NULL argument");
     FS_TRY(fill_zero(acc, 4 * sizeof(double), S(stream)));
-    FS_TRY(tv_loss_grad(Y3, nullptr, N, H, W, 1.f, acc, S(stream)));
+    FS_TRY(tv_loss_grad(Y3, nullptr, N, H, W, 1.f, acc + 2, S(stream)));
     return finalize_losses(acc, out, S(stream));
 }
 

@@ -1,0 +1,149 @@
+"""The Python mirror of the reference API and the three CLIs, on the GPU."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ckpt as ockpt  # noqa: E402
+from oracle import restate as R  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _relerr(got, want):
+    want = torch.as_tensor(want).double()
+    return float((torch.as_tensor(got).double().cpu() - want).abs().max() / max(want.abs().max().item(), 1e-30))
+
+
+def test_stylize_image_cli_reproduces_golden(built_lib, golden_dir, tmp_path):
+    """config 1: `stylize_image.py` on results/chicago.jpg with models/starry_final.ckpt
+    (README.md:59-61) -> decoded output vs the reference's shipped results/starry_chicago.jpg."""
+    import cv2
+    out = str(tmp_path / "styled.jpg")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "stylize_image.py"),
+                        "--input_img_path", os.path.join(golden_dir, "chicago.jpg"),
+                        "--output_img_path", out,
+                        "--model_path", os.path.join(golden_dir, "starry_final.ckpt")],
+                       capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = cv2.imread(out).astype(int)
+    gold = cv2.imread(os.path.join(golden_dir, "starry_chicago.jpg")).astype(int)
+    assert got.shape == gold.shape == (476, 712, 3)
+    d = np.abs(got - gold)
+    assert (d == 0).mean() >= 0.97 and d.mean() <= 0.05 and d.max() <= 10
+    # wrong --upsample_method / checkpoint mismatch is an error, like the reference's Saver
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "stylize_image.py"), "--input_img_path",
+                        os.path.join(golden_dir, "chicago.jpg"), "--model_path", str(tmp_path / "nope.ckpt")],
+                       capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode != 0 and "not found" in r.stderr
+
+
+def test_mirror_ops_and_create_net(built_lib, golden_dir):
+    from faststyle_b200 import im_transf_net as T
+    from faststyle_b200 import variables as V
+    p = ockpt.load(os.path.join(golden_dir, "candy_final.ckpt"))
+    x = np.random.RandomState(2).randint(0, 256, (1, 72, 64, 3)).astype(np.float32)
+    V.reset_default_graph()
+    V.Saver().restore(None, os.path.join(golden_dir, "candy_final.ckpt"))
+    with V.variable_scope('img_t_net'):
+        y = T.create_net(x, 'resize')
+        # op-by-op composition of the first layers (im_transf_net.py:34-40)
+        h = T.reflect_pad(x, 40)
+        with V.variable_scope('initconv_0'):
+            h = T.relu(T.inst_norm(T.conv2d(h, 3, 16, 9, [1, 1, 1, 1])))
+        with V.variable_scope('initconv_1'):
+            h = T.relu(T.inst_norm(T.conv2d(h, 16, 32, 3, [1, 2, 2, 1])))
+    taps = {}
+    with torch.no_grad():
+        yo = R.create_net(x, p, "resize", torch.float64, taps=taps)
+    assert float((y.double().cpu() - yo).abs().max()) / 255.0 < 2e-4
+    assert _relerr(h, taps["initconv_1"]) < 1e-5
+    with pytest.raises(AssertionError):
+        with V.variable_scope('img_t_net'):
+            T.create_net(x, 'bilinear')
+    with pytest.raises(NotImplementedError):
+        with V.variable_scope('img_t_net'):
+            T.create_net(x, 'deconv')
+    V.reset_default_graph()
+
+
+def test_vgg_class_grams_and_losses(built_lib, tmp_path):
+    from faststyle_b200 import losses, synth, utils
+    from faststyle_b200 import variables as V
+    from faststyle_b200.libs import vgg16
+    w = synth.synthetic_vgg_weights(7)
+    full = dict(w)
+    full["conv5_1_W"] = np.zeros((3, 3, 512, 512), np.float32); full["conv5_1_b"] = np.zeros(512, np.float32)
+    full["fc6_W"] = np.zeros((4, 4), np.float32); full["fc6_b"] = np.zeros(4, np.float32)
+    np.savez(tmp_path / "vgg16_weights.npz", **full)
+    x = np.random.RandomState(4).randint(0, 256, (2, 32, 48, 3)).astype(np.float32)
+    V.reset_default_graph()
+    with V.variable_scope('vgg'):
+        net = vgg16.vgg16(x)
+    net.load_weights(str(tmp_path / "vgg16_weights.npz"), None)     # sorted keys, stops at 'fc'
+    names = ['vgg/conv1_2:0', 'vgg/conv3_3:0']
+    layers = utils.get_layers(names)
+    grams = utils.get_grams(names)
+    L = R.vgg16_layers(x, w, "conv4_3", torch.float64)
+    assert _relerr(layers[1], R.nchw_to_nhwc(L["conv3_3"])) < 2e-4
+    assert _relerr(grams[0], R.gram(L["conv1_2"])) < 2e-4
+    tgt = [torch.zeros_like(R.nchw_to_nhwc(L["conv3_3"]))]
+    c = losses.content_loss([layers[1]], [t.float().cuda() for t in tgt], [2.0])
+    assert abs(float(c) - float(R.content_loss([L["conv3_3"]], [torch.zeros_like(L["conv3_3"])], [2.0]))) <= 3e-4 * float(c)
+    tg = [np.zeros((1, 64, 64), np.float32)]
+    s = losses.style_loss([grams[0]], tg, [5.0])
+    assert abs(float(s) - float(R.style_loss([R.gram(L["conv1_2"])], [torch.zeros(1, 64, 64, dtype=torch.float64)], [5.0]))) <= 3e-4 * float(s)
+    tv = losses.tv_loss(x)
+    assert abs(float(tv) - float(R.tv_loss(R.nhwc_to_nchw(torch.from_numpy(x).double())))) <= 1e-6 * float(tv)
+    with pytest.raises(KeyError):
+        utils.get_layers(['vgg/conv9_9:0'])
+    V.reset_default_graph()
+
+
+def test_train_cli_and_slow_style_cli(built_lib, golden_dir, tmp_path):
+    """train.py for a few steps on synthetic data: checkpoints appear at the reference's paths,
+    the final model loads back and stylizes; slow_style.py runs and lowers its loss."""
+    import cv2
+    env = dict(os.environ, VGG16_WEIGHTS="synthetic")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "train.py"), "--train_dir", "synthetic:64",
+                        "--model_name", "tiny", "--style_img_path", os.path.join(golden_dir, "starry_night_crop.jpg"),
+                        "--style_target_resize", "0.25", "--batch_size", "2", "--preprocess_size", "64", "64",
+                        "--num_steps_break", "11", "--num_steps_ckpt", "10", "--num_pipe_buffer", "8"],
+                       capture_output=True, text=True, cwd=str(tmp_path), env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l.split() for l in r.stdout.splitlines() if l[:1].isdigit()]
+    assert [int(l[0]) for l in lines] == [0, 10]                    # printed at ckpt / every-10 steps
+    assert float(lines[1][1]) < float(lines[0][1])                  # loss decreases
+    for f in ("training/tiny.ckpt-0.index", "training/tiny.ckpt-10.index", "models/tiny_final.ckpt.index",
+              "models/tiny_final.ckpt.data-00000-of-00001"):
+        assert os.path.exists(tmp_path / f), f
+    assert any("tfevents" in f for f in os.listdir(tmp_path / "summaries/train/tiny0"))
+    from faststyle_b200 import tf_bundle
+    final = tf_bundle.read_checkpoint(str(tmp_path / "models/tiny_final.ckpt"))
+    assert len(final) == 48                                          # trainable vars only (train.py:225)
+    full = tf_bundle.read_checkpoint(str(tmp_path / "training/tiny.ckpt-10"))
+    assert "global_step" in full and int(full["global_step"]) == 10 and "img_t_net/initconv_0/W/Adam_1" in full
+    # the trained model is usable by the stylize CLI
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "stylize_image.py"), "--input_img_path",
+                        os.path.join(golden_dir, "chicago.jpg"), "--content_target_resize", "0.25",
+                        "--output_img_path", str(tmp_path / "o.jpg"), "--model_path", "models/tiny_final.ckpt"],
+                       capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert cv2.imread(str(tmp_path / "o.jpg")) is not None
+    # slow_style
+    small = cv2.resize(cv2.imread(os.path.join(golden_dir, "chicago.jpg")), (96, 64))
+    cv2.imwrite(str(tmp_path / "c.jpg"), small)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "slow_style.py"), "--style_img_path",
+                        os.path.join(golden_dir, "starry_night_crop.jpg"), "--style_target_resize", "0.2",
+                        "--cont_img_path", str(tmp_path / "c.jpg"), "--num_steps_break", "20",
+                        "--output_img_path", str(tmp_path / "s.jpg")],
+                       capture_output=True, text=True, cwd=str(tmp_path), env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ls = [l.split() for l in r.stdout.splitlines() if l[:1].isdigit()]
+    assert [int(l[0]) for l in ls] == [0, 10, 20] and float(ls[-1][1]) < float(ls[0][1])
+    assert cv2.imread(str(tmp_path / "s.jpg")).shape == (64, 96, 3)
