@@ -94,6 +94,10 @@ int fs_engine_profile_read(fs_engine* e, int ncat, float* ms, double* flops, int
     FS_CHECK(e && ms && flops && launches && ncat >= 1 && ncat <= 64, "fs_engine_profile_read: bad argument");
     return e->e.prof_read(ncat, ms, flops, launches);
 }
+int fs_engine_profile_records(fs_engine* e, int max_rec, int* cat, float* ms, double* flops, int* count) {
+    FS_CHECK(e && cat && ms && flops && count && max_rec >= 0, "fs_engine_profile_records: bad argument");
+    return e->e.prof_records(max_rec, cat, ms, flops, count);
+}
 int fs_engine_destroy(fs_engine* e) { delete e; return 0; }
 size_t fs_engine_workspace_bytes(const fs_engine* e) { return e ? e->e.ws_bytes : 0; }
 int fs_engine_bind(fs_engine* e, void* workspace, size_t bytes) {

@@ -29,6 +29,18 @@ int Engine::pend(cudaStream_t st) {
     FS_CUDA(cudaEventRecord(prof_ev.back(), st));
     return 0;
 }
+int Engine::prof_records(int max_rec, int* cat, float* ms, double* flops, int* count) {
+    // per-launch records in issue order (does not reset; call before prof_read)
+    int n = (int)prof_cat.size();
+    *count = n;
+    for (int i = 0; i < n && i < max_rec; ++i) {
+        float t = 0.f;
+        FS_CUDA(cudaEventSynchronize(prof_ev[2 * i + 1]));
+        FS_CUDA(cudaEventElapsedTime(&t, prof_ev[2 * i], prof_ev[2 * i + 1]));
+        cat[i] = prof_cat[i]; ms[i] = t; flops[i] = prof_flops[i];
+    }
+    return 0;
+}
 int Engine::prof_read(int ncat, float* ms, double* flops, int* launches) {
     for (int i = 0; i < ncat; ++i) { ms[i] = 0.f; flops[i] = 0.0; launches[i] = 0; }
     for (size_t i = 0; i < prof_cat.size(); ++i) {

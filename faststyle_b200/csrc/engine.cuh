@@ -104,6 +104,7 @@ struct Engine {
     int pbegin(int cat, double flops, cudaStream_t st);
     int pend(cudaStream_t st);
     int prof_read(int ncat, float* ms, double* flops, int* launches);
+    int prof_records(int max_rec, int* cat, float* ms, double* flops, int* count);
 
     int plan();                          // fill geometry; returns 0 / error
     void layout(Arena& a);               // assign (or just size) workspace

@@ -18,7 +18,7 @@ namespace fs {
 
 namespace {
 
-struct RowInfo { int oy, ox; bool ok; };
+struct RowInfo { int oy, ox; bool ok; int off; unsigned mh, mw; };
 
 __device__ __forceinline__ float4 ldg4(const float* p) {
     return __ldg(reinterpret_cast<const float4*>(p));
@@ -93,6 +93,23 @@ __global__ void __launch_bounds__(NT) igemm_kernel(const IGemmArgs a) {
         rows[i].oy = mm / a.OW;
         rows[i].ox = mm - rows[i].oy * a.OW;
     }
+    // Fast gather (plain NHWC input, forward conv or stride-1 data gradient): the element offset is
+    // row_offset + tap_offset and the bounds test is two precomputed per-row bit masks.
+    const bool fast = a.in_mode == 0 && (a.gather == 0 || a.stride == 1);
+    const int sgn = a.gather == 0 ? 1 : -1;
+    if (fast) {
+#pragma unroll
+        for (int i = 0; i < A_F4; ++i) {
+            int by = a.gather == 0 ? rows[i].oy * a.stride - a.pad_t : rows[i].oy + a.pad_t;
+            int bx = a.gather == 0 ? rows[i].ox * a.stride - a.pad_l : rows[i].ox + a.pad_l;
+            unsigned mh = 0, mw = 0;
+            for (int k = 0; k < a.KH; ++k) { int y = by + sgn * k; if (y >= 0 && y < a.H) mh |= 1u << k; }
+            for (int k = 0; k < a.KW; ++k) { int x = bx + sgn * k; if (x >= 0 && x < a.W) mw |= 1u << k; }
+            rows[i].off = (by * a.W + bx) * a.C;
+            rows[i].mh = rows[i].ok ? mh : 0u;
+            rows[i].mw = mw;
+        }
+    }
 
     float4 ra[A_F4];
     float4 rb[B_F4];
@@ -104,9 +121,18 @@ __global__ void __launch_bounds__(NT) igemm_kernel(const IGemmArgs a) {
         int c = (kg4 - tap * C4) * 4;
         int kh = tap / a.KW;
         int kw = tap - kh * a.KW;
+        if (fast) {
+            const int tapoff = sgn * (kh * a.W + kw) * a.C + c;
 #pragma unroll
-        for (int i = 0; i < A_F4; ++i)
-            ra[i] = gather_a(a, in_n, rows[i].oy, rows[i].ox, rows[i].ok, kh, kw, c, k_ok);
+            for (int i = 0; i < A_F4; ++i) {
+                bool v = k_ok && (((rows[i].mh >> kh) & (rows[i].mw >> kw)) & 1u);
+                ra[i] = v ? ldg4(in_n + rows[i].off + tapoff) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < A_F4; ++i)
+                ra[i] = gather_a(a, in_n, rows[i].oy, rows[i].ox, rows[i].ok, kh, kw, c, k_ok);
+        }
 #pragma unroll
         for (int i = 0; i < B_F4; ++i) {
             int f = t + i * NT;
@@ -235,6 +261,8 @@ int launch_igemm(const IGemmArgs& a, cudaStream_t st) {
     FS_CHECK(a.out_mode == 0 || (a.OC % 16 == 0), "igemm: d2s store needs OC%%16==0");
     FS_CHECK(a.N > 0 && a.N <= 65535, "igemm: batch %d out of range", a.N);
     FS_CHECK(a.stride >= 1, "igemm: bad stride");
+    FS_CHECK(a.KH <= 16 && a.KW <= 16, "igemm: kernel larger than 16x16");
+    FS_CHECK((long long)a.H * a.W * a.C < (1LL << 30), "igemm: per-sample input too large for 32-bit offsets");
     if (a.OH <= 0 || a.OW <= 0) return 0;
     if (a.OC >= 128) return launch_cfg<128, 128, 8, 8, 256, 16>(a, st);
     if (a.OC > 32) return launch_cfg<128, 64, 8, 4, 256, 16>(a, st);

@@ -71,6 +71,8 @@ int fs_engine_set_tensor_path(fs_engine* e, int enabled);
 #define FS_PROF_NCAT 8
 int fs_engine_profile(fs_engine* e, int enabled);
 int fs_engine_profile_read(fs_engine* e, int ncat, float* ms, double* flops, int* launches);
+/* per-launch records (category, ms, algorithmic FLOPs) in issue order; call before _read */
+int fs_engine_profile_records(fs_engine* e, int max_rec, int* cat, float* ms, double* flops, int* count);
 /* output dims of the transform net (== VGG input dims when both are planned) */
 int fs_engine_output_dims(const fs_engine* e, int* OH, int* OW);
 /* device pointer + dims of a saved VGG activation (post-ReLU conv output) */
