@@ -363,4 +363,24 @@ int fs_conv3x3_tc_dgrad(const float* dy, const float* w, float* dx, void* scratc
     return launch_conv3x3_tc(a, S(stream));
 }
 
+/* test entry: weight gradient of a 3x3 stride-1 64->64 conv on the tensor path */
+int fs_wgrad3x3_tc(const float* x, const float* dy, float* dw, void* scratch, size_t scratch_bytes, int N, int H,
+                   int W, int padding_same, void* stream) {
+    FS_CHECK(x && dy && dw && scratch && ((uintptr_t)scratch & 1023) == 0, "fs_wgrad3x3_tc: bad argument");
+    const int OH = padding_same ? H : H - 2, OW = padding_same ? W : W - 2;
+    size_t xa = al1k((size_t)N * H * W * 64 * 2), da = al1k((size_t)N * OH * OW * 64 * 2);
+    size_t pa = (size_t)wgrad3x3_tc_partial_floats() * 4;
+    FS_CHECK(scratch_bytes >= 2 * xa + 2 * da + pa, "fs_wgrad3x3_tc: scratch too small");
+    char* p = (char*)scratch;
+    SplitPtr xs{(__nv_bfloat16*)p, (__nv_bfloat16*)(p + xa)};
+    SplitPtr ds{(__nv_bfloat16*)(p + 2 * xa), (__nv_bfloat16*)(p + 2 * xa + da)};
+    float* partial = (float*)(p + 2 * xa + 2 * da);
+    FS_TRY(split_bf16(x, xs, (long long)N * H * W * 64, S(stream)));
+    FS_TRY(split_bf16(dy, ds, (long long)N * OH * OW * 64, S(stream)));
+    return launch_wgrad3x3_tc(xs, ds, dw, partial, wgrad3x3_tc_partial_floats(), N, H, W, OH, OW, padding_same ? 1 : 0, S(stream));
+}
+size_t fs_wgrad3x3_tc_scratch_bytes(int N, int H, int W) {
+    return 4 * al1k((size_t)N * H * W * 64 * 2) + (size_t)wgrad3x3_tc_partial_floats() * 4 + 1024;
+}
+
 }  // extern "C"

@@ -98,4 +98,9 @@ struct WGradArgs {
 int launch_wgrad(const WGradArgs& a, cudaStream_t st);
 long long wgrad_partial_floats(int K, int OC, int groups);
 
+// direct 9x9 stride-1 SAME weight gradient for (CI,CO) in {(16,4),(4,16)}  (direct9x9.cu)
+long long wgrad9x9_partial_floats(int N, int H, int W);
+int launch_wgrad9x9(const float* in, const float* dy, float* out, float* partial, long long partial_cap, int N,
+                    int H, int W, int CI, int CO, cudaStream_t st);
+
 }  // namespace fs

@@ -231,6 +231,8 @@ void Engine::layout(Arena& a) {
                 int K = c.upconv ? 4 * c.cin : c.k * c.k * c.cin_s;
                 int OC = c.upconv ? 4 * c.cout : c.cout_s;
                 wgcap = maxll(wgcap, wgrad_partial_floats(K, OC, 1));
+                if (c.k == 9) wgcap = maxll(wgcap, wgrad9x9_partial_floats(N, c.inH, c.inW));
+                if (l >= 3 && l <= 12) wgcap = maxll(wgcap, wgrad3x3_tc_partial_floats());
             }
         }
         for (int l = 0; l < T_NCONV; ++l) {
@@ -427,7 +429,14 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
             wa.dy_bs = (long long)c.outH * c.outW * c.cout_s;
             const bool padded = (c.cin != c.cin_s) || (c.cout != c.cout_s);
             wa.out = padded ? wg_tmp : grads + c.offW;
-            PROF(PC_WGRAD, wgrad_flops(wa), launch_wgrad(wa, st));
+            if (tcl)
+                PROF(PC_WGRAD, wgrad_flops(wa), launch_wgrad3x3_tc(tsplit[l], tgsplit[ri], wa.out, wg_partial, wg_partial_cap,
+                                                                   N, c.inH, c.inW, c.outH, c.outW, 0, st));
+            else if (c.k == 9 && c.stride == 1 && c.same && c.cin_s * c.cout_s == 64)
+                PROF(PC_WGRAD, wgrad_flops(wa), launch_wgrad9x9(in_act, dRaw, wa.out, wg_partial, wg_partial_cap, N,
+                                                                c.inH, c.inW, c.cin_s, c.cout_s, st));
+            else
+                PROF(PC_WGRAD, wgrad_flops(wa), launch_wgrad(wa, st));
             if (padded) FS_TRY(unpad_taps(wg_tmp, grads + c.offW, c.k * c.k, c.cin, c.cout, c.cin_s, c.cout_s, st));
         }
         if (l == 0) break;                       // no gradient w.r.t. the input image (train.py:198-204)

@@ -34,4 +34,10 @@ struct Conv3x3TcArgs {
 int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st);
 bool conv3x3_tc_supported(int C, int OC, int W, int OW);
 
+// tcgen05 weight gradient of a 3x3 stride-1 64->64 convolution (wgrad_tc.cu):
+// x [N,H,W,64], dy [N,OH,OW,64] split planes -> out [3,3,64,64] fp32 (HWIO)
+long long wgrad3x3_tc_partial_floats();
+int launch_wgrad3x3_tc(SplitPtr x, SplitPtr dy, float* out, float* partial, long long partial_cap, int N, int H,
+                       int W, int OH, int OW, int pad, cudaStream_t st);
+
 }  // namespace fs

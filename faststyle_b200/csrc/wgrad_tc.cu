@@ -1,0 +1,266 @@
+// tcgen05 pixel-reduction GEMMs: weight gradient of the 3x3 64->64 residual convolutions.
+//
+//   dW[kh,kw,ci,co] = sum_{n,y,x} x[n, y+kh-pad, x+kw-pad, ci] * dy[n,y,x,co]
+//
+// GEMM view: D[M = (tap pair) x 64 ci, N = 64 co] += A[K = pixels, M]^T * B[K = pixels, N]; both operands
+// are "MN-major" (the reduction index - pixels - is the slow one: one 128-byte row of 64 channels per
+// pixel), which is exactly what a TMA box of the NHWC split-bf16 planes produces.  Per 8x16-pixel dy tile
+// and kw the kernel loads ONE x slab {64 ch, 16 px, 10 rows}; the taps kh=0,1,2 of that kw are the slab
+// at +kh*2048 B.  Two M=128 accumulators per kw cover them: group 0 = (kh0 | kh1), group 1 = (kh1 | kh2)
+// (the second 64-row half of an MN-major operand sits LBO = 2048 B after the first), so all MMAs are the
+// proven M=128 shape; kh1 is computed twice and the duplicate dropped (the whole job is ~8 us per layer).
+// Each persistent CTA accumulates its tiles in TMEM (6 accumulators x 64 columns), dumps one partial
+// [9,64,64] fp32 and a fixed-order reduction sums the CTAs' partials (deterministic).
+// Precision: split-bf16 x3 (hi*hi + hi*lo + lo*hi), fp32 accumulation - as conv3x3_tc.cu.
+#include <cuda.h>
+#include "tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace fs {
+
+namespace {
+
+using namespace tcptx;
+
+constexpr int TW = 16, TH = 8;
+constexpr int SLAB_BYTES = (TH + 2) * TW * 128;      // one plane of an x slab
+constexpr int DT_BYTES = TH * TW * 128;              // one plane of a dy tile
+constexpr int X_STAGE = 2 * SLAB_BYTES, D_STAGE = 2 * DT_BYTES;
+constexpr int STAGES = 2;
+constexpr int SMEM_BYTES = STAGES * (X_STAGE + D_STAGE) + 1024 + 256;
+constexpr int TMEM_COLS = 512;                       // 6 accumulators x 64 columns (power of two >= 384)
+
+// MN-major, 128B-swizzled operand: one 128-byte row (64 channels) per reduction index (pixel);
+// 8-row swizzle atoms every SBO = 1024 B; the next 64-channel group of M starts LBO bytes later.
+__device__ __forceinline__ uint64_t make_sdesc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ uint32_t make_idesc_mn() {
+    return (1u << 4) | (1u << 7) | (1u << 10)
+         | (1u << 15) | (1u << 16)                  // A and B are MN-major
+         | ((uint32_t)(64 >> 3) << 17)              // N = 64
+         | ((uint32_t)(128 >> 4) << 24);            // M = 128
+}
+
+struct WgParams {
+    int N, OH, OW, pad, tilesX, tilesY;
+    int total_tiles;
+    float* partial;            // [gridDim.x][9*64*64]
+};
+
+__global__ void __launch_bounds__(256, 1)
+wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+                   const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CUtensorMap tmD_lo,
+                   const WgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smemX = smem;
+    uint8_t* smemD = smem + STAGES * X_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smemD + STAGES * D_STAGE);
+    uint64_t* x_full = bars;
+    uint64_t* x_empty = x_full + STAGES;
+    uint64_t* d_full = x_empty + STAGES;
+    uint64_t* d_empty = d_full + STAGES;
+    uint64_t* done = d_empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmX_hi); prefetch_tmap(&tmX_lo); prefetch_tmap(&tmD_hi); prefetch_tmap(&tmD_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1);
+            mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 1);
+        }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        int sx = 0, sd = 0; uint32_t px = 0, pd = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const int tx = t % p.tilesX;
+            int r = t / p.tilesX;
+            const int ty = r % p.tilesY;
+            const int n = r / p.tilesY;
+            const int y0 = ty * TH, x0 = tx * TW;
+            mbar_wait(&d_empty[sd], pd ^ 1);
+            uint8_t* dd = smemD + sd * D_STAGE;
+            mbar_expect_tx(&d_full[sd], D_STAGE);
+            tma_load_4d(dd, &tmD_hi, &d_full[sd], 0, x0, y0, n);
+            tma_load_4d(dd + DT_BYTES, &tmD_lo, &d_full[sd], 0, x0, y0, n);
+            if (++sd == STAGES) { sd = 0; pd ^= 1; }
+            for (int kw = 0; kw < 3; ++kw) {
+                mbar_wait(&x_empty[sx], px ^ 1);
+                uint8_t* xd = smemX + sx * X_STAGE;
+                mbar_expect_tx(&x_full[sx], X_STAGE);
+                tma_load_4d(xd, &tmX_hi, &x_full[sx], 0, x0 + kw - p.pad, y0 - p.pad, n);
+                tma_load_4d(xd + SLAB_BYTES, &tmX_lo, &x_full[sx], 0, x0 + kw - p.pad, y0 - p.pad, n);
+                if (++sx == STAGES) { sx = 0; px ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc_mn();
+        int sx = 0, sd = 0; uint32_t px = 0, pd = 0;
+        bool first_tile = true;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            mbar_wait(&d_full[sd], pd);
+            tc_fence_after();
+            const uint32_t d_hi = smem_u32(smemD + sd * D_STAGE), d_lo = d_hi + DT_BYTES;
+            for (int kw = 0; kw < 3; ++kw) {
+                mbar_wait(&x_full[sx], px);
+                tc_fence_after();
+                const uint32_t x_hi = smem_u32(smemX + sx * X_STAGE), x_lo = x_hi + SLAB_BYTES;
+#pragma unroll
+                for (int grp = 0; grp < 2; ++grp) {
+                    const uint32_t acc = tmem_base + (uint32_t)((kw * 2 + grp) * 64);
+#pragma unroll
+                    for (int prod = 0; prod < 3; ++prod) {
+                        const uint32_t abase = (prod == 2 ? x_lo : x_hi) + (uint32_t)(grp * 2048);
+                        const uint32_t bbase = (prod == 1 ? d_lo : d_hi);
+#pragma unroll
+                        for (int ks = 0; ks < TH; ++ks) {
+                            tc_mma_bf16(acc, make_sdesc_mn(abase + ks * 2048, 2048), make_sdesc_mn(bbase + ks * 2048, 2048),
+                                        idesc, (first_tile && prod == 0 && ks == 0) ? 0u : 1u);
+                        }
+                    }
+                }
+                tc_commit(&x_empty[sx]);
+                if (++sx == STAGES) { sx = 0; px ^= 1; }
+            }
+            tc_commit(&d_empty[sd]);
+            if (++sd == STAGES) { sd = 0; pd ^= 1; }
+            first_tile = false;
+        }
+        tc_commit(done);
+    } else if (warp >= 4) {
+        // ===================== dump (4 warps = 128 TMEM lanes) =====================
+        const int ew = warp - 4;
+        const int row = ew * 32 + lane;              // accumulator row: 0..63 first tap, 64..127 second tap
+        mbar_wait(done, 0);
+        tc_fence_after();
+        float* part = p.partial + (long long)blockIdx.x * (9 * 64 * 64);
+        const bool has_tiles = (int)blockIdx.x < p.total_tiles;
+#pragma unroll 1
+        for (int a = 0; a < 6; ++a) {
+            const int kw = a >> 1, grp = a & 1;
+            const int kh = grp + (row >> 6);          // group 0: kh 0|1, group 1: kh 1|2
+            const bool keep = !(grp == 1 && row < 64);   // group 1's first half duplicates kh=1
+            const int tap = kh * 3 + kw, ci = row & 63;
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ++ch) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * 64 + ch * 32), v);
+                if (keep) {
+                    float* op = part + ((long long)tap * 64 + ci) * 64 + ch * 32;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<float4*>(op + i) = has_tiles ? make_float4(v[i], v[i + 1], v[i + 2], v[i + 3])
+                                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// out[i] = sum_b partial[b][i], fixed order
+__global__ void __launch_bounds__(256) reduce_cta_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                                  int elems, int nparts) {
+    __shared__ float red[8][33];
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lx;
+    float s = 0.f;
+    if (i < elems)
+        for (int b = ly; b < nparts; b += 8) s += partial[(long long)b * elems + i];
+    red[ly][lx] = s;
+    __syncthreads();
+    if (ly == 0 && i < elems) {
+        float r = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r += red[k][lx];
+        out[i] = r;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map(CUtensorMap* tm, const __nv_bfloat16* base, int N, int H, int W, int box_h) {
+    static EncodeTiledFn enc = nullptr;
+    if (!enc) {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        FS_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) == cudaSuccess && fp,
+                 "cuTensorMapEncodeTiled is not available from the CUDA driver");
+        enc = reinterpret_cast<EncodeTiledFn>(fp);
+    }
+    cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+    cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)box_h, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%dx%dx%dx64) failed: %d", N, H, W, (int)r);
+    return 0;
+}
+
+}  // namespace
+
+long long wgrad3x3_tc_partial_floats() { return 148LL * 9 * 64 * 64; }
+
+// x [N,H,W,64] and dy [N,OH,OW,64] as split planes; out [3,3,64,64] fp32 (HWIO); pad = conv zero padding
+int launch_wgrad3x3_tc(SplitPtr x, SplitPtr dy, float* out, float* partial, long long partial_cap, int N, int H,
+                       int W, int OH, int OW, int pad, cudaStream_t st) {
+    FS_CHECK(x.hi && x.lo && dy.hi && dy.lo && out && partial, "wgrad3x3_tc: NULL argument");
+    CUtensorMap tmX_hi, tmX_lo, tmD_hi, tmD_lo;
+    FS_TRY(make_map(&tmX_hi, x.hi, N, H, W, TH + 2));
+    FS_TRY(make_map(&tmX_lo, x.lo, N, H, W, TH + 2));
+    FS_TRY(make_map(&tmD_hi, dy.hi, N, OH, OW, TH));
+    FS_TRY(make_map(&tmD_lo, dy.lo, N, OH, OW, TH));
+    WgParams p;
+    p.N = N; p.OH = OH; p.OW = OW; p.pad = pad;
+    p.tilesX = cdiv(OW, TW); p.tilesY = cdiv(OH, TH);
+    p.total_tiles = N * p.tilesX * p.tilesY;
+    p.partial = partial;
+    int sms = 148;
+    {
+        int dev = 0; cudaGetDevice(&dev);
+        int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+        if (sms > 148) sms = 148;
+    }
+    int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    FS_CHECK(grid >= 1, "wgrad3x3_tc: empty problem");
+    FS_CHECK((long long)grid * 9 * 64 * 64 <= partial_cap, "wgrad3x3_tc: partial workspace too small");
+    static bool attr_set = false;
+    if (!attr_set) {
+        FS_CUDA(cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    wgrad3x3_tc_kernel<<<grid, 256, SMEM_BYTES, st>>>(tmX_hi, tmX_lo, tmD_hi, tmD_lo, p);
+    FS_LAUNCH_CHECK();
+    reduce_cta_partials_kernel<<<cdiv(9 * 64 * 64, 32), 256, 0, st>>>(partial, out, 9 * 64 * 64, grid);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace fs

@@ -177,6 +177,12 @@ int fs_conv3x3_tc_forward(const float* x, const float* w, const float* bias, flo
 int fs_conv3x3_tc_dgrad(const float* dy, const float* w, float* dx, void* scratch, size_t scratch_bytes,
                         int N, int H, int W, int C, int OC, int padding_same, void* stream);
 
+/* weight gradient of a 3x3 stride-1 64->64 convolution on the tensor path: x [N,H,W,64],
+ * dy [N,OH,OW,64] -> dw [3,3,64,64]; same semantics as fs_conv2d_wgrad */
+size_t fs_wgrad3x3_tc_scratch_bytes(int N, int H, int W);
+int fs_wgrad3x3_tc(const float* x, const float* dy, float* dw, void* scratch, size_t scratch_bytes, int N, int H,
+                   int W, int padding_same, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

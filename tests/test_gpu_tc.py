@@ -71,3 +71,28 @@ def test_conv3x3_tc_forward_and_dgrad(built_lib, case):
               same, _st())
     torch.cuda.synchronize()
     assert _relerr(dx, R.nchw_to_nhwc(xt.grad)) < 2e-5
+
+
+@pytest.mark.parametrize("case", [(1, 16, 16, 1), (2, 20, 18, 0), (3, 41, 37, 0), (2, 33, 40, 1)])
+def test_wgrad3x3_tc(built_lib, case):
+    """tcgen05 weight gradient (MN-major operands) of a 64->64 3x3 conv vs oracle autograd (fp64)."""
+    from faststyle_b200 import _lib
+    lib = _lib.load()
+    N, H, W, same = case
+    rng = np.random.RandomState(17 + H)
+    x = rng.standard_normal((N, H, W, 64)).astype(np.float32)
+    wt = torch.from_numpy((rng.standard_normal((3, 3, 64, 64)) * 0.05)).double().requires_grad_(True)
+    yo = R.conv2d_tf(R.nhwc_to_nchw(torch.from_numpy(x).double()), wt, 1, "SAME" if same else "VALID")
+    OH, OW = yo.shape[2], yo.shape[3]
+    dy = rng.standard_normal((N, OH, OW, 64)).astype(np.float32)
+    yo.backward(R.nhwc_to_nchw(torch.from_numpy(dy).double()))
+    xd, dyd = torch.from_numpy(x).cuda(), torch.from_numpy(dy).cuda()
+    nb = lib.fs_wgrad3x3_tc_scratch_bytes(N, H, W)
+    scratch = torch.empty(nb + 1024, dtype=torch.uint8, device="cuda")
+    sp = C.c_void_p(scratch.data_ptr() + (-scratch.data_ptr()) % 1024)
+    dw = torch.full((3, 3, 64, 64), float("nan"), device="cuda")
+    _lib.call("fs_wgrad3x3_tc", _ptr(xd), _ptr(dyd), _ptr(dw), sp, C.c_size_t(nb), N, H, W, same, _st())
+    torch.cuda.synchronize()
+    err = _relerr(dw, wt.grad)
+    print("wgrad3x3_tc", case, "rel err", err)
+    assert err < 2e-5
