@@ -53,6 +53,8 @@ __device__ __forceinline__ uint32_t make_idesc() {
 
 struct TcParams {
     int N, H, W, C, OH, OW, OC, pad;
+    int taps;                  // 3: 3x3 convolution, 1: 1x1 (per-sample GEMM, e.g. Gram backward)
+    int w_sample_rows;         // rows of the packed weight matrix per sample (0 = shared weights)
     int tilesX, tilesY, tilesN;
     long long total_tiles;
     const float* bias; const float* addend; const float* ref;
@@ -120,18 +122,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             const int n = (int)(r / p.tilesY);
             const int y0 = ty * TH - p.pad, x0 = tx * TW - p.pad, n0 = nt * BN;
             for (int cb = 0; cb < CB; ++cb) {
-                for (int kw = 0; kw < 3; ++kw) {
+                for (int kw = 0; kw < p.taps; ++kw) {
                     mbar_wait(&a_empty[sa], pa ^ 1);
                     uint8_t* dst = smemA + sa * K::A_STAGE_BYTES;
                     mbar_expect_tx(&a_full[sa], K::A_STAGE_BYTES);
                     tma_load_4d(dst, &tmA_hi, &a_full[sa], cb * KB, x0 + kw, y0, n);
                     tma_load_4d(dst + K::SLAB_BYTES, &tmA_lo, &a_full[sa], cb * KB, x0 + kw, y0, n);
                     if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
-                    for (int kh = 0; kh < 3; ++kh) {
+                    for (int kh = 0; kh < p.taps; ++kh) {
                         mbar_wait(&b_empty[sb], pb ^ 1);
                         uint8_t* bd = smemB + sb * K::B_STAGE_BYTES;
                         mbar_expect_tx(&b_full[sb], K::B_STAGE_BYTES);
-                        const int row = ((kh * 3 + kw) * CB + cb) * p.OC + n0;
+                        const int row = ((kh * p.taps + kw) * CB + cb) * p.OC + n0 + n * p.w_sample_rows;
                         tma_load_2d(bd, &tmB_hi, &b_full[sb], 0, row);
                         tma_load_2d(bd + K::BTILE_BYTES, &tmB_lo, &b_full[sb], 0, row);
                         if (++sb == K::B_STAGES) { sb = 0; pb ^= 1; }
@@ -150,12 +152,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             const uint32_t acc_base = tmem_base + (uint32_t)(as * K::NACC * BN);
             bool first = true;
             for (int cb = 0; cb < CB; ++cb) {
-                for (int kw = 0; kw < 3; ++kw) {
+                for (int kw = 0; kw < p.taps; ++kw) {
                     mbar_wait(&a_full[sa], pa);
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(smemA + sa * K::A_STAGE_BYTES);
                     const uint32_t a_lo = a_hi + K::SLAB_BYTES;
-                    for (int kh = 0; kh < 3; ++kh) {
+                    for (int kh = 0; kh < p.taps; ++kh) {
                         mbar_wait(&b_full[sb], pb);
                         tc_fence_after();
                         const uint32_t b_hi = smem_u32(smemB + sb * K::B_STAGE_BYTES);
@@ -389,11 +391,13 @@ int launch_cfg(const Conv3x3TcArgs& a, cudaStream_t st) {
     CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
     FS_TRY(make_act_map(&tmA_hi, a.x.hi, a.N, a.H, a.W, a.C, TH + 2));
     FS_TRY(make_act_map(&tmA_lo, a.x.lo, a.N, a.H, a.W, a.C, TH + 2));
-    const long long wrows = 9LL * (a.C / KB) * a.OC;
+    const long long wrows = a.one_by_one ? (long long)(a.per_sample_w ? a.N : 1) * (a.C / KB) * a.OC : 9LL * (a.C / KB) * a.OC;
     FS_TRY(make_w_map(&tmB_hi, a.w.hi, wrows, BN));
     FS_TRY(make_w_map(&tmB_lo, a.w.lo, wrows, BN));
     TcParams p;
     p.N = a.N; p.H = a.H; p.W = a.W; p.C = a.C; p.OH = a.OH; p.OW = a.OW; p.OC = a.OC; p.pad = a.pad;
+    p.taps = a.one_by_one ? 1 : 3;
+    p.w_sample_rows = a.one_by_one && a.per_sample_w ? (a.C / KB) * a.OC : 0;
     p.tilesX = cdiv(a.OW, TW); p.tilesY = cdiv(a.OH, TH); p.tilesN = a.OC / BN;
     p.total_tiles = (long long)a.N * p.tilesX * p.tilesY * p.tilesN;
     p.bias = a.bias; p.addend = a.addend; p.ref = a.ref; p.relu = a.relu;

@@ -271,6 +271,13 @@ void Engine::layout(Arena& a) {
             gramS[l] = st_ ? a.take<float>((long long)N * vc[l].cout * vc[l].cout) : nullptr;
             ctarget[l] = ct_ ? a.take<float>(n) : nullptr;
             if (st_) wgcap = maxll(wgcap, wgrad_partial_floats(vc[l].cout, vc[l].cout, N));
+            vtsplit[l].hi = vtsplit[l].lo = gsS[l].hi = gsS[l].lo = nullptr;
+            if (st_ && l >= 1) {
+                vtsplit[l].hi = a.take<__nv_bfloat16>(n); vtsplit[l].lo = a.take<__nv_bfloat16>(n);
+                long long ncc = (long long)N * vc[l].cout * vc[l].cout;
+                gsS[l].hi = a.take<__nv_bfloat16>(ncc); gsS[l].lo = a.take<__nv_bfloat16>(ncc);
+                wgcap = maxll(wgcap, gram_tc_partial_floats(N, vc[l].H * vc[l].W, vc[l].cout));
+            }
             vsplit[l].hi = vsplit[l].lo = nullptr;
             if (l >= 1) {
                 long long nin = (long long)N * vc[l].H * vc[l].W * vc[l].cin;
@@ -510,6 +517,7 @@ int Engine::vgg_forward(const float* packed, const float* img3, int upto, float*
             ta.bias = packed + vc[l].offB; ta.relu = 1;
             ta.out_f32 = out;
             if (l < upto && !pool_next) ta.out_split = vsplit[l + 1];     // next conv reads split planes
+            else if (vtsplit[l].hi) ta.out_split = vtsplit[l];            // style tap: Gram kernels read them
             PROF(PC_TC_VGG_FWD, tc_flops(ta), launch_conv3x3_tc(ta, st));
         } else {
             IGemmArgs a;
@@ -565,6 +573,14 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
     FS_CHECK(top >= 0, "no loss layers configured");
     FS_TRY(vgg_forward(packed, img3, top, nullptr, st));
 
+    // split-bf16 planes of activation l after vgg_forward(top): the next conv's input planes, or the
+    // dedicated planes of a style tap that is followed by a pool / is the top layer
+    auto act_planes = [&](int l, int top_) -> SplitPtr {
+        SplitPtr none = {nullptr, nullptr};
+        if (!use_tc || l < 1) return none;
+        if (l < top_ && !vc[l].pool_after) return vsplit[l + 1];
+        return vtsplit[l];
+    };
     // ---- losses (+ the Gram-space gradient S = coef*(G-T))
     for (int l = 0; l <= top; ++l) {
         const VConv& v = vc[l];
@@ -577,10 +593,16 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
             wa.KH = wa.KW = 1; wa.stride = 1;
             wa.OH = v.H; wa.OW = v.W; wa.OC = v.cout; wa.dy_bs = wa.in_bs;
             wa.N = N; wa.per_sample = 1; wa.scale = (float)(1.0 / hwc);
-            PROF(PC_GRAM_FWD, wgrad_flops(wa), launch_wgrad(wa, st));
+            const SplitPtr fp = act_planes(l, top);
+            if (fp.hi)
+                PROF(PC_GRAM_FWD, wgrad_flops(wa), launch_gram_tc(fp, gram[l], wg_partial, wg_partial_cap, N, v.H * v.W,
+                                                                  v.cout, wa.scale, st));
+            else
+                PROF(PC_GRAM_FWD, wgrad_flops(wa), launch_wgrad(wa, st));
             const double cc = (double)v.cout * v.cout;
             FS_TRY(style_loss_grad(gram[l], tg[l], gramS[l], N, v.cout * v.cout,
                                    (float)(4.0 * sw[l] / (cc * hwc)), sw[l] / cc, loss_acc + 1, st));
+            if (need_grad && fp.hi) FS_TRY(pack_gemm_b_tc(gramS[l], gsS[l], N, v.cout, st));
         }
         if (has_c[l])
             FS_TRY(sqdiff_sum(vact[l], ctarget[l], (long long)N * v.H * v.W * v.cout, cw[l] / hwc, loss_acc + 0, st));
@@ -619,8 +641,19 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
         if (!(use_tc && l >= 1)) return 0;
         return split_bf16(vgrad[idx], vgsplit[idx], (long long)N * vc[l].H * vc[l].W * vc[l].cout, st);
     };
-    auto gram_bwd = [&](int l, const float* addend, const float* ref, float* out) -> int {
+    auto gram_bwd = [&](int l, const float* addend, const float* ref, float* out, SplitPtr out_split) -> int {
         const VConv& v = vc[l];
+        const SplitPtr fp = act_planes(l, top);
+        if (fp.hi) {                     // dF = F * S as a per-sample 1x1 tensor-path GEMM
+            Conv3x3TcArgs ta;
+            memset(&ta, 0, sizeof(ta));
+            ta.x = fp; ta.w = gsS[l]; ta.one_by_one = 1; ta.per_sample_w = 1;
+            ta.N = N; ta.H = v.H; ta.W = v.W; ta.C = v.cout; ta.OH = v.H; ta.OW = v.W; ta.OC = v.cout; ta.pad = 0;
+            ta.addend = addend; ta.addH = v.H; ta.addW = v.W; ta.ref = ref;
+            ta.out_f32 = out; ta.out_split = out_split;
+            PROF(PC_GRAM_BWD, tc_flops(ta) / 9.0, launch_conv3x3_tc(ta, st));
+            return 0;
+        }
         IGemmArgs a;
         memset(&a, 0, sizeof(a));
         a.in = vact[l]; a.w = gramS[l]; a.w_bs = (long long)v.cout * v.cout; a.out = out; a.N = N;
@@ -652,8 +685,9 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
                     T = vgrad[ti];
                 }
                 int oi = pick(gi, ti, -1);
-                FS_TRY(gram_bwd(l, T, vact[l], vgrad[oi]));
-                FS_TRY(ensure_split(l, oi));
+                const bool tcg = act_planes(l, top).hi != nullptr;
+                FS_TRY(gram_bwd(l, T, vact[l], vgrad[oi], tcg ? vgsplit[oi] : no_split));
+                if (!tcg) FS_TRY(ensure_split(l, oi));
                 pi = oi;
             } else {
                 int oi = pick(gi, -1, -1);
@@ -671,7 +705,7 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
                     T = vgrad[ti];
                 }
                 ai = pick(pi, ti, -1);
-                FS_TRY(gram_bwd(l, T, nullptr, vgrad[ai]));
+                FS_TRY(gram_bwd(l, T, nullptr, vgrad[ai], no_split));
                 A = vgrad[ai];
             } else if (ct) {
                 ai = pick(pi, -1, -1);

@@ -94,6 +94,8 @@ struct Engine {
     int use_tc = 1;
     SplitPtr vsplit[V_NCONV];            // input planes of VGG conv l (l >= 1)
     SplitPtr vgsplit[4];                 // planes of vgrad[i]
+    SplitPtr vtsplit[V_NCONV];           // planes of a style-tapped activation when no later conv holds them
+    SplitPtr gsS[V_NCONV];               // packed per-sample Gram-space gradients S (tensor-path Gram backward)
     SplitPtr tsplit[T_NCONV];            // input planes of residual conv l (3..12)
     SplitPtr tgsplit[3];                 // planes of tgrad[i] (dRaw of residual convs)
     SplitPtr tw_f[T_NCONV], tw_d[T_NCONV];   // packed residual-conv weights (forward / data gradient)

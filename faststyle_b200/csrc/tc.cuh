@@ -24,6 +24,8 @@ struct Conv3x3TcArgs {
     int N, H, W, C;
     int OH, OW, OC;            // output dims (OC % 64 == 0)
     int pad;                   // zero padding on top/left (SAME: 1, VALID: 0, VALID data gradient: 2)
+    int one_by_one;            // 1: 1x1 'convolution' (pure GEMM over channels); pad must be 0
+    int per_sample_w;          // with one_by_one: weights are [N][C/64][OC][64] (one matrix per sample)
     // epilogue: v = acc + bias[c] + addend[pix,c]; relu; mask by ref[pix,c] > 0
     const float* bias; const float* addend; const float* ref;
     int relu;
@@ -39,5 +41,14 @@ bool conv3x3_tc_supported(int C, int OC, int W, int OW);
 long long wgrad3x3_tc_partial_floats();
 int launch_wgrad3x3_tc(SplitPtr x, SplitPtr dy, float* out, float* partial, long long partial_cap, int N, int H,
                        int W, int OH, int OW, int pad, cudaStream_t st);
+
+
+// B[n][cb][j][k] = S[n][cb*64+k][j] as split planes: packs per-sample [C,C] matrices for a 1x1 tensor-path GEMM
+int pack_gemm_b_tc(const float* S, SplitPtr out, int N, int C, cudaStream_t st);
+
+// tcgen05 Gram matrix G[n] = scale * F[n]^T F[n]; F [N,HW,C] split planes, G [N,C,C] fp32 (C % 64 == 0)
+long long gram_tc_partial_floats(int N, int HW, int C);
+int launch_gram_tc(SplitPtr f, float* G, float* partial, long long partial_cap, int N, int HW, int C, float scale,
+                   cudaStream_t st);
 
 }  // namespace fs

@@ -263,4 +263,228 @@ int launch_wgrad3x3_tc(SplitPtr x, SplitPtr dy, float* out, float* partial, long
     return 0;
 }
 
+
+// =====================================================================================
+// Gram matrix on tcgen05:  G[n][c1][c2] = scale * sum_p F[n,p,c1] * F[n,p,c2]   (reference utils.py:76-81)
+// Work item = (sample, 128-channel row tile, 64-channel column tile, pixel split); operands are MN-major
+// boxes {64 ch, 128 px} of the split planes viewed as [N, HW, C].  HBM/L2-bound for C <= 128.
+// =====================================================================================
+namespace {
+
+constexpr int GP = 128;                               // pixels per chunk
+constexpr int GBOX = GP * 128;                        // bytes of one {64 ch, 128 px} box
+constexpr int G_STAGE = 6 * GBOX;                     // A hi g0,g1 | A lo g0,g1 | B hi | B lo
+constexpr int G_STAGES = 2;
+constexpr int G_SMEM = G_STAGES * G_STAGE + 1024 + 256;
+
+struct GramParams {
+    int N, HW, C, mtiles, ntiles, ksplit, chunks_per_split;
+    float* partial;            // [N][ksplit][C][C]
+};
+
+__global__ void __launch_bounds__(256, 1)
+gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const GramParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_STAGES * G_STAGE);
+    uint64_t* full = bars;
+    uint64_t* empty = full + G_STAGES;
+    uint64_t* done = empty + G_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int item = blockIdx.x;
+    const int ks = item % p.ksplit; item /= p.ksplit;
+    const int nt = item % p.ntiles; item /= p.ntiles;
+    const int mt = item % p.mtiles;
+    const int n = item / p.mtiles;
+    const bool two_groups = p.C >= 128;               // C == 64: the second 64-row half aliases the first
+    const int pix0 = ks * p.chunks_per_split * GP;
+    int nchunks = p.chunks_per_split;
+    {
+        int total = (p.HW + GP - 1) / GP;
+        int first = ks * p.chunks_per_split;
+        if (first + nchunks > total) nchunks = total - first;
+        if (nchunks < 0) nchunks = 0;
+    }
+
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tm_hi); prefetch_tmap(&tm_lo); }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < G_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        int s = 0; uint32_t ph = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* d = smem + s * G_STAGE;
+            const int pix = pix0 + c * GP;
+            mbar_expect_tx(&full[s], (two_groups ? 6 : 4) * GBOX);
+            const int ca = mt * 128, cb = nt * 64;
+            tma_load_4d(d, &tm_hi, &full[s], ca, pix, n, 0);
+            tma_load_4d(d + 2 * GBOX, &tm_lo, &full[s], ca, pix, n, 0);
+            if (two_groups) {
+                tma_load_4d(d + GBOX, &tm_hi, &full[s], ca + 64, pix, n, 0);
+                tma_load_4d(d + 3 * GBOX, &tm_lo, &full[s], ca + 64, pix, n, 0);
+            }
+            tma_load_4d(d + 4 * GBOX, &tm_hi, &full[s], cb, pix, n, 0);
+            tma_load_4d(d + 5 * GBOX, &tm_lo, &full[s], cb, pix, n, 0);
+            if (++s == G_STAGES) { s = 0; ph ^= 1; }
+        }
+    } else if (warp == 1 && lane == 0) {
+        const uint32_t idesc = make_idesc_mn();
+        const uint32_t lbo = two_groups ? (uint32_t)GBOX : 0u;
+        int s = 0; uint32_t ph = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t base = smem_u32(smem + s * G_STAGE);
+            const uint32_t a_hi = base, a_lo = base + 2 * GBOX, b_hi = base + 4 * GBOX, b_lo = base + 5 * GBOX;
+#pragma unroll
+            for (int prod = 0; prod < 3; ++prod) {
+                const uint32_t ab = prod == 2 ? a_lo : a_hi, bb = prod == 1 ? b_lo : b_hi;
+#pragma unroll
+                for (int k = 0; k < GP / 16; ++k)
+                    tc_mma_bf16(tmem_base, make_sdesc_mn(ab + k * 2048, lbo), make_sdesc_mn(bb + k * 2048, 2048), idesc,
+                                (c == 0 && prod == 0 && k == 0) ? 0u : 1u);
+            }
+            tc_commit(&empty[s]);
+            if (++s == G_STAGES) { s = 0; ph ^= 1; }
+        }
+        tc_commit(done);
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        const int row = ew * 32 + lane;
+        mbar_wait(done, 0);
+        tc_fence_after();
+        const int c1 = mt * 128 + row;
+        float* out = p.partial + (((long long)n * p.ksplit + ks) * p.C + c1) * p.C + nt * 64;
+        const bool ok = (two_groups || row < 64) && c1 < p.C;
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ch * 32), v);
+            if (ok) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(out + ch * 32 + i) =
+                        nchunks > 0 ? make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 64);
+}
+
+// G[n][i] = scale * sum_ks partial[n][ks][i]
+__global__ void gram_reduce_kernel(const float* __restrict__ partial, float* __restrict__ G, long long cc4, int N,
+                                   int ksplit, float scale) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cc4 * N) return;
+    long long n = i / cc4, e = i - n * cc4;
+    const float4* p = reinterpret_cast<const float4*>(partial) + n * ksplit * cc4 + e;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < ksplit; ++k) {
+        float4 v = p[(long long)k * cc4];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reinterpret_cast<float4*>(G)[i] = make_float4(s.x * scale, s.y * scale, s.z * scale, s.w * scale);
+}
+
+__global__ void pack_gemm_b_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ hi,
+                                   __nv_bfloat16* __restrict__ lo, int N, int C) {
+    // out index: (((n*CB + cb)*C + j)*64 + k)  <-  S[n][cb*64+k][j]
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)N * C * C;
+    if (i >= total) return;
+    int k = (int)(i & 63);
+    long long r = i >> 6;
+    int j = (int)(r % C); r /= C;
+    int CB = C / 64;
+    int cb = (int)(r % CB);
+    int n = (int)(r / CB);
+    float v = S[((long long)n * C + cb * 64 + k) * C + j];
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+int gram_ksplit(int N, int HW, int C) {
+    int items = N * ((C + 127) / 128) * (C / 64);
+    int ks = (148 + items - 1) / items;
+    int chunks = (HW + GP - 1) / GP;
+    if (ks > chunks) ks = chunks;
+    if (ks < 1) ks = 1;
+    return ks;
+}
+
+int make_map3(CUtensorMap* tm, const __nv_bfloat16* base, int N, int HW, int C) {
+    static EncodeTiledFn enc = nullptr;
+    if (!enc) {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        FS_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) == cudaSuccess && fp,
+                 "cuTensorMapEncodeTiled is not available from the CUDA driver");
+        enc = reinterpret_cast<EncodeTiledFn>(fp);
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)HW, (cuuint64_t)N, 1};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)HW * C * 2, (cuuint64_t)N * HW * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)GP, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(gram %dx%dx%d) failed: %d", N, HW, C, (int)r);
+    return 0;
+}
+
+}  // namespace
+
+long long gram_tc_partial_floats(int N, int HW, int C) { return (long long)N * gram_ksplit(N, HW, C) * C * C; }
+
+int launch_gram_tc(SplitPtr f, float* G, float* partial, long long partial_cap, int N, int HW, int C, float scale,
+                   cudaStream_t st) {
+    FS_CHECK(f.hi && f.lo && G && partial, "gram_tc: NULL argument");
+    FS_CHECK(C % 64 == 0 && C >= 64, "gram_tc: C must be a multiple of 64");
+    GramParams p;
+    p.N = N; p.HW = HW; p.C = C;
+    p.mtiles = (C + 127) / 128; p.ntiles = C / 64;
+    p.ksplit = gram_ksplit(N, HW, C);
+    int chunks = (HW + GP - 1) / GP;
+    p.chunks_per_split = (chunks + p.ksplit - 1) / p.ksplit;
+    p.partial = partial;
+    FS_CHECK((long long)N * p.ksplit * C * C <= partial_cap, "gram_tc: partial workspace too small");
+    CUtensorMap tm_hi, tm_lo;
+    FS_TRY(make_map3(&tm_hi, f.hi, N, HW, C));
+    FS_TRY(make_map3(&tm_lo, f.lo, N, HW, C));
+    static bool attr_set = false;
+    if (!attr_set) {
+        FS_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+        attr_set = true;
+    }
+    int grid = N * p.mtiles * p.ntiles * p.ksplit;
+    gram_tc_kernel<<<grid, 256, G_SMEM, st>>>(tm_hi, tm_lo, p);
+    FS_LAUNCH_CHECK();
+    long long cc4 = (long long)C * C / 4;
+    gram_reduce_kernel<<<cdiv(cc4 * N, 256), 256, 0, st>>>(partial, G, cc4, N, p.ksplit, scale);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int pack_gemm_b_tc(const float* S, SplitPtr out, int N, int C, cudaStream_t st) {
+    FS_CHECK(C % 64 == 0, "pack_gemm_b_tc: C must be a multiple of 64");
+    long long total = (long long)N * C * C;
+    pack_gemm_b_kernel<<<cdiv(total, 256), 256, 0, st>>>(S, out.hi, out.lo, N, C);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace fs
