@@ -100,6 +100,8 @@ long long wgrad_partial_floats(int K, int OC, int groups);
 
 // direct 9x9 stride-1 SAME weight gradient for (CI,CO) in {(16,4),(4,16)}  (direct9x9.cu)
 long long wgrad9x9_partial_floats(int N, int H, int W);
+int launch_conv9x9(const float* in, const float* w, float* out, int N, int H, int W, int CI, int CO, cudaStream_t st);
+int flip_transpose_taps(const float* W, float* Wf, int T, int Ci, int Co, cudaStream_t st);
 int launch_wgrad9x9(const float* in, const float* dy, float* out, float* partial, long long partial_cap, int N,
                     int H, int W, int CI, int CO, cudaStream_t st);
 

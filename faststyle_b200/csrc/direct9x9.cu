@@ -70,6 +70,97 @@ __global__ void __launch_bounds__(NT9) wgrad9x9_kernel(const float* __restrict__
         *reinterpret_cast<float4*>(out + i * CO) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
 }
 
+// Direct forward convolution (also the data gradient, with flipped/transposed weights).
+// CTA = 32x32 output pixels; warp w owns columns 4w..4w+3, lane = row: every thread keeps a
+// 4-pixel x CO register tile, slides a 12-pixel input window along x per (kh, 4-channel group) and
+// reads the weights as warp-wide broadcasts: >= 12 FMAs per shared-memory load.
+constexpr int PITCH = HS + 1;     // row pitch (float4) that spreads the 32 row-lanes over all banks
+
+template <int CI, int CO>
+__global__ void __launch_bounds__(256, 2) conv9x9_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                         float* __restrict__ out, int H, int W) {
+    constexpr int CIQ = CI / 4, COQ = CO / 4;
+    extern __shared__ float4 sm4[];
+    float4* in_s = sm4;                              // [CIQ][HS][PITCH]
+    float4* w_s = sm4 + CIQ * HS * PITCH;            // [81][CI][COQ]
+    const int t = threadIdx.x;
+    const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS, n = blockIdx.z;
+    const float4* in4 = reinterpret_cast<const float4*>(in + (long long)n * H * W * CI);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = t; i < HS * HS * CIQ; i += 256) {
+        int pix = i / CIQ, c4 = i - pix * CIQ;
+        int py = pix / HS, px = pix - py * HS;
+        int yy = y0 - 4 + py, xx = x0 - 4 + px;
+        in_s[(c4 * HS + py) * PITCH + px] =
+            (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(in4 + ((long long)yy * W + xx) * CIQ + c4) : z;
+    }
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    for (int i = t; i < 81 * CI * COQ; i += 256) w_s[i] = __ldg(w4 + i);
+    __syncthreads();
+
+    const int wq = t >> 5, lane = t & 31;
+    float acc[4][CO];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < CO; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
+    for (int kh = 0; kh < 9; ++kh) {
+#pragma unroll 1
+        for (int cq = 0; cq < CIQ; ++cq) {
+            float iv[12][4];
+            const float4* ip = in_s + (cq * HS + lane + kh) * PITCH + 4 * wq;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                float4 v = ip[j];
+                iv[j][0] = v.x; iv[j][1] = v.y; iv[j][2] = v.z; iv[j][3] = v.w;
+            }
+            const float4* wp = w_s + ((kh * 9) * CI + cq * 4) * COQ;
+#pragma unroll
+            for (int kw = 0; kw < 9; ++kw) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                    for (int q = 0; q < COQ; ++q) {
+                        const float4 wv = wp[(kw * CI + c) * COQ + q];
+#pragma unroll
+                        for (int px = 0; px < 4; ++px) {
+                            const float xv = iv[px + kw][c];
+                            acc[px][q * 4 + 0] = fmaf(xv, wv.x, acc[px][q * 4 + 0]);
+                            acc[px][q * 4 + 1] = fmaf(xv, wv.y, acc[px][q * 4 + 1]);
+                            acc[px][q * 4 + 2] = fmaf(xv, wv.z, acc[px][q * 4 + 2]);
+                            acc[px][q * 4 + 3] = fmaf(xv, wv.w, acc[px][q * 4 + 3]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    const int oy = y0 + lane;
+    if (oy >= H) return;
+    float* orow = out + (((long long)n * H + oy) * W) * CO;
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+        const int ox = x0 + 4 * wq + px;
+        if (ox >= W) continue;
+#pragma unroll
+        for (int q = 0; q < COQ; ++q)
+            *reinterpret_cast<float4*>(orow + (long long)ox * CO + q * 4) =
+                make_float4(acc[px][q * 4], acc[px][q * 4 + 1], acc[px][q * 4 + 2], acc[px][q * 4 + 3]);
+    }
+}
+
+// Wf[80-tap][co][ci] = W[tap][ci][co]: weights that turn the data gradient into a forward convolution
+__global__ void flip_transpose_taps_kernel(const float* __restrict__ W, float* __restrict__ Wf, int T, int Ci, int Co) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)T * Ci * Co) return;
+    int ci = (int)(i % Ci);
+    long long r = i / Ci;
+    int co = (int)(r % Co);
+    int tf = (int)(r / Co);
+    Wf[i] = W[((long long)(T - 1 - tf) * Ci + ci) * Co + co];
+}
+
 // out[i] = sum_b partial[b][i]; 32 elements x 8 block-slices per CTA, fixed summation order
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                                               int elems, int nblocks) {
@@ -90,6 +181,31 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 }
 
 }  // namespace
+
+// 9x9 stride-1 SAME convolution, in [N,H,W,CI] -> out [N,H,W,CO], w [81,CI,CO]; (CI,CO) in {(4,16),(16,4)}
+int launch_conv9x9(const float* in, const float* w, float* out, int N, int H, int W, int CI, int CO, cudaStream_t st) {
+    FS_CHECK((CI == 16 && CO == 4) || (CI == 4 && CO == 16), "conv9x9: unsupported channel block %dx%d", CI, CO);
+    dim3 grid(cdiv(W, TS), cdiv(H, TS), N);
+    const size_t smem = (size_t)((CI / 4) * HS * PITCH + 81 * CI * (CO / 4)) * sizeof(float4);
+    if (CI == 4) {
+        static bool set = false;
+        if (!set) { FS_CUDA(cudaFuncSetAttribute(conv9x9_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+        conv9x9_kernel<4, 16><<<grid, 256, smem, st>>>(in, w, out, H, W);
+    } else {
+        static bool set = false;
+        if (!set) { FS_CUDA(cudaFuncSetAttribute(conv9x9_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+        conv9x9_kernel<16, 4><<<grid, 256, smem, st>>>(in, w, out, H, W);
+    }
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int flip_transpose_taps(const float* W, float* Wf, int T, int Ci, int Co, cudaStream_t st) {
+    long long n = (long long)T * Ci * Co;
+    flip_transpose_taps_kernel<<<cdiv(n, 256), 256, 0, st>>>(W, Wf, T, Ci, Co);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
 
 long long wgrad9x9_partial_floats(int N, int H, int W) {
     return (long long)N * cdiv(H, TS) * cdiv(W, TS) * 81 * 64;

@@ -12,6 +12,9 @@
 namespace fs {
 
 static const float IN_EPS = 1e-3f;       // reference im_transf_net.py:218
+static bool s2_collapsed(const TConv& c);
+// 9x9 stride-1 SAME layers with a 4x16 / 16x4 channel block run on the direct shared-memory kernels
+static bool direct9(const TConv& c) { return c.k == 9 && c.stride == 1 && c.same && !c.upconv && c.cin_s * c.cout_s == 64; }
 
 // ---------------------------------------------------------------- live per-kernel timing
 // Optional CUDA-event instrumentation of the GEMM-class launches of a step (bench.py roofline).
@@ -224,7 +227,7 @@ void Engine::layout(Arena& a) {
             if (l == 0 || l == 15) weff[l] = a.take<float>((long long)c.k * c.k * c.cin_s * c.cout_s);
             if (c.upconv) weff[l] = a.take<float>(16LL * c.cin * c.cout);
             if (tbw && l > 0) {
-                long long n2 = c.upconv ? 16LL * c.cin * c.cout : (long long)c.k * c.k * c.cin_s * c.cout_s;
+                long long n2 = (c.upconv || c.stride == 2) ? 16LL * c.cin * c.cout : (long long)c.k * c.k * c.cin_s * c.cout_s;
                 wefft[l] = a.take<float>(n2);
                 }
             if (tbw) {
@@ -329,11 +332,18 @@ int Engine::prep_transform_weights(const float* params, bool need_bwd, cudaStrea
         for (int l = 1; l < T_NCONV; ++l) {
             const TConv& c = tc[l];
             const float* src = weff[l] ? weff[l] : params + c.offW;
-            if (c.upconv) FS_TRY(transpose_taps(src, wefft[l], 4, c.cin, 4 * c.cout, st));
+            if (direct9(c)) FS_TRY(flip_transpose_taps(src, wefft[l], c.k * c.k, c.cin_s, c.cout_s, st));
+            else if (c.upconv) FS_TRY(transpose_taps(src, wefft[l], 4, c.cin, 4 * c.cout, st));
+            else if (s2_collapsed(c)) FS_TRY(s2_dgrad_collapse(src, wefft[l], c.cin, c.cout, st));
             else FS_TRY(transpose_taps(src, wefft[l], c.k * c.k, c.cin_s, c.cout_s, st));
         }
     }
     return 0;
+}
+
+// stride-2 3x3 SAME convs on even inputs (TF pad 0/1): data gradient runs in the 4-phase 2x2 form
+static bool s2_collapsed(const TConv& c) {
+    return !c.upconv && c.k == 3 && c.stride == 2 && c.pad_t == 0 && c.pad_l == 0 && c.inH % 2 == 0 && c.inW % 2 == 0;
 }
 
 static void conv_fwd_args(const TConv& c, int N, const float* in, const float* w, float* out, IGemmArgs& a) {
@@ -366,6 +376,10 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
             ta.N = N; ta.H = c.inH; ta.W = c.inW; ta.C = 64; ta.OH = c.outH; ta.OW = c.outW; ta.OC = 64; ta.pad = 0;
             ta.out_f32 = tb[l].raw;
             PROF(PC_TC_RES_FWD, tc_flops(ta), launch_conv3x3_tc(ta, st));
+        } else if (direct9(c)) {
+            IGemmArgs a;
+            conv_fwd_args(c, N, cur, weff[l], tb[l].raw, a);
+            PROF(PC_FFMA_CONV, igemm_flops(a), launch_conv9x9(cur, weff[l], tb[l].raw, N, c.inH, c.inW, c.cin_s, c.cout_s, st));
         } else {
             IGemmArgs a;
             conv_fwd_args(c, N, cur, weff[l] ? weff[l] : params + c.offW, tb[l].raw, a);
@@ -464,12 +478,22 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
             if (first_of_block) { held = -1; resid_dOut = nullptr; }
             continue;
         }
+        if (direct9(c)) {                        // data gradient = forward 9x9 conv with flipped weights
+            const double fl = 2.0 * N * c.inH * c.inW * 81.0 * c.cin_s * c.cout_s;
+            PROF(PC_FFMA_CONV, fl, launch_conv9x9(dRaw, wefft[l], dPrev, N, c.inH, c.inW, c.cout_s, c.cin_s, st));
+            dAct = dPrev; cur = pidx;
+            continue;
+        }
         IGemmArgs a;
         memset(&a, 0, sizeof(a));
         a.in = dRaw; a.w = wefft[l]; a.out = dPrev; a.N = N; a.gather = 1;
         if (c.upconv) {
             a.H = c.inH; a.W = c.inW; a.C = 4 * c.cout; a.in_mode = 1;
             a.in_bs = (long long)c.outH * c.outW * c.cout;
+            a.KH = a.KW = 2; a.stride = 1; a.pad_t = a.pad_l = 0;
+        } else if (s2_collapsed(c)) {
+            a.H = c.outH; a.W = c.outW; a.C = c.cout_s; a.in_mode = 0;
+            a.in_bs = (long long)c.outH * c.outW * c.cout_s;
             a.KH = a.KW = 2; a.stride = 1; a.pad_t = a.pad_l = 0;
         } else {
             a.H = c.outH; a.W = c.outW; a.C = c.cout_s; a.in_mode = 0;
@@ -478,6 +502,9 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         }
         a.OH = c.inH; a.OW = c.inW; a.OC = c.cin_s;
         a.out_bs = (long long)c.inH * c.inW * c.cin_s;
+        if (!c.upconv && s2_collapsed(c)) {          // 4 phases as channels, depth-to-space store
+            a.OH = c.inH / 2; a.OW = c.inW / 2; a.OC = 4 * c.cin_s; a.out_mode = 1;
+        }
         if (first_of_block) {                    // add the skip-path gradient, zero-padded by 2 px
             a.addend = resid_dOut; a.add_crop = 2; a.addH = resid_H; a.addW = resid_W;
             a.add_bs = (long long)resid_H * resid_W * 64;

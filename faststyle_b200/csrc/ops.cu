@@ -541,6 +541,24 @@ __global__ void upconv_collapse_grad_kernel(const float* __restrict__ dWc, float
     dW[i] = s;
 }
 
+// Stride-2 3x3 SAME(pad 0/1) data gradient as a 4-phase 2x2 gather over dy (sub-pixel form):
+//   dx[2m+p, 2n+q, ci] = sum_{a,b,co} dy[m-a, n-b, co] * Wd[a][b][co][(p*2+q)*Ci + ci]
+// with kh(p,a): p=0 -> {0,2}, p=1 -> {1,-};   2.25x fewer MACs than gathering all 9 taps.
+__global__ void s2_dgrad_collapse_kernel(const float* __restrict__ W, float* __restrict__ Wd, int Ci, int Co) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = 16LL * Ci * Co;
+    if (i >= total) return;
+    int ci = (int)(i % Ci);
+    long long r = i / Ci;
+    int pq = (int)(r % 4); r /= 4;
+    int co = (int)(r % Co); r /= Co;
+    int b = (int)(r % 2), a = (int)(r / 2);
+    int p = pq >> 1, q = pq & 1;
+    int kh = p == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : -1);
+    int kw = q == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : -1);
+    Wd[i] = (kh >= 0 && kw >= 0) ? W[(((long long)kh * 3 + kw) * Ci + ci) * Co + co] : 0.f;
+}
+
 inline int grid1(long long n, int bs = 256) { return (int)((n + bs - 1) / bs); }
 
 }  // namespace
@@ -710,6 +728,12 @@ int upconv_collapse(const float* W, float* Wc, int Ci, int Co, cudaStream_t st) 
 }
 int upconv_collapse_grad(const float* dWc, float* dW, int Ci, int Co, cudaStream_t st) {
     upconv_collapse_grad_kernel<<<grid1(9LL * Ci * Co), 256, 0, st>>>(dWc, dW, Ci, Co);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int s2_dgrad_collapse(const float* W, float* Wd, int Ci, int Co, cudaStream_t st) {
+    s2_dgrad_collapse_kernel<<<grid1(16LL * Ci * Co), 256, 0, st>>>(W, Wd, Ci, Co);
     FS_LAUNCH_CHECK();
     return 0;
 }

@@ -55,6 +55,8 @@ int transpose_taps(const float* src, float* dst, int T, int Ci, int Co, cudaStre
 // resize-conv collapse W[3,3,Ci,Co] -> W'[2,2,Ci,4Co] and its adjoint for gradients
 int upconv_collapse(const float* W, float* Wc, int Ci, int Co, cudaStream_t st);
 int upconv_collapse_grad(const float* dWc, float* dW, int Ci, int Co, cudaStream_t st);
+// 3x3 stride-2 (pad 0/1) conv: weights of the 4-phase 2x2 data-gradient form, [2][2][Co][4*Ci]
+int s2_dgrad_collapse(const float* W, float* Wd, int Ci, int Co, cudaStream_t st);
 
 int fill_zero(void* p, size_t bytes, cudaStream_t st);
 
