@@ -109,6 +109,32 @@ def load_style_image():
 
 
 # ----------------------------------------------------------------------------- CPU (oracle) arm
+def pick_cpu_threads():
+    """Thread count for the CPU arm: the best of a short calibration over {8,16,32,64,all} cores
+    (on a shared host `all` is often far slower than fewer threads - cgroup limits, SMT, NUMA)."""
+    from oracle import ckpt as ockpt, restate as R
+    params = ockpt.load(os.path.join(GOLDEN, "starry_final.ckpt"))
+    x = synthetic_batch(0, 2).numpy()
+    ncpu = os.cpu_count() or 1
+    try:
+        ncpu = min(ncpu, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu} | {ncpu})
+    best, best_t = ncpu, float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        with torch.no_grad():
+            R.create_net(x, params, "resize")
+            t0 = time.perf_counter()
+            R.create_net(x, params, "resize")
+            dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_train_step_setup():
     from oracle import ckpt as ockpt, restate as R
     from faststyle_b200 import synth
@@ -132,7 +158,7 @@ def run_reference(args, rank, world):
     host threads.  Only rank 0 works."""
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)
+    pick_cpu_threads()
     step = cpu_train_step_setup()
     sample_b = 4
     x = synthetic_batch(0, sample_b).numpy()
@@ -249,7 +275,10 @@ def run_ours(args, rank, local_rank, world):
         # whole-step tensor-pipe view (algorithmic FLOPs of one step / step time)
         step_tflops = GFLOP_PER_IMAGE_TRAIN * PER_GPU_BATCH / (ms / args.steps / 1e3) / 1e3
         # dominant kernel live: VGG conv3x3 64->64 @256^2 (conv1_2 shape) through the op C-ABI
-        prof = live_kernel_profile(eng, step_device)
+        def step_local():           # rank-local (no collective): the other ranks are waiting at the barrier below
+            eng.train_fwd_bwd(params, packed, x_dev, cfg, tgrams, grads=grads, losses=losses)
+            opt.step(grads)
+        prof = live_kernel_profile(eng, step_local)
         roof = dominant_kernel_roofline(prof, peaks, ms / args.steps)
         roof["step_tflops"] = step_tflops
         roof["step_frac_of_sustained"] = step_tflops / peaks["bf16_tflops_sustained"]
@@ -285,7 +314,8 @@ def run_ours(args, rank, local_rank, world):
 
 
 PROF_CATS = ["tc_vgg_conv_fwd", "tc_vgg_conv_dgrad", "tc_res_conv_fwd", "tc_res_conv_dgrad",
-             "ffma_conv", "wgrad", "gram_fwd", "gram_bwd"]
+             "ffma_conv", "wgrad", "gram_fwd", "gram_bwd", "instnorm_stats", "instnorm_apply", "instnorm_bwd",
+             "pointwise", "losses", "weight_prep"]
 
 
 def live_kernel_profile(eng, step_fn, steps=3):
@@ -354,7 +384,7 @@ def bench_forward(dev, params):
 
 
 def cpu_baseline():
-    torch.set_num_threads(os.cpu_count() or 1)
+    pick_cpu_threads()
     step = cpu_train_step_setup()
     b = 4
     x = synthetic_batch(0, b).numpy()

@@ -331,6 +331,28 @@ __global__ void pack_w3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __r
     lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+struct PackBatch { const float* w[16]; __nv_bfloat16* hi[16]; __nv_bfloat16* lo[16]; };
+
+__global__ void pack_w3x3_batch_kernel(const PackBatch pb, int Ci, int Co, int mode) {
+    const float* __restrict__ w = pb.w[blockIdx.y];
+    __nv_bfloat16* __restrict__ hi = pb.hi[blockIdx.y];
+    __nv_bfloat16* __restrict__ lo = pb.lo[blockIdx.y];
+    const int Kc = mode == 0 ? Ci : Co, Nn = mode == 0 ? Co : Ci, CB = Kc / 64;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 9LL * Kc * Nn) return;
+    int k = (int)(i % 64);
+    long long r = i / 64;
+    int n = (int)(r % Nn); r /= Nn;
+    int cb = (int)(r % CB);
+    int tap = (int)(r / CB);
+    int kh = tap / 3, kw = tap % 3;
+    float v = mode == 0 ? w[(((long long)kh * 3 + kw) * Ci + cb * 64 + k) * Co + n]
+                        : w[(((long long)(2 - kh) * 3 + (2 - kw)) * Ci + n) * Co + cb * 64 + k];
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -435,6 +457,17 @@ int split_bf16(const float* x, SplitPtr out, long long n, cudaStream_t st) {
     FS_CHECK(n % 4 == 0, "split_bf16: n %% 4 != 0");
     long long n4 = n / 4;
     split_bf16_kernel<<<cdiv(n4, 256), 256, 0, st>>>(x, out.hi, out.lo, n4);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int pack_w3x3_tc_batch(const float* const* w, const SplitPtr* out, int count, int Ci, int Co, int mode, cudaStream_t st) {
+    FS_CHECK(count >= 1 && count <= 16, "pack_w3x3_tc_batch: 1..16 matrices per launch");
+    FS_CHECK(Ci % 64 == 0 && Co % 64 == 0, "pack_w3x3_tc_batch: channels must be multiples of 64");
+    PackBatch pb;
+    for (int i = 0; i < count; ++i) { pb.w[i] = w[i]; pb.hi[i] = out[i].hi; pb.lo[i] = out[i].lo; }
+    dim3 grid(cdiv(9LL * Ci * Co, 256), count);
+    pack_w3x3_batch_kernel<<<grid, 256, 0, st>>>(pb, Ci, Co, mode);
     FS_LAUNCH_CHECK();
     return 0;
 }

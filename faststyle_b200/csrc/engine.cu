@@ -313,29 +313,30 @@ int Engine::bind(void* ws, size_t bytes) {
 // ---------------------------------------------------------------- transform net
 int Engine::prep_transform_weights(const float* params, bool need_bwd, cudaStream_t st) {
     FS_CHECK(bound && (flags & ENG_TRANSFORM), "engine has no transform plan / workspace");
-    FS_TRY(pad_taps(params + tc[0].offW, weff[0], 81, 3, 16, 4, 16, st));
-    FS_TRY(pad_taps(params + tc[15].offW, weff[15], 81, 16, 3, 16, 4, st));
-    FS_TRY(upconv_collapse(params + tc[13].offW, weff[13], tc[13].cin, tc[13].cout, st));
-    FS_TRY(upconv_collapse(params + tc[14].offW, weff[14], tc[14].cin, tc[14].cout, st));
+    PROF(PC_PREP, 0.0, pad_taps(params + tc[0].offW, weff[0], 81, 3, 16, 4, 16, st));
+    PROF(PC_PREP, 0.0, pad_taps(params + tc[15].offW, weff[15], 81, 16, 3, 16, 4, st));
+    PROF(PC_PREP, 0.0, upconv_collapse(params + tc[13].offW, weff[13], tc[13].cin, tc[13].cout, st));
+    PROF(PC_PREP, 0.0, upconv_collapse(params + tc[14].offW, weff[14], tc[14].cin, tc[14].cout, st));
     // 4-channel staging of the last layer's IN scale/shift (its flat slots are 3 floats, unaligned)
     FS_TRY(fill_zero(in15, 8 * sizeof(float), st));
     FS_CUDA(cudaMemcpyAsync(in15, params + tc[15].offG, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     FS_CUDA(cudaMemcpyAsync(in15 + 4, params + tc[15].offB, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (use_tc) {
-        for (int l = 3; l <= 12; ++l) {
-            FS_TRY(pack_w3x3_tc(params + tc[l].offW, tw_f[l], 64, 64, 0, st));
-            if (need_bwd) FS_TRY(pack_w3x3_tc(params + tc[l].offW, tw_d[l], 64, 64, 1, st));
-        }
+        const float* wsrc[10];
+        for (int l = 3; l <= 12; ++l) wsrc[l - 3] = params + tc[l].offW;
+        PROF(PC_PREP, 0.0, pack_w3x3_tc_batch(wsrc, &tw_f[3], 10, 64, 64, 0, st));
+        if (need_bwd) PROF(PC_PREP, 0.0, pack_w3x3_tc_batch(wsrc, &tw_d[3], 10, 64, 64, 1, st));
     }
     if (need_bwd) {
         FS_CHECK(flags & ENG_TRANSFORM_BWD, "engine was not created with a backward plan");
         for (int l = 1; l < T_NCONV; ++l) {
             const TConv& c = tc[l];
             const float* src = weff[l] ? weff[l] : params + c.offW;
-            if (direct9(c)) FS_TRY(flip_transpose_taps(src, wefft[l], c.k * c.k, c.cin_s, c.cout_s, st));
-            else if (c.upconv) FS_TRY(transpose_taps(src, wefft[l], 4, c.cin, 4 * c.cout, st));
-            else if (s2_collapsed(c)) FS_TRY(s2_dgrad_collapse(src, wefft[l], c.cin, c.cout, st));
-            else FS_TRY(transpose_taps(src, wefft[l], c.k * c.k, c.cin_s, c.cout_s, st));
+            if (use_tc && l >= 3 && l <= 12) continue;          // tensor path: packed above, no fp32 transpose
+            if (direct9(c)) PROF(PC_PREP, 0.0, flip_transpose_taps(src, wefft[l], c.k * c.k, c.cin_s, c.cout_s, st));
+            else if (c.upconv) PROF(PC_PREP, 0.0, transpose_taps(src, wefft[l], 4, c.cin, 4 * c.cout, st));
+            else if (s2_collapsed(c)) PROF(PC_PREP, 0.0, s2_dgrad_collapse(src, wefft[l], c.cin, c.cout, st));
+            else PROF(PC_PREP, 0.0, transpose_taps(src, wefft[l], c.k * c.k, c.cin_s, c.cout_s, st));
         }
     }
     return 0;
@@ -364,7 +365,7 @@ static void conv_fwd_args(const TConv& c, int N, const float* in, const float* w
 
 int Engine::transform_forward(const float* params, const float* x3, float* y3_out, cudaStream_t st) {
     FS_CHECK(bound && (flags & ENG_TRANSFORM), "engine has no transform plan / workspace");
-    FS_TRY(reflect_pad_c4(x3, xpad4, N, H, W, 40, st));
+    PROF(PC_POINTWISE, 0.0, reflect_pad_c4(x3, xpad4, N, H, W, 40, st));
     const float* cur = xpad4;
     for (int l = 0; l < T_NCONV; ++l) {
         const TConv& c = tc[l];
@@ -385,7 +386,7 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
             conv_fwd_args(c, N, cur, weff[l] ? weff[l] : params + c.offW, tb[l].raw, a);
             PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
         }
-        FS_TRY(instnorm_stats(tb[l].raw, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, in_partial, st));
+        PROF(PC_IN_STATS, 0.0, instnorm_stats(tb[l].raw, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, in_partial, st));
         const float* skip = nullptr;
         if (l >= 4 && l <= 12 && (l & 1) == 0) skip = tb[l - 2].act;       // residual: block input
         const bool last = l == T_NCONV - 1;
@@ -393,7 +394,7 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
         const float* b = last ? in15 + 4 : params + c.offB;
         float* out = last ? (y3_out ? y3_out : y3) : tb[l].act;
         const bool next_tc = use_tc && (l + 1) >= 3 && (l + 1) <= 12;      // next conv consumes split planes
-        FS_TRY(instnorm_apply(tb[l].raw, tb[l].mean, tb[l].rstd, g, b, skip, out, N, c.outH, c.outW,
+        PROF(PC_IN_APPLY, 0.0, instnorm_apply(tb[l].raw, tb[l].mean, tb[l].rstd, g, b, skip, out, N, c.outH, c.outW,
                               c.cout_s, c.act, last ? 1 : 0, st, next_tc ? tsplit[l + 1].hi : nullptr,
                               next_tc ? tsplit[l + 1].lo : nullptr));
         cur = tb[l].act;
@@ -423,7 +424,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         const int ri = pick2(cur, held);
         float* dRaw = tgrad[ri];
         const bool tcl = use_tc && l >= 3 && l <= 12;
-        FS_TRY(instnorm_bwd(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw, dg, db, N,
+        PROF(PC_IN_BWD, 0.0, instnorm_bwd(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw, dg, db, N,
                             c.outH * c.outW, c.cout_s, c.act, in_partial, m12, st,
                             tcl ? tgsplit[ri].hi : nullptr, tcl ? tgsplit[ri].lo : nullptr));
         if (last) {
@@ -443,7 +444,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
             wa.dy_bs = (long long)c.outH * c.outW * c.cout;
             wa.out = wg_tmp;
             PROF(PC_WGRAD, wgrad_flops(wa), launch_wgrad(wa, st));
-            FS_TRY(upconv_collapse_grad(wg_tmp, grads + c.offW, c.cin, c.cout, st));
+            PROF(PC_PREP, 0.0, upconv_collapse_grad(wg_tmp, grads + c.offW, c.cin, c.cout, st));
         } else {
             wa.C = c.cin_s; wa.KH = wa.KW = c.k; wa.stride = c.stride; wa.pad_t = c.pad_t; wa.pad_l = c.pad_l;
             wa.OH = c.outH; wa.OW = c.outW; wa.OC = c.cout_s; wa.dy_mode = 0;
@@ -458,7 +459,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
                                                                 c.inH, c.inW, c.cin_s, c.cout_s, st));
             else
                 PROF(PC_WGRAD, wgrad_flops(wa), launch_wgrad(wa, st));
-            if (padded) FS_TRY(unpad_taps(wg_tmp, grads + c.offW, c.k * c.k, c.cin, c.cout, c.cin_s, c.cout_s, st));
+            if (padded) PROF(PC_PREP, 0.0, unpad_taps(wg_tmp, grads + c.offW, c.k * c.k, c.cin, c.cout, c.cin_s, c.cout_s, st));
         }
         if (l == 0) break;                       // no gradient w.r.t. the input image (train.py:198-204)
         // ---- data gradient -> gradient w.r.t. the previous layer's activation
@@ -530,7 +531,7 @@ int Engine::vgg_forward(const float* packed, const float* img3, int upto, float*
                         cudaStream_t st) {
     FS_CHECK(bound && (flags & ENG_VGG), "engine has no VGG plan / workspace");
     FS_CHECK(upto >= 0 && upto < V_NCONV, "vgg_forward: bad layer %d", upto);
-    FS_TRY(vgg_preprocess_c4(img3, v_in4, (long long)N * VH * VW, st));
+    PROF(PC_POINTWISE, 0.0, vgg_preprocess_c4(img3, v_in4, (long long)N * VH * VW, st));
     const float* cur = v_in4;
     for (int l = 0; l <= upto; ++l) {
         float* out = (act_override && act_override[l]) ? act_override[l] : vact[l];
@@ -551,12 +552,12 @@ int Engine::vgg_forward(const float* packed, const float* img3, int upto, float*
             vgg_conv_args(vc[l], N, packed, cur, out, a);
             PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
             if (use_tc && l < upto && !pool_next)
-                FS_TRY(split_bf16(out, vsplit[l + 1], (long long)N * vc[l].H * vc[l].W * vc[l].cout, st));
+                PROF(PC_POINTWISE, 0.0, split_bf16(out, vsplit[l + 1], (long long)N * vc[l].H * vc[l].W * vc[l].cout, st));
         }
         cur = out;
         if (pool_next) {
             const bool sp = use_tc != 0;
-            FS_TRY(maxpool2x2_fwd(cur, vpool[l], N, vc[l].H, vc[l].W, vc[l].cout, st,
+            PROF(PC_POINTWISE, 0.0, maxpool2x2_fwd(cur, vpool[l], N, vc[l].H, vc[l].W, vc[l].cout, st,
                                   sp ? vsplit[l + 1].hi : nullptr, sp ? vsplit[l + 1].lo : nullptr));
             cur = vpool[l];
         }
@@ -627,12 +628,12 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
             else
                 PROF(PC_GRAM_FWD, wgrad_flops(wa), launch_wgrad(wa, st));
             const double cc = (double)v.cout * v.cout;
-            FS_TRY(style_loss_grad(gram[l], tg[l], gramS[l], N, v.cout * v.cout,
+            PROF(PC_LOSS, 0.0, style_loss_grad(gram[l], tg[l], gramS[l], N, v.cout * v.cout,
                                    (float)(4.0 * sw[l] / (cc * hwc)), sw[l] / cc, loss_acc + 1, st));
-            if (need_grad && fp.hi) FS_TRY(pack_gemm_b_tc(gramS[l], gsS[l], N, v.cout, st));
+            if (need_grad && fp.hi) PROF(PC_PREP, 0.0, pack_gemm_b_tc(gramS[l], gsS[l], N, v.cout, st));
         }
         if (has_c[l])
-            FS_TRY(sqdiff_sum(vact[l], ctarget[l], (long long)N * v.H * v.W * v.cout, cw[l] / hwc, loss_acc + 0, st));
+            PROF(PC_LOSS, 0.0, sqdiff_sum(vact[l], ctarget[l], (long long)N * v.H * v.W * v.cout, cw[l] / hwc, loss_acc + 0, st));
     }
     if (!need_grad) return 0;
 
@@ -708,18 +709,18 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
                 int ti = -1; const float* T = nullptr;
                 if (gp || ct) {
                     ti = pick(gi, -1, -1);
-                    FS_TRY(pool_bwd_combine(vact[l], gp, ct, cw2, 0, vgrad[ti], N, v.H, v.W, v.cout, st));
+                    PROF(PC_POINTWISE, 0.0, pool_bwd_combine(vact[l], gp, ct, cw2, 0, vgrad[ti], N, v.H, v.W, v.cout, st));
                     T = vgrad[ti];
                 }
                 int oi = pick(gi, ti, -1);
                 const bool tcg = act_planes(l, top).hi != nullptr;
                 FS_TRY(gram_bwd(l, T, vact[l], vgrad[oi], tcg ? vgsplit[oi] : no_split));
-                if (!tcg) FS_TRY(ensure_split(l, oi));
+                if (!tcg) PROF(PC_POINTWISE, 0.0, ensure_split(l, oi));
                 pi = oi;
             } else {
                 int oi = pick(gi, -1, -1);
-                FS_TRY(pool_bwd_combine(vact[l], gp, ct, cw2, 1, vgrad[oi], N, v.H, v.W, v.cout, st));
-                FS_TRY(ensure_split(l, oi));
+                PROF(PC_POINTWISE, 0.0, pool_bwd_combine(vact[l], gp, ct, cw2, 1, vgrad[oi], N, v.H, v.W, v.cout, st));
+                PROF(PC_POINTWISE, 0.0, ensure_split(l, oi));
                 pi = oi;
             }
         } else {
@@ -728,7 +729,7 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
                 int ti = -1; const float* T = nullptr;
                 if (ct) {
                     ti = pick(pi, -1, -1);
-                    FS_TRY(pool_bwd_combine(vact[l], nullptr, ct, cw2, 0, vgrad[ti], N, v.H, v.W, v.cout, st));
+                    PROF(PC_POINTWISE, 0.0, pool_bwd_combine(vact[l], nullptr, ct, cw2, 0, vgrad[ti], N, v.H, v.W, v.cout, st));
                     T = vgrad[ti];
                 }
                 ai = pick(pi, ti, -1);
@@ -736,7 +737,7 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
                 A = vgrad[ai];
             } else if (ct) {
                 ai = pick(pi, -1, -1);
-                FS_TRY(pool_bwd_combine(vact[l], nullptr, ct, cw2, 0, vgrad[ai], N, v.H, v.W, v.cout, st));
+                PROF(PC_POINTWISE, 0.0, pool_bwd_combine(vact[l], nullptr, ct, cw2, 0, vgrad[ai], N, v.H, v.W, v.cout, st));
                 A = vgrad[ai];
             }
             int oi = pick(pi, ai, -1);
@@ -761,7 +762,7 @@ int Engine::train_fwd_bwd(const float* params, const float* packed, const float*
     FS_TRY(vgg_content_targets(packed, x3, lc, st));                  // train.py:250-251
     FS_TRY(transform_forward(params, x3, Y, st));                     // train.py:161
     FS_TRY(vgg_loss_backward(packed, Y, lc, target_grams, true, st)); // train.py:165-184 + autodiff
-    if (lc.beta != 0.f) FS_TRY(tv_loss_grad(Y, dY4, N, VH, VW, lc.beta, loss_acc + 2, st));
+    if (lc.beta != 0.f) PROF(PC_LOSS, 0.0, tv_loss_grad(Y, dY4, N, VH, VW, lc.beta, loss_acc + 2, st));
     FS_TRY(transform_backward(params, dY4, grads, st));
     FS_TRY(finalize_losses(loss_acc, losses4, st));
     return 0;

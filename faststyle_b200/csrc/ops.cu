@@ -580,7 +580,7 @@ int vgg_preprocess_c4(const float* x, float* out, long long npix, cudaStream_t s
 
 int in_chunks(int N, int HW) {
     int c = (148 * 4 + N - 1) / N;
-    int maxc = HW / 1024;
+    int maxc = HW / 128;             // >= 128 pixels per chunk: enough CTAs to cover the SMs on small planes
     if (maxc < 1) maxc = 1;
     if (c > maxc) c = maxc;
     if (c > 64) c = 64;

@@ -17,6 +17,8 @@ int split_bf16(const float* x, SplitPtr out, long long n, cudaStream_t st);
 //   mode 1 (data gradient):  B[tap=(2-kh,2-kw)][cb][n=ci][k=co%64]      = W[kh,kw,n,cb*64+k]
 // Output: hi/lo planes of 9*(K/64)*N*64 bf16 each (K = reduction channels, N = output channels).
 int pack_w3x3_tc(const float* w, SplitPtr out, int Ci, int Co, int mode, cudaStream_t st);
+// same for up to 16 equally shaped weight tensors in ONE launch
+int pack_w3x3_tc_batch(const float* const* w, const SplitPtr* out, int count, int Ci, int Co, int mode, cudaStream_t st);
 
 struct Conv3x3TcArgs {
     SplitPtr x;                // input  [N,H,W,C]  split bf16 planes (C % 64 == 0)
