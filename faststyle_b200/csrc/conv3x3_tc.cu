@@ -29,7 +29,6 @@ using namespace tcptx;
 
 constexpr int TW = 16;            // tile width in pixels (16 px * 128 B = 2048 B per slab row)
 constexpr int KB = 64;            // channels per K block (= one 128-byte swizzle row of bf16)
-constexpr int A_STAGES = 2;
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row (1024 B) swizzle atoms.
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
@@ -65,6 +64,7 @@ struct TcParams {
 template <int TH, int BN>
 struct Cfg {
     static constexpr int NACC = TH / 8;
+    static constexpr int A_STAGES = (TH == 8) ? 3 : 2;             // small tiles: deeper slab ring (latency-bound)
     static constexpr int B_STAGES = (BN == 64) ? 4 : 2;
     static constexpr int SLAB_BYTES = (TH + 2) * TW * 128;        // one plane
     static constexpr int A_STAGE_BYTES = 2 * SLAB_BYTES;          // hi + lo
@@ -80,6 +80,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                   const TcParams p) {
     using K = Cfg<TH, BN>;
+    constexpr int A_STAGES = K::A_STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smemA = smem;
@@ -448,7 +449,13 @@ int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st) {
     FS_CHECK(a.out_f32 || a.out_split.hi, "conv3x3_tc: no output requested");
     FS_CHECK((a.out_split.hi == nullptr) == (a.out_split.lo == nullptr), "conv3x3_tc: split output needs both planes");
     FS_CHECK(a.OH > 0 && a.OW > 0 && a.N > 0, "conv3x3_tc: empty output");
-    const bool tall = a.OH > 8;
+    bool tall = a.OH > 8;
+    // small 64->64 problems (the residual convs): 16-row tiles give < 1.5 waves; 8-row tiles balance the SMs
+    // and their 3-deep slab ring hides the L2 miss latency
+    if (tall && a.C == 64 && a.OC == 64 && !a.one_by_one) {
+        long long tiles16 = (long long)a.N * cdiv(a.OH, 16) * cdiv(a.OW, TW);
+        if (tiles16 * 2 < 3LL * num_sms()) tall = false;
+    }
     if (a.OC % 128 == 0) return tall ? launch_cfg<16, 128>(a, st) : launch_cfg<8, 128>(a, st);
     return tall ? launch_cfg<16, 64>(a, st) : launch_cfg<8, 64>(a, st);
 }

@@ -5,6 +5,7 @@
 // halo) once in shared memory and every thread owns one (tap, 4x4 channel block) of the
 // 81 x CI x CO weight-gradient, so each staged element is reused 81 times from SMEM.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace fs {
 
@@ -150,6 +151,178 @@ __global__ void __launch_bounds__(256, 2) conv9x9_kernel(const float* __restrict
     }
 }
 
+// =====================================================================================
+// VGG conv1_1: 3x3 SAME, 3(4) -> 64, + bias + ReLU (reference libs/vgg16.py:45-55) and its data gradient
+// (64 -> 4).  Tile = 32 rows x 8 columns; lane = row, warp = (4-pixel column group, 16-channel group).
+// =====================================================================================
+constexpr int C1_ROWS = 32, C1_COLS = 8, C1_PITCH = 11;   // pitch 11 float4: the 32 row-lanes hit distinct banks
+
+__global__ void __launch_bounds__(256) conv3x3_c4_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ out,
+                                                             __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo,
+                                                             int H, int W) {
+    __shared__ float4 in_s[(C1_ROWS + 2) * C1_PITCH];
+    __shared__ float4 w_s[9 * 4 * 16];
+    __shared__ float4 b_s[16];
+    const int t = threadIdx.x;
+    const int x0 = blockIdx.x * C1_COLS, y0 = blockIdx.y * C1_ROWS, n = blockIdx.z;
+    const float4* in4 = reinterpret_cast<const float4*>(in + (long long)n * H * W * 4);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = t; i < (C1_ROWS + 2) * (C1_COLS + 2); i += 256) {
+        int py = i / (C1_COLS + 2), px = i - py * (C1_COLS + 2);
+        int yy = y0 - 1 + py, xx = x0 - 1 + px;
+        in_s[py * C1_PITCH + px] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(in4 + (long long)yy * W + xx) : z;
+    }
+    for (int i = t; i < 9 * 4 * 16; i += 256) w_s[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+    if (t < 16) b_s[t] = bias ? __ldg(reinterpret_cast<const float4*>(bias) + t) : z;
+    __syncthreads();
+    const int lane = t & 31, wq = t >> 5;
+    const int g = wq & 1, cog = wq >> 1;            // column group (4 px), output-channel group (16 ch)
+    float acc[4][16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        float iv[6][4];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            float4 v = in_s[(lane + kh) * C1_PITCH + 4 * g + j];
+            iv[j][0] = v.x; iv[j][1] = v.y; iv[j][2] = v.z; iv[j][3] = v.w;
+        }
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 wv = w_s[((kh * 3 + kw) * 4 + c) * 16 + cog * 4 + q];
+#pragma unroll
+                    for (int px = 0; px < 4; ++px) {
+                        const float xv = iv[px + kw][c];
+                        acc[px][q * 4 + 0] = fmaf(xv, wv.x, acc[px][q * 4 + 0]);
+                        acc[px][q * 4 + 1] = fmaf(xv, wv.y, acc[px][q * 4 + 1]);
+                        acc[px][q * 4 + 2] = fmaf(xv, wv.z, acc[px][q * 4 + 2]);
+                        acc[px][q * 4 + 3] = fmaf(xv, wv.w, acc[px][q * 4 + 3]);
+                    }
+                }
+    }
+    const int oy = y0 + lane;
+    if (oy >= H) return;
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+        const int ox = x0 + 4 * g + px;
+        if (ox >= W) continue;
+        const long long o = (((long long)n * H + oy) * W + ox) * 64 + cog * 16;
+        float r[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 b = b_s[cog * 4 + q];
+            r[q * 4 + 0] = fmaxf(acc[px][q * 4 + 0] + b.x, 0.f);
+            r[q * 4 + 1] = fmaxf(acc[px][q * 4 + 1] + b.y, 0.f);
+            r[q * 4 + 2] = fmaxf(acc[px][q * 4 + 2] + b.z, 0.f);
+            r[q * 4 + 3] = fmaxf(acc[px][q * 4 + 3] + b.w, 0.f);
+            *reinterpret_cast<float4*>(out + o + q * 4) = make_float4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+        }
+        if (shi) {
+            uint32_t hw[8], lw[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                __nv_bfloat16 h0 = __float2bfloat16_rn(r[2 * j]), h1 = __float2bfloat16_rn(r[2 * j + 1]);
+                __nv_bfloat16 l0 = __float2bfloat16_rn(r[2 * j] - __bfloat162float(h0));
+                __nv_bfloat16 l1 = __float2bfloat16_rn(r[2 * j + 1] - __bfloat162float(h1));
+                hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            *reinterpret_cast<uint4*>(shi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(shi + o + 8) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+            *reinterpret_cast<uint4*>(slo + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            *reinterpret_cast<uint4*>(slo + o + 8) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+        }
+    }
+}
+
+// dX[p][0..3] = sum_{tap,co} P[p + tap - 1][co] * Wf[tap][co][0..3]   (Wf = flipped/transposed conv1_1 weights)
+// warp = (column group, 16-channel slice of the reduction); the 4 slices are summed through shared memory.
+__global__ void __launch_bounds__(256) dgrad3x3_c4_kernel(const float* __restrict__ P, const float* __restrict__ wf,
+                                                          float* __restrict__ dx, int H, int W) {
+    extern __shared__ float4 sm4[];
+    float4* in_s = sm4;                                         // [16 channel quads][ROWS+2][PITCH]
+    float4* w_s = sm4 + 16 * (C1_ROWS + 2) * C1_PITCH;          // [9][64] float4
+    float4* red = w_s + 9 * 64;                                 // [3 slices][64 threads][4 px]
+    const int t = threadIdx.x;
+    const int x0 = blockIdx.x * C1_COLS, y0 = blockIdx.y * C1_ROWS, n = blockIdx.z;
+    const float4* p4 = reinterpret_cast<const float4*>(P + (long long)n * H * W * 64);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = t; i < (C1_ROWS + 2) * (C1_COLS + 2) * 16; i += 256) {
+        int cq = i & 15, pix = i >> 4;
+        int py = pix / (C1_COLS + 2), px = pix - py * (C1_COLS + 2);
+        int yy = y0 - 1 + py, xx = x0 - 1 + px;
+        in_s[(cq * (C1_ROWS + 2) + py) * C1_PITCH + px] =
+            (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(p4 + ((long long)yy * W + xx) * 16 + cq) : z;
+    }
+    for (int i = t; i < 9 * 64; i += 256) w_s[i] = __ldg(reinterpret_cast<const float4*>(wf) + i);
+    __syncthreads();
+    const int lane = t & 31, wq = t >> 5;
+    const int g = wq & 1, kq = wq >> 1;               // column group, reduction slice (channels 16kq..16kq+15)
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            const int cq = kq * 4 + c4;
+            float iv[6][4];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                float4 v = in_s[(cq * (C1_ROWS + 2) + lane + kh) * C1_PITCH + 4 * g + j];
+                iv[j][0] = v.x; iv[j][1] = v.y; iv[j][2] = v.z; iv[j][3] = v.w;
+            }
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 wv = w_s[(kh * 3 + kw) * 64 + cq * 4 + c];
+#pragma unroll
+                    for (int px = 0; px < 4; ++px) {
+                        const float xv = iv[px + kw][c];
+                        acc[px][0] = fmaf(xv, wv.x, acc[px][0]);
+                        acc[px][1] = fmaf(xv, wv.y, acc[px][1]);
+                        acc[px][2] = fmaf(xv, wv.z, acc[px][2]);
+                        acc[px][3] = fmaf(xv, wv.w, acc[px][3]);
+                    }
+                }
+        }
+    }
+    const int slot = g * 32 + lane;
+    if (kq > 0) {
+#pragma unroll
+        for (int px = 0; px < 4; ++px)
+            red[((kq - 1) * 64 + slot) * 4 + px] = make_float4(acc[px][0], acc[px][1], acc[px][2], acc[px][3]);
+    }
+    __syncthreads();
+    if (kq == 0) {
+        const int oy = y0 + lane;
+        if (oy >= H) return;
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+            const int ox = x0 + 4 * g + px;
+            if (ox >= W) continue;
+            float4 s = make_float4(acc[px][0], acc[px][1], acc[px][2], acc[px][3]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 v = red[(k * 64 + slot) * 4 + px];
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            *reinterpret_cast<float4*>(dx + (((long long)n * H + oy) * W + ox) * 4) = s;
+        }
+    }
+}
+
 // Wf[80-tap][co][ci] = W[tap][ci][co]: weights that turn the data gradient into a forward convolution
 __global__ void flip_transpose_taps_kernel(const float* __restrict__ W, float* __restrict__ Wf, int T, int Ci, int Co) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -196,6 +369,26 @@ int launch_conv9x9(const float* in, const float* w, float* out, int N, int H, in
         if (!set) { FS_CUDA(cudaFuncSetAttribute(conv9x9_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
         conv9x9_kernel<16, 4><<<grid, 256, smem, st>>>(in, w, out, H, W);
     }
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+// conv1_1 forward: in [N,H,W,4], w [9,4,64], bias [64] -> out [N,H,W,64] fp32 (+ optional split planes)
+int launch_conv3x3_c4_fwd(const float* in, const float* w, const float* bias, float* out, void* split_hi, void* split_lo,
+                          int N, int H, int W, cudaStream_t st) {
+    dim3 grid(cdiv(W, C1_COLS), cdiv(H, C1_ROWS), N);
+    conv3x3_c4_fwd_kernel<<<grid, 256, 0, st>>>(in, w, bias, out, (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo, H, W);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+// conv1_1 data gradient: P [N,H,W,64], wf [9,64,4] (flip_transpose_taps of the forward weights) -> dx [N,H,W,4]
+int launch_dgrad3x3_c4(const float* P, const float* wf, float* dx, int N, int H, int W, cudaStream_t st) {
+    const size_t smem = (size_t)(16 * (C1_ROWS + 2) * C1_PITCH + 9 * 64 + 3 * 64 * 4) * sizeof(float4);
+    static bool set = false;
+    if (!set) { FS_CUDA(cudaFuncSetAttribute(dgrad3x3_c4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+    dim3 grid(cdiv(W, C1_COLS), cdiv(H, C1_ROWS), N);
+    dgrad3x3_c4_kernel<<<grid, 256, smem, st>>>(P, wf, dx, H, W);
     FS_LAUNCH_CHECK();
     return 0;
 }

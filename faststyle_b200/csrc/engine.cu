@@ -160,7 +160,10 @@ int vgg_pack(const float* flat, float* packed, cudaStream_t st) {
         src += wn;
         FS_CUDA(cudaMemcpyAsync(packed + vc[l].offB, flat + src, vc[l].cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
         src += vc[l].cout;
-        FS_TRY(transpose_taps(packed + vc[l].offW, packed + vc[l].offWT, 9, vc[l].cin_s, vc[l].cout, st));
+        if (l == 0)      // conv1_1 runs on the direct kernels: its data gradient is a conv with flipped weights
+            FS_TRY(flip_transpose_taps(packed + vc[l].offW, packed + vc[l].offWT, 9, vc[l].cin_s, vc[l].cout, st));
+        else
+            FS_TRY(transpose_taps(packed + vc[l].offW, packed + vc[l].offWT, 9, vc[l].cin_s, vc[l].cout, st));
         if (l >= 1) {
             FS_TRY(pack_w3x3_tc(packed + vc[l].offW, vgg_tc_w(packed, vc[l], 0), vc[l].cin, vc[l].cout, 0, st));
             FS_TRY(pack_w3x3_tc(packed + vc[l].offW, vgg_tc_w(packed, vc[l], 1), vc[l].cin, vc[l].cout, 1, st));
@@ -547,12 +550,15 @@ int Engine::vgg_forward(const float* packed, const float* img3, int upto, float*
             if (l < upto && !pool_next) ta.out_split = vsplit[l + 1];     // next conv reads split planes
             else if (vtsplit[l].hi) ta.out_split = vtsplit[l];            // style tap: Gram kernels read them
             PROF(PC_TC_VGG_FWD, tc_flops(ta), launch_conv3x3_tc(ta, st));
+        } else if (l == 0) {             // conv1_1 (Cin = 3): direct shared-memory kernel, exact fp32
+            const bool sp = use_tc && l < upto && !pool_next;
+            PROF(PC_FFMA_CONV, 2.0 * N * vc[0].H * vc[0].W * 9.0 * 4 * 64,
+                 launch_conv3x3_c4_fwd(cur, packed + vc[0].offW, packed + vc[0].offB, out, sp ? vsplit[1].hi : nullptr,
+                                       sp ? vsplit[1].lo : nullptr, N, vc[0].H, vc[0].W, st));
         } else {
             IGemmArgs a;
             vgg_conv_args(vc[l], N, packed, cur, out, a);
             PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
-            if (use_tc && l < upto && !pool_next)
-                PROF(PC_POINTWISE, 0.0, split_bf16(out, vsplit[l + 1], (long long)N * vc[l].H * vc[l].W * vc[l].cout, st));
         }
         cur = out;
         if (pool_next) {
@@ -653,6 +659,11 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
             PROF(PC_TC_VGG_DGRAD, tc_flops(ta), launch_conv3x3_tc(ta, st));
             return 0;
         }
+        if (lsrc == 0 && !addend && !ref) {      // conv1_1 data gradient: direct kernel (64 -> 4 channels)
+            PROF(PC_FFMA_CONV, 2.0 * N * v.H * v.W * 9.0 * 4 * 64, launch_dgrad3x3_c4(P, packed + v.offWT, out, N, v.H, v.W, st));
+            return 0;
+        }
+        FS_CHECK(lsrc != 0, "conv1_1 data gradient with an epilogue is not supported");
         IGemmArgs a;
         memset(&a, 0, sizeof(a));
         a.in = P; a.w = packed + v.offWT; a.out = out; a.N = N; a.gather = 1;
