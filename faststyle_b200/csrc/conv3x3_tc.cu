@@ -142,51 +142,59 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // The whole warp runs the (warp-uniform) control flow and barrier waits; one elected lane issues.
+        // Shared-memory descriptors are built once per stage; each tcgen05.mma then costs one 64-bit add per
+        // operand, so the issue rate stays above the 32-64 tensor cycles an MMA takes.
         const uint32_t idesc = make_idesc<BN>();
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
         int as = 0; uint32_t pt = 0;
         for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             mbar_wait(&t_empty[as], pt ^ 1);
             tc_fence_after();
-            const uint32_t acc_base = tmem_base + (uint32_t)(as * K::NACC * BN);
+            const uint32_t acc_base = tb + (uint32_t)(as * K::NACC * BN);
             bool first = true;
             for (int cb = 0; cb < CB; ++cb) {
                 for (int kw = 0; kw < p.taps; ++kw) {
                     mbar_wait(&a_full[sa], pa);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smemA + sa * K::A_STAGE_BYTES);
-                    const uint32_t a_lo = a_hi + K::SLAB_BYTES;
+                    const uint64_t ad_hi = make_sdesc(smem_u32(smemA + sa * K::A_STAGE_BYTES));
+                    const uint64_t ad_lo = make_sdesc(smem_u32(smemA + sa * K::A_STAGE_BYTES + K::SLAB_BYTES));
                     for (int kh = 0; kh < p.taps; ++kh) {
                         mbar_wait(&b_full[sb], pb);
                         tc_fence_after();
-                        const uint32_t b_hi = smem_u32(smemB + sb * K::B_STAGE_BYTES);
-                        const uint32_t b_lo = b_hi + K::BTILE_BYTES;
+                        const uint64_t bd_hi = make_sdesc(smem_u32(smemB + sb * K::B_STAGE_BYTES));
+                        const uint64_t bd_lo = make_sdesc(smem_u32(smemB + sb * K::B_STAGE_BYTES + K::BTILE_BYTES));
+                        if (elect_one()) {
 #pragma unroll
-                        for (int acc = 0; acc < K::NACC; ++acc) {
-                            const uint32_t aoff = (uint32_t)((acc * 8 + kh) * TW * 128);
-                            const uint32_t d = acc_base + (uint32_t)(acc * BN);
+                            for (int acc = 0; acc < K::NACC; ++acc) {
+                                const uint64_t aoff = (uint64_t)((acc * 8 + kh) * (TW * 128 / 16));   // 16-byte units
+                                const uint32_t d = acc_base + (uint32_t)(acc * BN);
 #pragma unroll
-                            for (int prod = 0; prod < 3; ++prod) {
-                                const uint32_t abase = (prod == 2 ? a_lo : a_hi) + aoff;
-                                const uint32_t bbase = (prod == 1 ? b_lo : b_hi);
+                                for (int prod = 0; prod < 3; ++prod) {
+                                    const uint64_t ad = (prod == 2 ? ad_lo : ad_hi) + aoff;
+                                    const uint64_t bd = (prod == 1 ? bd_lo : bd_hi);
 #pragma unroll
-                                for (int k4 = 0; k4 < 4; ++k4) {
-                                    tc_mma_bf16(d, make_sdesc(abase + k4 * 32), make_sdesc(bbase + k4 * 32), idesc,
-                                                (first && prod == 0 && k4 == 0) ? 0u : 1u);
+                                    for (int k4 = 0; k4 < 4; ++k4)
+                                        tc_mma_bf16(d, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc,
+                                                    (first && prod == 0 && k4 == 0) ? 0u : 1u);
                                 }
                             }
+                            tc_commit(&b_empty[sb]);
                         }
+                        __syncwarp();
                         first = false;
-                        tc_commit(&b_empty[sb]);
                         if (++sb == K::B_STAGES) { sb = 0; pb ^= 1; }
                     }
-                    tc_commit(&a_empty[sa]);
+                    if (elect_one()) tc_commit(&a_empty[sa]);
+                    __syncwarp();
                     if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
                 }
             }
-            tc_commit(&t_full[as]);
+            if (elect_one()) tc_commit(&t_full[as]);
+            __syncwarp();
             if (++as == 2) { as = 0; pt ^= 1; }
         }
     } else if (warp >= 4) {
@@ -231,9 +239,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                         }
                         if (addp) {
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                float4 b = *reinterpret_cast<const float4*>(addp + c0 + i);
-                                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                            for (int i = 0; i < 32; i += 8) {
+                                float b[8];
+                                ldg256(addp + c0 + i, b);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[i + j] += b[j];
                             }
                         }
                         if (p.relu) {
@@ -243,26 +253,26 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                         if (p.ref) {
                             const float* rp = p.ref + pix * p.OC + c0;
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                float4 b = *reinterpret_cast<const float4*>(rp + i);
-                                v[i] = b.x > 0.f ? v[i] : 0.f; v[i + 1] = b.y > 0.f ? v[i + 1] : 0.f;
-                                v[i + 2] = b.z > 0.f ? v[i + 2] : 0.f; v[i + 3] = b.w > 0.f ? v[i + 3] : 0.f;
+                            for (int i = 0; i < 32; i += 8) {
+                                float b[8];
+                                ldg256(rp + i, b);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[i + j] = b[j] > 0.f ? v[i + j] : 0.f;
                             }
                         }
                         if (p.out_f32) {
                             float* op = p.out_f32 + pix * p.OC + c0;
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4)
-                                *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                            for (int i = 0; i < 32; i += 8) stg256(op + i, v + i);
                         }
                         if (p.out_hi) {
                             __nv_bfloat16* hp = p.out_hi + pix * p.OC + c0;
                             __nv_bfloat16* lp = p.out_lo + pix * p.OC + c0;
 #pragma unroll
-                            for (int i = 0; i < 32; i += 8) {
-                                uint32_t hw[4], lw[4];
+                            for (int i = 0; i < 32; i += 16) {
+                                uint32_t hw[8], lw[8];
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
+                                for (int j = 0; j < 8; ++j) {
                                     __nv_bfloat16 h0 = __float2bfloat16_rn(v[i + 2 * j]);
                                     __nv_bfloat16 h1 = __float2bfloat16_rn(v[i + 2 * j + 1]);
                                     __nv_bfloat16 l0 = __float2bfloat16_rn(v[i + 2 * j] - __bfloat162float(h0));
@@ -270,8 +280,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                                     hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
                                     lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
                                 }
-                                *reinterpret_cast<uint4*>(hp + i) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                                *reinterpret_cast<uint4*>(lp + i) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                                stg256_b32(hp + i, hw);
+                                stg256_b32(lp + i, lw);
                             }
                         }
                     }

@@ -6,6 +6,7 @@
 // 81 x CI x CO weight-gradient, so each staged element is reused 81 times from SMEM.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include "tc_ptx.cuh"
 
 namespace fs {
 
@@ -140,14 +141,29 @@ __global__ void __launch_bounds__(256, 2) conv9x9_kernel(const float* __restrict
     const int oy = y0 + lane;
     if (oy >= H) return;
     float* orow = out + (((long long)n * H + oy) * W) * CO;
+    if (CO == 4 && (W & 1) == 0 && x0 + 4 * wq + 3 < W) {        // 4 pixels x 4 channels = 64 contiguous bytes: two 256-bit stores
+        float r[16];
+#pragma unroll
+        for (int px = 0; px < 4; ++px)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[px * 4 + j] = acc[px][j];
+        tcptx::stg256(orow + (long long)(x0 + 4 * wq) * CO, r);
+        tcptx::stg256(orow + (long long)(x0 + 4 * wq) * CO + 8, r + 8);
+        return;
+    }
 #pragma unroll
     for (int px = 0; px < 4; ++px) {
         const int ox = x0 + 4 * wq + px;
         if (ox >= W) continue;
+        if (CO == 16) {
+            tcptx::stg256(orow + (long long)ox * CO, &acc[px][0]);
+            tcptx::stg256(orow + (long long)ox * CO + 8, &acc[px][8]);
+        } else {
 #pragma unroll
-        for (int q = 0; q < COQ; ++q)
-            *reinterpret_cast<float4*>(orow + (long long)ox * CO + q * 4) =
-                make_float4(acc[px][q * 4], acc[px][q * 4 + 1], acc[px][q * 4 + 2], acc[px][q * 4 + 3]);
+            for (int q = 0; q < COQ; ++q)
+                *reinterpret_cast<float4*>(orow + (long long)ox * CO + q * 4) =
+                    make_float4(acc[px][q * 4], acc[px][q * 4 + 1], acc[px][q * 4 + 2], acc[px][q * 4 + 3]);
+        }
     }
 }
 
@@ -223,8 +239,9 @@ __global__ void __launch_bounds__(256) conv3x3_c4_fwd_kernel(const float* __rest
             r[q * 4 + 1] = fmaxf(acc[px][q * 4 + 1] + b.y, 0.f);
             r[q * 4 + 2] = fmaxf(acc[px][q * 4 + 2] + b.z, 0.f);
             r[q * 4 + 3] = fmaxf(acc[px][q * 4 + 3] + b.w, 0.f);
-            *reinterpret_cast<float4*>(out + o + q * 4) = make_float4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
         }
+        tcptx::stg256(out + o, r);
+        tcptx::stg256(out + o + 8, r + 8);
         if (shi) {
             uint32_t hw[8], lw[8];
 #pragma unroll
@@ -235,10 +252,8 @@ __global__ void __launch_bounds__(256) conv3x3_c4_fwd_kernel(const float* __rest
                 hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
                 lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
             }
-            *reinterpret_cast<uint4*>(shi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(shi + o + 8) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-            *reinterpret_cast<uint4*>(slo + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            *reinterpret_cast<uint4*>(slo + o + 8) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+            tcptx::stg256_b32(shi + o, hw);
+            tcptx::stg256_b32(slo + o, lw);
         }
     }
 }

@@ -137,7 +137,18 @@ in_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dY,
         }
     }
     __syncthreads();
-    if (row < rows) {
+    // lanes t, t+CL, t+2CL, ... of a warp hold the same channels: fold them with shuffles first so that only
+    // CL lanes per warp touch the shared accumulators (CL <= 32; for CL = 64 every lane is distinct)
+    if (CL < 32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            for (int o = 16; o >= CL; o >>= 1) {
+                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+                s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+            }
+        }
+    }
+    if (CL >= 32 || (t & 31) < CL) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             atomicAdd(&sm[(lane * 4 + j) * 2 + 0], s1[j]);
@@ -149,23 +160,28 @@ in_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dY,
     for (int i = t; i < 2 * C; i += 256) dst[i] = sm[i];
 }
 
-__global__ void in_stats_finalize_kernel(const double* __restrict__ partial, float* __restrict__ mean,
-                                         float* __restrict__ rstd, int N, int C, int chunks, int HW,
-                                         float eps) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per (n, c): lanes split the chunks, fixed shuffle-tree order -> deterministic
+__global__ void __launch_bounds__(256)
+in_stats_finalize_kernel(const double* __restrict__ partial, float* __restrict__ mean, float* __restrict__ rstd,
+                         int N, int C, int chunks, int HW, float eps) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= N * C) return;
-    int n = i / C, c = i - n * C;
+    const int n = i / C, c = i - n * C;
     double s1 = 0, s2 = 0;
-    for (int k = 0; k < chunks; ++k) {
+    for (int k = lane; k < chunks; k += 32) {
         const double* p = partial + ((long long)n * chunks + k) * 2 * C + c * 2;
         s1 += p[0];
         s2 += p[1];
     }
-    double m = s1 / HW;
-    double var = s2 / HW - m * m;
-    if (var < 0) var = 0;
-    mean[i] = (float)m;
-    rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+        double m = s1 / HW;
+        double var = s2 / HW - m * m;
+        if (var < 0) var = 0;
+        mean[i] = (float)m;
+        rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+    }
 }
 
 __global__ void in_bwd_finalize_kernel(const double* __restrict__ partial, float* __restrict__ m12,
@@ -602,8 +618,7 @@ int instnorm_stats(const float* x, float* mean, float* rstd, int N, int HW, int 
     in_reduce_kernel<0><<<dim3(chunks, N), 256, 2 * C * sizeof(double), st>>>(
         x, nullptr, nullptr, nullptr, nullptr, nullptr, partial, HW, C, chunks, 0);
     FS_LAUNCH_CHECK();
-    in_stats_finalize_kernel<<<grid1((long long)N * C, 128), 128, 0, st>>>(partial, mean, rstd, N, C,
-                                                                         chunks, HW, eps);
+    in_stats_finalize_kernel<<<cdiv((long long)N * C, 8), 256, 0, st>>>(partial, mean, rstd, N, C, chunks, HW, eps);
     FS_LAUNCH_CHECK();
     return 0;
 }

@@ -113,41 +113,48 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_cons
                 if (++sx == STAGES) { sx = 0; px ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1) {
+        // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
         const uint32_t idesc = make_idesc_mn();
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         int sx = 0, sd = 0; uint32_t px = 0, pd = 0;
         bool first_tile = true;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             mbar_wait(&d_full[sd], pd);
             tc_fence_after();
-            const uint32_t d_hi = smem_u32(smemD + sd * D_STAGE), d_lo = d_hi + DT_BYTES;
+            const uint64_t dd_hi = make_sdesc_mn(smem_u32(smemD + sd * D_STAGE), 2048);
+            const uint64_t dd_lo = make_sdesc_mn(smem_u32(smemD + sd * D_STAGE + DT_BYTES), 2048);
             for (int kw = 0; kw < 3; ++kw) {
                 mbar_wait(&x_full[sx], px);
                 tc_fence_after();
-                const uint32_t x_hi = smem_u32(smemX + sx * X_STAGE), x_lo = x_hi + SLAB_BYTES;
+                const uint64_t xd_hi = make_sdesc_mn(smem_u32(smemX + sx * X_STAGE), 2048);
+                const uint64_t xd_lo = make_sdesc_mn(smem_u32(smemX + sx * X_STAGE + SLAB_BYTES), 2048);
+                if (elect_one()) {
 #pragma unroll
-                for (int grp = 0; grp < 2; ++grp) {
-                    const uint32_t acc = tmem_base + (uint32_t)((kw * 2 + grp) * 64);
+                    for (int grp = 0; grp < 2; ++grp) {
+                        const uint32_t acc = tb + (uint32_t)((kw * 2 + grp) * 64);
 #pragma unroll
-                    for (int prod = 0; prod < 3; ++prod) {
-                        const uint32_t abase = (prod == 2 ? x_lo : x_hi) + (uint32_t)(grp * 2048);
-                        const uint32_t bbase = (prod == 1 ? d_lo : d_hi);
+                        for (int prod = 0; prod < 3; ++prod) {
+                            const uint64_t ad = (prod == 2 ? xd_lo : xd_hi) + (uint64_t)(grp * 128);   // +2048 B
+                            const uint64_t bd = (prod == 1 ? dd_lo : dd_hi);
 #pragma unroll
-                        for (int ks = 0; ks < TH; ++ks) {
-                            tc_mma_bf16(acc, make_sdesc_mn(abase + ks * 2048, 2048), make_sdesc_mn(bbase + ks * 2048, 2048),
-                                        idesc, (first_tile && prod == 0 && ks == 0) ? 0u : 1u);
+                            for (int ks = 0; ks < TH; ++ks)
+                                tc_mma_bf16(acc, ad + (uint64_t)(ks * 128), bd + (uint64_t)(ks * 128), idesc,
+                                            (first_tile && prod == 0 && ks == 0) ? 0u : 1u);
                         }
                     }
+                    tc_commit(&x_empty[sx]);
                 }
-                tc_commit(&x_empty[sx]);
+                __syncwarp();
                 if (++sx == STAGES) { sx = 0; px ^= 1; }
             }
-            tc_commit(&d_empty[sd]);
+            if (elect_one()) tc_commit(&d_empty[sd]);
+            __syncwarp();
             if (++sd == STAGES) { sd = 0; pd ^= 1; }
             first_tile = false;
         }
-        tc_commit(done);
+        if (elect_one()) tc_commit(done);
+        __syncwarp();
     } else if (warp >= 4) {
         // ===================== dump (4 warps = 128 TMEM lanes) =====================
         const int ew = warp - 4;
@@ -338,27 +345,33 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             tma_load_4d(d + 5 * GBOX, &tm_lo, &full[s], cb, pix, n, 0);
             if (++s == G_STAGES) { s = 0; ph ^= 1; }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         const uint32_t idesc = make_idesc_mn();
         const uint32_t lbo = two_groups ? (uint32_t)GBOX : 0u;
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         int s = 0; uint32_t ph = 0;
         for (int c = 0; c < nchunks; ++c) {
             mbar_wait(&full[s], ph);
             tc_fence_after();
             const uint32_t base = smem_u32(smem + s * G_STAGE);
-            const uint32_t a_hi = base, a_lo = base + 2 * GBOX, b_hi = base + 4 * GBOX, b_lo = base + 5 * GBOX;
+            const uint64_t a_hi = make_sdesc_mn(base, lbo), a_lo = make_sdesc_mn(base + 2 * GBOX, lbo);
+            const uint64_t b_hi = make_sdesc_mn(base + 4 * GBOX, 2048), b_lo = make_sdesc_mn(base + 5 * GBOX, 2048);
+            if (elect_one()) {
 #pragma unroll
-            for (int prod = 0; prod < 3; ++prod) {
-                const uint32_t ab = prod == 2 ? a_lo : a_hi, bb = prod == 1 ? b_lo : b_hi;
+                for (int prod = 0; prod < 3; ++prod) {
+                    const uint64_t ab = prod == 2 ? a_lo : a_hi, bb = prod == 1 ? b_lo : b_hi;
 #pragma unroll
-                for (int k = 0; k < GP / 16; ++k)
-                    tc_mma_bf16(tmem_base, make_sdesc_mn(ab + k * 2048, lbo), make_sdesc_mn(bb + k * 2048, 2048), idesc,
-                                (c == 0 && prod == 0 && k == 0) ? 0u : 1u);
+                    for (int k = 0; k < GP / 16; ++k)
+                        tc_mma_bf16(tb, ab + (uint64_t)(k * 128), bb + (uint64_t)(k * 128), idesc,
+                                    (c == 0 && prod == 0 && k == 0) ? 0u : 1u);
+                }
+                tc_commit(&empty[s]);
             }
-            tc_commit(&empty[s]);
+            __syncwarp();
             if (++s == G_STAGES) { s = 0; ph ^= 1; }
         }
-        tc_commit(done);
+        if (elect_one()) tc_commit(done);
+        __syncwarp();
     } else if (warp >= 4) {
         const int ew = warp - 4;
         const int row = ew * 32 + lane;
