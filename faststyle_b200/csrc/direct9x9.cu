@@ -14,6 +14,7 @@ namespace {
 
 constexpr int TS = 32;            // tile side (output pixels)
 constexpr int HS = TS + 8;        // with the 4-px halo of a 9x9 window
+constexpr int TSY = 16, HSY = TSY + 8;   // weight-gradient tiles are 16 rows x 32 columns: 2-3 CTAs per SM
 constexpr int NT9 = 352;          // 11 warps; 324 = 81 taps x 4 channel blocks are active in the main loop
 
 // dW[kh,kw,ci,co] partial sums of one tile: partial[block][(tap*CI + ci)*CO + co]
@@ -23,19 +24,19 @@ __global__ void __launch_bounds__(NT9) wgrad9x9_kernel(const float* __restrict__
     static_assert(CI * CO == 64 && CI % 4 == 0 && CO % 4 == 0, "channel block must be 4x16 or 16x4");
     constexpr int CIQ = CI / 4, COQ = CO / 4;
     extern __shared__ float4 sm4[];
-    float4* in_s = sm4;                         // [HS][HS][CIQ]
-    float4* dy_s = sm4 + HS * HS * CIQ;         // [TS][TS][COQ]
+    float4* in_s = sm4;                         // [HSY][HS][CIQ]
+    float4* dy_s = sm4 + HSY * HS * CIQ;        // [TSY][TS][COQ]
     const int t = threadIdx.x;
-    const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS, n = blockIdx.z;
+    const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TSY, n = blockIdx.z;
     const float4* in4 = reinterpret_cast<const float4*>(in + (long long)n * H * W * CI);
     const float4* dy4 = reinterpret_cast<const float4*>(dy + (long long)n * H * W * CO);
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = t; i < HS * HS * CIQ; i += NT9) {
+    for (int i = t; i < HSY * HS * CIQ; i += NT9) {
         int pix = i / CIQ, c4 = i - pix * CIQ;
         int yy = y0 - 4 + pix / HS, xx = x0 - 4 + pix % HS;
         in_s[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(in4 + ((long long)yy * W + xx) * CIQ + c4) : z;
     }
-    for (int i = t; i < TS * TS * COQ; i += NT9) {
+    for (int i = t; i < TSY * TS * COQ; i += NT9) {
         int pix = i / COQ, c4 = i - pix * COQ;
         int yy = y0 + pix / TS, xx = x0 + pix % TS;
         dy_s[i] = (yy < H && xx < W) ? __ldg(dy4 + ((long long)yy * W + xx) * COQ + c4) : z;
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(NT9) wgrad9x9_kernel(const float* __restrict__
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int py = 0; py < TS; ++py) {
+    for (int py = 0; py < TSY; ++py) {
         const float4* ip = in_s + ((py + kh) * HS + kw) * CIQ + ciq;
         const float4* dp = dy_s + (py * TS) * COQ + coq;
 #pragma unroll 8
@@ -416,7 +417,7 @@ int flip_transpose_taps(const float* W, float* Wf, int T, int Ci, int Co, cudaSt
 }
 
 long long wgrad9x9_partial_floats(int N, int H, int W) {
-    return (long long)N * cdiv(H, TS) * cdiv(W, TS) * 81 * 64;
+    return (long long)N * cdiv(H, TSY) * cdiv(W, TS) * 81 * 64;
 }
 
 // in [N,H,W,CI], dy [N,H,W,CO] (9x9 stride-1 SAME conv: equal spatial dims); out [81,CI,CO]
@@ -425,15 +426,15 @@ int launch_wgrad9x9(const float* in, const float* dy, float* out, float* partial
     FS_CHECK((CI == 16 && CO == 4) || (CI == 4 && CO == 16), "wgrad9x9: unsupported channel block %dx%d", CI, CO);
     long long need = wgrad9x9_partial_floats(N, H, W);
     FS_CHECK(need <= partial_cap, "wgrad9x9: partial workspace too small (%lld > %lld floats)", need, partial_cap);
-    dim3 grid(cdiv(W, TS), cdiv(H, TS), N);
+    dim3 grid(cdiv(W, TS), cdiv(H, TSY), N);
     const int nblocks = grid.x * grid.y * grid.z;
     if (CI == 16) {
-        size_t smem = (size_t)(HS * HS * 4 + TS * TS * 1) * sizeof(float4);
+        size_t smem = (size_t)(HSY * HS * 4 + TSY * TS * 1) * sizeof(float4);
         static bool set16 = false;
         if (!set16) { FS_CUDA(cudaFuncSetAttribute(wgrad9x9_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set16 = true; }
         wgrad9x9_kernel<16, 4><<<grid, NT9, smem, st>>>(in, dy, partial, H, W);
     } else {
-        size_t smem = (size_t)(HS * HS * 1 + TS * TS * 4) * sizeof(float4);
+        size_t smem = (size_t)(HSY * HS * 1 + TSY * TS * 4) * sizeof(float4);
         static bool set4 = false;
         if (!set4) { FS_CUDA(cudaFuncSetAttribute(wgrad9x9_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set4 = true; }
         wgrad9x9_kernel<4, 16><<<grid, NT9, smem, st>>>(in, dy, partial, H, W);

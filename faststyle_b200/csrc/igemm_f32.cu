@@ -323,54 +323,82 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(const WGradArgs a, const WGeo
     }
     const int p0 = NT >= K4 ? t / K4 : 0;
 
+    // Pixel trackers: every thread follows PPT (A side) + B_F4 (dy side) pixels that advance by WP per step;
+    // (sample, oy, ox) are updated incrementally instead of two integer divisions per pixel per step.
+    struct Trk { int pix, ns, oy, ox; };
+    auto trk_init = [&](Trk& k, int pix) {
+        k.pix = pix;
+        int pp = pix < pend ? pix : pbeg;
+        k.ns = pp / g.M;
+        int m = pp - k.ns * g.M;
+        k.oy = m / a.OW;
+        k.ox = m - k.oy * a.OW;
+    };
+    auto trk_adv = [&](Trk& k) {
+        k.pix += WP;
+        k.ox += WP;
+        while (k.ox >= a.OW) {
+            k.ox -= a.OW;
+            if (++k.oy >= a.OH) { k.oy = 0; ++k.ns; }
+        }
+    };
+    Trk ta[PPT], tb[B_F4];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) trk_init(ta[i], pbeg + p0 + i * PSTEP);
+    // dy-side constants of this thread (its column group never changes)
+    int bn4[B_F4]; bool bok[B_F4]; int bpq[B_F4], bco[B_F4];
+#pragma unroll
+    for (int i = 0; i < B_F4; ++i) {
+        int f = t + i * NT;
+        int pb = f / (WN / 4);
+        bn4[i] = f - pb * (WN / 4);
+        int jcol = j0 + bn4[i] * 4;
+        bok[i] = f < B_TOT && jcol < a.OC;
+        int C0 = a.OC >> 2;
+        bpq[i] = a.dy_mode ? jcol / C0 : 0;
+        bco[i] = a.dy_mode ? jcol - bpq[i] * C0 : jcol;
+        trk_init(tb[i], pbeg + pb);
+    }
+    int apq[KPT], aco[KPT];
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {
+        int C0 = a.C >> 2;
+        apq[j] = a.in_mode ? kc[j] / C0 : 0;
+        aco[j] = a.in_mode ? kc[j] - apq[j] * C0 : kc[j];
+    }
+
     float4 ra[KPT][PPT], rb[B_F4];
-    auto load_step = [&](int s) {
+    auto load_step = [&](int) {
 #pragma unroll
         for (int i = 0; i < PPT; ++i) {
-            int pix = pbeg + s * WP + p0 + i * PSTEP;
-            bool pok = pix < pend;
-            int ns = 0, m = 0, oy = 0, ox = 0;
-            if (pok) { ns = pix / g.M; m = pix - ns * g.M; oy = m / a.OW; ox = m - oy * a.OW; }
-            const float* in_n = a.in + (long long)(grp * samples_per_group + ns) * a.in_bs;
+            const bool pok = ta[i].pix < pend;
+            const float* in_n = a.in + (long long)(grp * samples_per_group + ta[i].ns) * a.in_bs;
 #pragma unroll
             for (int j = 0; j < KPT; ++j) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (pok && kok[j]) {
-                    int iy = oy * a.stride - a.pad_t + kkh[j], ix = ox * a.stride - a.pad_l + kkw[j];
+                    int iy = ta[i].oy * a.stride - a.pad_t + kkh[j], ix = ta[i].ox * a.stride - a.pad_l + kkw[j];
                     if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
                         long long off;
                         if (a.in_mode == 0) off = ((long long)iy * a.W + ix) * a.C + kc[j];
-                        else {
-                            int C0 = a.C >> 2; int pq = kc[j] / C0, co = kc[j] - pq * C0;
-                            off = ((long long)(2 * iy + (pq >> 1)) * (2 * a.W) + 2 * ix + (pq & 1)) * C0 + co;
-                        }
+                        else off = ((long long)(2 * iy + (apq[j] >> 1)) * (2 * a.W) + 2 * ix + (apq[j] & 1)) * (a.C >> 2) + aco[j];
                         v = ldg4(in_n + off);
                     }
                 }
                 ra[j][i] = v;
             }
+            trk_adv(ta[i]);
         }
 #pragma unroll
         for (int i = 0; i < B_F4; ++i) {
-            int f = t + i * NT;
             rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (f < B_TOT) {
-                int p = f / (WN / 4), n4 = f - p * (WN / 4);
-                int pix = pbeg + s * WP + p;
-                int jcol = j0 + n4 * 4;
-                if (pix < pend && jcol < a.OC) {
-                    int ns = pix / g.M;
-                    int m = pix - ns * g.M;
-                    long long off;
-                    if (a.dy_mode == 0) off = (long long)m * a.OC + jcol;
-                    else {
-                        int oy = m / a.OW, ox = m - oy * a.OW;
-                        int C0 = a.OC >> 2; int pq = jcol / C0, co = jcol - pq * C0;
-                        off = ((long long)(2 * oy + (pq >> 1)) * (2 * a.OW) + 2 * ox + (pq & 1)) * C0 + co;
-                    }
-                    rb[i] = ldg4(a.dy + (long long)(grp * samples_per_group + ns) * a.dy_bs + off);
-                }
+            if (bok[i] && tb[i].pix < pend) {
+                long long off;
+                if (a.dy_mode == 0) off = ((long long)tb[i].oy * a.OW + tb[i].ox) * a.OC + bco[i];
+                else off = ((long long)(2 * tb[i].oy + (bpq[i] >> 1)) * (2 * a.OW) + 2 * tb[i].ox + (bpq[i] & 1)) * (a.OC >> 2) + bco[i];
+                rb[i] = ldg4(a.dy + (long long)(grp * samples_per_group + tb[i].ns) * a.dy_bs + off);
             }
+            trk_adv(tb[i]);
         }
     };
     auto store_step = [&](int buf) {
