@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libfaststyle_b200.so")
 
 FS_V_NCONV = 10
 FS_T_NCONV = 16
-ENG_TRANSFORM, ENG_TRANSFORM_BWD, ENG_VGG, ENG_VGG_BWD = 1, 2, 4, 8
+ENG_TRANSFORM, ENG_TRANSFORM_BWD, ENG_VGG, ENG_VGG_BWD, ENG_DECONV = 1, 2, 4, 8, 16
 
 
 class FsError(RuntimeError):

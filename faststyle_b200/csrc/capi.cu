@@ -61,7 +61,9 @@ int fs_vgg_pack(const float* flat, float* packed, void* stream) { return vgg_pac
 int fs_engine_create(int N, int H, int W, int flags, unsigned content_mask, unsigned style_mask,
                      fs_engine** out) {
     FS_CHECK(out != nullptr, "fs_engine_create: out is NULL");
-    FS_CHECK(flags != 0 && (flags & ~15) == 0, "fs_engine_create: bad flags 0x%x", flags);
+    FS_CHECK(flags != 0 && (flags & ~31) == 0, "fs_engine_create: bad flags 0x%x", flags);
+    FS_CHECK(!(flags & ENG_DECONV) || ((flags & ENG_TRANSFORM) && !(flags & ENG_TRANSFORM_BWD)),
+             "DECONV is a forward-only transform-net variant");
     FS_CHECK(!(flags & ENG_TRANSFORM_BWD) || (flags & ENG_TRANSFORM), "TRANSFORM_BWD needs TRANSFORM");
     FS_CHECK(!(flags & ENG_VGG_BWD) || (flags & ENG_VGG), "VGG_BWD needs VGG");
     FS_CHECK((content_mask >> V_NCONV) == 0 && (style_mask >> V_NCONV) == 0, "loss masks address layers > conv4_3");

@@ -253,6 +253,7 @@ void Engine::layout(Arena& a) {
         y3 = a.take<float>((long long)N * OH * OW * 3);
         in_partial = a.take<double>((long long)N * 64 * 64 * 2);
         in15 = a.take<float>(8);
+        wtmp15 = a.take<float>(81 * 64);
         if (tbw) {
             m12 = a.take<float>((long long)N * 64 * 2);
             for (int i = 0; i < 3; ++i) tgrad[i] = a.take<float>(maxact);
@@ -317,9 +318,20 @@ int Engine::bind(void* ws, size_t bytes) {
 int Engine::prep_transform_weights(const float* params, bool need_bwd, cudaStream_t st) {
     FS_CHECK(bound && (flags & ENG_TRANSFORM), "engine has no transform plan / workspace");
     PROF(PC_PREP, 0.0, pad_taps(params + tc[0].offW, weff[0], 81, 3, 16, 4, 16, st));
-    PROF(PC_PREP, 0.0, pad_taps(params + tc[15].offW, weff[15], 81, 16, 3, 16, 4, st));
-    PROF(PC_PREP, 0.0, upconv_collapse(params + tc[13].offW, weff[13], tc[13].cin, tc[13].cout, st));
-    PROF(PC_PREP, 0.0, upconv_collapse(params + tc[14].offW, weff[14], tc[14].cin, tc[14].cout, st));
+    if (flags & ENG_DECONV) {
+        // 'deconv' models (reference im_transf_net.py:57-63,158-190): W is [k,k,cout,cin] and the layer is
+        // tf.nn.conv2d_transpose = the data gradient of a SAME conv.  Stride 2: the 4-phase 2x2 sub-pixel form
+        // (the same machinery as the stride-2 data gradients); stride 1 (9x9): a conv with flipped weights.
+        FS_CHECK(!need_bwd, "training the 'deconv' upsampling variant is not implemented (forward only)");
+        PROF(PC_PREP, 0.0, s2_dgrad_collapse(params + tc[13].offW, weff[13], tc[13].cout, tc[13].cin, st));
+        PROF(PC_PREP, 0.0, s2_dgrad_collapse(params + tc[14].offW, weff[14], tc[14].cout, tc[14].cin, st));
+        PROF(PC_PREP, 0.0, pad_taps(params + tc[15].offW, wtmp15, 81, 3, 16, 4, 16, st));
+        PROF(PC_PREP, 0.0, flip_transpose_taps(wtmp15, weff[15], 81, 4, 16, st));
+    } else {
+        PROF(PC_PREP, 0.0, pad_taps(params + tc[15].offW, weff[15], 81, 16, 3, 16, 4, st));
+        PROF(PC_PREP, 0.0, upconv_collapse(params + tc[13].offW, weff[13], tc[13].cin, tc[13].cout, st));
+        PROF(PC_PREP, 0.0, upconv_collapse(params + tc[14].offW, weff[14], tc[14].cin, tc[14].cout, st));
+    }
     // 4-channel staging of the last layer's IN scale/shift (its flat slots are 3 floats, unaligned)
     FS_TRY(fill_zero(in15, 8 * sizeof(float), st));
     FS_CUDA(cudaMemcpyAsync(in15, params + tc[15].offG, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -387,6 +399,7 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
         } else {
             IGemmArgs a;
             conv_fwd_args(c, N, cur, weff[l] ? weff[l] : params + c.offW, tb[l].raw, a);
+            if (c.upconv && (flags & ENG_DECONV)) a.gather = 1;      // transposed conv: iy = oy - a
             PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
         }
         PROF(PC_IN_STATS, 0.0, instnorm_stats(tb[l].raw, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, in_partial, st));

@@ -44,7 +44,7 @@ struct LossConfig {
 
 enum ProfCat { PC_TC_VGG_FWD = 0, PC_TC_VGG_DGRAD, PC_TC_RES_FWD, PC_TC_RES_DGRAD, PC_FFMA_CONV, PC_WGRAD,
                PC_GRAM_FWD, PC_GRAM_BWD, PC_IN_STATS, PC_IN_APPLY, PC_IN_BWD, PC_POINTWISE, PC_LOSS, PC_PREP, PC_COUNT };
-enum EngineFlags { ENG_TRANSFORM = 1, ENG_TRANSFORM_BWD = 2, ENG_VGG = 4, ENG_VGG_BWD = 8 };
+enum EngineFlags { ENG_TRANSFORM = 1, ENG_TRANSFORM_BWD = 2, ENG_VGG = 4, ENG_VGG_BWD = 8, ENG_DECONV = 16 };
 
 struct Arena {
     char* base = nullptr; size_t off = 0; size_t cap = 0;
@@ -78,6 +78,7 @@ struct Engine {
     double* in_partial = nullptr;
     float* in15 = nullptr;               // 4-channel staging of the last layer's IN scale/shift
     float* gb_tmp = nullptr;
+    float* wtmp15 = nullptr;             // staging for the deconv variant of the last layer's weights
     float* m12 = nullptr;
     float* tgrad[3];                     // rotating gradient buffers (transform bwd)
     float* wg_partial = nullptr; long long wg_partial_cap = 0;

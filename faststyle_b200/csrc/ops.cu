@@ -346,53 +346,61 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restric
     }
 }
 
+// One thread per 2x2 pooling window and 4 channels: the four activations are read once (the previous
+// per-output-pixel form re-read every window four times).
 __global__ void pool_bwd_combine_kernel(const float* __restrict__ act, const float* __restrict__ gpool,
                                         const float* __restrict__ ctarget, float cw2, int apply_mask,
                                         float* __restrict__ out, int N, int H, int W, int C) {
     const int C4 = C >> 2, PH = (H + 1) >> 1, PW = (W + 1) >> 1;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)N * H * W * C4;
+    long long total = (long long)N * PH * PW * C4;
     if (i >= total) return;
     int c = (int)(i % C4) * 4;
-    long long pix = i / C4;
-    int x = (int)(pix % W);
-    long long r = pix / W;
-    int y = (int)(r % H);
-    int n = (int)(r / H);
-    float4 a4 = ld4(act + i * 4);
-    float a[4] = {a4.x, a4.y, a4.z, a4.w};
-    float res[4] = {0.f, 0.f, 0.f, 0.f};
-    if (gpool) {
-        int py = y >> 1, px = x >> 1;
-        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        int arg[4] = {0, 0, 0, 0};
+    long long pp = i / C4;
+    int px = (int)(pp % PW);
+    long long r = pp / PW;
+    int py = (int)(r % PH);
+    int n = (int)(r / PH);
+    float v[4][4];
+    bool in[4];
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int arg[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int yy = 2 * py + (k >> 1), xx = 2 * px + (k & 1);
-            if (yy < H && xx < W) {
-                float4 v4 = ld4(act + (((long long)n * H + yy) * W + xx) * C + c);
-                float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    for (int k = 0; k < 4; ++k) {
+        int yy = 2 * py + (k >> 1), xx = 2 * px + (k & 1);
+        in[k] = yy < H && xx < W;
+        if (in[k]) {
+            float4 v4 = ld4(act + (((long long)n * H + yy) * W + xx) * C + c);
+            v[k][0] = v4.x; v[k][1] = v4.y; v[k][2] = v4.z; v[k][3] = v4.w;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (v[j] > best[j]) { best[j] = v[j]; arg[j] = k; }
-            }
+            for (int j = 0; j < 4; ++j)
+                if (v[k][j] > best[j]) { best[j] = v[k][j]; arg[j] = k; }       // first maximum wins (scan order)
         }
-        int me = ((y & 1) << 1) | (x & 1);
-        float4 g4 = ld4(gpool + (((long long)n * PH + py) * PW + px) * C + c);
-        float g[4] = {g4.x, g4.y, g4.z, g4.w};
+    }
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    if (gpool) {
+        float4 g4 = ld4(gpool + i * 4);
+        g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
+    }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) res[j] = arg[j] == me ? g[j] : 0.f;
-    }
-    if (ctarget) {
-        float4 t4 = ld4(ctarget + i * 4);
-        res[0] += cw2 * (a[0] - t4.x); res[1] += cw2 * (a[1] - t4.y);
-        res[2] += cw2 * (a[2] - t4.z); res[3] += cw2 * (a[3] - t4.w);
-    }
-    if (apply_mask) {
+    for (int k = 0; k < 4; ++k) {
+        if (!in[k]) continue;
+        int yy = 2 * py + (k >> 1), xx = 2 * px + (k & 1);
+        long long o = (((long long)n * H + yy) * W + xx) * C + c;
+        float res[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) res[j] = a[j] > 0.f ? res[j] : 0.f;
+        for (int j = 0; j < 4; ++j) res[j] = (gpool && arg[j] == k) ? g[j] : 0.f;
+        if (ctarget) {
+            float4 t4 = ld4(ctarget + o);
+            res[0] += cw2 * (v[k][0] - t4.x); res[1] += cw2 * (v[k][1] - t4.y);
+            res[2] += cw2 * (v[k][2] - t4.z); res[3] += cw2 * (v[k][3] - t4.w);
+        }
+        if (apply_mask) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) res[j] = v[k][j] > 0.f ? res[j] : 0.f;
+        }
+        st4(out + o, make_float4(res[0], res[1], res[2], res[3]));
     }
-    st4(out + i * 4, make_float4(res[0], res[1], res[2], res[3]));
 }
 
 // ------------------------------------------------------------------ losses
@@ -674,7 +682,7 @@ int maxpool2x2_fwd(const float* x, float* out, int N, int H, int W, int C, cudaS
 int pool_bwd_combine(const float* act, const float* gpool, const float* ctarget, float cw2,
                      int apply_mask, float* out, int N, int H, int W, int C, cudaStream_t st) {
     FS_CHECK(C % 4 == 0, "pool_bwd: C%%4 != 0");
-    long long n = (long long)N * H * W * (C / 4);
+    long long n = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
     pool_bwd_combine_kernel<<<grid1(n), 256, 0, st>>>(act, gpool, ctarget, cw2, apply_mask, out, N, H, W, C);
     FS_LAUNCH_CHECK();
     return 0;

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ENG_TRANSFORM, ENG_TRANSFORM_BWD, ENG_VGG, ENG_VGG_BWD, FsError, LossConfigC
+from ._lib import ENG_DECONV, ENG_TRANSFORM, ENG_TRANSFORM_BWD, ENG_VGG, ENG_VGG_BWD, FsError, LossConfigC
 from .layout import (TRANSFORM_NPARAMS, VGG_CONV_NAMES, flatten_transform, flatten_vgg,
                      vgg_layer_index)
 
@@ -83,13 +83,13 @@ class Engine:
     """Plan + workspace for batch ``N`` of ``H x W`` RGB images."""
 
     def __init__(self, N, H, W, transform=False, transform_bwd=False, vgg=False, vgg_bwd=False,
-                 content_layers=(), style_layers=(), device="cuda:0"):
+                 content_layers=(), style_layers=(), device="cuda:0", deconv=False):
         _require_cuda()
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.N, self.H, self.W = int(N), int(H), int(W)
         flags = (ENG_TRANSFORM if transform or transform_bwd else 0) | (ENG_TRANSFORM_BWD if transform_bwd else 0) \
-            | (ENG_VGG if vgg or vgg_bwd else 0) | (ENG_VGG_BWD if vgg_bwd else 0)
+            | (ENG_VGG if vgg or vgg_bwd else 0) | (ENG_VGG_BWD if vgg_bwd else 0) | (ENG_DECONV if deconv else 0)
         self.flags = flags
         self._h = C.c_void_p()
         _lib.call("fs_engine_create", self.N, self.H, self.W, flags, _mask(content_layers),
@@ -216,5 +216,5 @@ class TFAdam:
                       ptr(self.step_counter), stream_ptr())
 
 
-def params_to_device(params: dict, device) -> torch.Tensor:
-    return torch.from_numpy(flatten_transform(params)).to(device)
+def params_to_device(params: dict, device, upsample_method="resize") -> torch.Tensor:
+    return torch.from_numpy(flatten_transform(params, upsample_method)).to(device)

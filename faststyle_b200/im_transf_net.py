@@ -15,7 +15,7 @@ import torch
 from . import ops
 from . import variables as V
 from .engine import Engine, f32, params_to_device
-from .layout import TRANSFORM_VARS, SCOPE
+from .layout import SCOPE, transform_vars
 
 _RNG = np.random.RandomState(0)
 _engines = {}
@@ -37,15 +37,11 @@ def create_net(X, upsample_method='deconv'):
     """Creates (evaluates) the transformation network on the NHWC batch ``X`` (values 0..255).
 
     :param X  NxHxWx3 array / tensor
-    :param upsample_method  'deconv' or 'resize'.  The shipped checkpoints and both CLIs use
-        'resize' (fused resize-convolution); the 'deconv' variant (conv2d_transpose,
-        im_transf_net.py:57-63,158-190) has no device kernel yet and raises.
+    :param upsample_method  'deconv' or 'resize'.  The shipped checkpoints and both CLIs default to
+        'resize' (fused resize-convolution).  'deconv' (conv2d_transpose, im_transf_net.py:57-63,158-190)
+        is supported for inference (forward); training that variant is not implemented.
     """
     assert(upsample_method in ['deconv', 'resize'])
-    if upsample_method == 'deconv':
-        raise NotImplementedError(
-            "upsample_method='deconv' (tf.nn.conv2d_transpose) is not implemented on the B200 "
-            "engine yet; the shipped models and the CLI defaults use 'resize'")
     scope = V.current_scope()
     if scope != SCOPE:
         raise ValueError("create_net must be called inside variable_scope('%s') so that variable names match "
@@ -53,19 +49,19 @@ def create_net(X, upsample_method='deconv'):
     # variables are declared relative to the current scope (created with the reference's
     # initialisers when a checkpoint has not been restored)
     params = {}
-    for full, shape in TRANSFORM_VARS:
+    for full, shape in transform_vars(upsample_method):
         rel = full[len(SCOPE) + 1:]
         params[full] = V.get_variable(rel, shape, _initializer_for(rel))
     dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
     x = f32(X, dev) if dev is not None else X
     N, H, W_, C_ = x.shape
     assert C_ == 3, "create_net expects RGB input (N x H x W x 3)"
-    key = (N, H, W_, str(dev))
+    key = (N, H, W_, str(dev), upsample_method)
     eng = _engines.get(key)
     if eng is None:
         _engines.clear()                      # keep at most one cached plan
-        eng = _engines[key] = Engine(N, H, W_, transform=True, device=dev)
-    return eng.transform_forward(params_to_device(params, dev), x)
+        eng = _engines[key] = Engine(N, H, W_, transform=True, device=dev, deconv=upsample_method == 'deconv')
+    return eng.transform_forward(params_to_device(params, dev, upsample_method), x)
 
 
 def _initializer_for(rel):
@@ -101,8 +97,11 @@ def upconv2d(X, n_ch_in, n_ch_out, kernel_size, strides):
 
 
 def deconv2d(X, n_ch_in, n_ch_out, kernel_size, strides):
-    """Transposed convolution (im_transf_net.py:158-190) - not implemented on the device yet."""
-    raise NotImplementedError("deconv2d (tf.nn.conv2d_transpose) has no B200 kernel yet")
+    """Transposed convolution, SAME, output = input * stride (im_transf_net.py:158-190).
+    Note the reversed channel order of the weight: [k, k, n_ch_out, n_ch_in]."""
+    assert strides[0] == 1 and strides[3] == 1 and strides[1] == strides[2]
+    W = V.get_variable('W', [kernel_size, kernel_size, n_ch_out, n_ch_in], _normal(1.0))
+    return ops.conv2d_transpose(X, W, strides[1])
 
 
 def relu(X):

@@ -30,6 +30,16 @@ def _build():
 
 
 TRANSFORM_VARS = _build()                       # resize-upsampling variant (shipped ckpts)
+# 'deconv' variant: conv2d_transpose weights are [k, k, cout, cin] (im_transf_net.py:173); same element
+# counts, hence the same flat offsets
+_DECONV_SHAPES = {SCOPE + "/upsample_0/W": (3, 3, 32, 64), SCOPE + "/upsample_1/W": (3, 3, 16, 32),
+                  SCOPE + "/upsample_2/W": (9, 9, 3, 16)}
+TRANSFORM_VARS_DECONV = [(n, _DECONV_SHAPES.get(n, s)) for n, s in TRANSFORM_VARS]
+
+
+def transform_vars(upsample_method="resize"):
+    assert upsample_method in ("resize", "deconv")
+    return TRANSFORM_VARS if upsample_method == "resize" else TRANSFORM_VARS_DECONV
 assert [n for n, _ in TRANSFORM_VARS] == sorted(n for n, _ in TRANSFORM_VARS)
 TRANSFORM_NPARAMS = int(sum(int(np.prod(s)) for _, s in TRANSFORM_VARS))
 assert TRANSFORM_NPARAMS == 424102
@@ -40,18 +50,18 @@ VGG_CHANNELS = [(3, 64), (64, 64), (64, 128), (128, 128), (128, 256), (256, 256)
                 (256, 512), (512, 512), (512, 512)]
 
 
-def transform_offsets() -> "OrderedDict[str, tuple[int, tuple]]":
+def transform_offsets(upsample_method="resize") -> "OrderedDict[str, tuple[int, tuple]]":
     out, off = OrderedDict(), 0
-    for name, shape in TRANSFORM_VARS:
+    for name, shape in transform_vars(upsample_method):
         out[name] = (off, shape)
         off += int(np.prod(shape))
     return out
 
 
-def flatten_transform(params: dict) -> np.ndarray:
+def flatten_transform(params: dict, upsample_method="resize") -> np.ndarray:
     """{name: array} -> flat float32 [424102] (names with or without the scope prefix)."""
     flat = np.empty(TRANSFORM_NPARAMS, np.float32)
-    for name, (off, shape) in transform_offsets().items():
+    for name, (off, shape) in transform_offsets(upsample_method).items():
         key = name if name in params else name[len(SCOPE) + 1:]
         if key not in params:
             raise KeyError("transform-net variable %r missing (wrong --upsample_method for this "

@@ -52,6 +52,24 @@ def conv2d(x, w, stride=1, padding="SAME", bias=None, relu=False):
     return y[..., :Co].contiguous() if wp.shape[3] != Co else y
 
 
+def conv2d_transpose(x, w, stride=2):
+    """tf.nn.conv2d_transpose, SAME, output = input*stride; ``w`` is [k,k,cout,cin]
+    (im_transf_net.py:158-190).  Computed as the data gradient of the SAME conv it transposes."""
+    x, w = _dev(x), _dev(w)
+    N, h, w_, Ci = x.shape
+    K, _, Co, Ci2 = w.shape
+    assert Ci2 == Ci
+    H, W_ = h * stride, w_ * stride
+    wp = F.pad(w, (0, (-Ci) % 4, 0, (-Co) % 4)).contiguous()          # conv weights [k,k,C=cout,OC=cin]
+    xp, _ = _pad_c(x)
+    Cp, OCp = wp.shape[2], wp.shape[3]
+    out = torch.empty((N, H, W_, Cp), dtype=torch.float32, device=x.device)
+    scratch = torch.empty(K * K * Cp * OCp, dtype=torch.float32, device=x.device)
+    _lib.call("fs_conv2d_dgrad", ptr(xp), ptr(wp), ptr(out), ptr(scratch), N, H, W_, Cp, K, K, OCp, stride, 1,
+              stream_ptr())
+    return out[..., :Co].contiguous() if Cp != Co else out
+
+
 def upconv2d(x, w):
     """Resize-conv: NN x4 + 3x3 stride-2 SAME conv, fused (im_transf_net.py:122-155)."""
     x, w = _dev(x), _dev(w)

@@ -50,7 +50,9 @@ int fs_vgg_pack(const float* flat, float* packed, void* stream);
 
 /* ------------------------------------------------------------------ engine plan */
 typedef struct fs_engine fs_engine;
-enum { FS_ENG_TRANSFORM = 1, FS_ENG_TRANSFORM_BWD = 2, FS_ENG_VGG = 4, FS_ENG_VGG_BWD = 8 };
+/* FS_ENG_DECONV: the transform net's 'deconv' upsampling variant (conv2d_transpose layers, reference
+ * im_transf_net.py:57-63); forward only.  Without it the 'resize' variant (resize-convolution) is planned. */
+enum { FS_ENG_TRANSFORM = 1, FS_ENG_TRANSFORM_BWD = 2, FS_ENG_VGG = 4, FS_ENG_VGG_BWD = 8, FS_ENG_DECONV = 16 };
 
 /* Plan for batch N of HxW RGB images.  content_mask / style_mask: bit l set =
  * VGG conv index l (0 = conv1_1 ... 9 = conv4_3) carries a content / style tap. */

@@ -66,7 +66,48 @@ def test_mirror_ops_and_create_net(built_lib, golden_dir):
     with pytest.raises(AssertionError):
         with V.variable_scope('img_t_net'):
             T.create_net(x, 'bilinear')
-    with pytest.raises(NotImplementedError):
+    V.reset_default_graph()
+
+
+def test_deconv_variant_forward(built_lib):
+    """upsample_method='deconv' (conv2d_transpose layers, im_transf_net.py:57-63,158-190): forward parity
+    with the oracle restatement (unpinned: the reference ships no deconv checkpoint or golden)."""
+    from faststyle_b200 import im_transf_net as T
+    from faststyle_b200 import variables as V
+    from faststyle_b200.layout import TRANSFORM_VARS_DECONV
+    rng = np.random.RandomState(5)
+    params = {}
+    for name, shape in TRANSFORM_VARS_DECONV:
+        leaf = name.rsplit("/", 1)[1]
+        if leaf.startswith("INscale"):
+            params[name] = (1.0 + 0.1 * rng.standard_normal(shape)).astype(np.float32)
+        elif leaf.startswith("INshift"):
+            params[name] = (0.1 * rng.standard_normal(shape)).astype(np.float32)
+        else:
+            params[name] = (rng.standard_normal(shape) * (0.3 if "upsample" in name else 0.1)).astype(np.float32)
+    x = rng.randint(0, 256, (2, 56, 64, 3)).astype(np.float32)
+    V.reset_default_graph()
+    for k, v in params.items():
+        V.set_variable(k, v)
+    with V.variable_scope('img_t_net'):
+        y = T.create_net(x, 'deconv')
+    with torch.no_grad():
+        yo = R.create_net(x, params, "deconv", torch.float64)
+    assert tuple(y.shape) == tuple(yo.shape)
+    assert float((y.double().cpu() - yo).abs().max()) / 255.0 < 2e-4
+    # single transposed-conv op (stride 2, [k,k,cout,cin] weights)
+    xs = rng.standard_normal((1, 9, 7, 8)).astype(np.float32)
+    w = rng.standard_normal((3, 3, 4, 8)).astype(np.float32)
+    V.reset_default_graph()
+    V.set_variable('t/W', w)
+    with V.variable_scope('t'):
+        d = T.deconv2d(xs, 8, 4, 3, [1, 2, 2, 1])
+    do = R.nchw_to_nhwc(R.deconv2d(R.nhwc_to_nchw(torch.from_numpy(xs).double()), torch.from_numpy(w).double(), 2))
+    assert tuple(d.shape) == (1, 18, 14, 4) and _relerr(d, do) < 1e-5
+    # a 'resize' checkpoint under --upsample_method deconv is a shape error, like the reference's Saver
+    V.reset_default_graph()
+    V.Saver().restore(None, os.path.join(os.path.dirname(__file__), "golden", "starry_final.ckpt"))
+    with pytest.raises(ValueError):
         with V.variable_scope('img_t_net'):
             T.create_net(x, 'deconv')
     V.reset_default_graph()

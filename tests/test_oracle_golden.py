@@ -86,3 +86,17 @@ def test_loss_definitions_small():
     assert float(R.style_loss([G], [torch.zeros(1, 2, 2, dtype=torch.float64)], [3.0])) == pytest.approx(3.0 * float((G ** 2).sum()) / 4)
     x = torch.tensor([[[[0., 1.], [3., 6.]]]], dtype=torch.float64)
     assert float(R.tv_loss(x)) == pytest.approx((1 ** 2 + 3 ** 2) + (3 ** 2 + 5 ** 2))
+
+
+def test_oracle_deconv_is_conv_gradient():
+    """tf.nn.conv2d_transpose(SAME) is DEFINED as the gradient of conv2d(SAME) w.r.t. its input
+    (im_transf_net.py:158-190): the oracle's deconv2d must equal autograd of conv2d_tf."""
+    g = torch.Generator().manual_seed(3)
+    for stride, k, hw in ((2, 3, (6, 5)), (1, 9, (7, 8)), (2, 3, (5, 7))):
+        x = torch.randn(2, 4, hw[0], hw[1], generator=g, dtype=torch.float64)          # transpose input: cin=4
+        w = torch.randn(k, k, 3, 4, generator=g, dtype=torch.float64)                  # [k,k,cout=3,cin=4]
+        big = torch.zeros(2, 3, hw[0] * stride, hw[1] * stride, dtype=torch.float64, requires_grad=True)
+        y = R.conv2d_tf(big, w, stride, "SAME")                                        # conv: 3 -> 4 channels
+        assert tuple(y.shape) == tuple(x.shape)
+        (gin,) = torch.autograd.grad(y, big, x)
+        assert float((R.deconv2d(x, w, stride) - gin).abs().max()) < 1e-10
