@@ -559,7 +559,9 @@ int Engine::vgg_forward(const float* packed, const float* img3, int upto, float*
             ta.N = N; ta.H = vc[l].H; ta.W = vc[l].W; ta.C = vc[l].cin;
             ta.OH = vc[l].H; ta.OW = vc[l].W; ta.OC = vc[l].cout; ta.pad = 1;
             ta.bias = packed + vc[l].offB; ta.relu = 1;
-            ta.out_f32 = out;
+            // content-target pass: only pooled layers, the targets and the last layer need an fp32 copy
+            const bool need_f32 = !act_override || pool_next || act_override[l] || l == upto;
+            ta.out_f32 = need_f32 ? out : nullptr;
             if (l < upto && !pool_next) ta.out_split = vsplit[l + 1];     // next conv reads split planes
             else if (vtsplit[l].hi) ta.out_split = vtsplit[l];            // style tap: Gram kernels read them
             PROF(PC_TC_VGG_FWD, tc_flops(ta), launch_conv3x3_tc(ta, st));
@@ -738,7 +740,8 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
                 }
                 int oi = pick(gi, ti, -1);
                 const bool tcg = act_planes(l, top).hi != nullptr;
-                FS_TRY(gram_bwd(l, T, vact[l], vgrad[oi], tcg ? vgsplit[oi] : no_split));
+                // P_l feeds the tensor-path data gradient of conv l: only its split planes are needed
+                FS_TRY(gram_bwd(l, T, vact[l], tcg ? nullptr : vgrad[oi], tcg ? vgsplit[oi] : no_split));
                 if (!tcg) PROF(PC_POINTWISE, 0.0, ensure_split(l, oi));
                 pi = oi;
             } else {
@@ -765,7 +768,7 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
                 A = vgrad[ai];
             }
             int oi = pick(pi, ai, -1);
-            FS_TRY(dgrad(l + 1, pi, vgrad[oi], (use_tc && l >= 1) ? vgsplit[oi] : no_split, A, vact[l]));
+            FS_TRY(dgrad(l + 1, pi, (use_tc && l >= 1) ? nullptr : vgrad[oi], (use_tc && l >= 1) ? vgsplit[oi] : no_split, A, vact[l]));
             pi = oi;
         }
     }
