@@ -482,7 +482,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 
 struct WCfg { int WK, WN, WP; };
 WCfg pick_wcfg(int OC) {
-    if (OC > 16) return {64, 64, 16};
+    if (OC > 32) return {64, 64, 16};
+    if (OC > 16) return {64, 32, 16};          // 17..32 output channels: a 64-wide tile would be half padding
     if (OC > 4) return {256, 16, 16};
     return {512, 4, 8};
 }
@@ -527,6 +528,7 @@ int launch_wgrad(const WGradArgs& a, cudaStream_t st) {
     FS_CHECK((long long)g.groups * g.splits <= 65535, "wgrad: too many z blocks");
     dim3 grid(cdiv(g.Ktot, c.WK), cdiv(a.OC, c.WN), g.groups * g.splits);
     if (c.WN == 64) wgrad_kernel<64, 64, 8, 16, 128><<<grid, 128, 0, st>>>(a, g);
+    else if (c.WN == 32) wgrad_kernel<64, 32, 8, 16, 64><<<grid, 64, 0, st>>>(a, g);
     else if (c.WN == 16) wgrad_kernel<256, 16, 8, 16, 128><<<grid, 128, 0, st>>>(a, g);
     else wgrad_kernel<512, 4, 8, 8, 64><<<grid, 64, 0, st>>>(a, g);
     FS_LAUNCH_CHECK();
