@@ -16,6 +16,14 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 long long g_launches = 0;
+int g_pdl = -1;
+int pdl_enabled() {
+    if (g_pdl < 0) {
+        const char* e = getenv("FS_PDL");
+        g_pdl = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_pdl;
+}
 }  // namespace fs
 
 using namespace fs;

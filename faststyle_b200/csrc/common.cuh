@@ -45,6 +45,45 @@ extern long long g_launches;
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// The step is a chain of ~240 short kernels (mean 30 us).  Every kernel is launched with the
+// programmatic-stream-serialization attribute and starts with FS_PDL_ENTER(): it releases its own
+// dependents at once and then waits for the WHOLE preceding grid to complete and flush
+// (griddepcontrol.wait), so memory ordering is exactly that of plain stream order while the launch
+// latency, CTA scheduling and the predecessor's tail overlap.  Nothing may touch global memory before
+// FS_PDL_ENTER() (the tensor-core kernels split it: FS_PDL_TRIGGER() first, then barrier init / TMEM
+// allocation / descriptor prefetch -- none of which reads global memory -- then FS_PDL_WAIT() by every
+// thread).  FS_PDL=0 in the environment turns the attribute off (the device side is then a no-op).
+extern int g_pdl;   // -1 unknown, 0 off, 1 on
+int pdl_enabled();
+
+#ifdef __CUDACC__
+#define FS_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define FS_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define FS_PDL_ENTER()    \
+    do {                  \
+        FS_PDL_TRIGGER(); \
+        FS_PDL_WAIT();    \
+    } while (0)
+
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);   // the error is picked up by FS_LAUNCH_CHECK
+}
+#endif
+
 // TF 'SAME' padding rule: out = ceil(n/s),
 // total = max((out-1)*s + k - n, 0), before = total/2.
 static inline void tf_same(int n, int k, int s, int* out, int* before) {

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(256, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                   const TcParams p) {
+    FS_PDL_TRIGGER();
     using K = Cfg<TH, BN>;
     constexpr int A_STAGES = K::A_STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -110,6 +111,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    FS_PDL_WAIT();                        // everything above is CTA-local setup
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0 && lane == 0) {
@@ -302,6 +304,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 // ------------------------------------------------------------------ helpers kernels
 __global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                   __nv_bfloat16* __restrict__ lo, long long n4) {
+    FS_PDL_ENTER();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     float4 v = *reinterpret_cast<const float4*>(x + i * 4);
@@ -321,6 +324,7 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __
 
 __global__ void pack_w3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
                                  __nv_bfloat16* __restrict__ lo, int Ci, int Co, int mode) {
+    FS_PDL_ENTER();
     // output index: (((tap*CB + cb)*Nn + n)*64 + k)
     const int Kc = mode == 0 ? Ci : Co;        // reduction channels
     const int Nn = mode == 0 ? Co : Ci;        // output channels
@@ -345,6 +349,7 @@ __global__ void pack_w3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __r
 struct PackBatch { const float* w[16]; __nv_bfloat16* hi[16]; __nv_bfloat16* lo[16]; };
 
 __global__ void pack_w3x3_batch_kernel(const PackBatch pb, int Ci, int Co, int mode) {
+    FS_PDL_ENTER();
     const float* __restrict__ w = pb.w[blockIdx.y];
     __nv_bfloat16* __restrict__ hi = pb.hi[blockIdx.y];
     __nv_bfloat16* __restrict__ lo = pb.lo[blockIdx.y];
@@ -442,7 +447,7 @@ int launch_cfg(const Conv3x3TcArgs& a, cudaStream_t st) {
         attr_set = true;
     }
     int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
-    conv3x3_tc_kernel<TH, BN><<<grid, 256, K::SMEM_BYTES, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    launch_k((conv3x3_tc_kernel<TH, BN>), dim3(grid), dim3(256), K::SMEM_BYTES, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     FS_LAUNCH_CHECK();
     return 0;
 }
@@ -473,7 +478,7 @@ int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st) {
 int split_bf16(const float* x, SplitPtr out, long long n, cudaStream_t st) {
     FS_CHECK(n % 4 == 0, "split_bf16: n %% 4 != 0");
     long long n4 = n / 4;
-    split_bf16_kernel<<<cdiv(n4, 256), 256, 0, st>>>(x, out.hi, out.lo, n4);
+    launch_k(split_bf16_kernel, dim3(cdiv(n4, 256)), dim3(256), 0, st, x, out.hi, out.lo, n4);
     FS_LAUNCH_CHECK();
     return 0;
 }
@@ -484,7 +489,7 @@ int pack_w3x3_tc_batch(const float* const* w, const SplitPtr* out, int count, in
     PackBatch pb;
     for (int i = 0; i < count; ++i) { pb.w[i] = w[i]; pb.hi[i] = out[i].hi; pb.lo[i] = out[i].lo; }
     dim3 grid(cdiv(9LL * Ci * Co, 256), count);
-    pack_w3x3_batch_kernel<<<grid, 256, 0, st>>>(pb, Ci, Co, mode);
+    launch_k(pack_w3x3_batch_kernel, dim3(grid), dim3(256), 0, st, pb, Ci, Co, mode);
     FS_LAUNCH_CHECK();
     return 0;
 }
@@ -492,7 +497,7 @@ int pack_w3x3_tc_batch(const float* const* w, const SplitPtr* out, int count, in
 int pack_w3x3_tc(const float* w, SplitPtr out, int Ci, int Co, int mode, cudaStream_t st) {
     FS_CHECK(Ci % 64 == 0 && Co % 64 == 0, "pack_w3x3_tc: channels must be multiples of 64");
     long long total = 9LL * Ci * Co;
-    pack_w3x3_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, out.hi, out.lo, Ci, Co, mode);
+    launch_k(pack_w3x3_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, w, out.hi, out.lo, Ci, Co, mode);
     FS_LAUNCH_CHECK();
     return 0;
 }

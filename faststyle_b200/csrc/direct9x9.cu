@@ -21,6 +21,7 @@ constexpr int NT9 = 352;          // 11 warps; 324 = 81 taps x 4 channel blocks 
 template <int CI, int CO>
 __global__ void __launch_bounds__(NT9) wgrad9x9_kernel(const float* __restrict__ in, const float* __restrict__ dy,
                                                        float* __restrict__ partial, int H, int W) {
+    FS_PDL_ENTER();
     static_assert(CI * CO == 64 && CI % 4 == 0 && CO % 4 == 0, "channel block must be 4x16 or 16x4");
     constexpr int CIQ = CI / 4, COQ = CO / 4;
     extern __shared__ float4 sm4[];
@@ -82,6 +83,7 @@ constexpr int PITCH = HS + 1;     // row pitch (float4) that spreads the 32 row-
 template <int CI, int CO>
 __global__ void __launch_bounds__(256, 2) conv9x9_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                          float* __restrict__ out, int H, int W) {
+    FS_PDL_ENTER();
     constexpr int CIQ = CI / 4, COQ = CO / 4;
     extern __shared__ float4 sm4[];
     float4* in_s = sm4;                              // [CIQ][HS][PITCH]
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(256) conv3x3_c4_fwd_kernel(const float* __rest
                                                              const float* __restrict__ bias, float* __restrict__ out,
                                                              __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo,
                                                              int H, int W) {
+    FS_PDL_ENTER();
     __shared__ float4 in_s[(C1_ROWS + 2) * C1_PITCH];
     __shared__ float4 w_s[9 * 4 * 16];
     __shared__ float4 b_s[16];
@@ -263,6 +266,7 @@ __global__ void __launch_bounds__(256) conv3x3_c4_fwd_kernel(const float* __rest
 // warp = (column group, 16-channel slice of the reduction); the 4 slices are summed through shared memory.
 __global__ void __launch_bounds__(256) dgrad3x3_c4_kernel(const float* __restrict__ P, const float* __restrict__ wf,
                                                           float* __restrict__ dx, int H, int W) {
+    FS_PDL_ENTER();
     extern __shared__ float4 sm4[];
     float4* in_s = sm4;                                         // [16 channel quads][ROWS+2][PITCH]
     float4* w_s = sm4 + 16 * (C1_ROWS + 2) * C1_PITCH;          // [9][64] float4
@@ -341,6 +345,7 @@ __global__ void __launch_bounds__(256) dgrad3x3_c4_kernel(const float* __restric
 
 // Wf[80-tap][co][ci] = W[tap][ci][co]: weights that turn the data gradient into a forward convolution
 __global__ void flip_transpose_taps_kernel(const float* __restrict__ W, float* __restrict__ Wf, int T, int Ci, int Co) {
+    FS_PDL_ENTER();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)T * Ci * Co) return;
     int ci = (int)(i % Ci);
@@ -353,6 +358,7 @@ __global__ void flip_transpose_taps_kernel(const float* __restrict__ W, float* _
 // out[i] = sum_b partial[b][i]; 32 elements x 8 block-slices per CTA, fixed summation order
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                                               int elems, int nblocks) {
+    FS_PDL_ENTER();
     __shared__ float red[8][33];
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + lx;
@@ -379,11 +385,11 @@ int launch_conv9x9(const float* in, const float* w, float* out, int N, int H, in
     if (CI == 4) {
         static bool set = false;
         if (!set) { FS_CUDA(cudaFuncSetAttribute(conv9x9_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
-        conv9x9_kernel<4, 16><<<grid, 256, smem, st>>>(in, w, out, H, W);
+        launch_k((conv9x9_kernel<4, 16>), dim3(grid), dim3(256), smem, st, in, w, out, H, W);
     } else {
         static bool set = false;
         if (!set) { FS_CUDA(cudaFuncSetAttribute(conv9x9_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
-        conv9x9_kernel<16, 4><<<grid, 256, smem, st>>>(in, w, out, H, W);
+        launch_k((conv9x9_kernel<16, 4>), dim3(grid), dim3(256), smem, st, in, w, out, H, W);
     }
     FS_LAUNCH_CHECK();
     return 0;
@@ -393,7 +399,7 @@ int launch_conv9x9(const float* in, const float* w, float* out, int N, int H, in
 int launch_conv3x3_c4_fwd(const float* in, const float* w, const float* bias, float* out, void* split_hi, void* split_lo,
                           int N, int H, int W, cudaStream_t st) {
     dim3 grid(cdiv(W, C1_COLS), cdiv(H, C1_ROWS), N);
-    conv3x3_c4_fwd_kernel<<<grid, 256, 0, st>>>(in, w, bias, out, (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo, H, W);
+    launch_k(conv3x3_c4_fwd_kernel, dim3(grid), dim3(256), 0, st, in, w, bias, out, (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo, H, W);
     FS_LAUNCH_CHECK();
     return 0;
 }
@@ -404,14 +410,14 @@ int launch_dgrad3x3_c4(const float* P, const float* wf, float* dx, int N, int H,
     static bool set = false;
     if (!set) { FS_CUDA(cudaFuncSetAttribute(dgrad3x3_c4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
     dim3 grid(cdiv(W, C1_COLS), cdiv(H, C1_ROWS), N);
-    dgrad3x3_c4_kernel<<<grid, 256, smem, st>>>(P, wf, dx, H, W);
+    launch_k(dgrad3x3_c4_kernel, dim3(grid), dim3(256), smem, st, P, wf, dx, H, W);
     FS_LAUNCH_CHECK();
     return 0;
 }
 
 int flip_transpose_taps(const float* W, float* Wf, int T, int Ci, int Co, cudaStream_t st) {
     long long n = (long long)T * Ci * Co;
-    flip_transpose_taps_kernel<<<cdiv(n, 256), 256, 0, st>>>(W, Wf, T, Ci, Co);
+    launch_k(flip_transpose_taps_kernel, dim3(cdiv(n, 256)), dim3(256), 0, st, W, Wf, T, Ci, Co);
     FS_LAUNCH_CHECK();
     return 0;
 }
@@ -432,15 +438,15 @@ int launch_wgrad9x9(const float* in, const float* dy, float* out, float* partial
         size_t smem = (size_t)(HSY * HS * 4 + TSY * TS * 1) * sizeof(float4);
         static bool set16 = false;
         if (!set16) { FS_CUDA(cudaFuncSetAttribute(wgrad9x9_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set16 = true; }
-        wgrad9x9_kernel<16, 4><<<grid, NT9, smem, st>>>(in, dy, partial, H, W);
+        launch_k((wgrad9x9_kernel<16, 4>), dim3(grid), dim3(NT9), smem, st, in, dy, partial, H, W);
     } else {
         size_t smem = (size_t)(HSY * HS * 1 + TSY * TS * 4) * sizeof(float4);
         static bool set4 = false;
         if (!set4) { FS_CUDA(cudaFuncSetAttribute(wgrad9x9_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set4 = true; }
-        wgrad9x9_kernel<4, 16><<<grid, NT9, smem, st>>>(in, dy, partial, H, W);
+        launch_k((wgrad9x9_kernel<4, 16>), dim3(grid), dim3(NT9), smem, st, in, dy, partial, H, W);
     }
     FS_LAUNCH_CHECK();
-    reduce_partials_kernel<<<cdiv(81 * 64, 32), 256, 0, st>>>(partial, out, 81 * 64, nblocks);
+    launch_k(reduce_partials_kernel, dim3(cdiv(81 * 64, 32)), dim3(256), 0, st, partial, out, 81 * 64, nblocks);
     FS_LAUNCH_CHECK();
     return 0;
 }

@@ -54,6 +54,7 @@ __device__ __forceinline__ float4 gather_a(const IGemmArgs& a, const float* in_n
 // BM x BN output tile, BK reduction slice, TM x TN register tile, NT threads.
 template <int BM, int BN, int TM, int TN, int NT, int BK>
 __global__ void __launch_bounds__(NT) igemm_kernel(const IGemmArgs a) {
+    FS_PDL_ENTER();
     constexpr int TXN = BN / TN;
     constexpr int TYN = NT / TXN;
     static_assert(TYN * TM == BM && TXN * TN == BN, "tile/thread mismatch");
@@ -248,7 +249,7 @@ template <int BM, int BN, int TM, int TN, int NT, int BK>
 int launch_cfg(const IGemmArgs& a, cudaStream_t st) {
     int M = a.OH * a.OW;
     dim3 grid(cdiv(M, BM), cdiv(a.OC, BN), a.N);
-    igemm_kernel<BM, BN, TM, TN, NT, BK><<<grid, NT, 0, st>>>(a);
+    launch_k((igemm_kernel<BM, BN, TM, TN, NT, BK>), dim3(grid), dim3(NT), 0, st, a);
     FS_LAUNCH_CHECK();
     return 0;
 }
@@ -288,6 +289,7 @@ struct WGeom {
 // WK x WN output tile (k rows x out channels), WP pixels per smem step, TK x 4 register tile.
 template <int WK, int WN, int TK, int WP, int NT>
 __global__ void __launch_bounds__(NT) wgrad_kernel(const WGradArgs a, const WGeom g) {
+    FS_PDL_ENTER();
     constexpr int TXN = WN / 4;
     constexpr int TYN = NT / TXN;
     static_assert(TYN * TK == WK, "tile/thread mismatch");
@@ -464,20 +466,37 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(const WGradArgs a, const WGeo
     }
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
-                                    long long tile_elems, int groups, int splits, float scale) {
-    long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long n4 = tile_elems / 4;
-    if (i4 >= n4 * groups) return;
-    long long grp = i4 / n4, e = i4 - grp * n4;
-    const float4* p = reinterpret_cast<const float4*>(partial) + grp * splits * n4 + e;
+// Sums the split partials of one float4 column in a fixed order: 8 split-lanes each take splits
+// y, y+8, ... (independent loads in flight), then lane 0 folds the 8 partial sums in order 0..7.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, long long tile_elems,
+                    int splits, float scale) {
+    FS_PDL_ENTER();
+    __shared__ float4 sm[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long n4 = tile_elems / 4;
+    const long long e = (long long)blockIdx.x * 32 + tx;
+    const long long grp = blockIdx.y;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < splits; ++k) {
-        float4 v = p[(long long)k * n4];
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    if (e < n4) {
+        const float4* p = reinterpret_cast<const float4*>(partial) + grp * splits * n4 + e;
+#pragma unroll 4
+        for (int k = ty; k < splits; k += 8) {
+            float4 v = p[(long long)k * n4];
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
     }
-    s.x *= scale; s.y *= scale; s.z *= scale; s.w *= scale;
-    reinterpret_cast<float4*>(out)[grp * n4 + e] = s;
+    sm[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && e < n4) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            float4 v = sm[k][tx];
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        s.x *= scale; s.y *= scale; s.z *= scale; s.w *= scale;
+        reinterpret_cast<float4*>(out)[grp * n4 + e] = s;
+    }
 }
 
 struct WCfg { int WK, WN, WP; };
@@ -527,15 +546,14 @@ int launch_wgrad(const WGradArgs& a, cudaStream_t st) {
     FS_CHECK(need <= a.partial_cap, "wgrad: partial workspace too small (%lld > %lld floats)", need, a.partial_cap);
     FS_CHECK((long long)g.groups * g.splits <= 65535, "wgrad: too many z blocks");
     dim3 grid(cdiv(g.Ktot, c.WK), cdiv(a.OC, c.WN), g.groups * g.splits);
-    if (c.WN == 64) wgrad_kernel<64, 64, 8, 16, 128><<<grid, 128, 0, st>>>(a, g);
-    else if (c.WN == 32) wgrad_kernel<64, 32, 8, 16, 64><<<grid, 64, 0, st>>>(a, g);
-    else if (c.WN == 16) wgrad_kernel<256, 16, 8, 16, 128><<<grid, 128, 0, st>>>(a, g);
-    else wgrad_kernel<512, 4, 8, 8, 64><<<grid, 64, 0, st>>>(a, g);
+    if (c.WN == 64) launch_k((wgrad_kernel<64, 64, 8, 16, 128>), dim3(grid), dim3(128), 0, st, a, g);
+    else if (c.WN == 32) launch_k((wgrad_kernel<64, 32, 8, 16, 64>), dim3(grid), dim3(64), 0, st, a, g);
+    else if (c.WN == 16) launch_k((wgrad_kernel<256, 16, 8, 16, 128>), dim3(grid), dim3(128), 0, st, a, g);
+    else launch_k((wgrad_kernel<512, 4, 8, 8, 64>), dim3(grid), dim3(64), 0, st, a, g);
     FS_LAUNCH_CHECK();
     long long tile_elems = (long long)g.Ktot * a.OC;
-    long long tot4 = tile_elems / 4 * g.groups;
-    wgrad_reduce_kernel<<<cdiv(tot4, 256), 256, 0, st>>>(a.partial, a.out, tile_elems, g.groups,
-                                                       g.splits, a.scale);
+    launch_k(wgrad_reduce_kernel, dim3(dim3((unsigned)cdiv(tile_elems / 4, 32), g.groups)), dim3(256), 0, st, 
+        a.partial, a.out, tile_elems, g.splits, a.scale);
     FS_LAUNCH_CHECK();
     return 0;
 }

@@ -56,6 +56,7 @@ __device__ __forceinline__ float in_affine(float x, float mean, float rstd, floa
 // ------------------------------------------------------------------ padding
 __global__ void reflect_pad_c4_kernel(const float* __restrict__ x, float* __restrict__ out, int N,
                                       int H, int W, int pad) {
+    FS_PDL_ENTER();
     int OH = H + 2 * pad, OW = W + 2 * pad;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)N * OH * OW) return;
@@ -74,6 +75,7 @@ __global__ void reflect_pad_c4_kernel(const float* __restrict__ x, float* __rest
 
 __global__ void vgg_preprocess_kernel(const float* __restrict__ x, float* __restrict__ out,
                                       long long npix) {
+    FS_PDL_ENTER();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
     const float* s = x + i * 3;
@@ -88,6 +90,7 @@ in_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dY,
                  const float* __restrict__ mean, const float* __restrict__ rstd,
                  const float* __restrict__ scale, const float* __restrict__ shift,
                  double* __restrict__ partial, int HW, int C, int chunks, int act) {
+    FS_PDL_ENTER();
     extern __shared__ double sm[];            // [C][2]
     const int t = threadIdx.x, n = blockIdx.y, chunk = blockIdx.x;
     const int CL = C >> 2, rows = 256 / CL;
@@ -164,6 +167,7 @@ in_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dY,
 __global__ void __launch_bounds__(256)
 in_stats_finalize_kernel(const double* __restrict__ partial, float* __restrict__ mean, float* __restrict__ rstd,
                          int N, int C, int chunks, int HW, float eps) {
+    FS_PDL_ENTER();
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= N * C) return;
     const int n = i / C, c = i - n * C;
@@ -187,6 +191,7 @@ in_stats_finalize_kernel(const double* __restrict__ partial, float* __restrict__
 __global__ void in_bwd_finalize_kernel(const double* __restrict__ partial, float* __restrict__ m12,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int N,
                                        int C, int chunks, int HW) {
+    FS_PDL_ENTER();
     // one block per channel; warp w handles samples w, w+8, ...; lanes split the chunks.
     // Fixed reduction order (lane tree, then warps 0..7 in order) -> deterministic.
     __shared__ double wsum[8][2];
@@ -224,6 +229,7 @@ __global__ void in_apply_kernel(const float* __restrict__ x, const float* __rest
                                 const float* __restrict__ shift, const float* __restrict__ skip,
                                 float* __restrict__ out, int N, int H, int W, int C, int act, int out3,
                                 __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo) {
+    FS_PDL_ENTER();
     const int C4 = C >> 2;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)N * H * W * C4;
@@ -263,6 +269,7 @@ __global__ void in_bwd_apply_kernel(const float* __restrict__ dY, const float* _
                                     const float* __restrict__ m12, float* __restrict__ dx, int N,
                                     int HW, int C, int act, __nv_bfloat16* __restrict__ shi,
                                     __nv_bfloat16* __restrict__ slo) {
+    FS_PDL_ENTER();
     const int C4 = C >> 2;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)N * HW * C4;
@@ -298,6 +305,7 @@ __global__ void in_bwd_apply_kernel(const float* __restrict__ dY, const float* _
 
 __global__ void add_padded_kernel(float* __restrict__ dst, const float* __restrict__ src, int N, int H,
                                   int W, int C, int crop) {
+    FS_PDL_ENTER();
     const int C4 = C >> 2;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)N * H * W * C4;
@@ -317,6 +325,7 @@ __global__ void add_padded_kernel(float* __restrict__ dst, const float* __restri
 __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int H,
                                    int W, int C, __nv_bfloat16* __restrict__ shi,
                                    __nv_bfloat16* __restrict__ slo) {
+    FS_PDL_ENTER();
     const int C4 = C >> 2, PH = (H + 1) >> 1, PW = (W + 1) >> 1;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)N * PH * PW * C4;
@@ -351,6 +360,7 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restric
 __global__ void pool_bwd_combine_kernel(const float* __restrict__ act, const float* __restrict__ gpool,
                                         const float* __restrict__ ctarget, float cw2, int apply_mask,
                                         float* __restrict__ out, int N, int H, int W, int C) {
+    FS_PDL_ENTER();
     const int C4 = C >> 2, PH = (H + 1) >> 1, PW = (W + 1) >> 1;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)N * PH * PW * C4;
@@ -406,6 +416,7 @@ __global__ void pool_bwd_combine_kernel(const float* __restrict__ act, const flo
 // ------------------------------------------------------------------ losses
 __global__ void sqdiff_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n4,
                                   double scale, double* acc) {
+    FS_PDL_ENTER();
     double s = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
          i += (long long)gridDim.x * blockDim.x) {
@@ -420,6 +431,7 @@ __global__ void sqdiff_sum_kernel(const float* __restrict__ a, const float* __re
 __global__ void style_loss_grad_kernel(const float* __restrict__ G, const float* __restrict__ T,
                                        float* __restrict__ S, long long total, int CC, float coef,
                                        double lscale, double* acc) {
+    FS_PDL_ENTER();
     double s = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -433,6 +445,7 @@ __global__ void style_loss_grad_kernel(const float* __restrict__ G, const float*
 
 __global__ void tv_kernel(const float* __restrict__ Y, float* __restrict__ dY4, int N, int H, int W,
                           float beta, double* acc) {
+    FS_PDL_ENTER();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)N * H * W;
     double s = 0;
@@ -461,6 +474,7 @@ __global__ void tv_kernel(const float* __restrict__ Y, float* __restrict__ dY4, 
 }
 
 __global__ void finalize_losses_kernel(const double* acc, float* out4) {
+    FS_PDL_ENTER();
     out4[0] = (float)acc[0];
     out4[1] = (float)acc[1];
     out4[2] = (float)acc[2];
@@ -471,6 +485,7 @@ __global__ void finalize_losses_kernel(const double* acc, float* out4) {
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
                             const int* __restrict__ step) {
+    FS_PDL_ENTER();
     __shared__ float lr_t_s;
     if (threadIdx.x == 0) {
         int t = *step + 1;
@@ -488,11 +503,13 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     v[i] = vi;
     p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
 }
-__global__ void incr_kernel(int* c) { *c += 1; }
+__global__ void incr_kernel(int* c) {
+    FS_PDL_ENTER(); *c += 1; }
 
 // ------------------------------------------------------------------ weight layouts
 __global__ void pad_taps_kernel(const float* __restrict__ src, float* __restrict__ dst, int T, int Ci,
                                 int Co, int Cip, int Cop, int unpad) {
+    FS_PDL_ENTER();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (!unpad) {
         if (i >= (long long)T * Cip * Cop) return;
@@ -513,6 +530,7 @@ __global__ void pad_taps_kernel(const float* __restrict__ src, float* __restrict
 
 __global__ void transpose_taps_kernel(const float* __restrict__ src, float* __restrict__ dst, int T,
                                       int Ci, int Co) {
+    FS_PDL_ENTER();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)T * Ci * Co) return;
     int ci = (int)(i % Ci);
@@ -529,6 +547,7 @@ __device__ __forceinline__ bool rsel(int p, int a, int k) {
 
 __global__ void upconv_collapse_kernel(const float* __restrict__ W, float* __restrict__ Wc, int Ci,
                                        int Co) {
+    FS_PDL_ENTER();
     // Wc[a][b][ci][(p*2+q)*Co + co]
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = 4LL * Ci * 4 * Co;
@@ -548,6 +567,7 @@ __global__ void upconv_collapse_kernel(const float* __restrict__ W, float* __res
 
 __global__ void upconv_collapse_grad_kernel(const float* __restrict__ dWc, float* __restrict__ dW,
                                             int Ci, int Co) {
+    FS_PDL_ENTER();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = 9LL * Ci * Co;
     if (i >= total) return;
@@ -569,6 +589,7 @@ __global__ void upconv_collapse_grad_kernel(const float* __restrict__ dWc, float
 //   dx[2m+p, 2n+q, ci] = sum_{a,b,co} dy[m-a, n-b, co] * Wd[a][b][co][(p*2+q)*Ci + ci]
 // with kh(p,a): p=0 -> {0,2}, p=1 -> {1,-};   2.25x fewer MACs than gathering all 9 taps.
 __global__ void s2_dgrad_collapse_kernel(const float* __restrict__ W, float* __restrict__ Wd, int Ci, int Co) {
+    FS_PDL_ENTER();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = 16LL * Ci * Co;
     if (i >= total) return;
@@ -591,13 +612,13 @@ inline int grid1(long long n, int bs = 256) { return (int)((n + bs - 1) / bs); }
 int reflect_pad_c4(const float* x, float* out, int N, int H, int W, int pad, cudaStream_t st) {
     FS_CHECK(pad < H && pad < W, "reflect_pad: pad %d must be smaller than the image (%dx%d)", pad, H, W);
     long long n = (long long)N * (H + 2 * pad) * (W + 2 * pad);
-    reflect_pad_c4_kernel<<<grid1(n), 256, 0, st>>>(x, out, N, H, W, pad);
+    launch_k(reflect_pad_c4_kernel, dim3(grid1(n)), dim3(256), 0, st, x, out, N, H, W, pad);
     FS_LAUNCH_CHECK();
     return 0;
 }
 
 int vgg_preprocess_c4(const float* x, float* out, long long npix, cudaStream_t st) {
-    vgg_preprocess_kernel<<<grid1(npix), 256, 0, st>>>(x, out, npix);
+    launch_k(vgg_preprocess_kernel, dim3(grid1(npix)), dim3(256), 0, st, x, out, npix);
     FS_LAUNCH_CHECK();
     return 0;
 }
@@ -623,10 +644,10 @@ int instnorm_stats(const float* x, float* mean, float* rstd, int N, int HW, int 
                    double* partial, cudaStream_t st) {
     FS_TRY(check_in_c(C));
     int chunks = in_chunks(N, HW);
-    in_reduce_kernel<0><<<dim3(chunks, N), 256, 2 * C * sizeof(double), st>>>(
+    launch_k((in_reduce_kernel<0>), dim3(dim3(chunks, N)), dim3(256), 2 * C * sizeof(double), st, 
         x, nullptr, nullptr, nullptr, nullptr, nullptr, partial, HW, C, chunks, 0);
     FS_LAUNCH_CHECK();
-    in_stats_finalize_kernel<<<cdiv((long long)N * C, 8), 256, 0, st>>>(partial, mean, rstd, N, C, chunks, HW, eps);
+    launch_k(in_stats_finalize_kernel, dim3(cdiv((long long)N * C, 8)), dim3(256), 0, st, partial, mean, rstd, N, C, chunks, HW, eps);
     FS_LAUNCH_CHECK();
     return 0;
 }
@@ -638,7 +659,7 @@ int instnorm_apply(const float* x, const float* mean, const float* rstd, const f
     FS_CHECK(!(split_hi && out3), "instnorm_apply: split output not available with out3");
     FS_CHECK(!out3 || C == 4, "instnorm_apply: out3 needs C==4");
     long long n = (long long)N * H * W * (C / 4);
-    in_apply_kernel<<<grid1(n), 256, 0, st>>>(x, mean, rstd, scale, shift, skip, out, N, H, W, C, act, out3,
+    launch_k(in_apply_kernel, dim3(grid1(n)), dim3(256), 0, st, x, mean, rstd, scale, shift, skip, out, N, H, W, C, act, out3,
                                               (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo);
     FS_LAUNCH_CHECK();
     return 0;
@@ -650,13 +671,13 @@ int instnorm_bwd(const float* dY, const float* x, const float* mean, const float
                  void* split_hi, void* split_lo) {
     FS_TRY(check_in_c(C));
     int chunks = in_chunks(N, HW);
-    in_reduce_kernel<1><<<dim3(chunks, N), 256, 2 * C * sizeof(double), st>>>(
+    launch_k((in_reduce_kernel<1>), dim3(dim3(chunks, N)), dim3(256), 2 * C * sizeof(double), st, 
         x, dY, mean, rstd, scale, shift, partial, HW, C, chunks, act);
     FS_LAUNCH_CHECK();
-    in_bwd_finalize_kernel<<<C, 256, 0, st>>>(partial, m12, dgamma, dbeta, N, C, chunks, HW);
+    launch_k(in_bwd_finalize_kernel, dim3(C), dim3(256), 0, st, partial, m12, dgamma, dbeta, N, C, chunks, HW);
     FS_LAUNCH_CHECK();
     long long n = (long long)N * HW * (C / 4);
-    in_bwd_apply_kernel<<<grid1(n), 256, 0, st>>>(dY, x, mean, rstd, scale, shift, m12, dx, N, HW, C, act,
+    launch_k(in_bwd_apply_kernel, dim3(grid1(n)), dim3(256), 0, st, dY, x, mean, rstd, scale, shift, m12, dx, N, HW, C, act,
                                                   (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo);
     FS_LAUNCH_CHECK();
     return 0;
@@ -664,7 +685,7 @@ int instnorm_bwd(const float* dY, const float* x, const float* mean, const float
 
 int add_padded(float* dst, const float* src, int N, int H, int W, int C, int crop, cudaStream_t st) {
     long long n = (long long)N * H * W * (C / 4);
-    add_padded_kernel<<<grid1(n), 256, 0, st>>>(dst, src, N, H, W, C, crop);
+    launch_k(add_padded_kernel, dim3(grid1(n)), dim3(256), 0, st, dst, src, N, H, W, C, crop);
     FS_LAUNCH_CHECK();
     return 0;
 }
@@ -673,7 +694,7 @@ int maxpool2x2_fwd(const float* x, float* out, int N, int H, int W, int C, cudaS
                    void* split_hi, void* split_lo) {
     FS_CHECK(C % 4 == 0, "maxpool: C%%4 != 0");
     long long n = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
-    maxpool_fwd_kernel<<<grid1(n), 256, 0, st>>>(x, out, N, H, W, C, (__nv_bfloat16*)split_hi,
+    launch_k(maxpool_fwd_kernel, dim3(grid1(n)), dim3(256), 0, st, x, out, N, H, W, C, (__nv_bfloat16*)split_hi,
                                                  (__nv_bfloat16*)split_lo);
     FS_LAUNCH_CHECK();
     return 0;
@@ -683,7 +704,7 @@ int pool_bwd_combine(const float* act, const float* gpool, const float* ctarget,
                      int apply_mask, float* out, int N, int H, int W, int C, cudaStream_t st) {
     FS_CHECK(C % 4 == 0, "pool_bwd: C%%4 != 0");
     long long n = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
-    pool_bwd_combine_kernel<<<grid1(n), 256, 0, st>>>(act, gpool, ctarget, cw2, apply_mask, out, N, H, W, C);
+    launch_k(pool_bwd_combine_kernel, dim3(grid1(n)), dim3(256), 0, st, act, gpool, ctarget, cw2, apply_mask, out, N, H, W, C);
     FS_LAUNCH_CHECK();
     return 0;
 }
@@ -692,7 +713,7 @@ int sqdiff_sum(const float* a, const float* b, long long n, double scale, double
     FS_CHECK(n % 4 == 0, "sqdiff_sum: n%%4 != 0");
     int blocks = grid1(n / 4);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    sqdiff_sum_kernel<<<blocks, 256, 0, st>>>(a, b, n / 4, scale, acc);
+    launch_k(sqdiff_sum_kernel, dim3(blocks), dim3(256), 0, st, a, b, n / 4, scale, acc);
     FS_LAUNCH_CHECK();
     return 0;
 }
@@ -702,61 +723,61 @@ int style_loss_grad(const float* G, const float* T, float* S, int N, int CC, flo
     long long total = (long long)N * CC;
     int blocks = grid1(total);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    style_loss_grad_kernel<<<blocks, 256, 0, st>>>(G, T, S, total, CC, coef, lscale, acc);
+    launch_k(style_loss_grad_kernel, dim3(blocks), dim3(256), 0, st, G, T, S, total, CC, coef, lscale, acc);
     FS_LAUNCH_CHECK();
     return 0;
 }
 
 int tv_loss_grad(const float* Y, float* dY4, int N, int H, int W, float beta, double* acc, cudaStream_t st) {
     long long n = (long long)N * H * W;
-    tv_kernel<<<grid1(n), 256, 0, st>>>(Y, dY4, N, H, W, beta, acc);
+    launch_k(tv_kernel, dim3(grid1(n)), dim3(256), 0, st, Y, dY4, N, H, W, beta, acc);
     FS_LAUNCH_CHECK();
     return 0;
 }
 
 int finalize_losses(const double* acc, float* out4, cudaStream_t st) {
-    finalize_losses_kernel<<<1, 1, 0, st>>>(acc, out4);
+    launch_k(finalize_losses_kernel, dim3(1), dim3(1), 0, st, acc, out4);
     FS_LAUNCH_CHECK();
     return 0;
 }
 
 int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
               float eps, int* step_counter, cudaStream_t st) {
-    adam_kernel<<<grid1(n), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, step_counter);
+    launch_k(adam_kernel, dim3(grid1(n)), dim3(256), 0, st, p, g, m, v, n, lr, b1, b2, eps, step_counter);
     FS_LAUNCH_CHECK();
-    incr_kernel<<<1, 1, 0, st>>>(step_counter);
+    launch_k(incr_kernel, dim3(1), dim3(1), 0, st, step_counter);
     FS_LAUNCH_CHECK();
     return 0;
 }
 
 int pad_taps(const float* src, float* dst, int T, int Ci, int Co, int Cip, int Cop, cudaStream_t st) {
-    pad_taps_kernel<<<grid1((long long)T * Cip * Cop), 256, 0, st>>>(src, dst, T, Ci, Co, Cip, Cop, 0);
+    launch_k(pad_taps_kernel, dim3(grid1((long long)T * Cip * Cop)), dim3(256), 0, st, src, dst, T, Ci, Co, Cip, Cop, 0);
     FS_LAUNCH_CHECK();
     return 0;
 }
 int unpad_taps(const float* src, float* dst, int T, int Ci, int Co, int Cip, int Cop, cudaStream_t st) {
-    pad_taps_kernel<<<grid1((long long)T * Ci * Co), 256, 0, st>>>(src, dst, T, Ci, Co, Cip, Cop, 1);
+    launch_k(pad_taps_kernel, dim3(grid1((long long)T * Ci * Co)), dim3(256), 0, st, src, dst, T, Ci, Co, Cip, Cop, 1);
     FS_LAUNCH_CHECK();
     return 0;
 }
 int transpose_taps(const float* src, float* dst, int T, int Ci, int Co, cudaStream_t st) {
-    transpose_taps_kernel<<<grid1((long long)T * Ci * Co), 256, 0, st>>>(src, dst, T, Ci, Co);
+    launch_k(transpose_taps_kernel, dim3(grid1((long long)T * Ci * Co)), dim3(256), 0, st, src, dst, T, Ci, Co);
     FS_LAUNCH_CHECK();
     return 0;
 }
 int upconv_collapse(const float* W, float* Wc, int Ci, int Co, cudaStream_t st) {
-    upconv_collapse_kernel<<<grid1(16LL * Ci * Co), 256, 0, st>>>(W, Wc, Ci, Co);
+    launch_k(upconv_collapse_kernel, dim3(grid1(16LL * Ci * Co)), dim3(256), 0, st, W, Wc, Ci, Co);
     FS_LAUNCH_CHECK();
     return 0;
 }
 int upconv_collapse_grad(const float* dWc, float* dW, int Ci, int Co, cudaStream_t st) {
-    upconv_collapse_grad_kernel<<<grid1(9LL * Ci * Co), 256, 0, st>>>(dWc, dW, Ci, Co);
+    launch_k(upconv_collapse_grad_kernel, dim3(grid1(9LL * Ci * Co)), dim3(256), 0, st, dWc, dW, Ci, Co);
     FS_LAUNCH_CHECK();
     return 0;
 }
 
 int s2_dgrad_collapse(const float* W, float* Wd, int Ci, int Co, cudaStream_t st) {
-    s2_dgrad_collapse_kernel<<<grid1(16LL * Ci * Co), 256, 0, st>>>(W, Wd, Ci, Co);
+    launch_k(s2_dgrad_collapse_kernel, dim3(grid1(16LL * Ci * Co)), dim3(256), 0, st, W, Wd, Ci, Co);
     FS_LAUNCH_CHECK();
     return 0;
 }

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(256, 1)
 wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
                    const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CUtensorMap tmD_lo,
                    const WgParams p) {
+    FS_PDL_TRIGGER();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smemX = smem;
@@ -87,6 +88,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    FS_PDL_WAIT();                        // everything above is CTA-local setup
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0 && lane == 0) {
@@ -191,6 +193,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_cons
 // out[i] = sum_b partial[b][i], fixed order
 __global__ void __launch_bounds__(256) reduce_cta_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                                                   int elems, int nparts) {
+    FS_PDL_ENTER();
     __shared__ float red[8][33];
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + lx;
@@ -263,9 +266,9 @@ int launch_wgrad3x3_tc(SplitPtr x, SplitPtr dy, float* out, float* partial, long
         FS_CUDA(cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    wgrad3x3_tc_kernel<<<grid, 256, SMEM_BYTES, st>>>(tmX_hi, tmX_lo, tmD_hi, tmD_lo, p);
+    launch_k(wgrad3x3_tc_kernel, dim3(grid), dim3(256), SMEM_BYTES, st, tmX_hi, tmX_lo, tmD_hi, tmD_lo, p);
     FS_LAUNCH_CHECK();
-    reduce_cta_partials_kernel<<<cdiv(9 * 64 * 64, 32), 256, 0, st>>>(partial, out, 9 * 64 * 64, grid);
+    launch_k(reduce_cta_partials_kernel, dim3(cdiv(9 * 64 * 64, 32)), dim3(256), 0, st, partial, out, 9 * 64 * 64, grid);
     FS_LAUNCH_CHECK();
     return 0;
 }
@@ -291,6 +294,7 @@ struct GramParams {
 
 __global__ void __launch_bounds__(256, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const GramParams p) {
+    FS_PDL_TRIGGER();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_STAGES * G_STAGE);
@@ -325,6 +329,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    FS_PDL_WAIT();                        // everything above is CTA-local setup
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0 && lane == 0) {
@@ -400,6 +405,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 // G[n][i] = scale * sum_ks partial[n][ks][i]
 __global__ void gram_reduce_kernel(const float* __restrict__ partial, float* __restrict__ G, long long cc4, int N,
                                    int ksplit, float scale) {
+    FS_PDL_ENTER();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cc4 * N) return;
     long long n = i / cc4, e = i - n * cc4;
@@ -414,6 +420,7 @@ __global__ void gram_reduce_kernel(const float* __restrict__ partial, float* __r
 
 __global__ void pack_gemm_b_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ hi,
                                    __nv_bfloat16* __restrict__ lo, int N, int C) {
+    FS_PDL_ENTER();
     // out index: (((n*CB + cb)*C + j)*64 + k)  <-  S[n][cb*64+k][j]
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)N * C * C;
@@ -484,10 +491,10 @@ int launch_gram_tc(SplitPtr f, float* G, float* partial, long long partial_cap, 
         attr_set = true;
     }
     int grid = N * p.mtiles * p.ntiles * p.ksplit;
-    gram_tc_kernel<<<grid, 256, G_SMEM, st>>>(tm_hi, tm_lo, p);
+    launch_k(gram_tc_kernel, dim3(grid), dim3(256), G_SMEM, st, tm_hi, tm_lo, p);
     FS_LAUNCH_CHECK();
     long long cc4 = (long long)C * C / 4;
-    gram_reduce_kernel<<<cdiv(cc4 * N, 256), 256, 0, st>>>(partial, G, cc4, N, p.ksplit, scale);
+    launch_k(gram_reduce_kernel, dim3(cdiv(cc4 * N, 256)), dim3(256), 0, st, partial, G, cc4, N, p.ksplit, scale);
     FS_LAUNCH_CHECK();
     return 0;
 }
@@ -495,7 +502,7 @@ int launch_gram_tc(SplitPtr f, float* G, float* partial, long long partial_cap, 
 int pack_gemm_b_tc(const float* S, SplitPtr out, int N, int C, cudaStream_t st) {
     FS_CHECK(C % 64 == 0, "pack_gemm_b_tc: C must be a multiple of 64");
     long long total = (long long)N * C * C;
-    pack_gemm_b_kernel<<<cdiv(total, 256), 256, 0, st>>>(S, out.hi, out.lo, N, C);
+    launch_k(pack_gemm_b_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, S, out.hi, out.lo, N, C);
     FS_LAUNCH_CHECK();
     return 0;
 }
