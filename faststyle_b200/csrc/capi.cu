@@ -70,8 +70,7 @@ int fs_engine_create(int N, int H, int W, int flags, unsigned content_mask, unsi
                      fs_engine** out) {
     FS_CHECK(out != nullptr, "fs_engine_create: out is NULL");
     FS_CHECK(flags != 0 && (flags & ~31) == 0, "fs_engine_create: bad flags 0x%x", flags);
-    FS_CHECK(!(flags & ENG_DECONV) || ((flags & ENG_TRANSFORM) && !(flags & ENG_TRANSFORM_BWD)),
-             "DECONV is a forward-only transform-net variant");
+    FS_CHECK(!(flags & ENG_DECONV) || (flags & ENG_TRANSFORM), "DECONV selects a transform-net variant: needs TRANSFORM");
     FS_CHECK(!(flags & ENG_TRANSFORM_BWD) || (flags & ENG_TRANSFORM), "TRANSFORM_BWD needs TRANSFORM");
     FS_CHECK(!(flags & ENG_VGG_BWD) || (flags & ENG_VGG), "VGG_BWD needs VGG");
     FS_CHECK((content_mask >> V_NCONV) == 0 && (style_mask >> V_NCONV) == 0, "loss masks address layers > conv4_3");
@@ -81,6 +80,8 @@ int fs_engine_create(int N, int H, int W, int flags, unsigned content_mask, unsi
     h->e.content_mask = content_mask; h->e.style_mask = style_mask;
     const char* env = getenv("FS_TENSOR_PATH");
     h->e.use_tc = (env && env[0] == '0') ? 0 : 1;
+    env = getenv("FS_IN_FUSED");
+    h->e.in_fused = (env && env[0] == '0') ? 0 : 1;
     int r = h->e.plan();
     if (r != 0) { delete h; return r; }
     Arena a;

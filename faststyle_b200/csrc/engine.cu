@@ -238,6 +238,7 @@ void Engine::layout(Arena& a) {
                 int OC = c.upconv ? 4 * c.cout : c.cout_s;
                 wgcap = maxll(wgcap, wgrad_partial_floats(K, OC, 1));
                 if (c.k == 9) wgcap = maxll(wgcap, wgrad9x9_partial_floats(N, c.inH, c.inW));
+                if ((flags & ENG_DECONV) && c.upconv) wgcap = maxll(wgcap, wgrad_partial_floats(9 * c.cout, c.cin, 1));
                 if (l >= 3 && l <= 12) wgcap = maxll(wgcap, wgrad3x3_tc_partial_floats());
             }
         }
@@ -251,7 +252,7 @@ void Engine::layout(Arena& a) {
             }
         }
         y3 = a.take<float>((long long)N * OH * OW * 3);
-        in_partial = a.take<double>((long long)N * 64 * 64 * 2);
+        in_partial = a.take<double>(in_scratch_doubles(N, 64));
         in15 = a.take<float>(8);
         wtmp15 = a.take<float>(81 * 64);
         if (tbw) {
@@ -310,6 +311,7 @@ int Engine::bind(void* ws, size_t bytes) {
     FS_CHECK(((uintptr_t)ws & 255) == 0, "engine: workspace must be 256-byte aligned");
     Arena a; a.base = (char*)ws; a.cap = bytes;
     layout(a);
+    if (in_partial) FS_TRY(in_scratch_init(in_partial, N, 64));
     bound = true;
     return 0;
 }
@@ -322,7 +324,6 @@ int Engine::prep_transform_weights(const float* params, bool need_bwd, cudaStrea
         // 'deconv' models (reference im_transf_net.py:57-63,158-190): W is [k,k,cout,cin] and the layer is
         // tf.nn.conv2d_transpose = the data gradient of a SAME conv.  Stride 2: the 4-phase 2x2 sub-pixel form
         // (the same machinery as the stride-2 data gradients); stride 1 (9x9): a conv with flipped weights.
-        FS_CHECK(!need_bwd, "training the 'deconv' upsampling variant is not implemented (forward only)");
         PROF(PC_PREP, 0.0, s2_dgrad_collapse(params + tc[13].offW, weff[13], tc[13].cout, tc[13].cin, st));
         PROF(PC_PREP, 0.0, s2_dgrad_collapse(params + tc[14].offW, weff[14], tc[14].cout, tc[14].cin, st));
         PROF(PC_PREP, 0.0, pad_taps(params + tc[15].offW, wtmp15, 81, 3, 16, 4, 16, st));
@@ -348,6 +349,7 @@ int Engine::prep_transform_weights(const float* params, bool need_bwd, cudaStrea
             const TConv& c = tc[l];
             const float* src = weff[l] ? weff[l] : params + c.offW;
             if (use_tc && l >= 3 && l <= 12) continue;          // tensor path: packed above, no fp32 transpose
+            if ((flags & ENG_DECONV) && l >= 13) continue;      // conv2d_transpose layers: backward uses W as stored
             if (direct9(c)) PROF(PC_PREP, 0.0, flip_transpose_taps(src, wefft[l], c.k * c.k, c.cin_s, c.cout_s, st));
             else if (c.upconv) PROF(PC_PREP, 0.0, transpose_taps(src, wefft[l], 4, c.cin, 4 * c.cout, st));
             else if (s2_collapsed(c)) PROF(PC_PREP, 0.0, s2_dgrad_collapse(src, wefft[l], c.cin, c.cout, st));
@@ -402,7 +404,7 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
             if (c.upconv && (flags & ENG_DECONV)) a.gather = 1;      // transposed conv: iy = oy - a
             PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
         }
-        PROF(PC_IN_STATS, 0.0, instnorm_stats(tb[l].raw, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, in_partial, st));
+        PROF(PC_IN_STATS, 0.0, instnorm_stats(tb[l].raw, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, in_partial, st, in_fused, 64));
         const float* skip = nullptr;
         if (l >= 4 && l <= 12 && (l & 1) == 0) skip = tb[l - 2].act;       // residual: block input
         const bool last = l == T_NCONV - 1;
@@ -442,7 +444,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         const bool tcl = use_tc && l >= 3 && l <= 12;
         PROF(PC_IN_BWD, 0.0, instnorm_bwd(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw, dg, db, N,
                             c.outH * c.outW, c.cout_s, c.act, in_partial, m12, st,
-                            tcl ? tgsplit[ri].hi : nullptr, tcl ? tgsplit[ri].lo : nullptr));
+                            tcl ? tgsplit[ri].hi : nullptr, tcl ? tgsplit[ri].lo : nullptr, in_fused, 64));
         if (last) {
             FS_CUDA(cudaMemcpyAsync(grads + c.offG, gb_tmp, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
             FS_CUDA(cudaMemcpyAsync(grads + c.offB, gb_tmp + 4, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -454,7 +456,24 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         wa.in = in_act; wa.dy = dRaw; wa.partial = wg_partial; wa.partial_cap = wg_partial_cap;
         wa.H = c.inH; wa.W = c.inW; wa.in_bs = (long long)c.inH * c.inW * c.cin_s;
         wa.N = N; wa.per_sample = 0; wa.scale = 1.f;
-        if (c.upconv) {
+        const bool dcv = (flags & ENG_DECONV) && l >= 13;     // conv2d_transpose layers (im_transf_net.py:57-63)
+        if (dcv && c.upconv) {
+            // y = conv2d_transpose(x, W[3,3,cout,cin], s2 SAME) is the data gradient of the SAME conv
+            // C: [2H,2W,cout] -> [H,W,cin] with HWIO filter W.  Hence dW = weight gradient of C with
+            // dRaw in the role of C's input and x in the role of C's output gradient.
+            wa.in = dRaw; wa.H = c.outH; wa.W = c.outW; wa.C = c.cout; wa.in_bs = (long long)c.outH * c.outW * c.cout;
+            wa.KH = wa.KW = 3; wa.stride = 2; wa.pad_t = wa.pad_l = 0;     // even input: TF SAME pads 0 / 1
+            wa.dy = in_act; wa.OH = c.inH; wa.OW = c.inW; wa.OC = c.cin; wa.dy_mode = 0;
+            wa.dy_bs = (long long)c.inH * c.inW * c.cin;
+            wa.out = grads + c.offW;
+            PROF(PC_WGRAD, wgrad_flops(wa), launch_wgrad(wa, st));
+        } else if (dcv) {
+            // 9x9 stride-1 conv2d_transpose 16 -> 3(4): dW[k, co, ci] = sum_p dRaw[p + k - 4, co] * x[p, ci]
+            const double fl = 2.0 * N * c.outH * c.outW * 81.0 * c.cin_s * c.cout_s;
+            PROF(PC_WGRAD, fl, launch_wgrad9x9(dRaw, in_act, wg_tmp, wg_partial, wg_partial_cap, N, c.inH, c.inW,
+                                               c.cout_s, c.cin_s, st));
+            PROF(PC_PREP, 0.0, unpad_taps(wg_tmp, grads + c.offW, 81, c.cout, c.cin, c.cout_s, c.cin_s, st));
+        } else if (c.upconv) {
             wa.C = c.cin; wa.KH = wa.KW = 2; wa.stride = 1;
             wa.OH = c.inH; wa.OW = c.inW; wa.OC = 4 * c.cout; wa.dy_mode = 1;
             wa.dy_bs = (long long)c.outH * c.outW * c.cout;
@@ -493,6 +512,22 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
             PROF(PC_TC_RES_DGRAD, tc_flops(ta), launch_conv3x3_tc(ta, st));
             dAct = dPrev; cur = pidx;
             if (first_of_block) { held = -1; resid_dOut = nullptr; }
+            continue;
+        }
+        if (dcv) {                               // data gradient of conv2d_transpose = the SAME conv itself
+            if (c.upconv) {
+                IGemmArgs a;
+                memset(&a, 0, sizeof(a));
+                a.in = dRaw; a.w = params + c.offW; a.out = dPrev; a.N = N;
+                a.H = c.outH; a.W = c.outW; a.C = c.cout; a.in_bs = (long long)c.outH * c.outW * c.cout;
+                a.KH = a.KW = 3; a.stride = 2; a.pad_t = a.pad_l = 0;
+                a.OH = c.inH; a.OW = c.inW; a.OC = c.cin; a.out_bs = (long long)c.inH * c.inW * c.cin;
+                PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
+            } else {                             // wtmp15 = W padded to [81, 4, 16]
+                const double fl = 2.0 * N * c.inH * c.inW * 81.0 * c.cin_s * c.cout_s;
+                PROF(PC_FFMA_CONV, fl, launch_conv9x9(dRaw, wtmp15, dPrev, N, c.inH, c.inW, c.cout_s, c.cin_s, st));
+            }
+            dAct = dPrev; cur = pidx;
             continue;
         }
         if (direct9(c)) {                        // data gradient = forward 9x9 conv with flipped weights

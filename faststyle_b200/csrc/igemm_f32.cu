@@ -466,22 +466,24 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(const WGradArgs a, const WGeo
     }
 }
 
-// Sums the split partials of one float4 column in a fixed order: 8 split-lanes each take splits
-// y, y+8, ... (independent loads in flight), then lane 0 folds the 8 partial sums in order 0..7.
+// Sums the split partials of one float4 column in a fixed order: 32 split-lanes each take splits
+// y, y+32, ... (independent loads in flight, 8 columns = one 128-byte line per split row), then lane 0 of the
+// column folds the 32 partial sums in order 0..31.  8 columns per CTA: a [K, OC] tile of a few thousand floats
+// still spreads over >100 CTAs (the first version used 32 columns x 8 lanes and ran 58 us on 36 CTAs).
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, long long tile_elems,
                     int splits, float scale) {
     FS_PDL_ENTER();
-    __shared__ float4 sm[8][32];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    __shared__ float4 sm[32][8];
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
     const long long n4 = tile_elems / 4;
-    const long long e = (long long)blockIdx.x * 32 + tx;
+    const long long e = (long long)blockIdx.x * 8 + tx;
     const long long grp = blockIdx.y;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (e < n4) {
         const float4* p = reinterpret_cast<const float4*>(partial) + grp * splits * n4 + e;
 #pragma unroll 4
-        for (int k = ty; k < splits; k += 8) {
+        for (int k = ty; k < splits; k += 32) {
             float4 v = p[(long long)k * n4];
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
@@ -490,7 +492,7 @@ wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, 
     __syncthreads();
     if (ty == 0 && e < n4) {
 #pragma unroll
-        for (int k = 1; k < 8; ++k) {
+        for (int k = 1; k < 32; ++k) {
             float4 v = sm[k][tx];
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
@@ -552,7 +554,7 @@ int launch_wgrad(const WGradArgs& a, cudaStream_t st) {
     else launch_k((wgrad_kernel<512, 4, 8, 8, 64>), dim3(grid), dim3(64), 0, st, a, g);
     FS_LAUNCH_CHECK();
     long long tile_elems = (long long)g.Ktot * a.OC;
-    launch_k(wgrad_reduce_kernel, dim3(dim3((unsigned)cdiv(tile_elems / 4, 32), g.groups)), dim3(256), 0, st, 
+    launch_k(wgrad_reduce_kernel, dim3(dim3((unsigned)cdiv(tile_elems / 4, 8), g.groups)), dim3(256), 0, st, 
         a.partial, a.out, tile_elems, g.splits, a.scale);
     FS_LAUNCH_CHECK();
     return 0;

@@ -74,10 +74,10 @@ def flatten_transform(params: dict, upsample_method="resize") -> np.ndarray:
     return flat
 
 
-def unflatten_transform(flat) -> "OrderedDict[str, np.ndarray]":
+def unflatten_transform(flat, upsample_method="resize") -> "OrderedDict[str, np.ndarray]":
     flat = np.asarray(flat, np.float32)
     return OrderedDict((n, flat[o:o + int(np.prod(s))].reshape(s).copy())
-                       for n, (o, s) in transform_offsets().items())
+                       for n, (o, s) in transform_offsets(upsample_method).items())
 
 
 def flatten_vgg(weights: dict) -> np.ndarray:

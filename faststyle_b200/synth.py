@@ -14,20 +14,23 @@ from collections import OrderedDict
 
 import numpy as np
 
-from .layout import TRANSFORM_VARS, VGG_CONV_NAMES, VGG_CHANNELS
+from .layout import VGG_CONV_NAMES, VGG_CHANNELS, transform_vars
 
 
-def init_transform_params(seed: int = 1) -> "OrderedDict[str, np.ndarray]":
+def init_transform_params(seed: int = 1, upsample_method: str = "resize") -> "OrderedDict[str, np.ndarray]":
+    """'deconv': all three upsample layers are deconv2d (im_transf_net.py:57-63) whose W uses the default
+    random_normal_initializer (stddev 1, :183) and the transposed [k,k,cout,cin] shape (:173)."""
     rng = np.random.RandomState(seed)
     out = OrderedDict()
-    for name, shape in TRANSFORM_VARS:
+    unit_std = ("upsample_0", "upsample_1") if upsample_method == "resize" else ("upsample_0", "upsample_1", "upsample_2")
+    for name, shape in transform_vars(upsample_method):
         leaf = name.rsplit("/", 1)[1]
         if leaf.startswith("INscale"):
             out[name] = np.ones(shape, np.float32)
         elif leaf.startswith("INshift"):
             out[name] = np.zeros(shape, np.float32)
         else:
-            std = 1.0 if name.split("/")[1] in ("upsample_0", "upsample_1") else 0.1
+            std = 1.0 if name.split("/")[1] in unit_std else 0.1
             out[name] = (rng.standard_normal(shape) * std).astype(np.float32)
     return out
 

@@ -18,7 +18,7 @@ from .layout import TRANSFORM_NPARAMS, unflatten_transform
 class Trainer:
     def __init__(self, params: dict, vgg_weights: dict, style_img, batch_size, preprocess_size,
                  content_layers, style_layers, content_weights, style_weights, beta, learn_rate,
-                 device="cuda:0", process_group=None):
+                 device="cuda:0", process_group=None, upsample_method="resize"):
         self.device = torch.device(device)
         self.pg = process_group
         self.world = 1
@@ -27,7 +27,8 @@ class Trainer:
             self.world = dist.get_world_size(process_group)
         H, W = int(preprocess_size[0]), int(preprocess_size[1])
         self.batch_size = int(batch_size)
-        self.params = params_to_device(params, self.device)
+        self.upsample_method = upsample_method
+        self.params = params_to_device(params, self.device, upsample_method)
         self.packed = pack_vgg(vgg_weights, self.device)
         self.cfg = make_loss_config(content_layers, content_weights, style_layers, style_weights, beta)
         # target Grams of the style image (train.py:143-151)
@@ -37,7 +38,8 @@ class Trainer:
         torch.cuda.synchronize(self.device)
         del seng
         self.engine = Engine(self.batch_size, H, W, transform_bwd=True, vgg_bwd=True,
-                             content_layers=content_layers, style_layers=style_layers, device=self.device)
+                             content_layers=content_layers, style_layers=style_layers, device=self.device,
+                             deconv=upsample_method == "deconv")
         self.opt = TFAdam(self.params, learn_rate)
         self.grads = torch.empty(TRANSFORM_NPARAMS, dtype=torch.float32, device=self.device)
         self.losses = torch.empty(4, dtype=torch.float32, device=self.device)
@@ -70,12 +72,12 @@ class Trainer:
 
     def variables(self) -> dict:
         """Current transform-net variables as {tf_name: ndarray} (for tf.train.Saver-style saving)."""
-        return unflatten_transform(self.params.detach().cpu().numpy())
+        return unflatten_transform(self.params.detach().cpu().numpy(), self.upsample_method)
 
     def optimizer_slots(self) -> dict:
         """Adam slot variables under TF's names (<var>/Adam, <var>/Adam_1, beta*_power)."""
-        m = unflatten_transform(self.opt.m.detach().cpu().numpy())
-        v = unflatten_transform(self.opt.v.detach().cpu().numpy())
+        m = unflatten_transform(self.opt.m.detach().cpu().numpy(), self.upsample_method)
+        v = unflatten_transform(self.opt.v.detach().cpu().numpy(), self.upsample_method)
         out = {}
         for k in m:
             out[k + "/Adam"] = m[k]

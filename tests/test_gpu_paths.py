@@ -180,3 +180,57 @@ def test_train_step_gradients(built_lib, starry, tensor_path):
         worst = max(worst, e)
         assert e < gtol, (name, e)
     print("worst relative gradient error", worst)
+
+
+def _deconv_params(rng):
+    from faststyle_b200.layout import TRANSFORM_VARS_DECONV
+    params = {}
+    for name, shape in TRANSFORM_VARS_DECONV:
+        leaf = name.rsplit("/", 1)[1]
+        if leaf.startswith("INscale"):
+            params[name] = (1.0 + 0.1 * rng.standard_normal(shape)).astype(np.float32)
+        elif leaf.startswith("INshift"):
+            params[name] = (0.1 * rng.standard_normal(shape)).astype(np.float32)
+        else:
+            params[name] = (rng.standard_normal(shape) * (0.3 if "upsample" in name else 0.1)).astype(np.float32)
+    return params
+
+
+@pytest.mark.parametrize("tensor_path", [False, True])
+def test_train_step_gradients_deconv(built_lib, tensor_path):
+    """SURVEY 8(f-3): training the 'deconv' upsampling variant (im_transf_net.py:57-63,158-190;
+    train.py --upsample_method deconv).  conv2d_transpose backward = the SAME conv (data gradient) and its
+    weight gradient with the roles of input / output-gradient swapped; checked against oracle autograd
+    (fp64).  Unpinned like the rest of the training path: the reference ships no deconv checkpoint."""
+    from faststyle_b200.engine import Engine, make_loss_config, pack_vgg, params_to_device
+    from faststyle_b200.layout import transform_offsets
+    N, H, W = 2, 48, 64
+    vggw, style, tg, rng = _setup_loss(N, H, W, seed=11)
+    params = _deconv_params(rng)
+    x = rng.randint(0, 256, (N, H, W, 3)).astype(np.float32)
+    ref = R.train_grads(x, params, vggw, tg, dtype=torch.float64, beta=1e-4, upsample_method="deconv")
+
+    packed = pack_vgg(vggw, "cuda")
+    cfg = make_loss_config(["conv3_3"], [1.0], STYLE, [5.0] * 4, 1e-4)
+    ltol, gtol, ctol = TOL[tensor_path]
+    eng = Engine(N, H, W, transform_bwd=True, vgg_bwd=True, content_layers=["conv3_3"], style_layers=STYLE,
+                 deconv=True)
+    eng.set_tensor_path(tensor_path)
+    tgd = [t.float().cuda().contiguous() for t in tg]
+    y = torch.empty((N, H, W, 3), device="cuda")
+    grads, losses = eng.train_fwd_bwd(params_to_device(params, "cuda", "deconv"), packed, x, cfg, tgd, y=y)
+    torch.cuda.synchronize()
+    assert float((y.double().cpu() - ref["Y"]).abs().max()) / 255.0 < 2e-4
+    L = losses.cpu().double()
+    for got, want in zip(L, [ref["content"], ref["style"], ref["tv"], ref["loss"]]):
+        assert abs(float(got) - float(want)) <= ltol * abs(float(want)) + 1e-12, (float(got), float(want))
+    g = grads.cpu().double()
+    offs = transform_offsets("deconv")
+    flat_ref = torch.cat([ref["grads"][n].flatten() for n in offs])
+    print("deconv train step tensor_path=%s: 1-cos(grad) %.3g" % (tensor_path, 1 - _cos(g, flat_ref)))
+    assert 1 - _cos(g, flat_ref) < ctol
+    for name, (off, shape) in offs.items():
+        want = ref["grads"][name]
+        got = g[off:off + want.numel()].view(want.shape)
+        e = float((got - want).abs().max() / max(want.abs().max().item(), 1e-30))
+        assert e < gtol, (name, e)

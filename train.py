@@ -65,8 +65,6 @@ def main(args):
     from faststyle_b200.summary import FileWriter
     from faststyle_b200.trainer import Trainer
 
-    if args.upsample_method != 'resize':
-        raise SystemExit("--upsample_method deconv has no B200 kernel yet (see DESIGN.md, row f-3)")
     if not args.train_dir or not args.model_name:
         raise SystemExit("--train_dir and --model_name are required")
 
@@ -87,13 +85,13 @@ def main(args):
     style_img = style_img[np.newaxis, :].astype(np.float32)
 
     # transform-net variables with the reference's initialisers (identical on every rank)
-    params = synth.init_transform_params(seed=1)
+    params = synth.init_transform_params(seed=1, upsample_method=args.upsample_method)
     if rank == 0:
         print('Precomputing target style layers.')
     trainer = Trainer(params, load_vgg_weights(), style_img, local_batch, args.preprocess_size,
                       args.loss_content_layers, args.loss_style_layers, args.content_weights,
                       args.style_weights, args.beta, args.learn_rate,
-                      device='cuda:%d' % local_rank, process_group=pg)
+                      device='cuda:%d' % local_rank, process_group=pg, upsample_method=args.upsample_method)
 
     batches = datapipe.batcher(args.train_dir, local_batch, args.preprocess_size, args.n_epochs,
                                max(args.num_pipe_buffer // world, local_batch), seed=1234, shard=(rank, world))
