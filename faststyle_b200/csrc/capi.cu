@@ -316,6 +316,15 @@ int fs_loss_style(const float* G, const float* T, int N, int CC, double scale, d
     FS_TRY(style_loss_grad(G, T, nullptr, N, CC, 0.f, scale, acc + 1, S(stream)));
     return finalize_losses(acc, out, S(stream));
 }
+int fs_frame_u8_to_f32(const unsigned char* in, float* out, long long n, void* stream) {
+    FS_CHECK(in && out && n > 0, "fs_frame_u8_to_f32: bad argument");
+    return frame_u8_to_f32(in, out, n, S(stream));
+}
+int fs_frame_f32_to_u8(const float* in, unsigned char* out, long long npix, int swap_rb, void* stream) {
+    FS_CHECK(in && out && npix > 0, "fs_frame_f32_to_u8: bad argument");
+    return frame_f32_to_u8(in, out, npix, swap_rb, S(stream));
+}
+
 int fs_loss_tv(const float* Y3, int N, int H, int W, double* acc, float* out, void* stream) {
     FS_CHECK(Y3 && acc && out, "fs_loss_tv: NULL argument");
     FS_TRY(fill_zero(acc, 4 * sizeof(double), S(stream)));

@@ -82,6 +82,34 @@ __global__ void vgg_preprocess_kernel(const float* __restrict__ x, float* __rest
     st4(out + i * 4, make_float4(s[0] - 123.68f, s[1] - 116.779f, s[2] - 103.939f, 0.f));
 }
 
+// ------------------------------------------------------------------ uint8 frames (streaming path)
+__global__ void u8_to_f32_kernel(const uchar4* __restrict__ in, float4* __restrict__ out, long long n4,
+                                 const unsigned char* __restrict__ in1, float* __restrict__ out1, long long n) {
+    FS_PDL_ENTER();
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) {
+        uchar4 v = in[i];
+        out[i] = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+    }
+    long long tail = n4 * 4 + i;                      // < 4 leftover bytes, handled by the first threads
+    if (i < 4 && tail < n) out1[tail] = (float)in1[tail];
+}
+
+// numpy astype(uint8) of a value in [0,255] truncates (stylize_webcam.py:89); swap_rb = cv2.COLOR_BGR2RGB (:90)
+__global__ void f32_to_u8_kernel(const float* __restrict__ in, unsigned char* __restrict__ out, long long npix,
+                                 int swap_rb) {
+    FS_PDL_ENTER();
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const float* s = in + i * 3;
+    float a = s[0], b = s[1], c = s[2];
+    unsigned char* o = out + i * 3;
+    unsigned char ua = (unsigned char)fminf(fmaxf(a, 0.f), 255.f);
+    unsigned char ub = (unsigned char)fminf(fmaxf(b, 0.f), 255.f);
+    unsigned char uc = (unsigned char)fminf(fmaxf(c, 0.f), 255.f);
+    o[0] = swap_rb ? uc : ua; o[1] = ub; o[2] = swap_rb ? ua : uc;
+}
+
 // ------------------------------------------------------------------ InstanceNorm
 // Optional fused finalize (counters != nullptr): see the tail of in_reduce_kernel.
 struct INFused {
@@ -685,6 +713,21 @@ int reflect_pad_c4(const float* x, float* out, int N, int H, int W, int pad, cud
 
 int vgg_preprocess_c4(const float* x, float* out, long long npix, cudaStream_t st) {
     launch_k(vgg_preprocess_kernel, dim3(grid1(npix)), dim3(256), 0, st, x, out, npix);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int frame_u8_to_f32(const unsigned char* in, float* out, long long n, cudaStream_t st) {
+    FS_CHECK(((uintptr_t)in & 3) == 0 && ((uintptr_t)out & 15) == 0, "frame_u8_to_f32: misaligned buffer");
+    long long n4 = n / 4;
+    launch_k(u8_to_f32_kernel, dim3(grid1(n4 > 4 ? n4 : 4)), dim3(256), 0, st, reinterpret_cast<const uchar4*>(in),
+             reinterpret_cast<float4*>(out), n4, in, out, n);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int frame_f32_to_u8(const float* in, unsigned char* out, long long npix, int swap_rb, cudaStream_t st) {
+    launch_k(f32_to_u8_kernel, dim3(grid1(npix)), dim3(256), 0, st, in, out, npix, swap_rb);
     FS_LAUNCH_CHECK();
     return 0;
 }

@@ -11,6 +11,10 @@ int reflect_pad_c4(const float* x, float* out, int N, int H, int W, int pad, cud
 // K9: x - VGG mean, channel pad 3->4             (reference libs/vgg16.py:41-42)
 int vgg_preprocess_c4(const float* x, float* out, long long npix, cudaStream_t st);
 
+// uint8 RGB/BGR frames <-> fp32 (streaming path, reference stylize_webcam.py:82-90)
+int frame_u8_to_f32(const unsigned char* in, float* out, long long n, cudaStream_t st);
+int frame_f32_to_u8(const float* in, unsigned char* out, long long npix, int swap_rb, cudaStream_t st);
+
 // K3: InstanceNorm                               (reference im_transf_net.py:218-247)
 struct INWork { double* partial; int max_chunks; };       // partial: [N][chunks][C][2] doubles
 int in_chunks(int N, int HW);

@@ -39,7 +39,7 @@ def create_net(X, upsample_method='deconv'):
     :param X  NxHxWx3 array / tensor
     :param upsample_method  'deconv' or 'resize'.  The shipped checkpoints and both CLIs default to
         'resize' (fused resize-convolution).  'deconv' (conv2d_transpose, im_transf_net.py:57-63,158-190)
-        is supported for inference (forward); training that variant is not implemented.
+        is supported for inference here and for training through train.py --upsample_method deconv.
     """
     assert(upsample_method in ['deconv', 'resize'])
     scope = V.current_scope()
@@ -51,7 +51,7 @@ def create_net(X, upsample_method='deconv'):
     params = {}
     for full, shape in transform_vars(upsample_method):
         rel = full[len(SCOPE) + 1:]
-        params[full] = V.get_variable(rel, shape, _initializer_for(rel))
+        params[full] = V.get_variable(rel, shape, _initializer_for(rel, upsample_method))
     dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
     x = f32(X, dev) if dev is not None else X
     N, H, W_, C_ = x.shape
@@ -64,13 +64,16 @@ def create_net(X, upsample_method='deconv'):
     return eng.transform_forward(params_to_device(params, dev, upsample_method), x)
 
 
-def _initializer_for(rel):
+def _initializer_for(rel, upsample_method='resize'):
     leaf = rel.rsplit("/", 1)[1]
     if leaf.startswith("INscale"):
         return _ones
     if leaf.startswith("INshift"):
         return _zeros
-    return _normal(1.0 if rel.split("/")[0] in ("upsample_0", "upsample_1") else 0.1)
+    # upconv2d / deconv2d use the default random_normal_initializer (stddev 1, im_transf_net.py:149,183);
+    # in the 'deconv' variant upsample_2 is a deconv2d too (:63)
+    unit = ("upsample_0", "upsample_1") + (("upsample_2",) if upsample_method == 'deconv' else ())
+    return _normal(1.0 if rel.split("/")[0] in unit else 0.1)
 
 
 # --------------------------------------------------------------------------- per-op mirrors

@@ -51,7 +51,8 @@ int fs_vgg_pack(const float* flat, float* packed, void* stream);
 /* ------------------------------------------------------------------ engine plan */
 typedef struct fs_engine fs_engine;
 /* FS_ENG_DECONV: the transform net's 'deconv' upsampling variant (conv2d_transpose layers, reference
- * im_transf_net.py:57-63); forward only.  Without it the 'resize' variant (resize-convolution) is planned. */
+ * im_transf_net.py:57-63,158-190; forward and backward).  Without it the 'resize' variant (resize-convolution)
+ * is planned. */
 enum { FS_ENG_TRANSFORM = 1, FS_ENG_TRANSFORM_BWD = 2, FS_ENG_VGG = 4, FS_ENG_VGG_BWD = 8, FS_ENG_DECONV = 16 };
 
 /* Plan for batch N of HxW RGB images.  content_mask / style_mask: bit l set =
@@ -168,6 +169,15 @@ int fs_gram_forward(const float* f, float* g, float* scratch, long long scratch_
 int fs_loss_sqdiff(const float* a, const float* b, long long n, double scale, double* acc, float* out, void* stream);
 int fs_loss_style(const float* G, const float* T, int N, int CC, double scale, double* acc, float* out, void* stream);
 int fs_loss_tv(const float* Y3, int N, int H, int W, double* acc, float* out, void* stream);
+
+/* ------------------------------------------------------------------ streaming frames
+ * Device-side uint8 <-> fp32 conversion around fs_transform_forward for the frame-by-frame path
+ * (reference stylize_webcam.py:82-90: the uint8 frame is fed as-is - the float cast happens inside
+ * feed_dict -, the result is cast with numpy astype(uint8), i.e. truncated, and channels 0/2 are
+ * swapped by cv2.cvtColor(COLOR_BGR2RGB)).  in/out are DEVICE pointers; n = number of bytes (4-byte
+ * aligned input, 16-byte aligned output); npix = number of 3-channel pixels. */
+int fs_frame_u8_to_f32(const unsigned char* in, float* out, long long n, void* stream);
+int fs_frame_f32_to_u8(const float* in, unsigned char* out, long long npix, int swap_rb, void* stream);
 
 /* ------------------------------------------------------------------ tensor-core path
  * 3x3 stride-1 convolution on the tcgen05 tensor pipe with split-bf16 operands

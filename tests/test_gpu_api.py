@@ -188,3 +188,55 @@ def test_train_cli_and_slow_style_cli(built_lib, golden_dir, tmp_path):
     ls = [l.split() for l in r.stdout.splitlines() if l[:1].isdigit()]
     assert [int(l[0]) for l in ls] == [0, 10, 20] and float(ls[-1][1]) < float(ls[0][1])
     assert cv2.imread(str(tmp_path / "s.jpg")).shape == (64, 96, 3)
+
+
+def test_frame_stylizer_and_webcam_cli(built_lib, golden_dir, tmp_path):
+    """the stylize_webcam.py loop body (:76-103).  A uint8 BGR frame is fed un-swapped, the
+    float result is truncated (ndarray.astype(uint8)) and channels 0/2 are swapped; the CUDA-graph replay
+    and the plain-launch form must agree bit for bit, and both with the oracle within one grey level."""
+    import subprocess
+    import sys
+    import cv2
+    from faststyle_b200.stream import FrameStylizer
+    from oracle import ckpt as ockpt
+    params = ockpt.load(os.path.join(golden_dir, "starry_final.ckpt"))
+    rng = np.random.RandomState(2)
+    H, W = 72, 88                                    # (H+80)%4 == 0: output size == input size
+    frames = [rng.randint(0, 256, (H, W, 3)).astype(np.uint8) for _ in range(3)]
+    fs_g = FrameStylizer(params, H, W, use_graph=True)
+    fs_e = FrameStylizer(params, H, W, use_graph=False)
+    assert fs_e.graph is None
+    for f in frames:
+        a, b = fs_g.stylize(f), fs_e.stylize(f)
+        assert a.dtype == np.uint8 and a.shape == (H, W, 3)
+        assert np.array_equal(a, b)
+        with torch.no_grad():
+            yo = R.create_net(f[np.newaxis].astype(np.float32), params, "resize", torch.float64)[0].numpy()
+        want = np.clip(yo, 0, 255).astype(np.uint8)[..., ::-1]
+        d = np.abs(a.astype(np.int32) - want.astype(np.int32))
+        assert d.max() <= 1 and (d != 0).mean() < 0.05      # truncation flips only values within ~0.01 level of an integer
+    print("frame stylizer: CUDA graph captured =", fs_g.graph is not None)
+
+    # the CLI on a video file instead of camera 0
+    src = str(tmp_path / "in.avi")
+    wr = cv2.VideoWriter(src, cv2.VideoWriter_fourcc(*'MJPG'), 15.0, (W, H))
+    assert wr.isOpened()
+    for f in frames:
+        wr.write(f)
+    wr.release()
+    out = str(tmp_path / "output.avi")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "stylize_webcam.py"), "--model_path",
+                        os.path.join(golden_dir, "starry_final.ckpt"), "--source", src, "--output", out,
+                        "--no_display"], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Resolution is: %d by %d" % (W, H) in r.stdout and "Stylised 3 frames" in r.stdout
+    cap = cv2.VideoCapture(out)
+    n = 0
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        assert fr.shape == (H, W, 3)
+        n += 1
+    assert n == 3

@@ -145,3 +145,17 @@ def test_loss_config_validation():
         make_loss_config(['conv3_3'], [1.0, 2.0], [], [], 0.0)      # losses.py:23
     with pytest.raises(ValueError):
         make_loss_config(['conv5_1'], [1.0], [], [], 0.0)
+
+
+def test_webcam_cli_keeps_reference_flags():
+    """stylize_webcam.py:17-38: --model_path, --upsample_method, --resolution with the reference's defaults;
+    our parser only ADDS flags (source / output / headless operation)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('cli_webcam', os.path.join(ROOT, 'stylize_webcam.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ns = vars(mod.setup_parser().parse_args([]))
+    ref = {'model_path': './models/starry_final.ckpt', 'upsample_method': 'resize', 'resolution': None}
+    assert {k: ns[k] for k in ref} == ref
+    assert vars(mod.setup_parser().parse_args(['--resolution', '640', '480']))['resolution'] == [640, 480]
+    assert set(ns) - set(ref) == {'source', 'output', 'no_display', 'max_frames'}
