@@ -76,6 +76,8 @@ SIGNATURES = {
     "fs_conv3x3_tc_forward": (_I, [_P, _P, _P, _P, _P, _SZ] + [_I] * 7 + [_P]),
     "fs_conv3x3_tc_dgrad": (_I, [_P, _P, _P, _P, _SZ] + [_I] * 6 + [_P]),
     "fs_wgrad3x3_tc_scratch_bytes": (_SZ, [_I, _I, _I]),
+    "fs_gram_tc_scratch_bytes": (_SZ, [_I, _I, _I, _I]),
+    "fs_gram_tc_forward": (_I, [_P, _P, _P, _SZ, _I, _I, _I, _I, _P]),
     "fs_wgrad3x3_tc": (_I, [_P, _P, _P, _P, _SZ, _I, _I, _I, _I, _P]),
 }
 

@@ -403,4 +403,22 @@ size_t fs_wgrad3x3_tc_scratch_bytes(int N, int H, int W) {
     return 4 * al1k((size_t)N * H * W * 64 * 2) + (size_t)wgrad3x3_tc_partial_floats() * 4 + 1024;
 }
 
+/* test entry: Gram matrix on the tensor path (the kernel the engine uses for style taps) */
+size_t fs_gram_tc_scratch_bytes(int N, int H, int W, int C) {
+    return 2 * al1k((size_t)N * H * W * C * 2) + (size_t)gram_tc_partial_floats(N, H * W, C) * 4 + 1024;
+}
+int fs_gram_tc_forward(const float* f, float* g, void* scratch, size_t scratch_bytes, int N, int H, int W, int C,
+                       void* stream) {
+    FS_CHECK(f && g && scratch && ((uintptr_t)scratch & 1023) == 0, "fs_gram_tc_forward: bad argument");
+    FS_CHECK(C % 64 == 0 && C >= 64, "fs_gram_tc_forward: C must be a multiple of 64");
+    FS_CHECK(scratch_bytes >= fs_gram_tc_scratch_bytes(N, H, W, C), "fs_gram_tc_forward: scratch too small");
+    size_t fa = al1k((size_t)N * H * W * C * 2);
+    char* p = (char*)scratch;
+    SplitPtr fs_{(__nv_bfloat16*)p, (__nv_bfloat16*)(p + fa)};
+    float* partial = (float*)(p + 2 * fa);
+    FS_TRY(split_bf16(f, fs_, (long long)N * H * W * C, S(stream)));
+    return launch_gram_tc(fs_, g, partial, gram_tc_partial_floats(N, H * W, C), N, H * W, C,
+                          (float)(1.0 / ((double)H * W * C)), S(stream));
+}
+
 }  // extern "C"

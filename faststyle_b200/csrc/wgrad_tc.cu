@@ -13,6 +13,7 @@
 // [9,64,64] fp32 and a fixed-order reduction sums the CTAs' partials (deterministic).
 // Precision: split-bf16 x3 (hi*hi + hi*lo + lo*hi), fp32 accumulation - as conv3x3_tc.cu.
 #include <cuda.h>
+#include <stdlib.h>
 #include "tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -42,10 +43,10 @@ __device__ __forceinline__ uint64_t make_sdesc_mn(uint32_t saddr, uint32_t lbo_b
     return d;
 }
 
-__device__ __forceinline__ uint32_t make_idesc_mn() {
+__device__ __forceinline__ uint32_t make_idesc_mn(int n = 64) {
     return (1u << 4) | (1u << 7) | (1u << 10)
          | (1u << 15) | (1u << 16)                  // A and B are MN-major
-         | ((uint32_t)(64 >> 3) << 17)              // N = 64
+         | ((uint32_t)(n >> 3) << 17)               // N (multiple of 16, <= 256)
          | ((uint32_t)(128 >> 4) << 24);            // M = 128
 }
 
@@ -402,6 +403,132 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     if (warp == 2) tmem_dealloc(tmem_base, 64);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Version 2: full-width rows.  Work item = (sample, 128-channel row tile, pixel split).  Per pixel chunk the
+// CTA loads ALL C/64 channel boxes of F once (hi + lo); the A operand (M = 128 rows = 2 boxes, LBO = box
+// stride) is a SUBSET of those boxes and the B operand is all of them (N = min(C, 256) per MMA, two N-halves
+// for C = 512), so F crosses L2->SMEM C/128 times instead of 1.5*C/64 times and every MMA is as wide as the
+// shape allows (A re-use from shared memory grows with N: the version-1 N = 64 tiles were bound by the
+// 128 B/clk shared-memory operand feed).  The accumulator [128, C] fp32 lives in TMEM (C <= 512 columns).
+// Chunk size gp is chosen so that one stage is <= 64 KB; 3-6 stages deep.
+struct Gram2Params {
+    int N, HW, C, mtiles, ksplit, total_chunks;
+    int gp, gbox, nbox, stages, stage_bytes, ncols;
+    float* partial;            // [N][ksplit][C][C]
+};
+
+__global__ void __launch_bounds__(256, 1)
+gram_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const Gram2Params p) {
+    FS_PDL_TRIGGER();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = full + 8;
+    uint64_t* done = empty + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int item = blockIdx.x;
+    const int ks = item % p.ksplit; item /= p.ksplit;
+    const int mt = item % p.mtiles;
+    const int n = item / p.mtiles;
+    const bool two_groups = p.C >= 128;               // C == 64: the second 64-row half aliases the first
+    // balanced pixel split: chunks [c_beg, c_end)
+    const int c_beg = (int)((long long)ks * p.total_chunks / p.ksplit);
+    const int c_end = (int)((long long)(ks + 1) * p.total_chunks / p.ksplit);
+    const int nchunks = c_end - c_beg;
+    const int plane = p.nbox * p.gbox;                // bytes of the hi (or lo) boxes of one stage
+
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tm_hi); prefetch_tmap(&tm_lo); }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.ncols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    FS_PDL_WAIT();                        // everything above is CTA-local setup
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        int s = 0; uint32_t ph = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* d = smem + s * p.stage_bytes;
+            const int pix = (c_beg + c) * p.gp;
+            mbar_expect_tx(&full[s], (uint32_t)(2 * plane));
+            for (int b = 0; b < p.nbox; ++b) {
+                tma_load_4d(d + b * p.gbox, &tm_hi, &full[s], b * 64, pix, n, 0);
+                tma_load_4d(d + plane + b * p.gbox, &tm_lo, &full[s], b * 64, pix, n, 0);
+            }
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+    } else if (warp == 1) {
+        const int nn = p.C < 256 ? p.C : 256;         // MMA N
+        const int nhalves = p.C / nn;                 // 1, or 2 for C = 512
+        const uint32_t idesc = make_idesc_mn(nn);
+        const uint32_t lboA = two_groups ? (uint32_t)p.gbox : 0u;
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const int ksteps = p.gp / 16;
+        int s = 0; uint32_t ph = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t base = smem_u32(smem + s * p.stage_bytes);
+            const uint32_t aoff = two_groups ? (uint32_t)(mt * 2 * p.gbox) : 0u;
+            const uint64_t a_hi = make_sdesc_mn(base + aoff, lboA), a_lo = make_sdesc_mn(base + plane + aoff, lboA);
+            if (elect_one()) {
+                for (int h = 0; h < nhalves; ++h) {
+                    const uint32_t boff = (uint32_t)(h * (nn / 64) * p.gbox);
+                    const uint64_t b_hi = make_sdesc_mn(base + boff, (uint32_t)p.gbox);
+                    const uint64_t b_lo = make_sdesc_mn(base + plane + boff, (uint32_t)p.gbox);
+                    const uint32_t acc = tb + (uint32_t)(h * nn);
+#pragma unroll
+                    for (int prod = 0; prod < 3; ++prod) {
+                        const uint64_t ab = prod == 2 ? a_lo : a_hi, bb = prod == 1 ? b_lo : b_hi;
+                        for (int k = 0; k < ksteps; ++k)
+                            tc_mma_bf16(acc, ab + (uint64_t)(k * 128), bb + (uint64_t)(k * 128), idesc,
+                                        (c == 0 && prod == 0 && k == 0) ? 0u : 1u);
+                    }
+                }
+                tc_commit(&empty[s]);
+            }
+            __syncwarp();
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        if (elect_one()) tc_commit(done);
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        const int row = ew * 32 + lane;
+        mbar_wait(done, 0);
+        tc_fence_after();
+        const int c1 = mt * 128 + row;
+        const bool ok = (two_groups || row < 64) && c1 < p.C;
+        float* out = p.partial + (((long long)n * p.ksplit + ks) * p.C + (ok ? c1 : 0)) * p.C;
+#pragma unroll 1
+        for (int ch = 0; ch < p.C / 32; ++ch) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ch * 32), v);
+            if (ok) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    float z[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) z[j] = nchunks > 0 ? v[i + j] : 0.f;
+                    stg256(out + ch * 32 + i, z);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.ncols);
+}
+
 // G[n][i] = scale * sum_ks partial[n][ks][i]
 __global__ void gram_reduce_kernel(const float* __restrict__ partial, float* __restrict__ G, long long cc4, int N,
                                    int ksplit, float scale) {
@@ -446,7 +573,7 @@ int gram_ksplit(int N, int HW, int C) {
     return ks;
 }
 
-int make_map3(CUtensorMap* tm, const __nv_bfloat16* base, int N, int HW, int C) {
+int make_map3(CUtensorMap* tm, const __nv_bfloat16* base, int N, int HW, int C, int gp = GP) {
     static EncodeTiledFn enc = nullptr;
     if (!enc) {
         void* fp = nullptr;
@@ -457,7 +584,7 @@ int make_map3(CUtensorMap* tm, const __nv_bfloat16* base, int N, int HW, int C) 
     }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)HW, (cuuint64_t)N, 1};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)HW * C * 2, (cuuint64_t)N * HW * C * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)GP, 1, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)gp, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -468,12 +595,74 @@ int make_map3(CUtensorMap* tm, const __nv_bfloat16* base, int N, int HW, int C) 
 
 }  // namespace
 
-long long gram_tc_partial_floats(int N, int HW, int C) { return (long long)N * gram_ksplit(N, HW, C) * C * C; }
+namespace {
+// version-2 plan (see gram_tc2_kernel)
+void gram2_plan(int N, int HW, int C, Gram2Params& p) {
+    p.N = N; p.HW = HW; p.C = C;
+    p.mtiles = C >= 128 ? C / 128 : 1;
+    p.nbox = C / 64;
+    p.gp = C <= 128 ? 128 : 16384 / C;              // C*gp*4 bytes per stage: 32 KB (C = 64) or 64 KB
+    p.gbox = p.gp * 128;
+    p.stage_bytes = 2 * p.nbox * p.gbox;
+    p.stages = 196608 / p.stage_bytes;
+    if (p.stages > 6) p.stages = 6;
+    p.total_chunks = (HW + p.gp - 1) / p.gp;
+    int items = N * p.mtiles;
+    int ks = 148 / items;
+    if (ks < 1) ks = 1;
+    if (ks > p.total_chunks) ks = p.total_chunks;
+    p.ksplit = ks;
+    p.ncols = C < 32 ? 32 : C;                      // 64 / 128 / 256 / 512: powers of two
+}
+bool gram2_supported(int C) { return C == 64 || C == 128 || C == 256 || C == 512; }
+int gram_version() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FS_GRAM_V2");
+        v = (e && e[0] == '0') ? 1 : 2;
+    }
+    return v;
+}
+}  // namespace
+
+long long gram_tc_partial_floats(int N, int HW, int C) {
+    long long v1 = (long long)N * gram_ksplit(N, HW, C) * C * C;
+    if (!gram2_supported(C)) return v1;
+    Gram2Params p;
+    gram2_plan(N, HW, C, p);
+    long long v2 = (long long)N * p.ksplit * C * C;
+    return v1 > v2 ? v1 : v2;
+}
+
+static int launch_gram_tc2(SplitPtr f, float* G, float* partial, long long partial_cap, int N, int HW, int C, float scale,
+                           cudaStream_t st) {
+    Gram2Params p;
+    gram2_plan(N, HW, C, p);
+    p.partial = partial;
+    FS_CHECK((long long)N * p.ksplit * C * C <= partial_cap, "gram_tc2: partial workspace too small");
+    CUtensorMap tm_hi, tm_lo;
+    FS_TRY(make_map3(&tm_hi, f.hi, N, HW, C, p.gp));
+    FS_TRY(make_map3(&tm_lo, f.lo, N, HW, C, p.gp));
+    const int smem = p.stages * p.stage_bytes + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FS_CUDA(cudaFuncSetAttribute(gram_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608 + 1024 + 256));
+        attr_set = true;
+    }
+    int grid = N * p.mtiles * p.ksplit;
+    launch_k(gram_tc2_kernel, dim3(grid), dim3(256), smem, st, tm_hi, tm_lo, p);
+    FS_LAUNCH_CHECK();
+    long long cc4 = (long long)C * C / 4;
+    launch_k(gram_reduce_kernel, dim3(cdiv(cc4 * N, 256)), dim3(256), 0, st, partial, G, cc4, N, p.ksplit, scale);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
 
 int launch_gram_tc(SplitPtr f, float* G, float* partial, long long partial_cap, int N, int HW, int C, float scale,
                    cudaStream_t st) {
     FS_CHECK(f.hi && f.lo && G && partial, "gram_tc: NULL argument");
     FS_CHECK(C % 64 == 0 && C >= 64, "gram_tc: C must be a multiple of 64");
+    if (gram_version() == 2 && gram2_supported(C)) return launch_gram_tc2(f, G, partial, partial_cap, N, HW, C, scale, st);
     GramParams p;
     p.N = N; p.HW = HW; p.C = C;
     p.mtiles = (C + 127) / 128; p.ntiles = C / 64;

@@ -197,6 +197,13 @@ size_t fs_wgrad3x3_tc_scratch_bytes(int N, int H, int W);
 int fs_wgrad3x3_tc(const float* x, const float* dy, float* dw, void* scratch, size_t scratch_bytes, int N, int H,
                    int W, int padding_same, void* stream);
 
+/* Gram matrix on the tensor path (the kernel the engine uses for the style taps): same semantics as
+ * fs_gram_forward, C a multiple of 64.  FS_GRAM_V2=0 in the environment selects the first-generation
+ * 128x64-tile kernel instead of the full-width one. */
+size_t fs_gram_tc_scratch_bytes(int N, int H, int W, int C);
+int fs_gram_tc_forward(const float* f, float* g, void* scratch, size_t scratch_bytes, int N, int H, int W, int C,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,3 +96,46 @@ def test_wgrad3x3_tc(built_lib, case):
     err = _relerr(dw, wt.grad)
     print("wgrad3x3_tc", case, "rel err", err)
     assert err < 2e-5
+
+
+GRAM_CASES = [
+    # N, H, W, C   (utils.py:66-83: G = F^T F / (h*w*c) per sample)
+    (2, 5, 7, 64),          # fewer pixels than one chunk (TMA zero fill)
+    (1, 33, 29, 128),       # ragged last chunk
+    (2, 17, 16, 256),       # two row tiles
+    (2, 9, 13, 512),        # four row tiles, two N halves (all 512 TMEM columns)
+    (3, 64, 64, 64),        # many chunks per split
+    (8, 256, 256, 64),      # BASELINE config 3/4 shapes, per-GPU batch 8: conv1_2
+    (8, 128, 128, 128),     # conv2_2
+    (8, 64, 64, 256),       # conv3_3
+    (8, 32, 32, 512),       # conv4_3
+    (1, 128, 128, 512),     # slow_style 1024x1024 (config 5): conv4_3
+]
+
+
+@pytest.mark.parametrize("case", GRAM_CASES)
+def test_gram_tc(built_lib, case):
+    """tcgen05 Gram kernel (split-bf16 x3, MN-major operands) vs an fp64 matmul of the same features, plus
+    size-independent properties: symmetry and trace(G) = sum(F^2)/(hwc).  Tolerance 2e-5 of max|G|."""
+    from faststyle_b200 import _lib
+    lib = _lib.load()
+    N, H, W, Cc = case
+    g = torch.Generator().manual_seed(1000 + H + Cc)
+    f = torch.rand((N, H, W, Cc), generator=g) * 3.0          # post-ReLU-like, non-negative
+    f[:, ::3] = 0.0
+    fd = f.cuda()
+    nb = lib.fs_gram_tc_scratch_bytes(N, H, W, Cc)
+    scratch = torch.empty(nb + 1024, dtype=torch.uint8, device="cuda")
+    sp = C.c_void_p(scratch.data_ptr() + (-scratch.data_ptr()) % 1024)
+    G = torch.full((N, Cc, Cc), float("nan"), device="cuda")
+    _lib.call("fs_gram_tc_forward", _ptr(fd), _ptr(G), sp, C.c_size_t(nb), N, H, W, Cc, _st())
+    torch.cuda.synchronize()
+    F2 = f.double().reshape(N, H * W, Cc)
+    want = torch.matmul(F2.transpose(1, 2), F2) / (H * W * Cc)
+    err = _relerr(G, want)
+    Gc = G.double().cpu()
+    sym = float((Gc - Gc.transpose(1, 2)).abs().max() / want.abs().max())
+    tr = float((torch.diagonal(Gc, dim1=1, dim2=2).sum(1) - (F2 ** 2).sum((1, 2)) / (H * W * Cc)).abs().max()
+               / want.abs().max())
+    print("gram_tc", case, "rel err %.3g asym %.3g trace %.3g" % (err, sym, tr))
+    assert err < 2e-5 and sym < 2e-5 and tr < 1e-4
