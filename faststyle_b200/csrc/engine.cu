@@ -252,7 +252,7 @@ void Engine::layout(Arena& a) {
             }
         }
         y3 = a.take<float>((long long)N * OH * OW * 3);
-        in_partial = a.take<double>(in_scratch_doubles(N, 64));
+        in_partial = a.take<double>((long long)N * 64 * 64 * 2);
         in15 = a.take<float>(8);
         wtmp15 = a.take<float>(81 * 64);
         if (tbw) {
@@ -311,7 +311,6 @@ int Engine::bind(void* ws, size_t bytes) {
     FS_CHECK(((uintptr_t)ws & 255) == 0, "engine: workspace must be 256-byte aligned");
     Arena a; a.base = (char*)ws; a.cap = bytes;
     layout(a);
-    if (in_partial) FS_TRY(in_scratch_init(in_partial, N, 64));
     bound = true;
     return 0;
 }
@@ -404,7 +403,7 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
             if (c.upconv && (flags & ENG_DECONV)) a.gather = 1;      // transposed conv: iy = oy - a
             PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
         }
-        PROF(PC_IN_STATS, 0.0, instnorm_stats(tb[l].raw, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, in_partial, st, in_fused, 64));
+        PROF(PC_IN_STATS, 0.0, instnorm_stats(tb[l].raw, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, in_partial, st));
         const float* skip = nullptr;
         if (l >= 4 && l <= 12 && (l & 1) == 0) skip = tb[l - 2].act;       // residual: block input
         const bool last = l == T_NCONV - 1;
@@ -444,7 +443,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         const bool tcl = use_tc && l >= 3 && l <= 12;
         PROF(PC_IN_BWD, 0.0, instnorm_bwd(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw, dg, db, N,
                             c.outH * c.outW, c.cout_s, c.act, in_partial, m12, st,
-                            tcl ? tgsplit[ri].hi : nullptr, tcl ? tgsplit[ri].lo : nullptr, in_fused, 64));
+                            tcl ? tgsplit[ri].hi : nullptr, tcl ? tgsplit[ri].lo : nullptr));
         if (last) {
             FS_CUDA(cudaMemcpyAsync(grads + c.offG, gb_tmp, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
             FS_CUDA(cudaMemcpyAsync(grads + c.offB, gb_tmp + 4, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));

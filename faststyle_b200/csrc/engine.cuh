@@ -76,7 +76,6 @@ struct Engine {
     float* wefft[T_NCONV];               // transposed weights for the data gradient
     float* y3 = nullptr;                 // [N,OH,OW,3] when the caller does not supply an output
     double* in_partial = nullptr;
-    int in_fused = 1;                    // InstanceNorm reductions finalise in their last CTA (FS_IN_FUSED=0: separate launches)
     float* in15 = nullptr;               // 4-channel staging of the last layer's IN scale/shift
     float* gb_tmp = nullptr;
     float* wtmp15 = nullptr;             // staging for the deconv variant of the last layer's weights

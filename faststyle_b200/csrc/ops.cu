@@ -111,21 +111,13 @@ __global__ void f32_to_u8_kernel(const float* __restrict__ in, unsigned char* __
 }
 
 // ------------------------------------------------------------------ InstanceNorm
-// Optional fused finalize (counters != nullptr): see the tail of in_reduce_kernel.
-struct INFused {
-    unsigned* counters;          // [N + 1], zero on entry, zero again on exit
-    double* nsum;                // [N][C][2] per-sample totals (MODE 1)
-    float *mean, *rstd;          // MODE 0 outputs
-    float *m12, *dgamma, *dbeta; // MODE 1 outputs
-    float eps; int N;
-};
 // MODE 0: sums of (x, x^2).   MODE 1: sums of (dz, dz*xhat) for the backward pass.
 template <int MODE>
 __global__ void __launch_bounds__(256)
 in_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dY,
                  const float* __restrict__ mean, const float* __restrict__ rstd,
                  const float* __restrict__ scale, const float* __restrict__ shift,
-                 double* __restrict__ partial, int HW, int C, int chunks, int act, const INFused f) {
+                 double* __restrict__ partial, int HW, int C, int chunks, int act) {
     FS_PDL_ENTER();
     extern __shared__ double sm[];            // [C][2]
     const int t = threadIdx.x, n = blockIdx.y, chunk = blockIdx.x;
@@ -197,64 +189,6 @@ in_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dY,
     __syncthreads();
     double* dst = partial + ((long long)n * chunks + chunk) * 2 * C;
     for (int i = t; i < 2 * C; i += 256) dst[i] = sm[i];
-    if (f.counters == nullptr) return;        // two-kernel form: a separate finalize launch follows
-
-    // ---- fused finalize: the LAST chunk-CTA of sample n folds that sample's partials (same fixed
-    // order as the stand-alone finalize kernels: lanes stride the chunks, xor-tree, so the result does
-    // not depend on which CTA happens to be last).  Counters are self-resetting.
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (t == 0) s_last = (atomicAdd(&f.counters[n], 1u) == (unsigned)(chunks - 1));
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const int w = t >> 5, l = t & 31;
-    const volatile double* pv = partial;
-    for (int c = w; c < C; c += 8) {
-        double a1 = 0, a2 = 0;
-        for (int k = l; k < chunks; k += 32) {
-            const volatile double* p = pv + ((long long)n * chunks + k) * 2 * C + c * 2;
-            a1 += p[0];
-            a2 += p[1];
-        }
-        a1 = warp_sum(a1);
-        a2 = warp_sum(a2);
-        if (l == 0) {
-            if (MODE == 0) {
-                double m = a1 / HW;
-                double var = a2 / HW - m * m;
-                if (var < 0) var = 0;
-                f.mean[(long long)n * C + c] = (float)m;
-                f.rstd[(long long)n * C + c] = (float)(1.0 / sqrt(var + (double)f.eps));
-            } else {
-                f.m12[((long long)n * C + c) * 2 + 0] = (float)(a1 / HW);
-                f.m12[((long long)n * C + c) * 2 + 1] = (float)(a2 / HW);
-                f.nsum[((long long)n * C + c) * 2 + 0] = a1;
-                f.nsum[((long long)n * C + c) * 2 + 1] = a2;
-            }
-        }
-    }
-    if (t == 0) f.counters[n] = 0u;
-    if (MODE == 0) return;
-    // ---- MODE 1: the last of the N sample-finalisers sums the per-sample totals over n = 0..N-1
-    __threadfence();
-    __syncthreads();
-    if (t == 0) s_last = (atomicAdd(&f.counters[f.N], 1u) == (unsigned)(f.N - 1));
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const volatile double* ns = f.nsum;
-    for (int c = t; c < C; c += 256) {
-        double bb = 0, gg = 0;
-        for (int k = 0; k < f.N; ++k) {
-            bb += ns[((long long)k * C + c) * 2 + 0];
-            gg += ns[((long long)k * C + c) * 2 + 1];
-        }
-        if (f.dgamma) f.dgamma[c] = (float)gg;
-        if (f.dbeta) f.dbeta[c] = (float)bb;
-    }
-    if (t == 0) f.counters[f.N] = 0u;
 }
 
 // one warp per (n, c): lanes split the chunks, fixed shuffle-tree order -> deterministic
@@ -749,37 +683,13 @@ static int check_in_c(int C) {
     return 0;
 }
 
-// layout of the fused-finalize tail that follows the [N][64][2C] partials in an INScratch buffer
-static INFused in_fused_view(double* partial, int N, int C, int fused) {
-    INFused f;
-    memset(&f, 0, sizeof(f));
-    if (!fused) return f;
-    double* tail = partial + in_partial_doubles(N, C);
-    f.nsum = tail;
-    f.counters = reinterpret_cast<unsigned*>(tail + (long long)N * C * 2);
-    f.N = N;
-    return f;
-}
-long long in_partial_doubles(int N, int C) { return (long long)N * 64 * 2 * C; }
-long long in_scratch_doubles(int N, int C) { return in_partial_doubles(N, C) + (long long)N * C * 2 + (N + 2) / 2 + 1; }
-int in_scratch_init(double* partial, int N, int C) {
-    // the completion counters must be zero before the first fused launch; they reset themselves afterwards
-    INFused f = in_fused_view(partial, N, C, 1);
-    FS_CUDA(cudaMemset(f.counters, 0, (N + 1) * sizeof(unsigned)));
-    FS_CUDA(cudaDeviceSynchronize());
-    return 0;
-}
-
 int instnorm_stats(const float* x, float* mean, float* rstd, int N, int HW, int C, float eps,
-                   double* partial, cudaStream_t st, int fused, int Cmax) {
+                   double* partial, cudaStream_t st) {
     FS_TRY(check_in_c(C));
     int chunks = in_chunks(N, HW);
-    INFused f = in_fused_view(partial, N, Cmax, fused);
-    f.mean = mean; f.rstd = rstd; f.eps = eps;
     launch_k((in_reduce_kernel<0>), dim3(dim3(chunks, N)), dim3(256), 2 * C * sizeof(double), st, 
-        x, nullptr, nullptr, nullptr, nullptr, nullptr, partial, HW, C, chunks, 0, f);
+        x, nullptr, nullptr, nullptr, nullptr, nullptr, partial, HW, C, chunks, 0);
     FS_LAUNCH_CHECK();
-    if (fused) return 0;
     launch_k(in_stats_finalize_kernel, dim3(cdiv((long long)N * C, 8)), dim3(256), 0, st, partial, mean, rstd, N, C, chunks, HW, eps);
     FS_LAUNCH_CHECK();
     return 0;
@@ -801,18 +711,14 @@ int instnorm_apply(const float* x, const float* mean, const float* rstd, const f
 int instnorm_bwd(const float* dY, const float* x, const float* mean, const float* rstd,
                  const float* scale, const float* shift, float* dx, float* dgamma, float* dbeta,
                  int N, int HW, int C, int act, double* partial, float* m12, cudaStream_t st,
-                 void* split_hi, void* split_lo, int fused, int Cmax) {
+                 void* split_hi, void* split_lo) {
     FS_TRY(check_in_c(C));
     int chunks = in_chunks(N, HW);
-    INFused f = in_fused_view(partial, N, Cmax, fused);
-    f.m12 = m12; f.dgamma = dgamma; f.dbeta = dbeta;
     launch_k((in_reduce_kernel<1>), dim3(dim3(chunks, N)), dim3(256), 2 * C * sizeof(double), st, 
-        x, dY, mean, rstd, scale, shift, partial, HW, C, chunks, act, f);
+        x, dY, mean, rstd, scale, shift, partial, HW, C, chunks, act);
     FS_LAUNCH_CHECK();
-    if (!fused) {
-        launch_k(in_bwd_finalize_kernel, dim3(C), dim3(256), 0, st, partial, m12, dgamma, dbeta, N, C, chunks, HW);
-        FS_LAUNCH_CHECK();
-    }
+    launch_k(in_bwd_finalize_kernel, dim3(C), dim3(256), 0, st, partial, m12, dgamma, dbeta, N, C, chunks, HW);
+    FS_LAUNCH_CHECK();
     long long n = (long long)N * HW * (C / 4);
     launch_k(in_bwd_apply_kernel, dim3(grid1(n)), dim3(256), 0, st, dY, x, mean, rstd, scale, shift, m12, dx, N, HW, C, act,
                                                   (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo);

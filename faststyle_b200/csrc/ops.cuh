@@ -18,13 +18,8 @@ int frame_f32_to_u8(const float* in, unsigned char* out, long long npix, int swa
 // K3: InstanceNorm                               (reference im_transf_net.py:218-247)
 struct INWork { double* partial; int max_chunks; };       // partial: [N][chunks][C][2] doubles
 int in_chunks(int N, int HW);
-// fused = 1: the reduction kernel's last CTA also finalises (one launch instead of two / of three for the
-// backward); `partial` must then be an in_scratch_doubles(N, Cmax) buffer prepared once by in_scratch_init.
-long long in_partial_doubles(int N, int C);
-long long in_scratch_doubles(int N, int Cmax);
-int in_scratch_init(double* partial, int N, int Cmax);
 int instnorm_stats(const float* x, float* mean, float* rstd, int N, int HW, int C, float eps,
-                   double* partial, cudaStream_t st, int fused = 0, int Cmax = 0);
+                   double* partial, cudaStream_t st);
 int instnorm_apply(const float* x, const float* mean, const float* rstd, const float* scale,
                    const float* shift, const float* skip, float* out, int N, int H, int W, int C,
                    int act, int out3, cudaStream_t st, void* split_hi = nullptr, void* split_lo = nullptr);
@@ -33,7 +28,7 @@ int instnorm_apply(const float* x, const float* mean, const float* rstd, const f
 int instnorm_bwd(const float* dY, const float* x, const float* mean, const float* rstd,
                  const float* scale, const float* shift, float* dx, float* dgamma, float* dbeta,
                  int N, int HW, int C, int act, double* partial, float* m12 /*[N][C][2]*/,
-                 cudaStream_t st, void* split_hi = nullptr, void* split_lo = nullptr, int fused = 0, int Cmax = 0);
+                 cudaStream_t st, void* split_hi = nullptr, void* split_lo = nullptr);
 // zero-pad-add:  dst[n, y+crop, x+crop, c] += src[n,y,x,c]   (skip-connection gradient)
 int add_padded(float* dst, const float* src, int N, int H, int W, int C, int crop, cudaStream_t st);
 
