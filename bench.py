@@ -315,7 +315,7 @@ def run_ours(args, rank, local_rank, world):
 
 PROF_CATS = ["tc_vgg_conv_fwd", "tc_vgg_conv_dgrad", "tc_res_conv_fwd", "tc_res_conv_dgrad",
              "ffma_conv", "wgrad", "gram_fwd", "gram_bwd", "instnorm_stats", "instnorm_apply", "instnorm_bwd",
-             "pointwise", "losses", "weight_prep"]
+             "pointwise", "losses", "weight_prep", "tc_s2_conv_fwd", "tc_s2_conv_dgrad"]
 
 
 def live_kernel_profile(eng, step_fn, steps=3):
@@ -344,7 +344,8 @@ def dominant_kernel_roofline(prof, peaks, step_ms):
     """Dominant kernel = the tcgen05 3x3 convolution (VGG fwd + dgrad + residual convs):
     achieved = algorithmic FLOPs of those launches (2*MACs; the three split-bf16 passes are NOT
     multiplied in) / their summed event time."""
-    names = [k for k in ("tc_vgg_conv_fwd", "tc_vgg_conv_dgrad", "tc_res_conv_fwd", "tc_res_conv_dgrad") if k in prof]
+    names = [k for k in ("tc_vgg_conv_fwd", "tc_vgg_conv_dgrad", "tc_res_conv_fwd", "tc_res_conv_dgrad",
+                         "tc_s2_conv_fwd", "tc_s2_conv_dgrad") if k in prof]
     if names:
         ms = sum(prof[k]["ms_per_step"] for k in names)
         gf = sum(prof[k]["gflop_per_step"] for k in names)

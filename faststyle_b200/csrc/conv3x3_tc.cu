@@ -52,7 +52,8 @@ __device__ __forceinline__ uint32_t make_idesc() {
 
 struct TcParams {
     int N, H, W, C, OH, OW, OC, pad;
-    int taps;                  // 3: 3x3 convolution, 1: 1x1 (per-sample GEMM, e.g. Gram backward)
+    int taps;                  // 3: 3x3 convolution, 2: 2x2 (collapsed stride-2 forms), 1: 1x1 (per-sample GEMM)
+    int in_s2d, out_d2s;       // space-to-depth input view (5-D tensor map) / depth-to-space fp32 store
     int w_sample_rows;         // rows of the packed weight matrix per sample (0 = shared weights)
     int tilesX, tilesY, tilesN;
     long long total_tiles;
@@ -129,8 +130,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     mbar_wait(&a_empty[sa], pa ^ 1);
                     uint8_t* dst = smemA + sa * K::A_STAGE_BYTES;
                     mbar_expect_tx(&a_full[sa], K::A_STAGE_BYTES);
-                    tma_load_4d(dst, &tmA_hi, &a_full[sa], cb * KB, x0 + kw, y0, n);
-                    tma_load_4d(dst + K::SLAB_BYTES, &tmA_lo, &a_full[sa], cb * KB, x0 + kw, y0, n);
+                    if (p.in_s2d) {       // channel block cb = row parity p of the [2H,2W,32] source (see make_act_map_s2d)
+                        tma_load_5d(dst, &tmA_hi, &a_full[sa], 0, x0 + kw, cb, y0, n);
+                        tma_load_5d(dst + K::SLAB_BYTES, &tmA_lo, &a_full[sa], 0, x0 + kw, cb, y0, n);
+                    } else {
+                        tma_load_4d(dst, &tmA_hi, &a_full[sa], cb * KB, x0 + kw, y0, n);
+                        tma_load_4d(dst + K::SLAB_BYTES, &tmA_lo, &a_full[sa], cb * KB, x0 + kw, y0, n);
+                    }
                     if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
                     for (int kh = 0; kh < p.taps; ++kh) {
                         mbar_wait(&b_empty[sb], pb ^ 1);
@@ -230,7 +236,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) +
                                            (uint32_t)(as * K::NACC * BN + acc * BN + ch * 32);
                     tmem_ld32(taddr, v);                // warp-collective: executed by all lanes
-                    if (ok) {
+                    if (ok && p.out_d2s) {
+                        // 32 output channels = one sub-pixel phase pq of the 2x upsampled result (OC = 4 * 32)
+                        const int pq = nt * (BN / 32) + ch;
+                        const long long pix2 = ((long long)n * (2 * p.OH) + 2 * oy + (pq >> 1)) * (2 * p.OW) + 2 * ox + (pq & 1);
+                        float* op = p.out_f32 + pix2 * 32;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) stg256(op + i, v + i);
+                    } else if (ok) {
                         const int c0 = nt * BN + ch * 32;
                         if (p.bias) {
 #pragma unroll
@@ -346,6 +359,25 @@ __global__ void pack_w3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __r
     lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+__global__ void pack_taps_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo, int T, int Kc, int Nn, int flip) {
+    FS_PDL_ENTER();
+    // output index: (((tap'*CB + cb)*Nn + n)*64 + k)  <-  w[tap][cb*64+k][n]
+    const int CB = Kc / 64;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)T * Kc * Nn) return;
+    int k = (int)(i % 64);
+    long long r = i / 64;
+    int n = (int)(r % Nn); r /= Nn;
+    int cb = (int)(r % CB);
+    int tp = (int)(r / CB);
+    int tap = flip ? T - 1 - tp : tp;
+    float v = w[((long long)tap * Kc + cb * 64 + k) * Nn + n];
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
 struct PackBatch { const float* w[16]; __nv_bfloat16* hi[16]; __nv_bfloat16* lo[16]; };
 
 __global__ void pack_w3x3_batch_kernel(const PackBatch pb, int Ci, int Co, int mode) {
@@ -398,6 +430,23 @@ int make_act_map(CUtensorMap* tm, const __nv_bfloat16* base, int N, int H, int W
     return 0;
 }
 
+// Space-to-depth view S[n, y, x, (p, q, c)] = T[n, 2y+p, 2x+q, c] of a plain [N, 2H, 2W, 32] tensor as a 5-D map
+// {64 = (q,c) contiguous, W (x), 2 (p), H (y), N}: the 64-channel block cb of S is the row parity p.
+int make_act_map_s2d(CUtensorMap* tm, const __nv_bfloat16* base, int N, int H, int W, int box_h) {
+    EncodeTiledFn enc = get_encode_fn();
+    FS_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    const cuuint64_t C0 = 32, FW = 2 * (cuuint64_t)W, FH = 2 * (cuuint64_t)H;
+    cuuint64_t dims[5] = {64, (cuuint64_t)W, 2, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[4] = {2 * C0 * 2, FW * C0 * 2, 2 * FW * C0 * 2, FH * FW * C0 * 2};
+    cuuint32_t box[5] = {(cuuint32_t)KB, (cuuint32_t)TW, 1, (cuuint32_t)box_h, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(s2d activation %dx%dx%d) failed: %d", N, H, W, (int)r);
+    return 0;
+}
+
 int make_w_map(CUtensorMap* tm, const __nv_bfloat16* base, long long rows, int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     FS_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -427,14 +476,21 @@ template <int TH, int BN>
 int launch_cfg(const Conv3x3TcArgs& a, cudaStream_t st) {
     using K = Cfg<TH, BN>;
     CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
-    FS_TRY(make_act_map(&tmA_hi, a.x.hi, a.N, a.H, a.W, a.C, TH + 2));
-    FS_TRY(make_act_map(&tmA_lo, a.x.lo, a.N, a.H, a.W, a.C, TH + 2));
-    const long long wrows = a.one_by_one ? (long long)(a.per_sample_w ? a.N : 1) * (a.C / KB) * a.OC : 9LL * (a.C / KB) * a.OC;
+    if (a.in_s2d) {
+        FS_TRY(make_act_map_s2d(&tmA_hi, a.x.hi, a.N, a.H, a.W, TH + 2));
+        FS_TRY(make_act_map_s2d(&tmA_lo, a.x.lo, a.N, a.H, a.W, TH + 2));
+    } else {
+        FS_TRY(make_act_map(&tmA_hi, a.x.hi, a.N, a.H, a.W, a.C, TH + 2));
+        FS_TRY(make_act_map(&tmA_lo, a.x.lo, a.N, a.H, a.W, a.C, TH + 2));
+    }
+    const int taps = a.one_by_one ? 1 : (a.taps ? a.taps : 3);
+    const long long wrows = a.one_by_one ? (long long)(a.per_sample_w ? a.N : 1) * (a.C / KB) * a.OC
+                                         : (long long)taps * taps * (a.C / KB) * a.OC;
     FS_TRY(make_w_map(&tmB_hi, a.w.hi, wrows, BN));
     FS_TRY(make_w_map(&tmB_lo, a.w.lo, wrows, BN));
     TcParams p;
     p.N = a.N; p.H = a.H; p.W = a.W; p.C = a.C; p.OH = a.OH; p.OW = a.OW; p.OC = a.OC; p.pad = a.pad;
-    p.taps = a.one_by_one ? 1 : 3;
+    p.taps = taps; p.in_s2d = a.in_s2d; p.out_d2s = a.out_d2s;
     p.w_sample_rows = a.one_by_one && a.per_sample_w ? (a.C / KB) * a.OC : 0;
     p.tilesX = cdiv(a.OW, TW); p.tilesY = cdiv(a.OH, TH); p.tilesN = a.OC / BN;
     p.total_tiles = (long long)a.N * p.tilesX * p.tilesY * p.tilesN;
@@ -464,6 +520,10 @@ int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st) {
     FS_CHECK(a.out_f32 || a.out_split.hi, "conv3x3_tc: no output requested");
     FS_CHECK((a.out_split.hi == nullptr) == (a.out_split.lo == nullptr), "conv3x3_tc: split output needs both planes");
     FS_CHECK(a.OH > 0 && a.OW > 0 && a.N > 0, "conv3x3_tc: empty output");
+    FS_CHECK(a.taps == 0 || a.taps == 2 || a.taps == 3, "conv3x3_tc: taps must be 2 or 3");
+    FS_CHECK(!a.in_s2d || (a.C == 128 && !a.one_by_one), "conv3x3_tc: the space-to-depth input view needs C == 128");
+    FS_CHECK(!a.out_d2s || (a.OC == 128 && a.out_f32 && !a.out_split.hi && !a.bias && !a.addend && !a.ref && !a.relu),
+             "conv3x3_tc: the depth-to-space store needs OC == 128 and a plain fp32 output");
     bool tall = a.OH > 8;
     // small 64->64 problems (the residual convs): 16-row tiles give < 1.5 waves; 8-row tiles balance the SMs
     // and their 3-deep slab ring hides the L2 miss latency
@@ -490,6 +550,14 @@ int pack_w3x3_tc_batch(const float* const* w, const SplitPtr* out, int count, in
     for (int i = 0; i < count; ++i) { pb.w[i] = w[i]; pb.hi[i] = out[i].hi; pb.lo[i] = out[i].lo; }
     dim3 grid(cdiv(9LL * Ci * Co, 256), count);
     launch_k(pack_w3x3_batch_kernel, dim3(grid), dim3(256), 0, st, pb, Ci, Co, mode);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int pack_taps_tc(const float* w, SplitPtr out, int T, int K, int Nn, int flip, cudaStream_t st) {
+    FS_CHECK(K % 64 == 0 && Nn % 64 == 0 && T >= 1, "pack_taps_tc: K and N must be multiples of 64");
+    long long total = (long long)T * K * Nn;
+    launch_k(pack_taps_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, w, out.hi, out.lo, T, K, Nn, flip);
     FS_LAUNCH_CHECK();
     return 0;
 }

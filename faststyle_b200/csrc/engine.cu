@@ -250,6 +250,14 @@ void Engine::layout(Arena& a) {
                 tw_f[l].hi = a.take<__nv_bfloat16>(9 * 64 * 64); tw_f[l].lo = a.take<__nv_bfloat16>(9 * 64 * 64);
                 if (tbw) { tw_d[l].hi = a.take<__nv_bfloat16>(9 * 64 * 64); tw_d[l].lo = a.take<__nv_bfloat16>(9 * 64 * 64); }
             }
+            if ((l == 2 && s2_collapsed(tc[2])) || (l == 13 && !(flags & ENG_DECONV))) {   // see Engine::tc2
+                long long n = (long long)N * tc[l].inH * tc[l].inW * tc[l].cin;
+                const long long wn = 16LL * tc[l].cin * tc[l].cout;                     // 4 taps x K x N
+                tsplit[l].hi = a.take<__nv_bfloat16>(n); tsplit[l].lo = a.take<__nv_bfloat16>(n);
+                tw_f[l].hi = a.take<__nv_bfloat16>(wn); tw_f[l].lo = a.take<__nv_bfloat16>(wn);
+                if (tbw) { tw_d[l].hi = a.take<__nv_bfloat16>(wn); tw_d[l].lo = a.take<__nv_bfloat16>(wn); }
+                if (l == 2) w2f = a.take<float>(wn);
+            }
         }
         y3 = a.take<float>((long long)N * OH * OW * 3);
         in_partial = a.take<double>((long long)N * 64 * 64 * 2);
@@ -258,8 +266,10 @@ void Engine::layout(Arena& a) {
         if (tbw) {
             m12 = a.take<float>((long long)N * 64 * 2);
             for (int i = 0; i < 3; ++i) tgrad[i] = a.take<float>(maxact);
-            {   // split companions only ever hold dRaw of residual convs (<= N*80*80*64 at 256^2)
+            {   // split companions hold dRaw of the tensor-path convs: residual (3..12), initconv_2, upsample_0
                 long long nres = (long long)N * tc[3].outH * tc[3].outW * 64;
+                nres = maxll(nres, (long long)N * tc[2].outH * tc[2].outW * tc[2].cout);
+                nres = maxll(nres, (long long)N * tc[13].outH * tc[13].outW * tc[13].cout);
                 for (int i = 0; i < 3; ++i) { tgsplit[i].hi = a.take<__nv_bfloat16>(nres); tgsplit[i].lo = a.take<__nv_bfloat16>(nres); }
             }
             wg_tmp = a.take<float>(81LL * 16 * 4 + 16LL * 64 * 32 + 1024);
@@ -341,6 +351,11 @@ int Engine::prep_transform_weights(const float* params, bool need_bwd, cudaStrea
         for (int l = 3; l <= 12; ++l) wsrc[l - 3] = params + tc[l].offW;
         PROF(PC_PREP, 0.0, pack_w3x3_tc_batch(wsrc, &tw_f[3], 10, 64, 64, 0, st));
         if (need_bwd) PROF(PC_PREP, 0.0, pack_w3x3_tc_batch(wsrc, &tw_d[3], 10, 64, 64, 1, st));
+        if (tc2(2)) {
+            PROF(PC_PREP, 0.0, s2_fwd_collapse(params + tc[2].offW, w2f, tc[2].cin, tc[2].cout, st));
+            PROF(PC_PREP, 0.0, pack_taps_tc(w2f, tw_f[2], 4, 4 * tc[2].cin, tc[2].cout, 0, st));
+        }
+        if (tc2(13)) PROF(PC_PREP, 0.0, pack_taps_tc(weff[13], tw_f[13], 4, tc[13].cin, 4 * tc[13].cout, 0, st));
     }
     if (need_bwd) {
         FS_CHECK(flags & ENG_TRANSFORM_BWD, "engine was not created with a backward plan");
@@ -354,6 +369,9 @@ int Engine::prep_transform_weights(const float* params, bool need_bwd, cudaStrea
             else if (s2_collapsed(c)) PROF(PC_PREP, 0.0, s2_dgrad_collapse(src, wefft[l], c.cin, c.cout, st));
             else PROF(PC_PREP, 0.0, transpose_taps(src, wefft[l], c.k * c.k, c.cin_s, c.cout_s, st));
         }
+        // tensor-path data gradients of the collapsed stride-2 layers: the gather forms correlate with the flipped taps
+        if (tc2(2)) PROF(PC_PREP, 0.0, pack_taps_tc(wefft[2], tw_d[2], 4, tc[2].cout, 4 * tc[2].cin, 1, st));
+        if (tc2(13)) PROF(PC_PREP, 0.0, pack_taps_tc(wefft[13], tw_d[13], 4, 4 * tc[13].cout, tc[13].cin, 1, st));
     }
     return 0;
 }
@@ -362,6 +380,15 @@ int Engine::prep_transform_weights(const float* params, bool need_bwd, cudaStrea
 static bool s2_collapsed(const TConv& c) {
     return !c.upconv && c.k == 3 && c.stride == 2 && c.pad_t == 0 && c.pad_l == 0 && c.inH % 2 == 0 && c.inW % 2 == 0;
 }
+
+bool Engine::tc2(int l) const {
+    if (!use_tc) return false;
+    if (l == 2) return s2_collapsed(tc[2]);
+    if (l == 13) return !(flags & ENG_DECONV);
+    return false;
+}
+
+static double tc2_flops(const Conv3x3TcArgs& a) { return 2.0 * a.N * a.OH * a.OW * (double)a.OC * 4.0 * a.C; }
 
 static void conv_fwd_args(const TConv& c, int N, const float* in, const float* w, float* out, IGemmArgs& a) {
     memset(&a, 0, sizeof(a));
@@ -393,6 +420,17 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
             ta.N = N; ta.H = c.inH; ta.W = c.inW; ta.C = 64; ta.OH = c.outH; ta.OW = c.outW; ta.OC = 64; ta.pad = 0;
             ta.out_f32 = tb[l].raw;
             PROF(PC_TC_RES_FWD, tc_flops(ta), launch_conv3x3_tc(ta, st));
+        } else if (tc2(l)) {
+            Conv3x3TcArgs ta;
+            memset(&ta, 0, sizeof(ta));
+            ta.x = tsplit[l]; ta.w = tw_f[l]; ta.N = N; ta.taps = 2; ta.pad = 0; ta.out_f32 = tb[l].raw;
+            if (l == 2) {        // 3x3 s2 = 2x2 s1 over the space-to-depth view of the 32-channel input
+                ta.in_s2d = 1; ta.H = c.inH / 2; ta.W = c.inW / 2; ta.C = 4 * c.cin;
+                ta.OH = c.outH; ta.OW = c.outW; ta.OC = c.cout;
+            } else {             // resize-conv = 4-phase 2x2 conv, depth-to-space store
+                ta.H = c.inH; ta.W = c.inW; ta.C = c.cin; ta.OH = c.inH; ta.OW = c.inW; ta.OC = 4 * c.cout; ta.out_d2s = 1;
+            }
+            PROF(PC_TC_S2_FWD, tc2_flops(ta), launch_conv3x3_tc(ta, st));
         } else if (direct9(c)) {
             IGemmArgs a;
             conv_fwd_args(c, N, cur, weff[l], tb[l].raw, a);
@@ -410,7 +448,7 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
         const float* g = last ? in15 : params + c.offG;
         const float* b = last ? in15 + 4 : params + c.offB;
         float* out = last ? (y3_out ? y3_out : y3) : tb[l].act;
-        const bool next_tc = use_tc && (l + 1) >= 3 && (l + 1) <= 12;      // next conv consumes split planes
+        const bool next_tc = (use_tc && (l + 1) >= 3 && (l + 1) <= 12) || tc2(l + 1);   // next conv consumes split planes
         PROF(PC_IN_APPLY, 0.0, instnorm_apply(tb[l].raw, tb[l].mean, tb[l].rstd, g, b, skip, out, N, c.outH, c.outW,
                               c.cout_s, c.act, last ? 1 : 0, st, next_tc ? tsplit[l + 1].hi : nullptr,
                               next_tc ? tsplit[l + 1].lo : nullptr));
@@ -441,9 +479,10 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         const int ri = pick2(cur, held);
         float* dRaw = tgrad[ri];
         const bool tcl = use_tc && l >= 3 && l <= 12;
+        const bool tcd = tcl || (l > 0 && tc2(l));           // the data gradient reads dRaw's split planes
         PROF(PC_IN_BWD, 0.0, instnorm_bwd(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw, dg, db, N,
                             c.outH * c.outW, c.cout_s, c.act, in_partial, m12, st,
-                            tcl ? tgsplit[ri].hi : nullptr, tcl ? tgsplit[ri].lo : nullptr));
+                            tcd ? tgsplit[ri].hi : nullptr, tcd ? tgsplit[ri].lo : nullptr));
         if (last) {
             FS_CUDA(cudaMemcpyAsync(grads + c.offG, gb_tmp, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
             FS_CUDA(cudaMemcpyAsync(grads + c.offB, gb_tmp + 4, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -511,6 +550,20 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
             PROF(PC_TC_RES_DGRAD, tc_flops(ta), launch_conv3x3_tc(ta, st));
             dAct = dPrev; cur = pidx;
             if (first_of_block) { held = -1; resid_dOut = nullptr; }
+            continue;
+        }
+        if (tc2(l)) {
+            Conv3x3TcArgs ta;
+            memset(&ta, 0, sizeof(ta));
+            ta.x = tgsplit[ri]; ta.w = tw_d[l]; ta.N = N; ta.taps = 2; ta.pad = 1; ta.out_f32 = dPrev;
+            if (l == 13) {       // dRaw [N,2H,2W,32] read through its space-to-depth view -> d(act) [N,H,W,64]
+                ta.in_s2d = 1; ta.H = c.inH; ta.W = c.inW; ta.C = 4 * c.cout; ta.OH = c.inH; ta.OW = c.inW; ta.OC = c.cin;
+            } else {             // 4 sub-pixel phases of dx as channels, depth-to-space store into [N,inH,inW,32]
+                ta.H = c.outH; ta.W = c.outW; ta.C = c.cout; ta.OH = c.inH / 2; ta.OW = c.inW / 2; ta.OC = 4 * c.cin;
+                ta.out_d2s = 1;
+            }
+            PROF(PC_TC_S2_DGRAD, tc2_flops(ta), launch_conv3x3_tc(ta, st));
+            dAct = dPrev; cur = pidx;
             continue;
         }
         if (dcv) {                               // data gradient of conv2d_transpose = the SAME conv itself

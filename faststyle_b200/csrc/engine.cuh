@@ -43,7 +43,8 @@ struct LossConfig {
 };
 
 enum ProfCat { PC_TC_VGG_FWD = 0, PC_TC_VGG_DGRAD, PC_TC_RES_FWD, PC_TC_RES_DGRAD, PC_FFMA_CONV, PC_WGRAD,
-               PC_GRAM_FWD, PC_GRAM_BWD, PC_IN_STATS, PC_IN_APPLY, PC_IN_BWD, PC_POINTWISE, PC_LOSS, PC_PREP, PC_COUNT };
+               PC_GRAM_FWD, PC_GRAM_BWD, PC_IN_STATS, PC_IN_APPLY, PC_IN_BWD, PC_POINTWISE, PC_LOSS, PC_PREP,
+               PC_TC_S2_FWD, PC_TC_S2_DGRAD, PC_COUNT };
 enum EngineFlags { ENG_TRANSFORM = 1, ENG_TRANSFORM_BWD = 2, ENG_VGG = 4, ENG_VGG_BWD = 8, ENG_DECONV = 16 };
 
 struct Arena {
@@ -97,9 +98,13 @@ struct Engine {
     SplitPtr vgsplit[4];                 // planes of vgrad[i]
     SplitPtr vtsplit[V_NCONV];           // planes of a style-tapped activation when no later conv holds them
     SplitPtr gsS[V_NCONV];               // packed per-sample Gram-space gradients S (tensor-path Gram backward)
-    SplitPtr tsplit[T_NCONV];            // input planes of residual conv l (3..12)
-    SplitPtr tgsplit[3];                 // planes of tgrad[i] (dRaw of residual convs)
-    SplitPtr tw_f[T_NCONV], tw_d[T_NCONV];   // packed residual-conv weights (forward / data gradient)
+    SplitPtr tsplit[T_NCONV];            // input planes of the tensor-path transform convs (2, 3..12, 13)
+    SplitPtr tgsplit[3];                 // planes of tgrad[i] (dRaw of the tensor-path transform convs)
+    SplitPtr tw_f[T_NCONV], tw_d[T_NCONV];   // packed weights (forward / data gradient)
+    float* w2f = nullptr;                // initconv_2 weights in the 2x2 space-to-depth form [2][2][128][64]
+    // stride-2 layers on the tensor path in their collapsed 2x2 stride-1 forms (K = N-side 64/128 channels):
+    // initconv_2 (3x3 s2 32->64, even input) and upsample_0 (resize-conv 64->32), forward + data gradient
+    bool tc2(int l) const;
 
     // live per-kernel timing (bench.py roofline)
     bool prof_on = false;

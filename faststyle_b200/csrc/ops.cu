@@ -632,6 +632,23 @@ __global__ void s2_dgrad_collapse_kernel(const float* __restrict__ W, float* __r
     Wd[i] = (kh >= 0 && kw >= 0) ? W[(((long long)kh * 3 + kw) * Ci + ci) * Co + co] : 0.f;
 }
 
+// Stride-2 3x3 SAME(pad 0/1) FORWARD conv as a 2x2 stride-1 conv over the space-to-depth view of the input:
+//   y[m, n, co] = sum_{a,b} sum_{p,q,ci} S[m+a, n+b, (p*2+q)*Ci + ci] * Wf[a][b][(p*2+q)*Ci + ci][co],
+//   S[Y, X, (p,q,ci)] = x[2Y+p, 2X+q, ci],   Wf = W[2a+p][2b+q] (zero where 2a+p or 2b+q == 3).
+__global__ void s2_fwd_collapse_kernel(const float* __restrict__ W, float* __restrict__ Wf, int Ci, int Co) {
+    FS_PDL_ENTER();
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = 16LL * Ci * Co;
+    if (i >= total) return;
+    int co = (int)(i % Co);
+    long long r = i / Co;
+    int ci = (int)(r % Ci); r /= Ci;
+    int pq = (int)(r % 4); r /= 4;
+    int b = (int)(r % 2), a = (int)(r / 2);
+    int kh = 2 * a + (pq >> 1), kw = 2 * b + (pq & 1);
+    Wf[i] = (kh < 3 && kw < 3) ? W[(((long long)kh * 3 + kw) * Ci + ci) * Co + co] : 0.f;
+}
+
 inline int grid1(long long n, int bs = 256) { return (int)((n + bs - 1) / bs); }
 
 }  // namespace
@@ -821,6 +838,12 @@ int upconv_collapse_grad(const float* dWc, float* dW, int Ci, int Co, cudaStream
 
 int s2_dgrad_collapse(const float* W, float* Wd, int Ci, int Co, cudaStream_t st) {
     launch_k(s2_dgrad_collapse_kernel, dim3(grid1(16LL * Ci * Co)), dim3(256), 0, st, W, Wd, Ci, Co);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int s2_fwd_collapse(const float* W, float* Wf, int Ci, int Co, cudaStream_t st) {
+    launch_k(s2_fwd_collapse_kernel, dim3(grid1(16LL * Ci * Co)), dim3(256), 0, st, W, Wf, Ci, Co);
     FS_LAUNCH_CHECK();
     return 0;
 }

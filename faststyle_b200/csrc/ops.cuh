@@ -62,6 +62,9 @@ int upconv_collapse_grad(const float* dWc, float* dW, int Ci, int Co, cudaStream
 // 3x3 stride-2 (pad 0/1) conv: weights of the 4-phase 2x2 data-gradient form, [2][2][Co][4*Ci]
 int s2_dgrad_collapse(const float* W, float* Wd, int Ci, int Co, cudaStream_t st);
 
+// 3x3 stride-2 (pad 0/1) conv: weights of the 2x2 stride-1 form over the space-to-depth input, [2][2][4*Ci][Co]
+int s2_fwd_collapse(const float* W, float* Wf, int Ci, int Co, cudaStream_t st);
+
 int fill_zero(void* p, size_t bytes, cudaStream_t st);
 
 }  // namespace fs

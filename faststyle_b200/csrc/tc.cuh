@@ -17,6 +17,9 @@ int split_bf16(const float* x, SplitPtr out, long long n, cudaStream_t st);
 //   mode 1 (data gradient):  B[tap=(2-kh,2-kw)][cb][n=ci][k=co%64]      = W[kh,kw,n,cb*64+k]
 // Output: hi/lo planes of 9*(K/64)*N*64 bf16 each (K = reduction channels, N = output channels).
 int pack_w3x3_tc(const float* w, SplitPtr out, int Ci, int Co, int mode, cudaStream_t st);
+// Generic tap-major GEMM weights w [T][K][Nn] fp32 -> B[tap'][cb][n][k] = w[tap][cb*64+k][n] split planes
+// (tap = T-1-tap' when flip: the data-gradient forms correlate with the flipped kernel)
+int pack_taps_tc(const float* w, SplitPtr out, int T, int K, int Nn, int flip, cudaStream_t st);
 // same for up to 16 equally shaped weight tensors in ONE launch
 int pack_w3x3_tc_batch(const float* const* w, const SplitPtr* out, int count, int Ci, int Co, int mode, cudaStream_t st);
 
@@ -26,6 +29,11 @@ struct Conv3x3TcArgs {
     int N, H, W, C;
     int OH, OW, OC;            // output dims (OC % 64 == 0)
     int pad;                   // zero padding on top/left (SAME: 1, VALID: 0, VALID data gradient: 2)
+    int taps;                  // kernel extent KH = KW: 0/3 = 3x3 (default), 2 = 2x2 (the collapsed stride-2 / resize
+                               // convolutions and their data gradients; weights packed by pack_taps_tc)
+    int in_s2d;                // 1: x is the space-to-depth view [N,H,W,C] of a plain [N,2H,2W,C/4] tensor (C == 128)
+    int out_d2s;               // 1: the [OH,OW,OC] result is stored depth-to-space into out_f32 [N,2OH,2OW,OC/4]
+                               //    (OC == 128; fp32 output only, no bias/addend/ref/relu/split)
     int one_by_one;            // 1: 1x1 'convolution' (pure GEMM over channels); pad must be 0
     int per_sample_w;          // with one_by_one: weights are [N][C/64][OC][64] (one matrix per sample)
     // epilogue: v = acc + bias[c] + addend[pix,c]; relu; mask by ref[pix,c] > 0

@@ -72,8 +72,9 @@ int fs_engine_set_tensor_path(fs_engine* e, int enabled);
  * 0 tc VGG conv fwd, 1 tc VGG dgrad, 2 tc residual conv fwd, 3 tc residual dgrad,
  * 4 FFMA implicit-GEMM / direct conv + dgrad, 5 weight gradients, 6 Gram forward, 7 Gram backward,
  * 8 InstanceNorm statistics, 9 InstanceNorm apply, 10 InstanceNorm backward, 11 pooling / padding /
- * split / other element-wise, 12 losses, 13 per-step weight preparation. */
-#define FS_PROF_NCAT 14
+ * split / other element-wise, 12 losses, 13 per-step weight preparation, 14 tc stride-2 / resize conv fwd
+ * (collapsed 2x2 forms), 15 their data gradients. */
+#define FS_PROF_NCAT 16
 int fs_engine_profile(fs_engine* e, int enabled);
 int fs_engine_profile_read(fs_engine* e, int ncat, float* ms, double* flops, int* launches);
 /* per-launch records (category, ms, algorithmic FLOPs) in issue order; call before _read */

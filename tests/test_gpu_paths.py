@@ -45,21 +45,27 @@ def test_transform_forward_matches_oracle(built_lib, starry):
     assert float((y32.double().cpu() - yo).abs().max()) / 255.0 <= 5e-5
 
 
-def test_transform_intermediates(built_lib, starry):
+@pytest.mark.parametrize("shape", [(1, 64, 72), (2, 52, 100), (1, 50, 61), (3, 41, 44)])
+def test_transform_intermediates(built_lib, starry, shape):
+    """Per-layer activations of create_net on the tensor path.  (64,72) / (52,100): initconv_2 sees an even
+    input and runs in its 2x2 space-to-depth form on tcgen05 (ragged 33x45 tiles for the second); (50,61) and
+    (41,44): odd inputs keep the generic stride-2 gather (TF SAME pads 1/1 there); upsample_0 is the 4-phase
+    tensor-path resize-conv in every case."""
     from faststyle_b200.engine import Engine, params_to_device
-    rng = np.random.RandomState(1)
-    x = rng.randint(0, 256, (1, 64, 72, 3)).astype(np.float32)
+    N, H, W = shape
+    rng = np.random.RandomState(1 + H)
+    x = rng.randint(0, 256, (N, H, W, 3)).astype(np.float32)
     taps = {}
     with torch.no_grad():
         R.create_net(x, starry, "resize", torch.float64, taps=taps)
-    eng = Engine(1, 64, 72, transform=True)
+    eng = Engine(N, H, W, transform=True)
     eng.transform_forward(params_to_device(starry, "cuda"), x)
     torch.cuda.synchronize()
     names = {0: "initconv_0", 1: "initconv_1", 2: "initconv_2", 4: "resblock_0", 12: "resblock_4",
              13: "upsample_0", 14: "upsample_1"}
     for idx, nm in names.items():
         got = eng.transform_activation(idx, 1)
-        assert _relerr(got, taps[nm]) < 2e-4, nm
+        assert _relerr(got, taps[nm]) < 2e-4, (nm, _relerr(got, taps[nm]))
     raw15 = eng.transform_activation(15, 0)[..., :3]
     assert _relerr(raw15, taps["upsample_2/conv"]) < 2e-4
 
