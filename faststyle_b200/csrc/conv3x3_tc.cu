@@ -75,8 +75,10 @@ struct Cfg {
     static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+constexpr int TC_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 epilogue (2 per TMEM lane quadrant)
+
 template <int TH, int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                   const TcParams p) {
@@ -105,7 +107,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < K::B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, K::TMEM_COLS);
@@ -206,8 +208,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             if (++as == 2) { as = 0; pt ^= 1; }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
-        const int ew = warp - 4;                       // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+        // ===================== epilogue (8 warps: 2 per 32-lane TMEM quadrant) =====================
+        // The two warps of a quadrant take alternate (accumulator, 32-channel chunk) items: the epilogue is a
+        // chain of dependent global loads (addend / ReLU-mask reference) and stores per item, so a second warp
+        // per quadrant doubles the memory-level parallelism of the memory-heavy launches (1x1 Gram backward,
+        // 64-channel layers at 256^2).
+        const int ew = (warp - 4) & 3;                 // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+        const int eg = (warp - 4) >> 2;                // 0 / 1: which half of the items
         const int row = ew * 32 + lane;                // MMA row = pixel within the 8x16 sub-tile
         const int prow = row >> 4, pcol = row & 15;
         int as = 0; uint32_t pt = 0;
@@ -220,7 +227,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             mbar_wait(&t_full[as], pt);
             tc_fence_after();
 #pragma unroll 1
-            for (int acc = 0; acc < K::NACC; ++acc) {
+            for (int item = eg; item < K::NACC * (BN / 32); item += 2) {
+                const int acc = item / (BN / 32), ch = item - acc * (BN / 32);
                 const int oy = ty * TH + acc * 8 + prow, ox = tx * TW + pcol;
                 const bool ok = oy < p.OH && ox < p.OW;
                 const long long pix = ((long long)n * p.OH + oy) * p.OW + ox;
@@ -230,8 +238,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     if (ay >= 0 && ay < p.addH && ax >= 0 && ax < p.addW)
                         addp = p.addend + (((long long)n * p.addH + ay) * p.addW + ax) * p.OC;
                 }
-#pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ++ch) {
+                {
                     float v[32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) +
                                            (uint32_t)(as * K::NACC * BN + acc * BN + ch * 32);
@@ -503,7 +510,7 @@ int launch_cfg(const Conv3x3TcArgs& a, cudaStream_t st) {
         attr_set = true;
     }
     int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
-    launch_k((conv3x3_tc_kernel<TH, BN>), dim3(grid), dim3(256), K::SMEM_BYTES, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    launch_k((conv3x3_tc_kernel<TH, BN>), dim3(grid), dim3(TC_THREADS), K::SMEM_BYTES, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     FS_LAUNCH_CHECK();
     return 0;
 }
