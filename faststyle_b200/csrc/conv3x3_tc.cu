@@ -532,11 +532,19 @@ int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st) {
     FS_CHECK(!a.out_d2s || (a.OC == 128 && a.out_f32 && !a.out_split.hi && !a.bias && !a.addend && !a.ref && !a.relu),
              "conv3x3_tc: the depth-to-space store needs OC == 128 and a plain fp32 output");
     bool tall = a.OH > 8;
-    // small 64->64 problems (the residual convs): 16-row tiles give < 1.5 waves; 8-row tiles balance the SMs
-    // and their 3-deep slab ring hides the L2 miss latency
-    if (tall && a.C == 64 && a.OC == 64 && !a.one_by_one) {
-        long long tiles16 = (long long)a.N * cdiv(a.OH, 16) * cdiv(a.OW, TW);
-        if (tiles16 * 2 < 3LL * num_sms()) tall = false;
+    // 16-row tiles amortise the slab halo (18 rows loaded per 16) but small problems leave SMs idle or end on a
+    // ragged last wave: estimate both tilings in units of one 8-row tile (x1.1 for the 10-rows-per-8 halo) and
+    // take the cheaper.  E.g. the residual convs (200 vs 400 tiles on 148 SMs) and conv4_1's data gradient
+    // (64 vs 128 tiles) run faster on 8-row tiles.
+    if (tall) {
+        const long long bn = a.OC % 128 == 0 ? 128 : 64;
+        const long long per = (long long)a.N * cdiv(a.OW, TW) * (a.OC / bn);
+        const long long t16 = per * cdiv(a.OH, 16), t8 = per * cdiv(a.OH, 8);
+        const long long sms = num_sms();
+        const double cost16 = 2.0 * (double)((t16 + sms - 1) / sms), cost8 = 1.1 * (double)((t8 + sms - 1) / sms);
+        if (cost8 < 0.85 * cost16) tall = false;
+        // the small 64->64 residual convs: 8-row tiles + their 3-deep slab ring also hide the L2 latency (measured)
+        if (a.C == 64 && a.OC == 64 && !a.one_by_one && t16 * 2 < 3 * sms) tall = false;
     }
     if (a.OC % 128 == 0) return tall ? launch_cfg<16, 128>(a, st) : launch_cfg<8, 128>(a, st);
     return tall ? launch_cfg<16, 64>(a, st) : launch_cfg<8, 64>(a, st);

@@ -244,8 +244,10 @@ __global__ void __launch_bounds__(256) conv3x3_c4_fwd_kernel(const float* __rest
             r[q * 4 + 2] = fmaxf(acc[px][q * 4 + 2] + b.z, 0.f);
             r[q * 4 + 3] = fmaxf(acc[px][q * 4 + 3] + b.w, 0.f);
         }
-        tcptx::stg256(out + o, r);
-        tcptx::stg256(out + o + 8, r + 8);
+        if (out) {
+            tcptx::stg256(out + o, r);
+            tcptx::stg256(out + o + 8, r + 8);
+        }
         if (shi) {
             uint32_t hw[8], lw[8];
 #pragma unroll
