@@ -261,8 +261,6 @@ void Engine::layout(Arena& a) {
         }
         y3 = a.take<float>((long long)N * OH * OW * 3);
         in_partial = a.take<double>((long long)N * 64 * 64 * 2);
-        in_sync = a.take<unsigned char>((long long)in_sync_bytes(N));
-        in_nsum = a.take<double>((long long)N * 64 * 2);
         in15 = a.take<float>(8);
         wtmp15 = a.take<float>(81 * 64);
         if (tbw) {
@@ -323,7 +321,6 @@ int Engine::bind(void* ws, size_t bytes) {
     FS_CHECK(((uintptr_t)ws & 255) == 0, "engine: workspace must be 256-byte aligned");
     Arena a; a.base = (char*)ws; a.cap = bytes;
     layout(a);
-    if (in_sync) FS_TRY(in_sync_init(in_sync, N));
     bound = true;
     return 0;
 }
@@ -444,9 +441,7 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
             if (c.upconv && (flags & ENG_DECONV)) a.gather = 1;      // transposed conv: iy = oy - a
             PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
         }
-        const int fchunks = in_fused ? in_fused_chunks(N, c.outH * c.outW, c.cout_s) : 0;
-        if (!fchunks)
-            PROF(PC_IN_STATS, 0.0, instnorm_stats(tb[l].raw, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, in_partial, st));
+        PROF(PC_IN_STATS, 0.0, instnorm_stats(tb[l].raw, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, in_partial, st));
         const float* skip = nullptr;
         if (l >= 4 && l <= 12 && (l & 1) == 0) skip = tb[l - 2].act;       // residual: block input
         const bool last = l == T_NCONV - 1;
@@ -454,12 +449,7 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
         const float* b = last ? in15 + 4 : params + c.offB;
         float* out = last ? (y3_out ? y3_out : y3) : tb[l].act;
         const bool next_tc = (use_tc && (l + 1) >= 3 && (l + 1) <= 12) || tc2(l + 1);   // next conv consumes split planes
-        if (fchunks)
-            PROF(PC_IN_APPLY, 0.0, instnorm_fwd_fused(tb[l].raw, tb[l].mean, tb[l].rstd, g, b, skip, out, N, c.outH, c.outW,
-                                  c.cout_s, IN_EPS, c.act, last ? 1 : 0, in_partial, in_sync, fchunks, st,
-                                  next_tc ? tsplit[l + 1].hi : nullptr, next_tc ? tsplit[l + 1].lo : nullptr));
-        else
-            PROF(PC_IN_APPLY, 0.0, instnorm_apply(tb[l].raw, tb[l].mean, tb[l].rstd, g, b, skip, out, N, c.outH, c.outW,
+        PROF(PC_IN_APPLY, 0.0, instnorm_apply(tb[l].raw, tb[l].mean, tb[l].rstd, g, b, skip, out, N, c.outH, c.outW,
                                   c.cout_s, c.act, last ? 1 : 0, st, next_tc ? tsplit[l + 1].hi : nullptr,
                                   next_tc ? tsplit[l + 1].lo : nullptr));
         cur = tb[l].act;
@@ -490,13 +480,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         float* dRaw = tgrad[ri];
         const bool tcl = use_tc && l >= 3 && l <= 12;
         const bool tcd = tcl || (l > 0 && tc2(l));           // the data gradient reads dRaw's split planes
-        const int fchunks = in_fused ? in_fused_chunks(N, c.outH * c.outW, c.cout_s) : 0;
-        if (fchunks)
-            PROF(PC_IN_BWD, 0.0, instnorm_bwd_fused(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw, dg, db, N,
-                                c.outH * c.outW, c.cout_s, c.act, in_partial, in_nsum, in_sync, fchunks, st,
-                                tcd ? tgsplit[ri].hi : nullptr, tcd ? tgsplit[ri].lo : nullptr));
-        else
-            PROF(PC_IN_BWD, 0.0, instnorm_bwd(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw, dg, db, N,
+        PROF(PC_IN_BWD, 0.0, instnorm_bwd(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw, dg, db, N,
                                 c.outH * c.outW, c.cout_s, c.act, in_partial, m12, st,
                                 tcd ? tgsplit[ri].hi : nullptr, tcd ? tgsplit[ri].lo : nullptr));
         if (last) {

@@ -77,9 +77,6 @@ struct Engine {
     float* wefft[T_NCONV];               // transposed weights for the data gradient
     float* y3 = nullptr;                 // [N,OH,OW,3] when the caller does not supply an output
     double* in_partial = nullptr;
-    int in_fused = 1;                    // InstanceNorm sites run as ONE launch each (FS_IN_FUSED=0: 2 / 3 launches)
-    void* in_sync = nullptr;             // per-sample barrier counters of the fused InstanceNorm kernels
-    double* in_nsum = nullptr;           // [N][64][2] per-sample totals for d(scale), d(shift)
     float* in15 = nullptr;               // 4-channel staging of the last layer's IN scale/shift
     float* gb_tmp = nullptr;
     float* wtmp15 = nullptr;             // staging for the deconv variant of the last layer's weights

@@ -134,31 +134,42 @@ __device__ __forceinline__ void in_reduce_chunk(const float* __restrict__ x, con
     const float* xn = x + (long long)n * HW * C + lane * 4;
     const float* dn = MODE == 1 ? dY + (long long)n * HW * C + lane * 4 : nullptr;
     if (row < rows) {
-        for (int p = beg + row; p < end; p += rows) {
-            float4 v = ld4(xn + (long long)p * C);
-            float xv[4] = {v.x, v.y, v.z, v.w};
-            if (MODE == 0) {
+        // 4 pixels per trip, all loads issued before the (fp64) accumulation: the planes are L2-resident and the
+        // loop is latency-bound otherwise.  Out-of-range slots contribute exact zeros.
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = beg + row; p < end; p += 4 * rows) {
+            float4 xq[4], dq[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    double d = (double)xv[j];
-                    s1[j] += d;
-                    s2[j] += d * d;
-                }
-            } else {
-                float4 dv = ld4(dn + (long long)p * C);
-                float dy[4] = {dv.x, dv.y, dv.z, dv.w};
+            for (int u = 0; u < 4; ++u) {
+                const int pu = p + u * rows;
+                xq[u] = pu < end ? ld4(xn + (long long)pu * C) : z4;
+                if (MODE == 1) dq[u] = pu < end ? ld4(dn + (long long)pu * C) : z4;
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float xh = (xv[j] - mu[j]) * rs[j];
-                    float dz = dy[j];
-                    if (act == ACT_RELU) {
-                        dz = __fmaf_rn(xh, g[j], b[j]) > 0.f ? dz : 0.f;
-                    } else if (act == ACT_TANH255) {
-                        float th = tanhf(__fmaf_rn(xh, g[j], b[j]));
-                        dz = dz * 127.5f * (1.f - th * th);
+            for (int u = 0; u < 4; ++u) {
+                float xv[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w};
+                if (MODE == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        double d = (double)xv[j];
+                        s1[j] += d;
+                        s2[j] += d * d;
                     }
-                    s1[j] += (double)dz;
-                    s2[j] += (double)dz * (double)xh;
+                } else {
+                    float dy[4] = {dq[u].x, dq[u].y, dq[u].z, dq[u].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float xh = (xv[j] - mu[j]) * rs[j];
+                        float dz = dy[j];
+                        if (act == ACT_RELU) {
+                            dz = __fmaf_rn(xh, g[j], b[j]) > 0.f ? dz : 0.f;
+                        } else if (act == ACT_TANH255) {
+                            float th = tanhf(__fmaf_rn(xh, g[j], b[j]));
+                            dz = dz * 127.5f * (1.f - th * th);
+                        }
+                        s1[j] += (double)dz;
+                        s2[j] += (double)dz * (double)xh;
+                    }
                 }
             }
         }
@@ -263,11 +274,15 @@ __global__ void in_bwd_finalize_kernel(const double* __restrict__ partial, float
 }
 
 // one float4 (4 channels of one pixel) of the InstanceNorm forward: affine + activation (+ cropped skip) + stores
-__device__ __forceinline__ void in_apply_elem(const float* __restrict__ x, const float4 mu, const float4 rs, const float4 g,
-                                              const float4 b, const float* __restrict__ skip, float* __restrict__ out,
-                                              long long i, int n, int p, int c, int H, int W, int C, int act, int out3,
+__device__ __forceinline__ const float* in_skip_ptr(const float* skip, int n, int p, int c, int H, int W, int C) {
+    int y = p / W, xx = p - y * W;
+    return skip + (((long long)n * (H + 4) + y + 2) * (W + 4) + xx + 2) * C + c;
+}
+// v = the raw value, s = the (cropped) skip value (ignored unless has_skip)
+__device__ __forceinline__ void in_apply_elem(const float4 v, const float4 s, bool has_skip, const float4 mu, const float4 rs,
+                                              const float4 g, const float4 b, float* __restrict__ out,
+                                              long long i, int n, int p, int H, int W, int act, int out3,
                                               __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo) {
-    float4 v = ld4(x + i * 4);
     float r[4] = {in_affine(v.x, mu.x, rs.x, g.x, b.x), in_affine(v.y, mu.y, rs.y, g.y, b.y),
                   in_affine(v.z, mu.z, rs.z, g.z, b.z), in_affine(v.w, mu.w, rs.w, g.w, b.w)};
 #pragma unroll
@@ -275,11 +290,7 @@ __device__ __forceinline__ void in_apply_elem(const float* __restrict__ x, const
         if (act == ACT_RELU) r[j] = fmaxf(r[j], 0.f);
         else if (act == ACT_TANH255) r[j] = __fmaf_rn(127.5f, tanhf(r[j]), 127.5f);
     }
-    if (skip) {
-        int y = p / W, xx = p - y * W;
-        float4 s = ld4(skip + (((long long)n * (H + 4) + y + 2) * (W + 4) + xx + 2) * C + c);
-        r[0] += s.x; r[1] += s.y; r[2] += s.z; r[3] += s.w;
-    }
+    if (has_skip) { r[0] += s.x; r[1] += s.y; r[2] += s.z; r[3] += s.w; }
     if (out3) {
         float* o = out + ((long long)n * H * W + p) * 3;
         o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
@@ -304,16 +315,17 @@ __global__ void in_apply_kernel(const float* __restrict__ x, const float* __rest
     int HW = H * W;
     int n = (int)(pix / HW);
     int p = (int)(pix - (long long)n * HW);
-    in_apply_elem(x, ld4(mean + (long long)n * C + c), ld4(rstd + (long long)n * C + c), ld4(scale + c), ld4(shift + c),
-                  skip, out, i, n, p, c, H, W, C, act, out3, shi, slo);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    in_apply_elem(ld4(x + i * 4), skip ? ld4(in_skip_ptr(skip, n, p, c, H, W, C)) : z4, skip != nullptr,
+                  ld4(mean + (long long)n * C + c), ld4(rstd + (long long)n * C + c), ld4(scale + c), ld4(shift + c),
+                  out, i, n, p, H, W, act, out3, shi, slo);
 }
 
 // one float4 of the InstanceNorm backward: dx = g*rstd*(dz - mean(dz) - xhat*mean(dz*xhat))
-__device__ __forceinline__ void in_bwd_elem(const float* __restrict__ dY, const float* __restrict__ x, const float* mu,
+__device__ __forceinline__ void in_bwd_elem(const float4 xv4, const float4 dv4, const float* mu,
                                             const float* rs, const float* g, const float* b, const float* m1,
                                             const float* m2, float* __restrict__ dx, long long i, int act,
                                             __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo) {
-    float4 xv4 = ld4(x + i * 4), dv4 = ld4(dY + i * 4);
     float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w}, dy[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
     float r[4];
 #pragma unroll
@@ -353,171 +365,7 @@ __global__ void in_bwd_apply_kernel(const float* __restrict__ dY, const float* _
     float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
     float g[4] = {g4.x, g4.y, g4.z, g4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
     float m1[4] = {ma.x, ma.z, mb.x, mb.z}, m2[4] = {ma.y, ma.w, mb.y, mb.w};
-    in_bwd_elem(dY, x, mu, rs, g, b, m1, m2, dx, i, act, shi, slo);
-}
-
-// ------------------------------------------------------------------ fused InstanceNorm (one launch per site)
-// The chunk-CTAs of one sample meet at a per-sample counter barrier between the reduction and the apply phase:
-// reduce chunk -> publish partial -> wait for the sample's other chunks -> fold the partials (every CTA, fixed
-// order: deterministic) -> apply on the same chunk (the re-read hits L2).  All CTAs of the grid must be
-// co-resident (the launcher bounds the grid by the occupancy); a stuck barrier traps instead of hanging.
-struct INSync { unsigned* arrive; unsigned* leave; unsigned* all; };   // [N], [N], [1]; zero between launches
-
-__device__ __forceinline__ void in_sample_barrier(const INSync sy, int n, int chunks) {
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        atomicAdd(&sy.arrive[n], 1u);
-        const long long t0 = clock64();
-        while (*reinterpret_cast<volatile unsigned*>(&sy.arrive[n]) < (unsigned)chunks) {
-            __nanosleep(64);
-            if (clock64() - t0 > 4000000000LL) {
-                printf("instnorm: sample barrier timed out (sample %d, block %d)\n", n, blockIdx.x);
-                __trap();
-            }
-        }
-        __threadfence();
-        // the last CTA to leave re-arms the barrier for the next launch
-        if (atomicAdd(&sy.leave[n], 1u) == (unsigned)(chunks - 1)) { sy.arrive[n] = 0u; sy.leave[n] = 0u; }
-    }
-    __syncthreads();
-}
-
-// sum of p[0], p[stride], ..., p[(count-1)*stride] in index order; loads issued 8 at a time so that the chain costs
-// count/8 memory round trips instead of count
-__device__ __forceinline__ double strided_sum(const volatile double* p, long long stride, int count) {
-    double acc = 0;
-    for (int k = 0; k < count; k += 8) {
-        double v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (k + j < count) ? p[(long long)(k + j) * stride] : 0.0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc += v[j];
-    }
-    return acc;
-}
-
-// Totals of the sample's `chunks` partial vectors [2C] into tot[2C] (shared).  256 threads: value v = t % 2C,
-// chunk group gi = t / 2C takes chunks gi, gi+groups, ...; the groups are then added in order.  Fixed order.
-__device__ __forceinline__ void in_fold_partials(const double* partial_n, double* tot, double* scratch, int C, int chunks) {
-    const int t = threadIdx.x, nv = 2 * C;
-    const int groups = 256 / nv;                       // >= 1 (C <= 128)
-    const int v = t % nv, gi = t / nv;
-    double acc = 0;
-    if (gi < groups) {
-        const int cnt = (chunks - gi + groups - 1) / groups;
-        acc = cnt > 0 ? strided_sum(partial_n + (long long)gi * nv + v, (long long)groups * nv, cnt) : 0.0;
-    }
-    scratch[t] = acc;
-    __syncthreads();
-    if (t < nv) {
-        double a = 0;
-        for (int g = 0; g < groups; ++g) a += scratch[g * nv + t];
-        tot[t] = a;
-    }
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(256)
-in_fused_fwd_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd,
-                    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ skip,
-                    float* __restrict__ out, double* __restrict__ partial, const INSync sy, int H, int W, int C,
-                    int chunks, float eps, int act, int out3, __nv_bfloat16* __restrict__ shi,
-                    __nv_bfloat16* __restrict__ slo) {
-    FS_PDL_ENTER();
-    extern __shared__ double sm[];            // [C][2] sums | [256] fold scratch | [C][2] floats (mean, rstd)
-    const int t = threadIdx.x, n = blockIdx.y, chunk = blockIdx.x;
-    const int HW = H * W;
-    const int per = (HW + chunks - 1) / chunks;
-    const int beg = chunk * per, end = min(beg + per, HW);
-    in_reduce_chunk<0>(x, nullptr, nullptr, nullptr, nullptr, nullptr, sm, n, beg, end, HW, C, 0);
-    double* dst = partial + ((long long)n * chunks + chunk) * 2 * C;
-    for (int i = t; i < 2 * C; i += 256) dst[i] = sm[i];
-    in_sample_barrier(sy, n, chunks);
-    // fold the sample's partials (identical order in every CTA)
-    double* scratch = sm + 2 * C;                              // [256]
-    float* st = reinterpret_cast<float*>(scratch + 256);       // [C][2]: mean, rstd
-    in_fold_partials(partial + (long long)n * chunks * 2 * C, sm, scratch, C, chunks);
-    for (int c = t; c < C; c += 256) {
-        const double a1 = sm[c * 2], a2 = sm[c * 2 + 1];
-        double m = a1 / HW;
-        double var = a2 / HW - m * m;
-        if (var < 0) var = 0;
-        const float mf = (float)m, rf = (float)(1.0 / sqrt(var + (double)eps));
-        st[c * 2 + 0] = mf; st[c * 2 + 1] = rf;
-        if (chunk == 0) { mean[(long long)n * C + c] = mf; rstd[(long long)n * C + c] = rf; }
-    }
-    __syncthreads();
-    const int CL = C >> 2, rows = 256 / CL;
-    const int lane = t % CL, row = t / CL;
-    if (row >= rows) return;
-    const int c = lane * 4;
-    const float4 mu = make_float4(st[c * 2], st[c * 2 + 2], st[c * 2 + 4], st[c * 2 + 6]);
-    const float4 rs = make_float4(st[c * 2 + 1], st[c * 2 + 3], st[c * 2 + 5], st[c * 2 + 7]);
-    const float4 g = ld4(scale + c), b = ld4(shift + c);
-    for (int p = beg + row; p < end; p += rows) {
-        const long long i = ((long long)n * HW + p) * CL + lane;
-        in_apply_elem(x, mu, rs, g, b, skip, out, i, n, p, c, H, W, C, act, out3, shi, slo);
-    }
-}
-
-__global__ void __launch_bounds__(256)
-in_fused_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ x, const float* __restrict__ mean,
-                    const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
-                    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                    double* __restrict__ partial, double* __restrict__ nsum, const INSync sy, int N, int HW, int C,
-                    int chunks, int act, __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo) {
-    FS_PDL_ENTER();
-    extern __shared__ double sm[];            // [C][2] sums | [256] fold scratch | [C][2] floats (mean dz, mean dz*xhat)
-    const int t = threadIdx.x, n = blockIdx.y, chunk = blockIdx.x;
-    const int per = (HW + chunks - 1) / chunks;
-    const int beg = chunk * per, end = min(beg + per, HW);
-    in_reduce_chunk<1>(x, dY, mean, rstd, scale, shift, sm, n, beg, end, HW, C, act);
-    double* dst = partial + ((long long)n * chunks + chunk) * 2 * C;
-    for (int i = t; i < 2 * C; i += 256) dst[i] = sm[i];
-    in_sample_barrier(sy, n, chunks);
-    double* scratch = sm + 2 * C;                              // [256]
-    float* st = reinterpret_cast<float*>(scratch + 256);       // [C][2]: m1, m2
-    in_fold_partials(partial + (long long)n * chunks * 2 * C, sm, scratch, C, chunks);
-    for (int c = t; c < C; c += 256) {
-        const double a1 = sm[c * 2], a2 = sm[c * 2 + 1];
-        st[c * 2 + 0] = (float)(a1 / HW); st[c * 2 + 1] = (float)(a2 / HW);
-        if (chunk == 0) { nsum[((long long)n * C + c) * 2 + 0] = a1; nsum[((long long)n * C + c) * 2 + 1] = a2; }
-    }
-    __syncthreads();
-    const int CL = C >> 2, rows = 256 / CL;
-    const int lane = t % CL, row = t / CL;
-    if (row < rows) {
-        const int c = lane * 4;
-        float mu[4], rs[4], g[4], b[4], m1[4], m2[4];
-        float4 v;
-        v = ld4(mean + (long long)n * C + c); mu[0] = v.x; mu[1] = v.y; mu[2] = v.z; mu[3] = v.w;
-        v = ld4(rstd + (long long)n * C + c); rs[0] = v.x; rs[1] = v.y; rs[2] = v.z; rs[3] = v.w;
-        v = ld4(scale + c); g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
-        v = ld4(shift + c); b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { m1[j] = st[(c + j) * 2]; m2[j] = st[(c + j) * 2 + 1]; }
-        for (int p = beg + row; p < end; p += rows) {
-            const long long i = ((long long)n * HW + p) * CL + lane;
-            in_bwd_elem(dY, x, mu, rs, g, b, m1, m2, dx, i, act, shi, slo);
-        }
-    }
-    // d(gamma), d(beta): the chunk-0 CTA of the LAST sample to get here sums the per-sample totals over n = 0..N-1
-    if (chunk != 0) return;
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (t == 0) s_last = (atomicAdd(sy.all, 1u) == (unsigned)(N - 1));
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    for (int c = t; c < C; c += 256) {
-        const double bb = strided_sum(nsum + (long long)c * 2 + 0, 2LL * C, N);
-        const double gg = strided_sum(nsum + (long long)c * 2 + 1, 2LL * C, N);
-        if (dgamma) dgamma[c] = (float)gg;
-        if (dbeta) dbeta[c] = (float)bb;
-    }
-    if (t == 0) *sy.all = 0u;
+    in_bwd_elem(ld4(x + i * 4), ld4(dY + i * 4), mu, rs, g, b, m1, m2, dx, i, act, shi, slo);
 }
 
 __global__ void add_padded_kernel(float* __restrict__ dst, const float* __restrict__ src, int N, int H,
@@ -928,71 +776,6 @@ int instnorm_bwd(const float* dY, const float* x, const float* mean, const float
     long long n = (long long)N * HW * (C / 4);
     launch_k(in_bwd_apply_kernel, dim3(grid1(n)), dim3(256), 0, st, dY, x, mean, rstd, scale, shift, m12, dx, N, HW, C, act,
                                                   (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo);
-    FS_LAUNCH_CHECK();
-    return 0;
-}
-
-// ---- fused single-launch forms (per-sample barrier; see in_fused_fwd_kernel)
-size_t in_sync_bytes(int N) { return ((size_t)(2 * N + 2) * sizeof(unsigned) + 255) & ~(size_t)255; }
-int in_sync_init(void* sync, int N) {
-    FS_CUDA(cudaMemset(sync, 0, in_sync_bytes(N)));
-    FS_CUDA(cudaDeviceSynchronize());
-    return 0;
-}
-static INSync in_sync_view(void* sync, int N) {
-    INSync sy;
-    sy.arrive = reinterpret_cast<unsigned*>(sync);
-    sy.leave = sy.arrive + N;
-    sy.all = sy.leave + N;
-    return sy;
-}
-// chunk-CTAs per sample such that the whole grid is co-resident with a 2x margin (0 = use the separate kernels)
-int in_fused_chunks(int N, int HW, int C) {
-    static int cap = -1;
-    if (cap < 0) {
-        int dev = 0, sms = 0, occ_f = 0, occ_b = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const size_t smem = 2 * 256 * sizeof(double) + 256 * sizeof(double) + 2 * 256 * sizeof(float);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, in_fused_fwd_kernel, 256, smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, in_fused_bwd_kernel, 256, smem);
-        int occ = occ_f < occ_b ? occ_f : occ_b;
-        cap = sms > 0 && occ > 0 ? sms * occ / 2 : 0;
-        (void)cudaGetLastError();
-    }
-    if (C > 128 || N <= 0) return 0;
-    int c = cap / N;
-    int maxc = HW / 128;
-    if (maxc < 1) maxc = 1;
-    if (c > maxc) c = maxc;
-    if (c > 32) c = 32;
-    return c < 1 ? 0 : c;
-}
-
-int instnorm_fwd_fused(const float* x, float* mean, float* rstd, const float* scale, const float* shift,
-                       const float* skip, float* out, int N, int H, int W, int C, float eps, int act, int out3,
-                       double* partial, void* sync, int chunks, cudaStream_t st, void* split_hi, void* split_lo) {
-    FS_TRY(check_in_c(C));
-    FS_CHECK(chunks >= 1 && chunks <= 64 && C <= 128, "instnorm_fwd_fused: bad plan (chunks %d, C %d)", chunks, C);
-    FS_CHECK(!(split_hi && out3), "instnorm_fwd_fused: split output not available with out3");
-    FS_CHECK(!out3 || C == 4, "instnorm_fwd_fused: out3 needs C==4");
-    const size_t smem = 2 * C * sizeof(double) + 256 * sizeof(double) + 2 * C * sizeof(float);
-    launch_k(in_fused_fwd_kernel, dim3(chunks, N), dim3(256), smem, st, x, mean, rstd, scale, shift, skip, out, partial,
-             in_sync_view(sync, N), H, W, C, chunks, eps, act, out3, (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo);
-    FS_LAUNCH_CHECK();
-    return 0;
-}
-
-int instnorm_bwd_fused(const float* dY, const float* x, const float* mean, const float* rstd, const float* scale,
-                       const float* shift, float* dx, float* dgamma, float* dbeta, int N, int HW, int C, int act,
-                       double* partial, double* nsum, void* sync, int chunks, cudaStream_t st, void* split_hi,
-                       void* split_lo) {
-    FS_TRY(check_in_c(C));
-    FS_CHECK(chunks >= 1 && chunks <= 64 && C <= 128, "instnorm_bwd_fused: bad plan (chunks %d, C %d)", chunks, C);
-    const size_t smem = 2 * C * sizeof(double) + 256 * sizeof(double) + 2 * C * sizeof(float);
-    launch_k(in_fused_bwd_kernel, dim3(chunks, N), dim3(256), smem, st, dY, x, mean, rstd, scale, shift, dx, dgamma, dbeta,
-             partial, nsum, in_sync_view(sync, N), N, HW, C, chunks, act, (__nv_bfloat16*)split_hi,
-             (__nv_bfloat16*)split_lo);
     FS_LAUNCH_CHECK();
     return 0;
 }

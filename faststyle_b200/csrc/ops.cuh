@@ -29,21 +29,6 @@ int instnorm_bwd(const float* dY, const float* x, const float* mean, const float
                  const float* scale, const float* shift, float* dx, float* dgamma, float* dbeta,
                  int N, int HW, int C, int act, double* partial, float* m12 /*[N][C][2]*/,
                  cudaStream_t st, void* split_hi = nullptr, void* split_lo = nullptr);
-// Single-launch forms: the chunk-CTAs of a sample synchronise at a counter barrier between the reduction and the
-// apply phase (stats + apply, or reduce + finalize + apply for the backward).  `sync` = in_sync_bytes(N) bytes
-// prepared once by in_sync_init; chunks = in_fused_chunks(N, HW, C) (0: not applicable, use the calls above);
-// nsum: N*C*2 doubles.  Arithmetic and summation order per element are those of the separate kernels.
-size_t in_sync_bytes(int N);
-int in_sync_init(void* sync, int N);
-int in_fused_chunks(int N, int HW, int C);
-int instnorm_fwd_fused(const float* x, float* mean, float* rstd, const float* scale, const float* shift,
-                       const float* skip, float* out, int N, int H, int W, int C, float eps, int act, int out3,
-                       double* partial, void* sync, int chunks, cudaStream_t st, void* split_hi = nullptr,
-                       void* split_lo = nullptr);
-int instnorm_bwd_fused(const float* dY, const float* x, const float* mean, const float* rstd, const float* scale,
-                       const float* shift, float* dx, float* dgamma, float* dbeta, int N, int HW, int C, int act,
-                       double* partial, double* nsum, void* sync, int chunks, cudaStream_t st,
-                       void* split_hi = nullptr, void* split_lo = nullptr);
 // zero-pad-add:  dst[n, y+crop, x+crop, c] += src[n,y,x,c]   (skip-connection gradient)
 int add_padded(float* dst, const float* src, int N, int H, int W, int C, int crop, cudaStream_t st);
 
