@@ -358,10 +358,11 @@ def dominant_kernel_roofline(prof, peaks, step_ms):
     achieved = gf / ms                      # GFLOP / ms == TFLOP/s
     return {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
             "frac": achieved / peaks["bf16_tflops_sustained"],
-            # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r01e_ncu_tc_kernels.md),
-            # averaged over the 8 captured launches of this kernel; per-launch values and the algorithmic bytes
-            # are tabulated there (e.g. conv1_2: 352 MB moved vs 402 MB algorithmic - no re-reads from HBM).
-            "traffic": 97.6e6 if names else None, "traffic_unit": "bytes/launch (ncu, mean of 8 captured launches)",
+            # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r01p_ncu_tc_kernels.md),
+            # averaged over the 30 captured launches of this kernel (content pass, transform convs, main VGG pass);
+            # per-launch values are tabulated there (e.g. conv1_2: 352 MB moved = 134 MB split input + 217 MB
+            # output planes - no re-reads from HBM).
+            "traffic": 59.1e6 if names else None, "traffic_unit": "bytes/launch (ncu, mean of 30 captured launches)",
             "peak_source": peaks["source"] +
             " cuBLAS bf16 sustained (kernel timed inside a long step)",
             "kernel": kernel, "precision": precision, "kernel_ms_per_step": ms, "launches_per_step": launches,
