@@ -244,10 +244,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                                            (uint32_t)(as * K::NACC * BN + acc * BN + ch * 32);
                     tmem_ld32(taddr, v);                // warp-collective: executed by all lanes
                     if (ok && p.out_d2s) {
-                        // 32 output channels = one sub-pixel phase pq of the 2x upsampled result (OC = 4 * 32)
-                        const int pq = nt * (BN / 32) + ch;
-                        const long long pix2 = ((long long)n * (2 * p.OH) + 2 * oy + (pq >> 1)) * (2 * p.OW) + 2 * ox + (pq & 1);
-                        float* op = p.out_f32 + pix2 * 32;
+                        const int cq = nt * (BN / 32) + ch;           // which 32-channel quarter of OC = 128
+                        float* op;
+                        if (p.out_d2s == 1) {
+                            // 32 output channels = one sub-pixel phase pq of the 2x upsampled result (OC = 4 * 32)
+                            const long long pix2 = ((long long)n * (2 * p.OH) + 2 * oy + (cq >> 1)) * (2 * p.OW) + 2 * ox + (cq & 1);
+                            op = p.out_f32 + pix2 * 32;
+                        } else {
+                            // paired pixels, OC = (e, p, q, 16): quarter (e, p) = both column phases q of row phase p of
+                            // source pixel 2*ox+e -> 2 adjacent pixels x 16 channels of the [2OH, 4OW, 16] result
+                            const long long pix2 = ((long long)n * (2 * p.OH) + 2 * oy + (cq & 1)) * (4 * p.OW) + 4 * ox + 2 * (cq >> 1);
+                            op = p.out_f32 + pix2 * 16;
+                        }
 #pragma unroll
                         for (int i = 0; i < 32; i += 8) stg256(op + i, v + i);
                     } else if (ok) {

@@ -250,15 +250,16 @@ void Engine::layout(Arena& a) {
                 tw_f[l].hi = a.take<__nv_bfloat16>(9 * 64 * 64); tw_f[l].lo = a.take<__nv_bfloat16>(9 * 64 * 64);
                 if (tbw) { tw_d[l].hi = a.take<__nv_bfloat16>(9 * 64 * 64); tw_d[l].lo = a.take<__nv_bfloat16>(9 * 64 * 64); }
             }
-            if ((l == 2 && s2_collapsed(tc[2])) || (l == 13 && !(flags & ENG_DECONV))) {   // see Engine::tc2
+            if (tc2_layout(l)) {
                 long long n = (long long)N * tc[l].inH * tc[l].inW * tc[l].cin;
-                const long long wn = 16LL * tc[l].cin * tc[l].cout;                     // 4 taps x K x N
+                const long long wn = 4LL * 128 * 64;                                    // 4 taps x K x N, all four layers
                 tsplit[l].hi = a.take<__nv_bfloat16>(n); tsplit[l].lo = a.take<__nv_bfloat16>(n);
                 tw_f[l].hi = a.take<__nv_bfloat16>(wn); tw_f[l].lo = a.take<__nv_bfloat16>(wn);
                 if (tbw) { tw_d[l].hi = a.take<__nv_bfloat16>(wn); tw_d[l].lo = a.take<__nv_bfloat16>(wn); }
-                if (l == 2) w2f = a.take<float>(wn);
             }
         }
+        w2f = a.take<float>(4LL * 128 * 64);
+        wpair = a.take<float>(4LL * 128 * 64);
         y3 = a.take<float>((long long)N * OH * OW * 3);
         in_partial = a.take<double>((long long)N * 64 * 64 * 2);
         in15 = a.take<float>(8);
@@ -268,8 +269,7 @@ void Engine::layout(Arena& a) {
             for (int i = 0; i < 3; ++i) tgrad[i] = a.take<float>(maxact);
             {   // split companions hold dRaw of the tensor-path convs: residual (3..12), initconv_2, upsample_0
                 long long nres = (long long)N * tc[3].outH * tc[3].outW * 64;
-                nres = maxll(nres, (long long)N * tc[2].outH * tc[2].outW * tc[2].cout);
-                nres = maxll(nres, (long long)N * tc[13].outH * tc[13].outW * tc[13].cout);
+                for (int l : {1, 2, 13, 14}) nres = maxll(nres, (long long)N * tc[l].outH * tc[l].outW * tc[l].cout);
                 for (int i = 0; i < 3; ++i) { tgsplit[i].hi = a.take<__nv_bfloat16>(nres); tgsplit[i].lo = a.take<__nv_bfloat16>(nres); }
             }
             wg_tmp = a.take<float>(81LL * 16 * 4 + 16LL * 64 * 32 + 1024);
@@ -351,11 +351,20 @@ int Engine::prep_transform_weights(const float* params, bool need_bwd, cudaStrea
         for (int l = 3; l <= 12; ++l) wsrc[l - 3] = params + tc[l].offW;
         PROF(PC_PREP, 0.0, pack_w3x3_tc_batch(wsrc, &tw_f[3], 10, 64, 64, 0, st));
         if (need_bwd) PROF(PC_PREP, 0.0, pack_w3x3_tc_batch(wsrc, &tw_d[3], 10, 64, 64, 1, st));
+        if (tc2(1)) {        // 3x3 s2 16->32: space-to-depth form [4][64][32], then pixel pairing -> [4][128][64]
+            PROF(PC_PREP, 0.0, s2_fwd_collapse(params + tc[1].offW, w2f, tc[1].cin, tc[1].cout, st));
+            PROF(PC_PREP, 0.0, pair_taps(w2f, wpair, 4 * tc[1].cin, tc[1].cout, 1, 0, st));
+            PROF(PC_PREP, 0.0, pack_taps_tc(wpair, tw_f[1], 4, 128, 64, 0, st));
+        }
         if (tc2(2)) {
             PROF(PC_PREP, 0.0, s2_fwd_collapse(params + tc[2].offW, w2f, tc[2].cin, tc[2].cout, st));
             PROF(PC_PREP, 0.0, pack_taps_tc(w2f, tw_f[2], 4, 4 * tc[2].cin, tc[2].cout, 0, st));
         }
         if (tc2(13)) PROF(PC_PREP, 0.0, pack_taps_tc(weff[13], tw_f[13], 4, tc[13].cin, 4 * tc[13].cout, 0, st));
+        if (tc2(14)) {       // resize-conv 32->16: collapsed [4][32][64], paired -> [4][64][128]
+            PROF(PC_PREP, 0.0, pair_taps(weff[14], wpair, tc[14].cin, 4 * tc[14].cout, 0, 0, st));
+            PROF(PC_PREP, 0.0, pack_taps_tc(wpair, tw_f[14], 4, 64, 128, 0, st));
+        }
     }
     if (need_bwd) {
         FS_CHECK(flags & ENG_TRANSFORM_BWD, "engine was not created with a backward plan");
@@ -370,8 +379,16 @@ int Engine::prep_transform_weights(const float* params, bool need_bwd, cudaStrea
             else PROF(PC_PREP, 0.0, transpose_taps(src, wefft[l], c.k * c.k, c.cin_s, c.cout_s, st));
         }
         // tensor-path data gradients of the collapsed stride-2 layers: the gather forms correlate with the flipped taps
+        if (tc2(1)) {        // wefft[1] = [4][32][4*16] gather form, paired -> [4][64][128]
+            PROF(PC_PREP, 0.0, pair_taps(wefft[1], wpair, tc[1].cout, 4 * tc[1].cin, 0, 1, st));
+            PROF(PC_PREP, 0.0, pack_taps_tc(wpair, tw_d[1], 4, 64, 128, 1, st));
+        }
         if (tc2(2)) PROF(PC_PREP, 0.0, pack_taps_tc(wefft[2], tw_d[2], 4, tc[2].cout, 4 * tc[2].cin, 1, st));
         if (tc2(13)) PROF(PC_PREP, 0.0, pack_taps_tc(wefft[13], tw_d[13], 4, 4 * tc[13].cout, tc[13].cin, 1, st));
+        if (tc2(14)) {       // wefft[14] = [4][4*16][32] gather form over the space-to-depth view, paired -> [4][128][64]
+            PROF(PC_PREP, 0.0, pair_taps(wefft[14], wpair, 4 * tc[14].cout, tc[14].cin, 1, 1, st));
+            PROF(PC_PREP, 0.0, pack_taps_tc(wpair, tw_d[14], 4, 128, 64, 1, st));
+        }
     }
     return 0;
 }
@@ -381,11 +398,35 @@ static bool s2_collapsed(const TConv& c) {
     return !c.upconv && c.k == 3 && c.stride == 2 && c.pad_t == 0 && c.pad_l == 0 && c.inH % 2 == 0 && c.inW % 2 == 0;
 }
 
-bool Engine::tc2(int l) const {
-    if (!use_tc) return false;
+bool Engine::tc2_layout(int l) const {
     if (l == 2) return s2_collapsed(tc[2]);
     if (l == 13) return !(flags & ENG_DECONV);
+    if (l == 1) return s2_collapsed(tc[1]) && tc[1].outW % 2 == 0;           // paired along x
+    if (l == 14) return !(flags & ENG_DECONV) && tc[14].inW % 2 == 0;
     return false;
+}
+bool Engine::tc2(int l) const { return use_tc && l >= 1 && l < T_NCONV && tc2_layout(l); }
+
+// Arguments of the tensor-path launch for transform conv l (1, 2, 13, 14) in its 2x2 form.
+//   forward : x = tsplit[l] (planes of the layer input),  out = raw conv output
+//   backward: x = tgsplit[ri] (planes of dRaw),            out = gradient w.r.t. the layer input
+// Two shapes occur (with or without pixel pairing): "s2d in -> plain out" (C = 128, OC = 64) and
+// "plain in -> depth-to-space out" (C = 64, OC = 128).
+int Engine::tc2_args(int l, bool bwd, int ri, float* out, Conv3x3TcArgs& ta) const {
+    const TConv& c = tc[l];
+    memset(&ta, 0, sizeof(ta));
+    ta.N = N; ta.taps = 2; ta.pad = bwd ? 1 : 0; ta.out_f32 = out;
+    ta.x = bwd ? tgsplit[ri] : tsplit[l];
+    ta.w = bwd ? tw_d[l] : tw_f[l];
+    const bool paired = (l == 1 || l == 14);
+    const int pw = paired ? 2 : 1;                       // pixels per GEMM-space pixel
+    // does this launch read a space-to-depth view?  stride-2 conv forward / resize-conv backward
+    const bool s2d_in = (c.upconv != 0) == bwd;
+    const int gh = c.upconv ? c.inH : c.outH, gw = (c.upconv ? c.inW : c.outW) / pw;   // GEMM-space dims
+    ta.H = gh; ta.W = gw; ta.OH = gh; ta.OW = gw;
+    if (s2d_in) { ta.in_s2d = 1; ta.C = 128; ta.OC = 64; }
+    else { ta.C = 64; ta.OC = 128; ta.out_d2s = paired ? 2 : 1; }
+    return 0;
 }
 
 static double tc2_flops(const Conv3x3TcArgs& a) { return 2.0 * a.N * a.OH * a.OW * (double)a.OC * 4.0 * a.C; }
@@ -422,14 +463,7 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
             PROF(PC_TC_RES_FWD, tc_flops(ta), launch_conv3x3_tc(ta, st));
         } else if (tc2(l)) {
             Conv3x3TcArgs ta;
-            memset(&ta, 0, sizeof(ta));
-            ta.x = tsplit[l]; ta.w = tw_f[l]; ta.N = N; ta.taps = 2; ta.pad = 0; ta.out_f32 = tb[l].raw;
-            if (l == 2) {        // 3x3 s2 = 2x2 s1 over the space-to-depth view of the 32-channel input
-                ta.in_s2d = 1; ta.H = c.inH / 2; ta.W = c.inW / 2; ta.C = 4 * c.cin;
-                ta.OH = c.outH; ta.OW = c.outW; ta.OC = c.cout;
-            } else {             // resize-conv = 4-phase 2x2 conv, depth-to-space store
-                ta.H = c.inH; ta.W = c.inW; ta.C = c.cin; ta.OH = c.inH; ta.OW = c.inW; ta.OC = 4 * c.cout; ta.out_d2s = 1;
-            }
+            FS_TRY(tc2_args(l, false, -1, tb[l].raw, ta));
             PROF(PC_TC_S2_FWD, tc2_flops(ta), launch_conv3x3_tc(ta, st));
         } else if (direct9(c)) {
             IGemmArgs a;
@@ -554,14 +588,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         }
         if (tc2(l)) {
             Conv3x3TcArgs ta;
-            memset(&ta, 0, sizeof(ta));
-            ta.x = tgsplit[ri]; ta.w = tw_d[l]; ta.N = N; ta.taps = 2; ta.pad = 1; ta.out_f32 = dPrev;
-            if (l == 13) {       // dRaw [N,2H,2W,32] read through its space-to-depth view -> d(act) [N,H,W,64]
-                ta.in_s2d = 1; ta.H = c.inH; ta.W = c.inW; ta.C = 4 * c.cout; ta.OH = c.inH; ta.OW = c.inW; ta.OC = c.cin;
-            } else {             // 4 sub-pixel phases of dx as channels, depth-to-space store into [N,inH,inW,32]
-                ta.H = c.outH; ta.W = c.outW; ta.C = c.cout; ta.OH = c.inH / 2; ta.OW = c.inW / 2; ta.OC = 4 * c.cin;
-                ta.out_d2s = 1;
-            }
+            FS_TRY(tc2_args(l, true, ri, dPrev, ta));
             PROF(PC_TC_S2_DGRAD, tc2_flops(ta), launch_conv3x3_tc(ta, st));
             dAct = dPrev; cur = pidx;
             continue;

@@ -101,10 +101,14 @@ struct Engine {
     SplitPtr tsplit[T_NCONV];            // input planes of the tensor-path transform convs (2, 3..12, 13)
     SplitPtr tgsplit[3];                 // planes of tgrad[i] (dRaw of the tensor-path transform convs)
     SplitPtr tw_f[T_NCONV], tw_d[T_NCONV];   // packed weights (forward / data gradient)
-    float* w2f = nullptr;                // initconv_2 weights in the 2x2 space-to-depth form [2][2][128][64]
-    // stride-2 layers on the tensor path in their collapsed 2x2 stride-1 forms (K = N-side 64/128 channels):
-    // initconv_2 (3x3 s2 32->64, even input) and upsample_0 (resize-conv 64->32), forward + data gradient
+    float* w2f = nullptr;                // initconv_1/2 weights in the 2x2 space-to-depth form (fp32 staging)
+    float* wpair = nullptr;              // pixel-paired 2x2 weights (fp32 staging, one layer at a time)
+    // stride-2 layers on the tensor path in their collapsed 2x2 stride-1 forms: initconv_2 (3x3 s2 32->64) and
+    // upsample_0 (resize-conv 64->32) have 64/128 channels on both sides as they are; initconv_1 (16->32) and
+    // upsample_1 (32->16) get there by pairing horizontally adjacent pixels (pair_taps).  Forward + data gradient.
     bool tc2(int l) const;
+    bool tc2_layout(int l) const;        // geometry part of tc2 (independent of use_tc)
+    int tc2_args(int l, bool bwd, int ri, float* out, Conv3x3TcArgs& ta) const;
 
     // live per-kernel timing (bench.py roofline)
     bool prof_on = false;

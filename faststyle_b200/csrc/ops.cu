@@ -686,6 +686,36 @@ __global__ void s2_fwd_collapse_kernel(const float* __restrict__ W, float* __res
     Wf[i] = (kh < 3 && kw < 3) ? W[(((long long)kh * 3 + kw) * Ci + ci) * Co + co] : 0.f;
 }
 
+// Pixel pairing of a 2x2-tap GEMM whose channel sides are too narrow for a 64-channel K block: two horizontally
+// adjacent pixels become one "pixel" with twice the channels on BOTH sides, W [2][2][K0][N0] -> Wp [2][2][2K0][2N0].
+// Output pixel X = 2j+e reads input pixel X+b (correlation) or X-b (gather) = 2(j +/- kwp) + h, hence
+//   Wp[a][kwp][kidx(h,k)][e*N0 + n] = W[a][b][k][n],  b = 2kwp + h - e (correlation) | e - h + 2kwp (gather), 0 if b not in {0,1}.
+// kmode 0: plain input, kidx = h*K0 + k.  kmode 1: the input is a space-to-depth view, k = (p*2+q)*c0 + c, and the
+// paired view keeps the row parity p outermost: kidx = p*K0 + h*(K0/2) + q*c0 + c (c0 = K0/4).
+__global__ void pair_taps_kernel(const float* __restrict__ W, float* __restrict__ Wp, int K0, int N0, int kmode, int gather) {
+    FS_PDL_ENTER();
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = 16LL * K0 * N0;
+    if (i >= total) return;
+    int np = (int)(i % (2 * N0));
+    long long r = i / (2 * N0);
+    int kp = (int)(r % (2 * K0)); r /= 2 * K0;
+    int kwp = (int)(r % 2), a = (int)(r / 2);
+    int e = np / N0, n = np - e * N0;
+    int h, k;
+    if (kmode == 0) {
+        h = kp / K0; k = kp - h * K0;
+    } else {
+        int c0 = K0 / 4;
+        int p = kp / K0, rem = kp - p * K0;
+        h = rem / (K0 / 2); rem -= h * (K0 / 2);
+        int q = rem / c0, c = rem - q * c0;
+        k = (p * 2 + q) * c0 + c;
+    }
+    int b = gather ? e - h + 2 * kwp : 2 * kwp + h - e;
+    Wp[i] = (b == 0 || b == 1) ? W[(((long long)a * 2 + b) * K0 + k) * N0 + n] : 0.f;
+}
+
 inline int grid1(long long n, int bs = 256) { return (int)((n + bs - 1) / bs); }
 
 }  // namespace
@@ -881,6 +911,13 @@ int s2_dgrad_collapse(const float* W, float* Wd, int Ci, int Co, cudaStream_t st
 
 int s2_fwd_collapse(const float* W, float* Wf, int Ci, int Co, cudaStream_t st) {
     launch_k(s2_fwd_collapse_kernel, dim3(grid1(16LL * Ci * Co)), dim3(256), 0, st, W, Wf, Ci, Co);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int pair_taps(const float* W, float* Wp, int K0, int N0, int kmode, int gather, cudaStream_t st) {
+    FS_CHECK(K0 % 4 == 0 && N0 >= 1, "pair_taps: bad channel counts");
+    launch_k(pair_taps_kernel, dim3(grid1(16LL * K0 * N0)), dim3(256), 0, st, W, Wp, K0, N0, kmode, gather);
     FS_LAUNCH_CHECK();
     return 0;
 }

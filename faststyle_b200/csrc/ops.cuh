@@ -65,6 +65,9 @@ int s2_dgrad_collapse(const float* W, float* Wd, int Ci, int Co, cudaStream_t st
 // 3x3 stride-2 (pad 0/1) conv: weights of the 2x2 stride-1 form over the space-to-depth input, [2][2][4*Ci][Co]
 int s2_fwd_collapse(const float* W, float* Wf, int Ci, int Co, cudaStream_t st);
 
+// pixel pairing of a 2x2-tap GEMM, W [2][2][K0][N0] -> Wp [2][2][2*K0][2*N0] (see pair_taps_kernel)
+int pair_taps(const float* W, float* Wp, int K0, int N0, int kmode, int gather, cudaStream_t st);
+
 int fill_zero(void* p, size_t bytes, cudaStream_t st);
 
 }  // namespace fs

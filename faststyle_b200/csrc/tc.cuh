@@ -33,6 +33,7 @@ struct Conv3x3TcArgs {
                                // convolutions and their data gradients; weights packed by pack_taps_tc)
     int in_s2d;                // 1: x is the space-to-depth view [N,H,W,C] of a plain [N,2H,2W,C/4] tensor (C == 128)
     int out_d2s;               // 1: the [OH,OW,OC] result is stored depth-to-space into out_f32 [N,2OH,2OW,OC/4]
+                               // 2: same for pixel-paired operands, OC = (e,p,q,16) -> out_f32 [N,2OH,4OW,16]
                                //    (OC == 128; fp32 output only, no bias/addend/ref/relu/split)
     int one_by_one;            // 1: 1x1 'convolution' (pure GEMM over channels); pad must be 0
     int per_sample_w;          // with one_by_one: weights are [N][C/64][OC][64] (one matrix per sample)
