@@ -4,6 +4,8 @@
 // implicit-GEMM tiles (the im2col gather dominates).  Here a CTA stages a 32x32 pixel tile (+4 px
 // halo) once in shared memory and every thread owns one (tap, 4x4 channel block) of the
 // 81 x CI x CO weight-gradient, so each staged element is reused 81 times from SMEM.
+// A 4-channel side is always RGB padded with a zero 4th channel here (the engine is the only caller): the
+// kernels skip that channel's FMAs (a quarter of the work) - its inputs are zero and its outputs stay zero.
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include "tc_ptx.cuh"
@@ -62,9 +64,9 @@ __global__ void __launch_bounds__(NT9) wgrad9x9_kernel(const float* __restrict__
             const float av[4] = {a.x, a.y, a.z, a.w};
             const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < (CI == 4 ? 3 : 4); ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                for (int j = 0; j < (CO == 4 ? 3 : 4); ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
     }
     const long long blk = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(256, 2) conv9x9_kernel(const float* __restrict
 #pragma unroll
             for (int kw = 0; kw < 9; ++kw) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < (CI == 4 ? 3 : 4); ++c) {
 #pragma unroll
                     for (int q = 0; q < COQ; ++q) {
                         const float4 wv = wp[(kw * CI + c) * COQ + q];
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(256, 2) conv9x9_kernel(const float* __restrict
                             acc[px][q * 4 + 0] = fmaf(xv, wv.x, acc[px][q * 4 + 0]);
                             acc[px][q * 4 + 1] = fmaf(xv, wv.y, acc[px][q * 4 + 1]);
                             acc[px][q * 4 + 2] = fmaf(xv, wv.z, acc[px][q * 4 + 2]);
-                            acc[px][q * 4 + 3] = fmaf(xv, wv.w, acc[px][q * 4 + 3]);
+                            if (CO != 4) acc[px][q * 4 + 3] = fmaf(xv, wv.w, acc[px][q * 4 + 3]);
                         }
                     }
                 }
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(256) conv3x3_c4_fwd_kernel(const float* __rest
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < 3; ++c)          // the 4th input channel is the zero pad of RGB
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 wv = w_s[((kh * 3 + kw) * 4 + c) * 16 + cog * 4 + q];
@@ -314,8 +316,7 @@ __global__ void __launch_bounds__(256) dgrad3x3_c4_kernel(const float* __restric
                         const float xv = iv[px + kw][c];
                         acc[px][0] = fmaf(xv, wv.x, acc[px][0]);
                         acc[px][1] = fmaf(xv, wv.y, acc[px][1]);
-                        acc[px][2] = fmaf(xv, wv.z, acc[px][2]);
-                        acc[px][3] = fmaf(xv, wv.w, acc[px][3]);
+                        acc[px][2] = fmaf(xv, wv.z, acc[px][2]);   // channel 3 = zero pad of RGB: stays 0
                     }
                 }
         }

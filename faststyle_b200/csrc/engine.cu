@@ -429,6 +429,8 @@ int Engine::tc2_args(int l, bool bwd, int ri, float* out, Conv3x3TcArgs& ta) con
     return 0;
 }
 
+// 9x9 layers: algorithmic FLOPs with the real channel counts (the padded RGB channel is skipped by the kernels)
+static double conv9_flops(const TConv& c, int N) { return 2.0 * N * c.outH * c.outW * 81.0 * c.cin * c.cout; }
 static double tc2_flops(const Conv3x3TcArgs& a) { return 2.0 * a.N * a.OH * a.OW * (double)a.OC * 4.0 * a.C; }
 
 static void conv_fwd_args(const TConv& c, int N, const float* in, const float* w, float* out, IGemmArgs& a) {
@@ -468,7 +470,7 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
         } else if (direct9(c)) {
             IGemmArgs a;
             conv_fwd_args(c, N, cur, weff[l], tb[l].raw, a);
-            PROF(PC_FFMA_CONV, igemm_flops(a), launch_conv9x9(cur, weff[l], tb[l].raw, N, c.inH, c.inW, c.cin_s, c.cout_s, st));
+            PROF(PC_FFMA_CONV, conv9_flops(c, N), launch_conv9x9(cur, weff[l], tb[l].raw, N, c.inH, c.inW, c.cin_s, c.cout_s, st));
         } else {
             IGemmArgs a;
             conv_fwd_args(c, N, cur, weff[l] ? weff[l] : params + c.offW, tb[l].raw, a);
@@ -541,7 +543,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
             PROF(PC_WGRAD, wgrad_flops(wa), launch_wgrad(wa, st));
         } else if (dcv) {
             // 9x9 stride-1 conv2d_transpose 16 -> 3(4): dW[k, co, ci] = sum_p dRaw[p + k - 4, co] * x[p, ci]
-            const double fl = 2.0 * N * c.outH * c.outW * 81.0 * c.cin_s * c.cout_s;
+            const double fl = conv9_flops(c, N);
             PROF(PC_WGRAD, fl, launch_wgrad9x9(dRaw, in_act, wg_tmp, wg_partial, wg_partial_cap, N, c.inH, c.inW,
                                                c.cout_s, c.cin_s, st));
             PROF(PC_PREP, 0.0, unpad_taps(wg_tmp, grads + c.offW, 81, c.cout, c.cin, c.cout_s, c.cin_s, st));
@@ -562,7 +564,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
                 PROF(PC_WGRAD, wgrad_flops(wa), launch_wgrad3x3_tc(tsplit[l], tgsplit[ri], wa.out, wg_partial, wg_partial_cap,
                                                                    N, c.inH, c.inW, c.outH, c.outW, 0, st));
             else if (c.k == 9 && c.stride == 1 && c.same && c.cin_s * c.cout_s == 64)
-                PROF(PC_WGRAD, wgrad_flops(wa), launch_wgrad9x9(in_act, dRaw, wa.out, wg_partial, wg_partial_cap, N,
+                PROF(PC_WGRAD, conv9_flops(c, N), launch_wgrad9x9(in_act, dRaw, wa.out, wg_partial, wg_partial_cap, N,
                                                                 c.inH, c.inW, c.cin_s, c.cout_s, st));
             else
                 PROF(PC_WGRAD, wgrad_flops(wa), launch_wgrad(wa, st));
@@ -603,14 +605,14 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
                 a.OH = c.inH; a.OW = c.inW; a.OC = c.cin; a.out_bs = (long long)c.inH * c.inW * c.cin;
                 PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
             } else {                             // wtmp15 = W padded to [81, 4, 16]
-                const double fl = 2.0 * N * c.inH * c.inW * 81.0 * c.cin_s * c.cout_s;
+                const double fl = conv9_flops(c, N);
                 PROF(PC_FFMA_CONV, fl, launch_conv9x9(dRaw, wtmp15, dPrev, N, c.inH, c.inW, c.cout_s, c.cin_s, st));
             }
             dAct = dPrev; cur = pidx;
             continue;
         }
         if (direct9(c)) {                        // data gradient = forward 9x9 conv with flipped weights
-            const double fl = 2.0 * N * c.inH * c.inW * 81.0 * c.cin_s * c.cout_s;
+            const double fl = conv9_flops(c, N);
             PROF(PC_FFMA_CONV, fl, launch_conv9x9(dRaw, wefft[l], dPrev, N, c.inH, c.inW, c.cout_s, c.cin_s, st));
             dAct = dPrev; cur = pidx;
             continue;
@@ -683,7 +685,7 @@ int Engine::vgg_forward(const float* packed, const float* img3, int upto, float*
             const bool sp = use_tc && l < upto && !pool_next;
             // content-target pass: conv1_1's fp32 copy is dead unless it is a target itself (conv1_2 reads the planes)
             float* out0 = (sp && act_override && !act_override[0]) ? nullptr : out;
-            PROF(PC_FFMA_CONV, 2.0 * N * vc[0].H * vc[0].W * 9.0 * 4 * 64,
+            PROF(PC_FFMA_CONV, 2.0 * N * vc[0].H * vc[0].W * 9.0 * 3 * 64,
                  launch_conv3x3_c4_fwd(cur, packed + vc[0].offW, packed + vc[0].offB, out0, sp ? vsplit[1].hi : nullptr,
                                        sp ? vsplit[1].lo : nullptr, N, vc[0].H, vc[0].W, st));
         } else {
@@ -791,7 +793,7 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
             return 0;
         }
         if (lsrc == 0 && !addend && !ref) {      // conv1_1 data gradient: direct kernel (64 -> 4 channels)
-            PROF(PC_FFMA_CONV, 2.0 * N * v.H * v.W * 9.0 * 4 * 64, launch_dgrad3x3_c4(P, packed + v.offWT, out, N, v.H, v.W, st));
+            PROF(PC_FFMA_CONV, 2.0 * N * v.H * v.W * 9.0 * 3 * 64, launch_dgrad3x3_c4(P, packed + v.offWT, out, N, v.H, v.W, st));
             return 0;
         }
         FS_CHECK(lsrc != 0, "conv1_1 data gradient with an epilogue is not supported");
