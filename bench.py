@@ -284,6 +284,8 @@ def run_ours(args, rank, local_rank, world):
         roof["step_frac_of_sustained"] = step_tflops / peaks["bf16_tflops_sustained"]
         # transform forward only, batch 32 (BASELINE.json configs[1])
         extra["transform_fwd_b32_images_per_s"] = bench_forward(dev, params)
+        if world == 1:       # BASELINE.json configs[4] (single-GPU Gatys optimisation at 1024x1024)
+            extra["slow_style_1024"] = bench_slow_style(dev, packed, tgrams)
         if world == 1 and not args.no_cpu_baseline:
             cpu_base = cpu_baseline()
     if world > 1:
@@ -388,6 +390,37 @@ def bench_forward(dev, params):
     e1.record()
     torch.cuda.synchronize()
     return B * reps / (e0.elapsed_time(e1) / 1e3)
+
+
+def bench_slow_style(dev, packed, tgrams):
+    """BASELINE.json configs[4]: slow_style.py 1024x1024 Gatys iteration (VGG16 fwd + Gram + losses + pixel gradient
+    + TF-Adam on the image, lr 10, beta 1e-4) - iterations/s and algorithmic TFLOP/s (1.2356 TFLOP per iteration)."""
+    from faststyle_b200.engine import Engine, TFAdam, make_loss_config
+    S = 1024
+    eng = Engine(1, S, S, vgg_bwd=True, content_layers=CONTENT_LAYERS, style_layers=STYLE_LAYERS, device=dev)
+    cfg = make_loss_config(CONTENT_LAYERS, [1.0], STYLE_LAYERS, [5.0] * 4, 1e-4)
+    g = torch.Generator().manual_seed(0)
+    content = torch.randint(0, 256, (1, S, S, 3), generator=g).float().to(dev)
+    g2 = torch.Generator().manual_seed(2)
+    x = (torch.rand((1, S, S, 3), generator=g2) * 255.0).to(dev).contiguous()
+    eng.set_content_targets(packed, content, cfg)
+    opt = TFAdam(x.view(-1), 10.0)
+
+    def it():
+        _, grad = eng.perceptual_loss(packed, x, cfg, tgrams)
+        opt.step(grad.view(-1))
+    for _ in range(3):
+        it()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        it()
+    e1.record()
+    torch.cuda.synchronize()
+    ips = reps / (e0.elapsed_time(e1) / 1e3)
+    return {"iters_per_s": ips, "ms_per_iter": 1e3 / ips, "tflops_algorithmic": 1.2356 * ips}
 
 
 def cpu_baseline():

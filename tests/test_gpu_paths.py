@@ -243,3 +243,72 @@ def test_train_step_gradients_deconv(built_lib, tensor_path):
         got = g[off:off + want.numel()].view(want.shape)
         e = float((got - want).abs().max() / max(want.abs().max().item(), 1e-30))
         assert e < gtol, (name, e)
+
+
+def test_train_step_batch_additivity_full_size(built_lib, starry):
+    """BASELINE configs 3/4 at full size (per-GPU batch 8, 256x256) through a size-independent property: the
+    reference's losses SUM over the batch (losses.py:32-37,63-64) and InstanceNorm is per sample, so
+    grads(batch of 8) == grads(images 0-3) + grads(images 4-7) and likewise for the loss scalars - the identity
+    the data-parallel all-reduce(SUM) relies on.  fp32 summation order is the only difference."""
+    from faststyle_b200.engine import Engine, make_loss_config, pack_vgg, params_to_device
+    N, H, W = 8, 256, 256
+    vggw, style, tg, rng = _setup_loss(N, H, W, seed=21)
+    x = rng.randint(0, 256, (N, H, W, 3)).astype(np.float32)
+    packed = pack_vgg(vggw, "cuda")
+    cfg = make_loss_config(["conv3_3"], [1.0], STYLE, [5.0] * 4, 1e-4)
+    tgd = [t.float().cuda().contiguous() for t in tg]
+    p = params_to_device(starry, "cuda")
+    e8 = Engine(N, H, W, transform_bwd=True, vgg_bwd=True, content_layers=["conv3_3"], style_layers=STYLE)
+    g8, l8 = e8.train_fwd_bwd(p, packed, x, cfg, tgd)
+    g8, l8 = g8.double().cpu(), l8.double().cpu()
+    del e8
+    e4 = Engine(4, H, W, transform_bwd=True, vgg_bwd=True, content_layers=["conv3_3"], style_layers=STYLE)
+    ga, la = e4.train_fwd_bwd(p, packed, x[:4], cfg, tgd)
+    ga, la = ga.double().cpu(), la.double().cpu()
+    gb, lb = e4.train_fwd_bwd(p, packed, x[4:], cfg, tgd)
+    gb, lb = gb.double().cpu(), lb.double().cpu()
+    torch.cuda.synchronize()
+    assert torch.isfinite(g8).all() and float(g8.abs().max()) > 0
+    rel = float((g8 - (ga + gb)).abs().max() / g8.abs().max())
+    print("batch additivity at 8x256x256: grad rel-to-max %.3g, losses %s vs %s" % (rel, l8.tolist(), (la + lb).tolist()))
+    assert rel < 1e-4
+    assert 1 - _cos(g8, ga + gb) < 1e-9
+    for a, b in zip(l8, la + lb):
+        assert abs(float(a) - float(b)) <= 1e-5 * abs(float(b)) + 1e-12
+
+
+def test_slow_style_step_1024(built_lib):
+    """BASELINE config 5 at full size: slow_style.py:116-154 loss + pixel gradient of a 1024x1024 variable image
+    (VGG16 + Gram path only) against the oracle's autograd in fp32 on the host cores (~20 s), plus the Gram
+    symmetry property on the largest taps.  Tolerances as test_perceptual_loss_and_pixel_gradient (tensor path)."""
+    from faststyle_b200.engine import Engine, make_loss_config, pack_vgg
+    N, H, W = 1, 1024, 1024
+    vggw, style, tg, _ = _setup_loss(N, H, W)
+    g = torch.Generator().manual_seed(0)
+    content = torch.randint(0, 256, (N, H, W, 3), generator=g).float().numpy()
+    g2 = torch.Generator().manual_seed(2)
+    xvar = (torch.rand((N, H, W, 3), generator=g2) * 255.0).numpy()
+    torch.set_num_threads(max(1, min(32, os.cpu_count() or 1)))
+    with torch.no_grad():
+        ct = [R.vgg16_layers(content, vggw, "conv3_3", torch.float32)["conv3_3"]]
+    ref = R.slow_style_grads(xvar, ct, vggw, tg, beta=1e-4, dtype=torch.float32)
+
+    packed = pack_vgg(vggw, "cuda")
+    cfg = make_loss_config(["conv3_3"], [1.0], STYLE, [5.0] * 4, 1e-4)
+    eng = Engine(N, H, W, vgg_bwd=True, content_layers=["conv3_3"], style_layers=STYLE)
+    eng.set_content_targets(packed, content, cfg)
+    tgd = [t.float().cuda().contiguous() for t in tg]
+    losses, grad = eng.perceptual_loss(packed, xvar, cfg, tgd)
+    torch.cuda.synchronize()
+    L = losses.cpu().double()
+    errs = [abs(float(got) - float(want)) / max(abs(float(want)), 1e-30)
+            for got, want in zip(L, [ref["content"], ref["style"], ref["tv"], ref["loss"]])]
+    print("slow_style 1024^2: loss rel errs %s, grad relmax %.3g, 1-cos %.3g" %
+          (["%.2g" % e for e in errs], _relerr(grad, ref["grad"]), 1 - _cos(grad, ref["grad"])))
+    assert max(errs) <= 1e-3
+    assert 1 - _cos(grad, ref["grad"]) < 1e-5
+    grams = eng.vgg_grams(packed, xvar, STYLE)
+    torch.cuda.synchronize()
+    for G in grams:
+        Gc = G.double().cpu()
+        assert float((Gc - Gc.transpose(1, 2)).abs().max() / Gc.abs().max()) < 2e-5
