@@ -549,7 +549,7 @@ int launch_wgrad(const WGradArgs& a, cudaStream_t st) {
     FS_CHECK((long long)g.groups * g.splits <= 65535, "wgrad: too many z blocks");
     dim3 grid(cdiv(g.Ktot, c.WK), cdiv(a.OC, c.WN), g.groups * g.splits);
     if (c.WN == 64) launch_k((wgrad_kernel<64, 64, 8, 16, 128>), dim3(grid), dim3(128), 0, st, a, g);
-    else if (c.WN == 32) launch_k((wgrad_kernel<64, 32, 8, 16, 64>), dim3(grid), dim3(64), 0, st, a, g);
+    else if (c.WN == 32) launch_k((wgrad_kernel<64, 32, 4, 16, 128>), dim3(grid), dim3(128), 0, st, a, g);   // 4 warps: the stride-2 gather is latency-bound
     else if (c.WN == 16) launch_k((wgrad_kernel<256, 16, 8, 16, 128>), dim3(grid), dim3(128), 0, st, a, g);
     else launch_k((wgrad_kernel<512, 4, 8, 8, 64>), dim3(grid), dim3(64), 0, st, a, g);
     FS_LAUNCH_CHECK();
