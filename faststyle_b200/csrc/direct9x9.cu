@@ -17,15 +17,21 @@ namespace {
 constexpr int TS = 32;            // tile side (output pixels)
 constexpr int HS = TS + 8;        // with the 4-px halo of a 9x9 window
 constexpr int TSY = 16, HSY = TSY + 8;   // weight-gradient tiles are 16 rows x 32 columns: 2-3 CTAs per SM
-constexpr int NT9 = 352;          // 11 warps; 324 = 81 taps x 4 channel blocks are active in the main loop
+constexpr int NT9 = 256;          // 2 row-groups x 108 workers (9 kh x 3 kw-triples x 4 channel blocks)
+constexpr int WG9 = 108;
 
-// dW[kh,kw,ci,co] partial sums of one tile: partial[block][(tap*CI + ci)*CO + co]
+// dW[kh,kw,ci,co] partial sums of one tile: partial[2*block + rowgroup][(tap*CI + ci)*CO + co].
+// A worker owns THREE horizontally adjacent taps (kw = 3g..3g+2) of one 4x4 channel block and walks a row of the
+// tile with a 3-deep register window over the input: one new input float4 + one dy float4 per pixel feed 36-48
+// FMAs (the first version - one tap per thread, 2 loads per 16 FMAs - ran at 92 % of the shared-memory pipe and
+// 46 % of the FMA pipe, profiles/r01t).  The two row groups take rows 0-7 / 8-15 of the tile.
 template <int CI, int CO>
 __global__ void __launch_bounds__(NT9) wgrad9x9_kernel(const float* __restrict__ in, const float* __restrict__ dy,
                                                        float* __restrict__ partial, int H, int W) {
     FS_PDL_ENTER();
     static_assert(CI * CO == 64 && CI % 4 == 0 && CO % 4 == 0, "channel block must be 4x16 or 16x4");
     constexpr int CIQ = CI / 4, COQ = CO / 4;
+    constexpr int IR = CI == 4 ? 3 : 4, JR = CO == 4 ? 3 : 4;      // a 4-channel side is zero-padded RGB
     extern __shared__ float4 sm4[];
     float4* in_s = sm4;                         // [HSY][HS][CIQ]
     float4* dy_s = sm4 + HSY * HS * CIQ;        // [TSY][TS][COQ]
@@ -45,35 +51,47 @@ __global__ void __launch_bounds__(NT9) wgrad9x9_kernel(const float* __restrict__
         dy_s[i] = (yy < H && xx < W) ? __ldg(dy4 + ((long long)yy * W + xx) * COQ + c4) : z;
     }
     __syncthreads();
-    if (t >= 324) return;
-    const int tap = t >> 2, q = t & 3;
+    if (t >= 2 * WG9) return;
+    const int rg = t / WG9, r = t - rg * WG9;           // row group, worker
+    const int q = r & 3, tg = r >> 2;                    // channel block, tap triple 0..26
+    const int kh = tg / 3, kw0 = (tg - kh * 3) * 3;
     const int ciq = q / COQ, coq = q - ciq * COQ;
-    const int kh = tap / 9, kw = tap - kh * 9;
-    float acc[4][4];
+    float acc[3][4][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int k = 0; k < 3; ++k)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int py = 0; py < TSY; ++py) {
-        const float4* ip = in_s + ((py + kh) * HS + kw) * CIQ + ciq;
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[k][i][j] = 0.f;
+    for (int py = rg * (TSY / 2); py < (rg + 1) * (TSY / 2); ++py) {
+        const float4* ip = in_s + ((py + kh) * HS + kw0) * CIQ + ciq;
         const float4* dp = dy_s + (py * TS) * COQ + coq;
+        float4 a0 = ip[0], a1 = ip[CIQ];
 #pragma unroll 8
         for (int px = 0; px < TS; ++px) {
-            const float4 a = ip[px * CIQ];
+            const float4 a2 = ip[(px + 2) * CIQ];
             const float4 b = dp[px * COQ];
-            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float av[3][4] = {{a0.x, a0.y, a0.z, a0.w}, {a1.x, a1.y, a1.z, a1.w}, {a2.x, a2.y, a2.z, a2.w}};
             const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int i = 0; i < (CI == 4 ? 3 : 4); ++i)
+            for (int k = 0; k < 3; ++k)
 #pragma unroll
-                for (int j = 0; j < (CO == 4 ? 3 : 4); ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                for (int i = 0; i < IR; ++i)
+#pragma unroll
+                    for (int j = 0; j < JR; ++j) acc[k][i][j] = fmaf(av[k][i], bv[j], acc[k][i][j]);
+            a0 = a1; a1 = a2;
         }
     }
     const long long blk = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    float* out = partial + blk * (81 * 64) + (tap * CI + ciq * 4) * CO + coq * 4;
+    float* outp = partial + (blk * 2 + rg) * (81 * 64);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<float4*>(out + i * CO) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    for (int k = 0; k < 3; ++k) {
+        const int tap = kh * 9 + kw0 + k;
+        float* out = outp + (tap * CI + ciq * 4) * CO + coq * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4*>(out + i * CO) = make_float4(acc[k][i][0], acc[k][i][1], acc[k][i][2], acc[k][i][3]);
+    }
 }
 
 // Direct forward convolution (also the data gradient, with flipped/transposed weights).
@@ -268,49 +286,54 @@ __global__ void __launch_bounds__(256) conv3x3_c4_fwd_kernel(const float* __rest
 
 // dX[p][0..3] = sum_{tap,co} P[p + tap - 1][co] * Wf[tap][co][0..3]   (Wf = flipped/transposed conv1_1 weights)
 // warp = (column group, 16-channel slice of the reduction); the 4 slices are summed through shared memory.
+constexpr int C1_QP = 4;     // channel quads staged per pass (16 of the 64 channels): 45 KB of shared memory, 5 CTAs per SM
+
 __global__ void __launch_bounds__(256) dgrad3x3_c4_kernel(const float* __restrict__ P, const float* __restrict__ wf,
                                                           float* __restrict__ dx, int H, int W) {
     FS_PDL_ENTER();
     extern __shared__ float4 sm4[];
-    float4* in_s = sm4;                                         // [16 channel quads][ROWS+2][PITCH]
-    float4* w_s = sm4 + 16 * (C1_ROWS + 2) * C1_PITCH;          // [9][64] float4
+    float4* in_s = sm4;                                         // [C1_QP channel quads][ROWS+2][PITCH]
+    float4* w_s = sm4 + C1_QP * (C1_ROWS + 2) * C1_PITCH;       // [9][64] float4
     float4* red = w_s + 9 * 64;                                 // [3 slices][64 threads][4 px]
     const int t = threadIdx.x;
     const int x0 = blockIdx.x * C1_COLS, y0 = blockIdx.y * C1_ROWS, n = blockIdx.z;
     const float4* p4 = reinterpret_cast<const float4*>(P + (long long)n * H * W * 64);
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = t; i < (C1_ROWS + 2) * (C1_COLS + 2) * 16; i += 256) {
-        int cq = i & 15, pix = i >> 4;
-        int py = pix / (C1_COLS + 2), px = pix - py * (C1_COLS + 2);
-        int yy = y0 - 1 + py, xx = x0 - 1 + px;
-        in_s[(cq * (C1_ROWS + 2) + py) * C1_PITCH + px] =
-            (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(p4 + ((long long)yy * W + xx) * 16 + cq) : z;
-    }
     for (int i = t; i < 9 * 64; i += 256) w_s[i] = __ldg(reinterpret_cast<const float4*>(wf) + i);
-    __syncthreads();
     const int lane = t & 31, wq = t >> 5;
-    const int g = wq & 1, kq = wq >> 1;               // column group, reduction slice (channels 16kq..16kq+15)
+    const int g = wq & 1, kq = wq >> 1;               // column group, channel quad of the pass owned by this warp
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    // The 64 gradient channels are staged 16 at a time (the first version staged all 64: 117 KB of shared memory,
+    // ONE resident CTA per SM, 12 % warp occupancy and a latency-bound load phase - profiles/r01t).
+#pragma unroll 1
+    for (int pass = 0; pass < 16 / C1_QP; ++pass) {
+        if (pass) __syncthreads();
+        for (int i = t; i < (C1_ROWS + 2) * (C1_COLS + 2) * C1_QP; i += 256) {
+            int cq = i % C1_QP, pix = i / C1_QP;
+            int py = pix / (C1_COLS + 2), px = pix - py * (C1_COLS + 2);
+            int yy = y0 - 1 + py, xx = x0 - 1 + px;
+            in_s[(cq * (C1_ROWS + 2) + py) * C1_PITCH + px] =
+                (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(p4 + ((long long)yy * W + xx) * 16 + pass * C1_QP + cq) : z;
+        }
+        __syncthreads();
+        const int cqg = pass * C1_QP + kq;            // global channel quad
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-            const int cq = kq * 4 + c4;
+        for (int kh = 0; kh < 3; ++kh) {
             float iv[6][4];
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-                float4 v = in_s[(cq * (C1_ROWS + 2) + lane + kh) * C1_PITCH + 4 * g + j];
+                float4 v = in_s[(kq * (C1_ROWS + 2) + lane + kh) * C1_PITCH + 4 * g + j];
                 iv[j][0] = v.x; iv[j][1] = v.y; iv[j][2] = v.z; iv[j][3] = v.w;
             }
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const float4 wv = w_s[(kh * 3 + kw) * 64 + cq * 4 + c];
+                    const float4 wv = w_s[(kh * 3 + kw) * 64 + cqg * 4 + c];
 #pragma unroll
                     for (int px = 0; px < 4; ++px) {
                         const float xv = iv[px + kw][c];
@@ -409,7 +432,7 @@ int launch_conv3x3_c4_fwd(const float* in, const float* w, const float* bias, fl
 
 // conv1_1 data gradient: P [N,H,W,64], wf [9,64,4] (flip_transpose_taps of the forward weights) -> dx [N,H,W,4]
 int launch_dgrad3x3_c4(const float* P, const float* wf, float* dx, int N, int H, int W, cudaStream_t st) {
-    const size_t smem = (size_t)(16 * (C1_ROWS + 2) * C1_PITCH + 9 * 64 + 3 * 64 * 4) * sizeof(float4);
+    const size_t smem = (size_t)(C1_QP * (C1_ROWS + 2) * C1_PITCH + 9 * 64 + 3 * 64 * 4) * sizeof(float4);
     static bool set = false;
     if (!set) { FS_CUDA(cudaFuncSetAttribute(dgrad3x3_c4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
     dim3 grid(cdiv(W, C1_COLS), cdiv(H, C1_ROWS), N);
@@ -426,7 +449,7 @@ int flip_transpose_taps(const float* W, float* Wf, int T, int Ci, int Co, cudaSt
 }
 
 long long wgrad9x9_partial_floats(int N, int H, int W) {
-    return (long long)N * cdiv(H, TSY) * cdiv(W, TS) * 81 * 64;
+    return 2LL * N * cdiv(H, TSY) * cdiv(W, TS) * 81 * 64;      // two row groups per tile
 }
 
 // in [N,H,W,CI], dy [N,H,W,CO] (9x9 stride-1 SAME conv: equal spatial dims); out [81,CI,CO]
@@ -449,7 +472,7 @@ int launch_wgrad9x9(const float* in, const float* dy, float* out, float* partial
         launch_k((wgrad9x9_kernel<4, 16>), dim3(grid), dim3(NT9), smem, st, in, dy, partial, H, W);
     }
     FS_LAUNCH_CHECK();
-    launch_k(reduce_partials_kernel, dim3(cdiv(81 * 64, 32)), dim3(256), 0, st, partial, out, 81 * 64, nblocks);
+    launch_k(reduce_partials_kernel, dim3(cdiv(81 * 64, 32)), dim3(256), 0, st, partial, out, 81 * 64, 2 * nblocks);
     FS_LAUNCH_CHECK();
     return 0;
 }
