@@ -240,6 +240,7 @@ void Engine::layout(Arena& a) {
                 if (c.k == 9) wgcap = maxll(wgcap, wgrad9x9_partial_floats(N, c.inH, c.inW));
                 if ((flags & ENG_DECONV) && c.upconv) wgcap = maxll(wgcap, wgrad_partial_floats(9 * c.cout, c.cin, 1));
                 if (l >= 3 && l <= 12) wgcap = maxll(wgcap, wgrad3x3_tc_partial_floats());
+                if (tc2_layout(l)) wgcap = maxll(wgcap, wgrad2x2_tc_partial_floats());
             }
         }
         for (int l = 0; l < T_NCONV; ++l) {
@@ -273,6 +274,7 @@ void Engine::layout(Arena& a) {
                 for (int i = 0; i < 3; ++i) { tgsplit[i].hi = a.take<__nv_bfloat16>(nres); tgsplit[i].lo = a.take<__nv_bfloat16>(nres); }
             }
             wg_tmp = a.take<float>(81LL * 16 * 4 + 16LL * 64 * 32 + 1024);
+            wg_tmp2 = a.take<float>(16LL * 64 * 32);
             gb_tmp = a.take<float>(8);
         }
     }
@@ -431,6 +433,7 @@ int Engine::tc2_args(int l, bool bwd, int ri, float* out, Conv3x3TcArgs& ta) con
 
 // 9x9 layers: algorithmic FLOPs with the real channel counts (the padded RGB channel is skipped by the kernels)
 static double conv9_flops(const TConv& c, int N) { return 2.0 * N * c.outH * c.outW * 81.0 * c.cin * c.cout; }
+static double wgrad_flops_tc2(int N, int gh, int gw) { return 2.0 * N * gh * gw * 4.0 * 64.0 * 128.0; }
 static double tc2_flops(const Conv3x3TcArgs& a) { return 2.0 * a.N * a.OH * a.OW * (double)a.OC * 4.0 * a.C; }
 
 static void conv_fwd_args(const TConv& c, int N, const float* in, const float* w, float* out, IGemmArgs& a) {
@@ -547,6 +550,21 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
             PROF(PC_WGRAD, fl, launch_wgrad9x9(dRaw, in_act, wg_tmp, wg_partial, wg_partial_cap, N, c.inH, c.inW,
                                                c.cout_s, c.cin_s, st));
             PROF(PC_PREP, 0.0, unpad_taps(wg_tmp, grads + c.offW, 81, c.cout, c.cin, c.cout_s, c.cin_s, st));
+        } else if (tc2(l)) {
+            // weight gradient of the 2x2 form on tcgen05: X = the layer's input planes, dY = dRaw's planes, the
+            // 128-channel side through its space-to-depth view; then back through the pairing / collapse adjoints
+            const bool paired = (l == 1 || l == 14);
+            const int gh = c.upconv ? c.inH : c.outH, gw = (c.upconv ? c.inW : c.outW) / (paired ? 2 : 1);
+            PROF(PC_WGRAD, wgrad_flops_tc2(N, gh, gw), launch_wgrad2x2_tc(tsplit[l], c.upconv ? 0 : 1, tgsplit[ri], c.upconv ? 1 : 0,
+                                                                          wg_tmp, wg_partial, wg_partial_cap, N, gh, gw, st));
+            const float* wsrc = wg_tmp;
+            if (paired) {
+                if (c.upconv) PROF(PC_PREP, 0.0, unpair_taps(wg_tmp, wg_tmp2, c.cin, 4 * c.cout, 0, st));
+                else PROF(PC_PREP, 0.0, unpair_taps(wg_tmp, wg_tmp2, 4 * c.cin, c.cout, 1, st));
+                wsrc = wg_tmp2;
+            }
+            if (c.upconv) PROF(PC_PREP, 0.0, upconv_collapse_grad(wsrc, grads + c.offW, c.cin, c.cout, st));
+            else PROF(PC_PREP, 0.0, s2_fwd_collapse_grad(wsrc, grads + c.offW, c.cin, c.cout, st));
         } else if (c.upconv) {
             wa.C = c.cin; wa.KH = wa.KW = 2; wa.stride = 1;
             wa.OH = c.inH; wa.OW = c.inW; wa.OC = 4 * c.cout; wa.dy_mode = 1;

@@ -84,6 +84,7 @@ struct Engine {
     float* tgrad[3];                     // rotating gradient buffers (transform bwd)
     float* wg_partial = nullptr; long long wg_partial_cap = 0;
     float* wg_tmp = nullptr;             // padded / collapsed weight-gradient staging
+    float* wg_tmp2 = nullptr;            // un-paired weight-gradient staging (tensor-path 2x2 forms)
     // vgg
     float* v_in4 = nullptr;              // [N,VH,VW,4]
     float* vact[V_NCONV]; float* vpool[V_NCONV];

@@ -716,6 +716,49 @@ __global__ void pair_taps_kernel(const float* __restrict__ W, float* __restrict_
     Wp[i] = (b == 0 || b == 1) ? W[(((long long)a * 2 + b) * K0 + k) * N0 + n] : 0.f;
 }
 
+// adjoint of pair_taps in its correlation form (gradients of paired weights back to the unpaired 2x2 weights):
+//   dW[a][b][k][n] = sum over (kwp, h, e) with 2kwp + h - e == b of dWp[a][kwp][kidx(h,k)][e*N0 + n]
+__global__ void unpair_taps_kernel(const float* __restrict__ dWp, float* __restrict__ dW, int K0, int N0, int kmode) {
+    FS_PDL_ENTER();
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = 4LL * K0 * N0;
+    if (i >= total) return;
+    int n = (int)(i % N0);
+    long long r = i / N0;
+    int k = (int)(r % K0); r /= K0;
+    int b = (int)(r % 2), a = (int)(r / 2);
+    float s = 0.f;
+#pragma unroll
+    for (int kwp = 0; kwp < 2; ++kwp)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int e = 2 * kwp + h - b;
+            if (e < 0 || e > 1) continue;
+            int kp;
+            if (kmode == 0) kp = h * K0 + k;
+            else {
+                int c0 = K0 / 4, pq = k / c0, c = k - pq * c0;
+                kp = (pq >> 1) * K0 + h * (K0 / 2) + (pq & 1) * c0 + c;
+            }
+            s += dWp[(((long long)a * 2 + kwp) * (2 * K0) + kp) * (2 * N0) + e * N0 + n];
+        }
+    dW[i] = s;
+}
+
+// adjoint of s2_fwd_collapse: dW[kh][kw][ci][co] = dWf[kh>>1][kw>>1][((kh&1)*2 + (kw&1))*Ci + ci][co]
+__global__ void s2_fwd_collapse_grad_kernel(const float* __restrict__ dWf, float* __restrict__ dW, int Ci, int Co) {
+    FS_PDL_ENTER();
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = 9LL * Ci * Co;
+    if (i >= total) return;
+    int co = (int)(i % Co);
+    long long r = i / Co;
+    int ci = (int)(r % Ci); r /= Ci;
+    int kw = (int)(r % 3), kh = (int)(r / 3);
+    int a = kh >> 1, b = kw >> 1, pq = (kh & 1) * 2 + (kw & 1);
+    dW[i] = dWf[((((long long)a * 2 + b) * 4 + pq) * Ci + ci) * Co + co];
+}
+
 inline int grid1(long long n, int bs = 256) { return (int)((n + bs - 1) / bs); }
 
 }  // namespace
@@ -918,6 +961,17 @@ int s2_fwd_collapse(const float* W, float* Wf, int Ci, int Co, cudaStream_t st) 
 int pair_taps(const float* W, float* Wp, int K0, int N0, int kmode, int gather, cudaStream_t st) {
     FS_CHECK(K0 % 4 == 0 && N0 >= 1, "pair_taps: bad channel counts");
     launch_k(pair_taps_kernel, dim3(grid1(16LL * K0 * N0)), dim3(256), 0, st, W, Wp, K0, N0, kmode, gather);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int unpair_taps(const float* dWp, float* dW, int K0, int N0, int kmode, cudaStream_t st) {
+    launch_k(unpair_taps_kernel, dim3(grid1(4LL * K0 * N0)), dim3(256), 0, st, dWp, dW, K0, N0, kmode);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+int s2_fwd_collapse_grad(const float* dWf, float* dW, int Ci, int Co, cudaStream_t st) {
+    launch_k(s2_fwd_collapse_grad_kernel, dim3(grid1(9LL * Ci * Co)), dim3(256), 0, st, dWf, dW, Ci, Co);
     FS_LAUNCH_CHECK();
     return 0;
 }

@@ -54,6 +54,11 @@ int launch_wgrad3x3_tc(SplitPtr x, SplitPtr dy, float* out, float* partial, long
                        int W, int OH, int OW, int pad, cudaStream_t st);
 
 
+// tcgen05 weight gradient of the 2x2-tap forms (wgrad_tc.cu): out [2,2,Cx,Cy], (Cx,Cy) = (64,128) | (128,64)
+long long wgrad2x2_tc_partial_floats();
+int launch_wgrad2x2_tc(SplitPtr x, int x_s2d, SplitPtr dy, int dy_s2d, float* out, float* partial, long long partial_cap,
+                       int N, int GH, int GW, cudaStream_t st);
+
 // B[n][cb][j][k] = S[n][cb*64+k][j] as split planes: packs per-sample [C,C] matrices for a 1x1 tensor-path GEMM
 int pack_gemm_b_tc(const float* S, SplitPtr out, int N, int C, cudaStream_t st);
 

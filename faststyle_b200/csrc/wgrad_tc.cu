@@ -191,6 +191,173 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_cons
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Weight gradient of the 2x2-tap forms of the stride-2 / resize convolutions (initconv_1/2, upsample_0/1; see
+// conv3x3_tc.cu "2x2-tap mode"):  dWc[a,b,cx,cy] = sum_{n,y,x} X[n, y+a, x+b, cx] * dY[n, y, x, cy]
+// with (Cx, Cy) = (64, 128) or (128, 64); the 128-channel side is a space-to-depth view read through a 5-D tensor
+// map whose 64-channel block index is the row parity.  Same structure as wgrad3x3_tc_kernel: per 8x16-pixel tile
+// one dY tile and, per (kw, 64-channel block of X), one slab whose kh = 0 | 1 rows form the two 64-row halves of an
+// M = 128 MN-major operand; N = Cy per MMA; 2*CBx accumulators [128, Cy] stay in TMEM (256 columns) over all
+// tiles of the CTA; fixed-order reduction of the per-CTA partials [4, Cx, Cy].
+struct Wg2Params {
+    int tilesX, tilesY, total_tiles;
+    int cbx, cby;              // 64-channel blocks of X / dY (one of them is 2)
+    int x_s2d, dy_s2d;
+    float* partial;            // [gridDim.x][4*Cx*Cy]
+};
+constexpr int W2_XSTAGE = 2 * SLAB_BYTES;              // hi + lo slab of one (kw, cbx)
+constexpr int W2_DSTAGE_MAX = 2 * 2 * DT_BYTES;         // hi + lo of up to two 64-channel boxes
+constexpr int W2_SMEM = STAGES * (W2_XSTAGE + W2_DSTAGE_MAX) + 1024 + 256;
+
+__global__ void __launch_bounds__(256, 1)
+wgrad2x2_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+                   const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CUtensorMap tmD_lo,
+                   const Wg2Params p) {
+    FS_PDL_TRIGGER();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smemX = smem;
+    uint8_t* smemD = smem + STAGES * W2_XSTAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smemD + STAGES * W2_DSTAGE_MAX);
+    uint64_t* x_full = bars;
+    uint64_t* x_empty = x_full + STAGES;
+    uint64_t* d_full = x_empty + STAGES;
+    uint64_t* d_empty = d_full + STAGES;
+    uint64_t* done = d_empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    const int Cy = p.cby * 64;
+    const int dplane = p.cby * DT_BYTES;              // bytes of the hi (or lo) boxes of one dY stage
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmX_hi); prefetch_tmap(&tmX_lo); prefetch_tmap(&tmD_hi); prefetch_tmap(&tmD_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1);
+            mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 1);
+        }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    FS_PDL_WAIT();                        // everything above is CTA-local setup
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        int sx = 0, sd = 0; uint32_t px = 0, pd = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const int tx = t % p.tilesX;
+            int r = t / p.tilesX;
+            const int ty = r % p.tilesY;
+            const int n = r / p.tilesY;
+            const int y0 = ty * TH, x0 = tx * TW;
+            mbar_wait(&d_empty[sd], pd ^ 1);
+            uint8_t* dd = smemD + sd * W2_DSTAGE_MAX;
+            mbar_expect_tx(&d_full[sd], (uint32_t)(2 * dplane));
+            for (int b = 0; b < p.cby; ++b) {
+                if (p.dy_s2d) {
+                    tma_load_5d(dd + b * DT_BYTES, &tmD_hi, &d_full[sd], 0, x0, b, y0, n);
+                    tma_load_5d(dd + dplane + b * DT_BYTES, &tmD_lo, &d_full[sd], 0, x0, b, y0, n);
+                } else {
+                    tma_load_4d(dd + b * DT_BYTES, &tmD_hi, &d_full[sd], b * 64, x0, y0, n);
+                    tma_load_4d(dd + dplane + b * DT_BYTES, &tmD_lo, &d_full[sd], b * 64, x0, y0, n);
+                }
+            }
+            if (++sd == STAGES) { sd = 0; pd ^= 1; }
+            for (int kw = 0; kw < 2; ++kw) {
+                for (int cb = 0; cb < p.cbx; ++cb) {
+                    mbar_wait(&x_empty[sx], px ^ 1);
+                    uint8_t* xd = smemX + sx * W2_XSTAGE;
+                    mbar_expect_tx(&x_full[sx], W2_XSTAGE);
+                    if (p.x_s2d) {
+                        tma_load_5d(xd, &tmX_hi, &x_full[sx], 0, x0 + kw, cb, y0, n);
+                        tma_load_5d(xd + SLAB_BYTES, &tmX_lo, &x_full[sx], 0, x0 + kw, cb, y0, n);
+                    } else {
+                        tma_load_4d(xd, &tmX_hi, &x_full[sx], cb * 64, x0 + kw, y0, n);
+                        tma_load_4d(xd + SLAB_BYTES, &tmX_lo, &x_full[sx], cb * 64, x0 + kw, y0, n);
+                    }
+                    if (++sx == STAGES) { sx = 0; px ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc_mn(Cy);
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        int sx = 0, sd = 0; uint32_t px = 0, pd = 0;
+        bool first_tile = true;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            mbar_wait(&d_full[sd], pd);
+            tc_fence_after();
+            const uint32_t dbase = smem_u32(smemD + sd * W2_DSTAGE_MAX);
+            const uint64_t dd_hi = make_sdesc_mn(dbase, (uint32_t)DT_BYTES);
+            const uint64_t dd_lo = make_sdesc_mn(dbase + dplane, (uint32_t)DT_BYTES);
+            for (int kw = 0; kw < 2; ++kw) {
+                for (int cb = 0; cb < p.cbx; ++cb) {
+                    mbar_wait(&x_full[sx], px);
+                    tc_fence_after();
+                    const uint64_t xd_hi = make_sdesc_mn(smem_u32(smemX + sx * W2_XSTAGE), 2048);
+                    const uint64_t xd_lo = make_sdesc_mn(smem_u32(smemX + sx * W2_XSTAGE + SLAB_BYTES), 2048);
+                    if (elect_one()) {
+                        const uint32_t acc = tb + (uint32_t)((kw * p.cbx + cb) * Cy);
+#pragma unroll
+                        for (int prod = 0; prod < 3; ++prod) {
+                            const uint64_t ad = (prod == 2 ? xd_lo : xd_hi);
+                            const uint64_t bd = (prod == 1 ? dd_lo : dd_hi);
+#pragma unroll
+                            for (int ks = 0; ks < TH; ++ks)
+                                tc_mma_bf16(acc, ad + (uint64_t)(ks * 128), bd + (uint64_t)(ks * 128), idesc,
+                                            (first_tile && prod == 0 && ks == 0) ? 0u : 1u);
+                        }
+                        tc_commit(&x_empty[sx]);
+                    }
+                    __syncwarp();
+                    if (++sx == STAGES) { sx = 0; px ^= 1; }
+                }
+            }
+            if (elect_one()) tc_commit(&d_empty[sd]);
+            __syncwarp();
+            if (++sd == STAGES) { sd = 0; pd ^= 1; }
+            first_tile = false;
+        }
+        if (elect_one()) tc_commit(done);
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== dump (4 warps = 128 TMEM lanes) =====================
+        const int ew = warp - 4;
+        const int row = ew * 32 + lane;              // accumulator row: 0..63 tap row kh = 0, 64..127 kh = 1
+        mbar_wait(done, 0);
+        tc_fence_after();
+        const int Cx = p.cbx * 64;
+        float* part = p.partial + (long long)blockIdx.x * (4 * Cx * Cy);
+        const bool has_tiles = (int)blockIdx.x < p.total_tiles;
+        const int kh = row >> 6;
+#pragma unroll 1
+        for (int a = 0; a < 2 * p.cbx; ++a) {
+            const int kw = a / p.cbx, cb = a - kw * p.cbx;
+            const int tap = kh * 2 + kw, cx = cb * 64 + (row & 63);
+            float* op = part + ((long long)tap * Cx + cx) * Cy;
+#pragma unroll 1
+            for (int ch = 0; ch < Cy / 32; ++ch) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * Cy + ch * 32), v);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(op + ch * 32 + i) = has_tiles ? make_float4(v[i], v[i + 1], v[i + 2], v[i + 3])
+                                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
 // out[i] = sum_b partial[b][i], fixed order
 __global__ void __launch_bounds__(256) reduce_cta_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                                                   int elems, int nparts) {
@@ -274,6 +441,78 @@ int launch_wgrad3x3_tc(SplitPtr x, SplitPtr dy, float* out, float* partial, long
     return 0;
 }
 
+
+namespace {
+// 5-D space-to-depth view {64 = (q,c), W, 2 (p), H, N} of a plain [N, 2H, 2W, 32] tensor (cf. conv3x3_tc.cu)
+int make_map_s2d(CUtensorMap* tm, const __nv_bfloat16* base, int N, int H, int W, int box_h) {
+    static EncodeTiledFn enc = nullptr;
+    if (!enc) {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        FS_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) == cudaSuccess && fp,
+                 "cuTensorMapEncodeTiled is not available from the CUDA driver");
+        enc = reinterpret_cast<EncodeTiledFn>(fp);
+    }
+    const cuuint64_t C0 = 32, FW = 2 * (cuuint64_t)W, FH = 2 * (cuuint64_t)H;
+    cuuint64_t dims[5] = {64, (cuuint64_t)W, 2, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[4] = {2 * C0 * 2, FW * C0 * 2, 2 * FW * C0 * 2, FH * FW * C0 * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)TW, 1, (cuuint32_t)box_h, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(s2d %dx%dx%d) failed: %d", N, H, W, (int)r);
+    return 0;
+}
+}  // namespace
+
+long long wgrad2x2_tc_partial_floats() { return 148LL * 4 * 64 * 128; }
+
+// x, dy: split planes in GEMM space [N, GH, GW, .]; the side flagged s2d has 128 channels and is the space-to-depth
+// view of a plain [N, 2GH, 2GW, 32] tensor, the other side is a plain 64-channel tensor.  out [2,2,Cx,Cy] fp32.
+int launch_wgrad2x2_tc(SplitPtr x, int x_s2d, SplitPtr dy, int dy_s2d, float* out, float* partial, long long partial_cap,
+                       int N, int GH, int GW, cudaStream_t st) {
+    FS_CHECK(x.hi && x.lo && dy.hi && dy.lo && out && partial, "wgrad2x2_tc: NULL argument");
+    FS_CHECK((x_s2d != 0) != (dy_s2d != 0), "wgrad2x2_tc: exactly one side is the 128-channel space-to-depth view");
+    CUtensorMap tmX_hi, tmX_lo, tmD_hi, tmD_lo;
+    if (x_s2d) {
+        FS_TRY(make_map_s2d(&tmX_hi, x.hi, N, GH, GW, TH + 2));
+        FS_TRY(make_map_s2d(&tmX_lo, x.lo, N, GH, GW, TH + 2));
+        FS_TRY(make_map(&tmD_hi, dy.hi, N, GH, GW, TH));
+        FS_TRY(make_map(&tmD_lo, dy.lo, N, GH, GW, TH));
+    } else {
+        FS_TRY(make_map(&tmX_hi, x.hi, N, GH, GW, TH + 2));
+        FS_TRY(make_map(&tmX_lo, x.lo, N, GH, GW, TH + 2));
+        FS_TRY(make_map_s2d(&tmD_hi, dy.hi, N, GH, GW, TH));
+        FS_TRY(make_map_s2d(&tmD_lo, dy.lo, N, GH, GW, TH));
+    }
+    Wg2Params p;
+    p.tilesX = cdiv(GW, TW); p.tilesY = cdiv(GH, TH);
+    p.total_tiles = N * p.tilesX * p.tilesY;
+    p.cbx = x_s2d ? 2 : 1; p.cby = dy_s2d ? 2 : 1;
+    p.x_s2d = x_s2d; p.dy_s2d = dy_s2d;
+    p.partial = partial;
+    int sms = 148;
+    {
+        int dev = 0; cudaGetDevice(&dev);
+        int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+        if (sms > 148) sms = 148;
+    }
+    int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    FS_CHECK(grid >= 1, "wgrad2x2_tc: empty problem");
+    const int elems = 4 * 64 * 128;
+    FS_CHECK((long long)grid * elems <= partial_cap, "wgrad2x2_tc: partial workspace too small");
+    static bool attr_set = false;
+    if (!attr_set) {
+        FS_CUDA(cudaFuncSetAttribute(wgrad2x2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM));
+        attr_set = true;
+    }
+    launch_k(wgrad2x2_tc_kernel, dim3(grid), dim3(256), W2_SMEM, st, tmX_hi, tmX_lo, tmD_hi, tmD_lo, p);
+    FS_LAUNCH_CHECK();
+    launch_k(reduce_cta_partials_kernel, dim3(cdiv(elems, 32)), dim3(256), 0, st, partial, out, elems, grid);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
 
 // =====================================================================================
 // Gram matrix on tcgen05:  G[n][c1][c2] = scale * sum_p F[n,p,c1] * F[n,p,c2]   (reference utils.py:76-81)
