@@ -559,8 +559,8 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
                                                                           wg_tmp, wg_partial, wg_partial_cap, N, gh, gw, st));
             const float* wsrc = wg_tmp;
             if (paired) {
-                if (c.upconv) PROF(PC_PREP, 0.0, unpair_taps(wg_tmp, wg_tmp2, c.cin, 4 * c.cout, 0, st));
-                else PROF(PC_PREP, 0.0, unpair_taps(wg_tmp, wg_tmp2, 4 * c.cin, c.cout, 1, st));
+                if (c.upconv) PROF(PC_PREP, 0.0, unpair_taps(wg_tmp, wg_tmp2, c.cin, 4 * c.cout, 0, 1, st));   // dY side: paired s2d view
+                else PROF(PC_PREP, 0.0, unpair_taps(wg_tmp, wg_tmp2, 4 * c.cin, c.cout, 1, 0, st));
                 wsrc = wg_tmp2;
             }
             if (c.upconv) PROF(PC_PREP, 0.0, upconv_collapse_grad(wsrc, grads + c.offW, c.cin, c.cout, st));

@@ -718,7 +718,10 @@ __global__ void pair_taps_kernel(const float* __restrict__ W, float* __restrict_
 
 // adjoint of pair_taps in its correlation form (gradients of paired weights back to the unpaired 2x2 weights):
 //   dW[a][b][k][n] = sum over (kwp, h, e) with 2kwp + h - e == b of dWp[a][kwp][kidx(h,k)][e*N0 + n]
-__global__ void unpair_taps_kernel(const float* __restrict__ dWp, float* __restrict__ dW, int K0, int N0, int kmode) {
+// n_s2d: the N side of dWp came from a paired space-to-depth view, whose channel order is (p; e, q, c) instead of
+// the (e; p, q, c) order of pair_taps: column e*N0 + n with n = p*(N0/2) + r sits at p*N0 + e*(N0/2) + r.
+__global__ void unpair_taps_kernel(const float* __restrict__ dWp, float* __restrict__ dW, int K0, int N0, int kmode,
+                                   int n_s2d) {
     FS_PDL_ENTER();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = 4LL * K0 * N0;
@@ -740,7 +743,9 @@ __global__ void unpair_taps_kernel(const float* __restrict__ dWp, float* __restr
                 int c0 = K0 / 4, pq = k / c0, c = k - pq * c0;
                 kp = (pq >> 1) * K0 + h * (K0 / 2) + (pq & 1) * c0 + c;
             }
-            s += dWp[(((long long)a * 2 + kwp) * (2 * K0) + kp) * (2 * N0) + e * N0 + n];
+            int col = e * N0 + n;
+            if (n_s2d) { int p = n / (N0 / 2), r2 = n - p * (N0 / 2); col = p * N0 + e * (N0 / 2) + r2; }
+            s += dWp[(((long long)a * 2 + kwp) * (2 * K0) + kp) * (2 * N0) + col];
         }
     dW[i] = s;
 }
@@ -965,8 +970,8 @@ int pair_taps(const float* W, float* Wp, int K0, int N0, int kmode, int gather, 
     return 0;
 }
 
-int unpair_taps(const float* dWp, float* dW, int K0, int N0, int kmode, cudaStream_t st) {
-    launch_k(unpair_taps_kernel, dim3(grid1(4LL * K0 * N0)), dim3(256), 0, st, dWp, dW, K0, N0, kmode);
+int unpair_taps(const float* dWp, float* dW, int K0, int N0, int kmode, int n_s2d, cudaStream_t st) {
+    launch_k(unpair_taps_kernel, dim3(grid1(4LL * K0 * N0)), dim3(256), 0, st, dWp, dW, K0, N0, kmode, n_s2d);
     FS_LAUNCH_CHECK();
     return 0;
 }

@@ -69,7 +69,7 @@ int s2_fwd_collapse(const float* W, float* Wf, int Ci, int Co, cudaStream_t st);
 int pair_taps(const float* W, float* Wp, int K0, int N0, int kmode, int gather, cudaStream_t st);
 
 // adjoints (weight gradients back through pair_taps / s2_fwd_collapse)
-int unpair_taps(const float* dWp, float* dW, int K0, int N0, int kmode, cudaStream_t st);
+int unpair_taps(const float* dWp, float* dW, int K0, int N0, int kmode, int n_s2d, cudaStream_t st);
 int s2_fwd_collapse_grad(const float* dWf, float* dW, int Ci, int Co, cudaStream_t st);
 
 int fill_zero(void* p, size_t bytes, cudaStream_t st);
