@@ -300,8 +300,10 @@ def run_ours(args, rank, local_rank, world):
                                    "VGG16 weights, style starry_night_crop.jpg" % (PER_GPU_BATCH, HW, HW),
                        "global_batch": PER_GPU_BATCH * world, "parallelism": "dp%d" % world,
                        "l2": "per-step working set ~1.3 GB >> 126 MB L2, no explicit flush",
-                       "precision": "fp32 storage; 3x3 convs with 64-multiple channels: split-bf16 x3 on tcgen05 "
-                                    "(fp32-class, 16 mantissa bits), fp32 accumulate; everything else fp32 FFMA"},
+                       "precision": "fp32 storage; VGG conv1_2..conv4_3, the residual convs, the four stride-2 / "
+                                    "resize convs (2x2 forms) incl. data + weight gradients, Gram fwd/bwd: split-bf16 x3 "
+                                    "on tcgen05 (fp32-class, 16 mantissa bits), fp32 accumulate; 9x9 convs, conv1_1, "
+                                    "InstanceNorm, pooling, losses, Adam: exact fp32 on CUDA cores"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s",
                     "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": 16,

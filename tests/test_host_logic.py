@@ -159,3 +159,29 @@ def test_webcam_cli_keeps_reference_flags():
     assert {k: ns[k] for k in ref} == ref
     assert vars(mod.setup_parser().parse_args(['--resolution', '640', '480']))['resolution'] == [640, 480]
     assert set(ns) - set(ref) == {'source', 'output', 'no_display', 'max_frames'}
+
+
+def test_deconv_variant_host_plumbing():
+    """'deconv' models (im_transf_net.py:57-63,173,183): transposed weight shapes at the same flat offsets, unit-stddev
+    initialisers for all three deconv2d layers, flatten/unflatten round trip, and train.py accepting the flag."""
+    import importlib.util
+    from faststyle_b200 import synth
+    from faststyle_b200.layout import (TRANSFORM_NPARAMS, flatten_transform, transform_offsets, unflatten_transform)
+    p = synth.init_transform_params(seed=3, upsample_method='deconv')
+    assert p['img_t_net/upsample_0/W'].shape == (3, 3, 32, 64)
+    assert p['img_t_net/upsample_1/W'].shape == (3, 3, 16, 32)
+    assert p['img_t_net/upsample_2/W'].shape == (9, 9, 3, 16)
+    assert 0.8 < p['img_t_net/upsample_2/W'].std() < 1.2 and 0.05 < p['img_t_net/initconv_0/W'].std() < 0.15
+    r = synth.init_transform_params(seed=3, upsample_method='resize')
+    assert r['img_t_net/upsample_2/W'].shape == (9, 9, 16, 3) and r['img_t_net/upsample_2/W'].std() < 0.15
+    flat = flatten_transform(p, 'deconv')
+    assert flat.shape == (TRANSFORM_NPARAMS,)
+    back = unflatten_transform(flat, 'deconv')
+    assert all(np.array_equal(back[k], p[k]) for k in p)
+    assert [o for o, _ in transform_offsets('deconv').values()] == [o for o, _ in transform_offsets('resize').values()]
+    with pytest.raises(ValueError):
+        flatten_transform(p, 'resize')              # wrong variant for these shapes, like the reference's Saver
+    spec = importlib.util.spec_from_file_location('cli_train2', os.path.join(ROOT, 'train.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.setup_parser().parse_args(['--upsample_method', 'deconv']).upsample_method == 'deconv'
