@@ -70,6 +70,7 @@ SIGNATURES = {
     "fs_loss_sqdiff": (_I, [_P, _P, _LL, C.c_double, _P, _P, _P]),
     "fs_loss_style": (_I, [_P, _P, _I, _I, C.c_double, _P, _P, _P]),
     "fs_loss_tv": (_I, [_P, _I, _I, _I, _P, _P, _P]),
+    "fs_resize_bicubic_tf1_u8": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "fs_frame_u8_to_f32": (_I, [_P, _P, _LL, _P]),
     "fs_frame_f32_to_u8": (_I, [_P, _P, _LL, _I, _P]),
     "fs_conv3x3_tc_scratch_bytes": (_SZ, [_I, _I, _I, _I, _I]),

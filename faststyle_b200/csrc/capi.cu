@@ -323,6 +323,11 @@ int fs_frame_f32_to_u8(const float* in, unsigned char* out, long long npix, int 
     return frame_f32_to_u8(in, out, npix, swap_rb, S(stream));
 }
 
+int fs_resize_bicubic_tf1_u8(const unsigned char* in, float* out, int H, int W, int OH, int OW, void* stream) {
+    FS_CHECK(in && out, "fs_resize_bicubic_tf1_u8: NULL argument");
+    return resize_bicubic_tf1_u8(in, out, H, W, OH, OW, S(stream));
+}
+
 int fs_loss_tv(const float* Y3, int N, int H, int W, double* acc, float* out, void* stream) {
     FS_CHECK(Y3 && acc && out, "fs_loss_tv: NULL argument");
     FS_TRY(fill_zero(acc, 4 * sizeof(double), S(stream)));

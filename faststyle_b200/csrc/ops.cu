@@ -110,6 +110,60 @@ __global__ void f32_to_u8_kernel(const float* __restrict__ in, unsigned char* __
     o[0] = swap_rb ? uc : ua; o[1] = ub; o[2] = swap_rb ? ua : uc;
 }
 
+// ------------------------------------------------------------------ input pipeline: TF-1.0 bicubic resize
+// tf.image.resize_images(method=2) of TF 1.0 (reference datapipe.py:25): align_corners = False, no half-pixel
+// centres (pos = out * in/out), A = -0.75, coefficients from a 1024-entry table indexed by rint(delta * 1024),
+// border taps clamped.  Arithmetic order and roundings are those of the host restatement
+// (faststyle_b200/datapipe.py::resize_bicubic_tf1: 4 rows combined first, then the 4 columns), every operation
+// individually rounded (no FMA contraction), so the two agree bit for bit.
+__device__ __forceinline__ void bicubic_taps(int o, float scale, int in_size, int* idx, float* w) {
+    const float pos = __fmul_rn(scale, (float)o);
+    const float fl = floorf(pos);
+    const int loc = (int)fl;
+    const float delta = __fsub_rn(pos, fl);
+    const int off = (int)rintf(__fmul_rn(delta, 1024.f));
+    const float A = -0.75f;
+    auto t0 = [&](int k) {          // table[2k]:   ((A+2)x - (A+3)) x x + 1
+        const float x = (float)k / 1024.f;
+        return __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(A + 2.f, x), A + 3.f), x), x), 1.f);
+    };
+    auto t1 = [&](int k) {          // table[2k+1]: ((A x1 - 5A) x1 + 8A) x1 - 4A,  x1 = x + 1
+        const float x1 = __fadd_rn((float)k / 1024.f, 1.f);
+        return __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, x1), 5.f * A), x1), 8.f * A), x1), 4.f * A);
+    };
+    w[0] = t1(off); w[1] = t0(off); w[2] = t0(1024 - off); w[3] = t1(1024 - off);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) idx[k] = min(max(loc - 1 + k, 0), in_size - 1);
+}
+
+__global__ void resize_bicubic_tf1_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, int H, int W,
+                                          int OH, int OW, float sy, float sx) {
+    FS_PDL_ENTER();
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
+    if (ox >= OW) return;
+    int iy[4], ix[4];
+    float wy[4], wx[4];
+    bicubic_taps(oy, sy, H, iy, wy);
+    bicubic_taps(ox, sx, W, ix, wx);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float r = 0.f;           // rows[oy, ix[j], c] = sum_k img[iy[k], ix[j], c] * wy[k], k in order
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float v = (float)in[((long long)iy[k] * W + ix[j]) * 3 + c];
+                const float pr = __fmul_rn(v, wy[k]);
+                r = k == 0 ? pr : __fadd_rn(r, pr);
+            }
+            const float pr = __fmul_rn(r, wx[j]);
+            acc = j == 0 ? pr : __fadd_rn(acc, pr);
+        }
+        out[((long long)oy * OW + ox) * 3 + c] = acc;
+    }
+}
+
 // ------------------------------------------------------------------ InstanceNorm
 // MODE 0: sums of (x, x^2).   MODE 1: sums of (dz, dz*xhat) for the backward pass.
 // Reduces pixels [beg, end) of sample n into the CTA's shared accumulators sm[C][2] (valid after the call).
@@ -794,6 +848,14 @@ int frame_u8_to_f32(const unsigned char* in, float* out, long long n, cudaStream
 
 int frame_f32_to_u8(const float* in, unsigned char* out, long long npix, int swap_rb, cudaStream_t st) {
     launch_k(f32_to_u8_kernel, dim3(grid1(npix)), dim3(256), 0, st, in, out, npix, swap_rb);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int resize_bicubic_tf1_u8(const unsigned char* in, float* out, int H, int W, int OH, int OW, cudaStream_t st) {
+    FS_CHECK(H >= 1 && W >= 1 && OH >= 1 && OW >= 1 && OH <= 65535, "resize_bicubic: bad dims %dx%d -> %dx%d", H, W, OH, OW);
+    const float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
+    launch_k(resize_bicubic_tf1_kernel, dim3(grid1(OW, 128), OH), dim3(128), 0, st, in, out, H, W, OH, OW, sy, sx);
     FS_LAUNCH_CHECK();
     return 0;
 }

@@ -15,6 +15,9 @@ int vgg_preprocess_c4(const float* x, float* out, long long npix, cudaStream_t s
 int frame_u8_to_f32(const unsigned char* in, float* out, long long n, cudaStream_t st);
 int frame_f32_to_u8(const float* in, unsigned char* out, long long npix, int swap_rb, cudaStream_t st);
 
+// input pipeline: tf.image.resize_images(method=2) of TF 1.0 on a uint8 HWC image (reference datapipe.py:25)
+int resize_bicubic_tf1_u8(const unsigned char* in, float* out, int H, int W, int OH, int OW, cudaStream_t st);
+
 // K3: InstanceNorm                               (reference im_transf_net.py:218-247)
 struct INWork { double* partial; int max_chunks; };       // partial: [N][chunks][C][2] doubles
 int in_chunks(int N, int HW);

@@ -151,3 +151,21 @@ def tv_sum(Y):
     acc, out = _loss_bufs(Y.device)
     _lib.call("fs_loss_tv", ptr(Y), N, H, W_, ptr(acc), ptr(out), stream_ptr())
     return out[2]
+
+
+def resize_bicubic_tf1(img_u8, out_h, out_w, out=None):
+    """tf.image.resize_images(img, [out_h, out_w], method=2) of TF 1.0 on the GPU (reference datapipe.py:25):
+    ``img_u8`` is one decoded HWC uint8 RGB image (numpy or CUDA tensor); returns / fills a float32 CUDA
+    tensor [out_h, out_w, 3]."""
+    _require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if isinstance(img_u8, np.ndarray):
+        img_u8 = torch.from_numpy(np.ascontiguousarray(img_u8))
+    if img_u8.dtype != torch.uint8 or img_u8.dim() != 3 or img_u8.shape[2] != 3:
+        raise _lib.FsError("resize_bicubic_tf1 expects an HWC uint8 RGB image")
+    src = img_u8.to(dev, non_blocking=True).contiguous()
+    if out is None:
+        out = torch.empty((out_h, out_w, 3), dtype=torch.float32, device=dev)
+    _lib.call("fs_resize_bicubic_tf1_u8", ptr(src), ptr(out), int(src.shape[0]), int(src.shape[1]), int(out_h),
+              int(out_w), stream_ptr())
+    return out

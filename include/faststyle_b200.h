@@ -180,6 +180,12 @@ int fs_loss_tv(const float* Y3, int N, int H, int W, double* acc, float* out, vo
 int fs_frame_u8_to_f32(const unsigned char* in, float* out, long long n, void* stream);
 int fs_frame_f32_to_u8(const float* in, unsigned char* out, long long npix, int swap_rb, void* stream);
 
+/* ------------------------------------------------------------------ input pipeline
+ * tf.image.resize_images(img, resize_shape, method=2) of TensorFlow 1.0 (reference datapipe.py:14-26,
+ * `preprocessing`): legacy bicubic (A = -0.75, 1024-entry coefficient table, no half-pixel centres, clamped
+ * borders) of one decoded uint8 HWC RGB image into a float32 [OH, OW, 3] slot of the batch.  Device pointers. */
+int fs_resize_bicubic_tf1_u8(const unsigned char* in, float* out, int H, int W, int OH, int OW, void* stream);
+
 /* ------------------------------------------------------------------ tensor-core path
  * 3x3 stride-1 convolution on the tcgen05 tensor pipe with split-bf16 operands
  * (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM); C and OC multiples of 64.

@@ -240,3 +240,34 @@ def test_frame_stylizer_and_webcam_cli(built_lib, golden_dir, tmp_path):
         assert fr.shape == (H, W, 3)
         n += 1
     assert n == 3
+
+
+@pytest.mark.parametrize("shape", [((480, 640), (256, 256)), ((97, 131), (256, 256)), ((256, 256), (256, 256)),
+                                   ((333, 500), (128, 192)), ((5, 7), (16, 9))])
+def test_gpu_bicubic_resize_matches_host_restatement(built_lib, shape):
+    """datapipe.preprocessing (datapipe.py:14-26) on the device.  The kernel follows the host
+    restatement of TF-1.0's legacy bicubic operation by operation (same table quantisation, same summation order,
+    no FMA contraction), so the two agree to the last bit; tolerance stated: max-abs 1e-4 on the 0..255 scale.
+    Unpinned like the host restatement itself (TensorFlow is not available to generate goldens)."""
+    from faststyle_b200 import datapipe
+    from faststyle_b200.ops import resize_bicubic_tf1
+    (h, w), (oh, ow) = shape
+    rng = np.random.RandomState(h * 7 + w)
+    img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+    want = datapipe.resize_bicubic_tf1(img, oh, ow)
+    got = resize_bicubic_tf1(img, oh, ow).cpu().numpy()
+    d = np.abs(got - want)
+    print("bicubic", shape, "max abs diff", d.max(), "exact", bool((got == want).all()))
+    assert got.shape == (oh, ow, 3) and d.max() <= 1e-4
+
+
+def test_gpu_preprocessor_batch(built_lib):
+    from faststyle_b200 import datapipe
+    rng = np.random.RandomState(0)
+    imgs = [rng.randint(0, 256, s).astype(np.uint8) for s in [(300, 400, 3), (256, 256, 3), (128, 500, 3)]]
+    prep = datapipe.GpuPreprocessor(3, (256, 256))
+    got = prep(imgs).cpu().numpy()
+    want = np.stack([datapipe.resize_bicubic_tf1(i, 256, 256) for i in imgs])
+    assert got.shape == (3, 256, 256, 3) and np.abs(got - want).max() <= 1e-4
+    got2 = prep(imgs[::-1]).cpu().numpy()           # staging buffer reuse
+    assert np.abs(got2 - want[::-1]).max() <= 1e-4

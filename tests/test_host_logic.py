@@ -185,3 +185,14 @@ def test_deconv_variant_host_plumbing():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.setup_parser().parse_args(['--upsample_method', 'deconv']).upsample_method == 'deconv'
+
+
+def test_batcher_raw_mode():
+    """raw=True hands the decoded uint8 images (un-resized) to the device-side preprocessor; same order and
+    shuffle as the float path for the same seed."""
+    from faststyle_b200 import datapipe
+    a = datapipe.batcher('synthetic:12', 4, (256, 256), 1, 4, seed=5)
+    b = datapipe.batcher('synthetic:12', 4, (256, 256), 1, 4, seed=5, raw=True)
+    fa, rb = next(a), next(b)
+    assert isinstance(rb, list) and len(rb) == 4 and rb[0].dtype == np.uint8 and rb[0].shape == (256, 256, 3)
+    assert fa.shape == (4, 256, 256, 3) and np.array_equal(fa, np.stack(rb).astype(np.float32))

@@ -93,8 +93,11 @@ def main(args):
                       args.style_weights, args.beta, args.learn_rate,
                       device='cuda:%d' % local_rank, process_group=pg, upsample_method=args.upsample_method)
 
+    gpu_prep = os.environ.get('FS_GPU_PREPROCESS', '0') == '1'      # resize + float cast on the device (same arithmetic)
     batches = datapipe.batcher(args.train_dir, local_batch, args.preprocess_size, args.n_epochs,
-                               max(args.num_pipe_buffer // world, local_batch), seed=1234, shard=(rank, world))
+                               max(args.num_pipe_buffer // world, local_batch), seed=1234, shard=(rank, world),
+                               raw=gpu_prep)
+    prep = datapipe.GpuPreprocessor(local_batch, args.preprocess_size, 'cuda:%d' % local_rank) if gpu_prep else None
 
     run_name = args.run_name
     writer = None
@@ -126,6 +129,8 @@ def main(args):
         while True:
             current_step = trainer.global_step
             batch = next(batches)
+            if prep is not None:
+                batch = prep(batch)
             want_log = (current_step % args.num_steps_ckpt == 0) or (current_step % 10 == 0)
             if rank == 0 and current_step % args.num_steps_ckpt == 0:
                 save('training/%s.ckpt-%d' % (args.model_name, current_step), with_slots=True)
