@@ -15,4 +15,4 @@ for f in sys.argv[1:]:
         tot += v["ms_per_step"]
         print("   %-20s %.3f ms  %3d launches  %s" % (k, v["ms_per_step"], v["launches_per_step"],
                                                      "%.1f TF" % v["tflops"] if v["tflops"] else ""))
-    print("   sum %.3f ms;  fwd b32 %.0f img/s" % (tot, d.get("transform_fwd_b32_images_per_s", 0)))
+    print("   sum %.3f ms;  fwd b32 %s img/s" % (tot, d.get("transform_fwd_b32_images_per_s", 0)))
