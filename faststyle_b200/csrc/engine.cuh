@@ -59,7 +59,6 @@ struct Arena {
 
 struct Engine {
     int N, H, W, flags;
-    int upsample_deconv = 0;
     unsigned content_mask = 0, style_mask = 0;   // VGG conv indices with loss taps
     // transform plan
     TConv tc[T_NCONV];

@@ -422,24 +422,6 @@ __global__ void in_bwd_apply_kernel(const float* __restrict__ dY, const float* _
     in_bwd_elem(ld4(x + i * 4), ld4(dY + i * 4), mu, rs, g, b, m1, m2, dx, i, act, shi, slo);
 }
 
-__global__ void add_padded_kernel(float* __restrict__ dst, const float* __restrict__ src, int N, int H,
-                                  int W, int C, int crop) {
-    FS_PDL_ENTER();
-    const int C4 = C >> 2;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)N * H * W * C4;
-    if (i >= total) return;
-    int c = (int)(i % C4) * 4;
-    long long pix = i / C4;
-    int x = (int)(pix % W);
-    long long r = pix / W;
-    int y = (int)(r % H);
-    int n = (int)(r / H);
-    float* d = dst + (((long long)n * (H + 2 * crop) + y + crop) * (W + 2 * crop) + x + crop) * C + c;
-    float4 a = ld4(d), s = ld4(src + i * 4);
-    st4(d, make_float4(a.x + s.x, a.y + s.y, a.z + s.z, a.w + s.w));
-}
-
 // ------------------------------------------------------------------ pooling
 __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int H,
                                    int W, int C, __nv_bfloat16* __restrict__ shi,
@@ -916,13 +898,6 @@ int instnorm_bwd(const float* dY, const float* x, const float* mean, const float
     long long n = (long long)N * HW * (C / 4);
     launch_k(in_bwd_apply_kernel, dim3(grid1(n)), dim3(256), 0, st, dY, x, mean, rstd, scale, shift, m12, dx, N, HW, C, act,
                                                   (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo);
-    FS_LAUNCH_CHECK();
-    return 0;
-}
-
-int add_padded(float* dst, const float* src, int N, int H, int W, int C, int crop, cudaStream_t st) {
-    long long n = (long long)N * H * W * (C / 4);
-    launch_k(add_padded_kernel, dim3(grid1(n)), dim3(256), 0, st, dst, src, N, H, W, C, crop);
     FS_LAUNCH_CHECK();
     return 0;
 }

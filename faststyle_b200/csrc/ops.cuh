@@ -19,7 +19,6 @@ int frame_f32_to_u8(const float* in, unsigned char* out, long long npix, int swa
 int resize_bicubic_tf1_u8(const unsigned char* in, float* out, int H, int W, int OH, int OW, cudaStream_t st);
 
 // K3: InstanceNorm                               (reference im_transf_net.py:218-247)
-struct INWork { double* partial; int max_chunks; };       // partial: [N][chunks][C][2] doubles
 int in_chunks(int N, int HW);
 int instnorm_stats(const float* x, float* mean, float* rstd, int N, int HW, int C, float eps,
                    double* partial, cudaStream_t st);
@@ -32,8 +31,6 @@ int instnorm_bwd(const float* dY, const float* x, const float* mean, const float
                  const float* scale, const float* shift, float* dx, float* dgamma, float* dbeta,
                  int N, int HW, int C, int act, double* partial, float* m12 /*[N][C][2]*/,
                  cudaStream_t st, void* split_hi = nullptr, void* split_lo = nullptr);
-// zero-pad-add:  dst[n, y+crop, x+crop, c] += src[n,y,x,c]   (skip-connection gradient)
-int add_padded(float* dst, const float* src, int N, int H, int W, int C, int crop, cudaStream_t st);
 
 // K8: 2x2 s2 SAME max-pool                        (reference libs/vgg16.py:67-71)
 int maxpool2x2_fwd(const float* x, float* out, int N, int H, int W, int C, cudaStream_t st,
