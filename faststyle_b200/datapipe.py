@@ -165,6 +165,64 @@ def _image_stream(train_dir, num_epochs, rng):
                     yield cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
 
 
+class Prefetcher:
+    """The reference's input pipeline runs on TF queue-runner threads beside the training loop
+    (train.py:241-242, shuffle_batch capacity = min_after_dequeue + 3 batches, datapipe.py:72-77).  This is the same
+    producer/consumer split without TensorFlow: one daemon thread drives the batch iterator (TFRecord parsing, JPEG
+    decode - OpenCV releases the GIL -, resize, shuffle) into a bounded queue of ``depth`` batches; the consumer
+    sees the batches in the producer's order and the producer's terminal exception (OutOfRangeError)."""
+
+    _END = object()
+
+    def __init__(self, iterator, depth=3):
+        import queue
+        import threading
+        self._q = queue.Queue(maxsize=max(1, int(depth)))
+        self._it = iterator
+        self._exc = None
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, name="faststyle-datapipe", daemon=True)
+        self._t.start()
+
+    def _put(self, item):
+        import queue
+        while not self._stop.is_set():
+            try:
+                self._q.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def _run(self):
+        try:
+            for item in self._it:
+                if not self._put(item):
+                    return
+        except BaseException as e:          # noqa: BLE001 - handed to the consumer
+            self._exc = e
+        self._put(self._END)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        item = self._q.get()
+        if item is self._END:
+            self._q.put(self._END)          # stay terminated for later calls
+            if self._exc is not None:
+                raise self._exc
+            raise StopIteration
+        return item
+
+    def close(self):
+        self._stop.set()
+
+
+def prefetch(iterator, depth=3):
+    return Prefetcher(iterator, depth)
+
+
 class GpuPreprocessor:
     """datapipe.preprocessing (reference datapipe.py:14-26) on the device: the host only decodes; each uint8 image
     goes up through a pinned staging buffer and `fs_resize_bicubic_tf1_u8` writes it, resized and cast to float32,

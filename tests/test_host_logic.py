@@ -196,3 +196,41 @@ def test_batcher_raw_mode():
     fa, rb = next(a), next(b)
     assert isinstance(rb, list) and len(rb) == 4 and rb[0].dtype == np.uint8 and rb[0].shape == (256, 256, 3)
     assert fa.shape == (4, 256, 256, 3) and np.array_equal(fa, np.stack(rb).astype(np.float32))
+
+
+def test_prefetcher_order_and_termination():
+    """Background input thread (the reference's queue runners, train.py:241-242): same batches in the same order,
+    bounded depth, and the pipeline's OutOfRangeError reaches the training loop."""
+    import time
+    from faststyle_b200 import datapipe
+    ref = list(_take(datapipe.batcher('synthetic:10', 2, (256, 256), 1, 2, seed=9), 100))
+    pf = datapipe.prefetch(datapipe.batcher('synthetic:10', 2, (256, 256), 1, 2, seed=9), depth=2)
+    got = []
+    with pytest.raises(datapipe.OutOfRangeError):
+        while True:
+            got.append(next(pf))
+    assert len(got) == len(ref) == 5 and all(np.array_equal(a, b) for a, b in zip(got, ref))
+    with pytest.raises(datapipe.OutOfRangeError):       # stays terminated
+        next(pf)
+
+    def slow():
+        for i in range(4):
+            time.sleep(0.05)
+            yield i
+    pf = datapipe.prefetch(slow(), depth=3)
+    time.sleep(0.3)                                      # producer runs ahead while the consumer is busy
+    t0 = time.time()
+    assert [next(pf) for _ in range(4)] == [0, 1, 2, 3]
+    assert time.time() - t0 < 0.1
+    with pytest.raises(StopIteration):
+        next(pf)
+    pf.close()
+
+
+def _take(it, n):
+    from faststyle_b200 import datapipe
+    try:
+        for _ in range(n):
+            yield next(it)
+    except datapipe.OutOfRangeError:
+        return

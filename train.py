@@ -98,6 +98,9 @@ def main(args):
                                max(args.num_pipe_buffer // world, local_batch), seed=1234, shard=(rank, world),
                                raw=gpu_prep)
     prep = datapipe.GpuPreprocessor(local_batch, args.preprocess_size, 'cuda:%d' % local_rank) if gpu_prep else None
+    # the reference feeds through queue-runner threads with room for 3 batches beyond the shuffle buffer
+    # (train.py:241-242, datapipe.py:72-77): decode / resize / shuffle run beside the training loop here too
+    batches = datapipe.prefetch(batches, 3)
 
     run_name = args.run_name
     writer = None
@@ -149,6 +152,7 @@ def main(args):
             print('Done training.')
     finally:
         # always leave the trained transform network behind (train.py:283-288)
+        batches.close()
         if rank == 0:
             save('models/%s_final.ckpt' % args.model_name, with_slots=False)
             writer.close()
