@@ -439,7 +439,7 @@ def cpu_baseline():
     b = 4
     x = synthetic_batch(0, b).numpy()
     step(x)
-    n = 3
+    n = 12                                 # ~10 s of CPU work on the GPU box's host cores
     t0 = time.perf_counter()
     for _ in range(n):
         step(x)
