@@ -80,6 +80,8 @@ int fs_engine_create(int N, int H, int W, int flags, unsigned content_mask, unsi
     h->e.content_mask = content_mask; h->e.style_mask = style_mask;
     const char* env = getenv("FS_TENSOR_PATH");
     h->e.use_tc = (env && env[0] == '0') ? 0 : 1;
+    env = getenv("FS_IN_EPILOGUE");
+    h->e.in_epi = (env && env[0] == '0') ? 0 : 1;
     int r = h->e.plan();
     if (r != 0) { delete h; return r; }
     Arena a;

@@ -76,6 +76,8 @@ struct Engine {
     float* wefft[T_NCONV];               // transposed weights for the data gradient
     float* y3 = nullptr;                 // [N,OH,OW,3] when the caller does not supply an output
     double* in_partial = nullptr;
+    double* in_sums = nullptr;           // [N][64][2] (sum, sum sq) accumulated by the tensor-path conv epilogues; zero between uses
+    int in_epi = 1;                      // FS_IN_EPILOGUE=0: separate statistics pass for every layer
     float* in15 = nullptr;               // 4-channel staging of the last layer's IN scale/shift
     float* gb_tmp = nullptr;
     float* wtmp15 = nullptr;             // staging for the deconv variant of the last layer's weights
