@@ -928,6 +928,7 @@ int Engine::train_fwd_bwd(const float* params, const float* packed, const float*
              "image matches the content targets (got %dx%d -> %dx%d)", H, W, OH, OW);
     float* Y = y3_out ? y3_out : y3;
     FS_TRY(prep_transform_weights(params, true, st));
+    weights_prepared = false;                      // the caller's optimiser step changes the parameters
     FS_TRY(fill_zero(loss_acc, 4 * sizeof(double), st));
     FS_TRY(vgg_content_targets(packed, x3, lc, st));                  // train.py:250-251
     FS_TRY(transform_forward(params, x3, Y, st));                     // train.py:161

@@ -96,6 +96,9 @@ struct Engine {
     double* loss_acc = nullptr;          // double[4]
     // tensor-core path (tcgen05): split-bf16 companions of the tensors feeding 3x3 convs
     int use_tc = 1;
+    // inference with fixed weights: prepare (pad / collapse / pair / pack) once, skip the ~25 preparation launches
+    // of every later forward.  Cleared by any call that may have changed the parameters or the path.
+    int frozen_weights = 0; bool weights_prepared = false;
     SplitPtr vsplit[V_NCONV];            // input planes of VGG conv l (l >= 1)
     SplitPtr vgsplit[4];                 // planes of vgrad[i]
     SplitPtr vtsplit[V_NCONV];           // planes of a style-tapped activation when no later conv holds them
