@@ -222,11 +222,38 @@ def run_ours(args, rank, local_rank, world):
             dist.all_reduce(grads, op=dist.ReduceOp.SUM)       # loss is a batch SUM (losses.py:32-37)
         opt.step(grads)
 
+    # End-to-end step with the input copy of step i+1 overlapped with the compute of step i (the reference's queue
+    # runners do the same on the host side): two device buffers, a copy stream, and events both ways - the compute
+    # stream waits for "copy done", the copy stream waits for "last reader of this buffer done".
+    copy_stream = torch.cuda.Stream(device=dev)
+    xbuf = [x_dev, torch.empty_like(x_dev)]
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    state = {"i": 0, "primed": False}
+
+    def enqueue_copy(slot):
+        copy_stream.wait_event(consumed[slot])
+        with torch.cuda.stream(copy_stream):
+            xbuf[slot].copy_(x_host, non_blocking=True)
+            copied[slot].record(copy_stream)
+
     def step_e2e():
-        x_dev.copy_(x_host, non_blocking=True)
-        step_device()
+        main = torch.cuda.current_stream()
+        slot = state["i"] & 1
+        if not state["primed"]:
+            consumed[0].record(main); consumed[1].record(main)
+            enqueue_copy(slot)
+            state["primed"] = True
+        main.wait_event(copied[slot])
+        eng.train_fwd_bwd(params, packed, xbuf[slot], cfg, tgrams, grads=grads, losses=losses)
+        consumed[slot].record(main)
+        enqueue_copy(slot ^ 1)                      # next step's input goes up while this step computes
+        if world > 1:
+            dist.all_reduce(grads, op=dist.ReduceOp.SUM)
+        opt.step(grads)
         loss_host.copy_(losses, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        main.synchronize()
+        state["i"] += 1
 
     def barrier():
         if world > 1:

@@ -80,6 +80,8 @@ int fs_engine_create(int N, int H, int W, int flags, unsigned content_mask, unsi
     h->e.content_mask = content_mask; h->e.style_mask = style_mask;
     const char* env = getenv("FS_TENSOR_PATH");
     h->e.use_tc = (env && env[0] == '0') ? 0 : 1;
+    env = getenv("FS_IN_EPILOGUE");
+    h->e.in_epi = (env && env[0] == '0') ? 0 : 1;
     int r = h->e.plan();
     if (r != 0) { delete h; return r; }
     Arena a;
@@ -92,6 +94,7 @@ int fs_engine_create(int N, int H, int W, int flags, unsigned content_mask, unsi
 int fs_engine_set_tensor_path(fs_engine* e, int enabled) {
     FS_CHECK(e, "NULL engine");
     e->e.use_tc = enabled ? 1 : 0;
+    e->e.weights_prepared = false;
     return 0;
 }
 int fs_engine_profile(fs_engine* e, int enabled) {
@@ -135,9 +138,19 @@ int fs_engine_transform_activation(const fs_engine* e, int conv_index, int stage
     return 0;
 }
 
+int fs_engine_set_frozen_weights(fs_engine* e, int frozen) {
+    FS_CHECK(e, "NULL engine");
+    e->e.frozen_weights = frozen ? 1 : 0;
+    e->e.weights_prepared = false;
+    return 0;
+}
+
 int fs_transform_forward(fs_engine* e, const float* params, const float* x3, float* y3, void* stream) {
     FS_CHECK(e && params && x3 && y3, "fs_transform_forward: NULL argument");
-    FS_TRY(e->e.prep_transform_weights(params, false, S(stream)));
+    if (!(e->e.frozen_weights && e->e.weights_prepared)) {
+        FS_TRY(e->e.prep_transform_weights(params, false, S(stream)));
+        e->e.weights_prepared = true;
+    }
     return e->e.transform_forward(params, x3, y3, S(stream));
 }
 

@@ -60,7 +60,24 @@ struct TcParams {
     const float* bias; const float* addend; const float* ref;
     int relu, add_crop, addH, addW;
     float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+    double* stats; int stats_c;       // [N][stats_c][2] running (sum, sum of squares) of the raw output per real channel
 };
+
+// Sum of s[0..31] over the 32 lanes of a warp for 32 quantities at once: lane L returns the total of quantity L.
+// Butterfly transposition: 16+8+4+2+1 = 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_transpose_sum(float* s, int lane) {
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const bool up = (lane & step) != 0;
+#pragma unroll
+        for (int i = 0; i < step; ++i) {
+            const float send = up ? s[i] : s[i + step];
+            const float keep = up ? s[i + step] : s[i];
+            s[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+        }
+    }
+    return s[0];
+}
 
 template <int TH, int BN>
 struct Cfg {
@@ -77,7 +94,7 @@ struct Cfg {
 
 constexpr int TC_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 epilogue (2 per TMEM lane quadrant)
 
-template <int TH, int BN>
+template <int TH, int BN, bool STATS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -243,6 +260,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) +
                                            (uint32_t)(as * K::NACC * BN + acc * BN + ch * 32);
                     tmem_ld32(taddr, v);                // warp-collective: executed by all lanes
+                    if (STATS) {
+                        // InstanceNorm statistics of the raw conv output, fused here so that the activation is not
+                        // read again: per 32-pixel x 32-channel block a butterfly reduction leaves lane L with the
+                        // (fp32) sums of channel c0+L, accumulated in fp64 per (sample, real channel).  All lanes
+                        // take part; pixels outside the image contribute zeros.
+                        float tsum[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) tsum[i] = ok ? v[i] : 0.f;
+                        const float s1 = warp_transpose_sum(tsum, lane);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) tsum[i] = ok ? v[i] * v[i] : 0.f;
+                        const float s2 = warp_transpose_sum(tsum, lane);
+                        const int cch = (nt * BN + ch * 32 + lane) % p.stats_c;
+                        double* sp = p.stats + ((long long)n * p.stats_c + cch) * 2;
+                        atomicAdd(sp, (double)s1);
+                        atomicAdd(sp + 1, (double)s2);
+                    }
                     if (ok && p.out_d2s) {
                         const int cq = nt * (BN / 32) + ch;           // which 32-channel quarter of OC = 128
                         float* op;
@@ -487,8 +521,8 @@ int num_sms() {
     return n;
 }
 
-template <int TH, int BN>
-int launch_cfg(const Conv3x3TcArgs& a, cudaStream_t st) {
+template <int TH, int BN, bool STATS>
+int launch_cfg_s(const Conv3x3TcArgs& a, cudaStream_t st) {
     using K = Cfg<TH, BN>;
     CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
     if (a.in_s2d) {
@@ -512,15 +546,21 @@ int launch_cfg(const Conv3x3TcArgs& a, cudaStream_t st) {
     p.bias = a.bias; p.addend = a.addend; p.ref = a.ref; p.relu = a.relu;
     p.add_crop = a.add_crop; p.addH = a.addH; p.addW = a.addW;
     p.out_f32 = a.out_f32; p.out_hi = a.out_split.hi; p.out_lo = a.out_split.lo;
+    p.stats = a.stats; p.stats_c = a.stats_c;
     static bool attr_set = false;
     if (!attr_set) {
-        FS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<TH, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+        FS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<TH, BN, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
         attr_set = true;
     }
     int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
-    launch_k((conv3x3_tc_kernel<TH, BN>), dim3(grid), dim3(TC_THREADS), K::SMEM_BYTES, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    launch_k((conv3x3_tc_kernel<TH, BN, STATS>), dim3(grid), dim3(TC_THREADS), K::SMEM_BYTES, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     FS_LAUNCH_CHECK();
     return 0;
+}
+
+template <int TH, int BN>
+int launch_cfg(const Conv3x3TcArgs& a, cudaStream_t st) {
+    return a.stats ? launch_cfg_s<TH, BN, true>(a, st) : launch_cfg_s<TH, BN, false>(a, st);
 }
 
 }  // namespace
@@ -536,6 +576,9 @@ int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st) {
     FS_CHECK((a.out_split.hi == nullptr) == (a.out_split.lo == nullptr), "conv3x3_tc: split output needs both planes");
     FS_CHECK(a.OH > 0 && a.OW > 0 && a.N > 0, "conv3x3_tc: empty output");
     FS_CHECK(a.taps == 0 || a.taps == 2 || a.taps == 3, "conv3x3_tc: taps must be 2 or 3");
+    FS_CHECK(!a.stats || (a.stats_c >= 16 && a.stats_c <= 64 && (a.stats_c & (a.stats_c - 1)) == 0 && !a.bias && !a.relu &&
+                          !a.addend && !a.ref),
+             "conv3x3_tc: fused statistics are for raw transform-net conv outputs (16/32/64 real channels)");
     FS_CHECK(!a.in_s2d || (a.C == 128 && !a.one_by_one), "conv3x3_tc: the space-to-depth input view needs C == 128");
     FS_CHECK(!a.out_d2s || (a.OC == 128 && a.out_f32 && !a.out_split.hi && !a.bias && !a.addend && !a.ref && !a.relu),
              "conv3x3_tc: the depth-to-space store needs OC == 128 and a plain fp32 output");

@@ -27,7 +27,8 @@ constexpr int WG9 = 108;
 // 46 % of the FMA pipe, profiles/r01t).  The two row groups take rows 0-7 / 8-15 of the tile.
 template <int CI, int CO>
 __global__ void __launch_bounds__(NT9) wgrad9x9_kernel(const float* __restrict__ in, const float* __restrict__ dy,
-                                                       float* __restrict__ partial, int H, int W) {
+                                                       float* __restrict__ partial, int H, int W, int tilesX,
+                                                       int tilesY, int total_tiles) {
     FS_PDL_ENTER();
     static_assert(CI * CO == 64 && CI % 4 == 0 && CO % 4 == 0, "channel block must be 4x16 or 16x4");
     constexpr int CIQ = CI / 4, COQ = CO / 4;
@@ -36,22 +37,8 @@ __global__ void __launch_bounds__(NT9) wgrad9x9_kernel(const float* __restrict__
     float4* in_s = sm4;                         // [HSY][HS][CIQ]
     float4* dy_s = sm4 + HSY * HS * CIQ;        // [TSY][TS][COQ]
     const int t = threadIdx.x;
-    const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TSY, n = blockIdx.z;
-    const float4* in4 = reinterpret_cast<const float4*>(in + (long long)n * H * W * CI);
-    const float4* dy4 = reinterpret_cast<const float4*>(dy + (long long)n * H * W * CO);
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = t; i < HSY * HS * CIQ; i += NT9) {
-        int pix = i / CIQ, c4 = i - pix * CIQ;
-        int yy = y0 - 4 + pix / HS, xx = x0 - 4 + pix % HS;
-        in_s[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(in4 + ((long long)yy * W + xx) * CIQ + c4) : z;
-    }
-    for (int i = t; i < TSY * TS * COQ; i += NT9) {
-        int pix = i / COQ, c4 = i - pix * COQ;
-        int yy = y0 + pix / TS, xx = x0 + pix % TS;
-        dy_s[i] = (yy < H && xx < W) ? __ldg(dy4 + ((long long)yy * W + xx) * COQ + c4) : z;
-    }
-    __syncthreads();
-    if (t >= 2 * WG9) return;
+    const bool worker = t < 2 * WG9;
     const int rg = t / WG9, r = t - rg * WG9;           // row group, worker
     const int q = r & 3, tg = r >> 2;                    // channel block, tap triple 0..26
     const int kh = tg / 3, kw0 = (tg - kh * 3) * 3;
@@ -63,27 +50,50 @@ __global__ void __launch_bounds__(NT9) wgrad9x9_kernel(const float* __restrict__
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[k][i][j] = 0.f;
-    for (int py = rg * (TSY / 2); py < (rg + 1) * (TSY / 2); ++py) {
-        const float4* ip = in_s + ((py + kh) * HS + kw0) * CIQ + ciq;
-        const float4* dp = dy_s + (py * TS) * COQ + coq;
-        float4 a0 = ip[0], a1 = ip[CIQ];
+    // persistent over tiles: the accumulators stay in registers, so a CTA writes ONE partial per row group
+    // (148*3 CTAs x 2 x 20 KB = 18 MB instead of one per tile = 77 MB at batch 8, 336^2)
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tx = tile % tilesX;
+        const int rr = tile / tilesX;
+        const int ty = rr % tilesY, n = rr / tilesY;
+        const int x0 = tx * TS, y0 = ty * TSY;
+        const float4* in4 = reinterpret_cast<const float4*>(in + (long long)n * H * W * CI);
+        const float4* dy4 = reinterpret_cast<const float4*>(dy + (long long)n * H * W * CO);
+        __syncthreads();                                 // the previous tile's readers are done
+        for (int i = t; i < HSY * HS * CIQ; i += NT9) {
+            int pix = i / CIQ, c4 = i - pix * CIQ;
+            int yy = y0 - 4 + pix / HS, xx = x0 - 4 + pix % HS;
+            in_s[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(in4 + ((long long)yy * W + xx) * CIQ + c4) : z;
+        }
+        for (int i = t; i < TSY * TS * COQ; i += NT9) {
+            int pix = i / COQ, c4 = i - pix * COQ;
+            int yy = y0 + pix / TS, xx = x0 + pix % TS;
+            dy_s[i] = (yy < H && xx < W) ? __ldg(dy4 + ((long long)yy * W + xx) * COQ + c4) : z;
+        }
+        __syncthreads();
+        if (!worker) continue;
+        for (int py = rg * (TSY / 2); py < (rg + 1) * (TSY / 2); ++py) {
+            const float4* ip = in_s + ((py + kh) * HS + kw0) * CIQ + ciq;
+            const float4* dp = dy_s + (py * TS) * COQ + coq;
+            float4 a0 = ip[0], a1 = ip[CIQ];
 #pragma unroll 8
-        for (int px = 0; px < TS; ++px) {
-            const float4 a2 = ip[(px + 2) * CIQ];
-            const float4 b = dp[px * COQ];
-            const float av[3][4] = {{a0.x, a0.y, a0.z, a0.w}, {a1.x, a1.y, a1.z, a1.w}, {a2.x, a2.y, a2.z, a2.w}};
-            const float bv[4] = {b.x, b.y, b.z, b.w};
+            for (int px = 0; px < TS; ++px) {
+                const float4 a2 = ip[(px + 2) * CIQ];
+                const float4 b = dp[px * COQ];
+                const float av[3][4] = {{a0.x, a0.y, a0.z, a0.w}, {a1.x, a1.y, a1.z, a1.w}, {a2.x, a2.y, a2.z, a2.w}};
+                const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
+                for (int k = 0; k < 3; ++k)
 #pragma unroll
-                for (int i = 0; i < IR; ++i)
+                    for (int i = 0; i < IR; ++i)
 #pragma unroll
-                    for (int j = 0; j < JR; ++j) acc[k][i][j] = fmaf(av[k][i], bv[j], acc[k][i][j]);
-            a0 = a1; a1 = a2;
+                        for (int j = 0; j < JR; ++j) acc[k][i][j] = fmaf(av[k][i], bv[j], acc[k][i][j]);
+                a0 = a1; a1 = a2;
+            }
         }
     }
-    const long long blk = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    float* outp = partial + (blk * 2 + rg) * (81 * 64);
+    if (!worker) return;
+    float* outp = partial + ((long long)blockIdx.x * 2 + rg) * (81 * 64);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int tap = kh * 9 + kw0 + k;
@@ -448,8 +458,12 @@ int flip_transpose_taps(const float* W, float* Wf, int T, int Ci, int Co, cudaSt
     return 0;
 }
 
+constexpr int WG9_MAX_CTAS = 148 * 3;
+
 long long wgrad9x9_partial_floats(int N, int H, int W) {
-    return 2LL * N * cdiv(H, TSY) * cdiv(W, TS) * 81 * 64;      // two row groups per tile
+    long long tiles = (long long)N * cdiv(H, TSY) * cdiv(W, TS);
+    if (tiles > WG9_MAX_CTAS) tiles = WG9_MAX_CTAS;
+    return 2LL * tiles * 81 * 64;      // two row groups per CTA
 }
 
 // in [N,H,W,CI], dy [N,H,W,CO] (9x9 stride-1 SAME conv: equal spatial dims); out [81,CI,CO]
@@ -458,18 +472,19 @@ int launch_wgrad9x9(const float* in, const float* dy, float* out, float* partial
     FS_CHECK((CI == 16 && CO == 4) || (CI == 4 && CO == 16), "wgrad9x9: unsupported channel block %dx%d", CI, CO);
     long long need = wgrad9x9_partial_floats(N, H, W);
     FS_CHECK(need <= partial_cap, "wgrad9x9: partial workspace too small (%lld > %lld floats)", need, partial_cap);
-    dim3 grid(cdiv(W, TS), cdiv(H, TSY), N);
-    const int nblocks = grid.x * grid.y * grid.z;
+    const int tilesX = cdiv(W, TS), tilesY = cdiv(H, TSY);
+    const int total = N * tilesX * tilesY;
+    const int nblocks = total < WG9_MAX_CTAS ? total : WG9_MAX_CTAS;
     if (CI == 16) {
         size_t smem = (size_t)(HSY * HS * 4 + TSY * TS * 1) * sizeof(float4);
         static bool set16 = false;
         if (!set16) { FS_CUDA(cudaFuncSetAttribute(wgrad9x9_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set16 = true; }
-        launch_k((wgrad9x9_kernel<16, 4>), dim3(grid), dim3(NT9), smem, st, in, dy, partial, H, W);
+        launch_k((wgrad9x9_kernel<16, 4>), dim3(nblocks), dim3(NT9), smem, st, in, dy, partial, H, W, tilesX, tilesY, total);
     } else {
         size_t smem = (size_t)(HSY * HS * 1 + TSY * TS * 4) * sizeof(float4);
         static bool set4 = false;
         if (!set4) { FS_CUDA(cudaFuncSetAttribute(wgrad9x9_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set4 = true; }
-        launch_k((wgrad9x9_kernel<4, 16>), dim3(grid), dim3(NT9), smem, st, in, dy, partial, H, W);
+        launch_k((wgrad9x9_kernel<4, 16>), dim3(nblocks), dim3(NT9), smem, st, in, dy, partial, H, W, tilesX, tilesY, total);
     }
     FS_LAUNCH_CHECK();
     launch_k(reduce_partials_kernel, dim3(cdiv(81 * 64, 32)), dim3(256), 0, st, partial, out, 81 * 64, 2 * nblocks);

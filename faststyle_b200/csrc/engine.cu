@@ -263,6 +263,7 @@ void Engine::layout(Arena& a) {
         wpair = a.take<float>(4LL * 128 * 64);
         y3 = a.take<float>((long long)N * OH * OW * 3);
         in_partial = a.take<double>((long long)N * 64 * 64 * 2);
+        in_sums = a.take<double>((long long)N * 64 * 2);
         in15 = a.take<float>(8);
         wtmp15 = a.take<float>(81 * 64);
         if (tbw) {
@@ -323,6 +324,7 @@ int Engine::bind(void* ws, size_t bytes) {
     FS_CHECK(((uintptr_t)ws & 255) == 0, "engine: workspace must be 256-byte aligned");
     Arena a; a.base = (char*)ws; a.cap = bytes;
     layout(a);
+    if (in_sums) { FS_CUDA(cudaMemset(in_sums, 0, (size_t)N * 64 * 2 * sizeof(double))); FS_CUDA(cudaDeviceSynchronize()); }
     bound = true;
     return 0;
 }
@@ -465,10 +467,12 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
             ta.x = tsplit[l]; ta.w = tw_f[l];
             ta.N = N; ta.H = c.inH; ta.W = c.inW; ta.C = 64; ta.OH = c.outH; ta.OW = c.outW; ta.OC = 64; ta.pad = 0;
             ta.out_f32 = tb[l].raw;
+            if (in_epi) { ta.stats = in_sums; ta.stats_c = 64; }
             PROF(PC_TC_RES_FWD, tc_flops(ta), launch_conv3x3_tc(ta, st));
         } else if (tc2(l)) {
             Conv3x3TcArgs ta;
             FS_TRY(tc2_args(l, false, -1, tb[l].raw, ta));
+            if (in_epi) { ta.stats = in_sums; ta.stats_c = c.cout; }
             PROF(PC_TC_S2_FWD, tc2_flops(ta), launch_conv3x3_tc(ta, st));
         } else if (direct9(c)) {
             IGemmArgs a;
@@ -480,7 +484,10 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
             if (c.upconv && (flags & ENG_DECONV)) a.gather = 1;      // transposed conv: iy = oy - a
             PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
         }
-        PROF(PC_IN_STATS, 0.0, instnorm_stats(tb[l].raw, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, in_partial, st));
+        if (in_epi && (tcl || tc2(l)))
+            PROF(PC_IN_STATS, 0.0, instnorm_stats_from_sums(in_sums, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, st));
+        else
+            PROF(PC_IN_STATS, 0.0, instnorm_stats(tb[l].raw, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, in_partial, st));
         const float* skip = nullptr;
         if (l >= 4 && l <= 12 && (l & 1) == 0) skip = tb[l - 2].act;       // residual: block input
         const bool last = l == T_NCONV - 1;
@@ -921,6 +928,7 @@ int Engine::train_fwd_bwd(const float* params, const float* packed, const float*
              "image matches the content targets (got %dx%d -> %dx%d)", H, W, OH, OW);
     float* Y = y3_out ? y3_out : y3;
     FS_TRY(prep_transform_weights(params, true, st));
+    weights_prepared = false;                      // the caller's optimiser step changes the parameters
     FS_TRY(fill_zero(loss_acc, 4 * sizeof(double), st));
     FS_TRY(vgg_content_targets(packed, x3, lc, st));                  // train.py:250-251
     FS_TRY(transform_forward(params, x3, Y, st));                     // train.py:161

@@ -76,6 +76,8 @@ struct Engine {
     float* wefft[T_NCONV];               // transposed weights for the data gradient
     float* y3 = nullptr;                 // [N,OH,OW,3] when the caller does not supply an output
     double* in_partial = nullptr;
+    double* in_sums = nullptr;           // [N][64][2] (sum, sum sq) accumulated by the tensor-path conv epilogues; zero between uses
+    int in_epi = 1;                      // FS_IN_EPILOGUE=0: separate statistics pass for every layer
     float* in15 = nullptr;               // 4-channel staging of the last layer's IN scale/shift
     float* gb_tmp = nullptr;
     float* wtmp15 = nullptr;             // staging for the deconv variant of the last layer's weights
@@ -94,6 +96,9 @@ struct Engine {
     double* loss_acc = nullptr;          // double[4]
     // tensor-core path (tcgen05): split-bf16 companions of the tensors feeding 3x3 convs
     int use_tc = 1;
+    // inference with fixed weights: prepare (pad / collapse / pair / pack) once, skip the ~25 preparation launches
+    // of every later forward.  Cleared by any call that may have changed the parameters or the path.
+    int frozen_weights = 0; bool weights_prepared = false;
     SplitPtr vsplit[V_NCONV];            // input planes of VGG conv l (l >= 1)
     SplitPtr vgsplit[4];                 // planes of vgrad[i]
     SplitPtr vtsplit[V_NCONV];           // planes of a style-tapped activation when no later conv holds them

@@ -291,6 +291,21 @@ in_stats_finalize_kernel(const double* __restrict__ partial, float* __restrict__
     }
 }
 
+// mean / rstd from the (sum, sum of squares) a conv epilogue accumulated; zeroes the sums for the next launch
+__global__ void in_stats_from_sums_kernel(double* __restrict__ sums, float* __restrict__ mean, float* __restrict__ rstd,
+                                          int NC, int HW, float eps) {
+    FS_PDL_ENTER();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NC) return;
+    const double s1 = sums[2 * i], s2 = sums[2 * i + 1];
+    sums[2 * i] = 0.0; sums[2 * i + 1] = 0.0;
+    const double m = s1 / HW;
+    double var = s2 / HW - m * m;
+    if (var < 0) var = 0;
+    mean[i] = (float)m;
+    rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
 __global__ void in_bwd_finalize_kernel(const double* __restrict__ partial, float* __restrict__ m12,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int N,
                                        int C, int chunks, int HW) {
@@ -867,6 +882,12 @@ int instnorm_stats(const float* x, float* mean, float* rstd, int N, int HW, int 
         x, nullptr, nullptr, nullptr, nullptr, nullptr, partial, HW, C, chunks, 0);
     FS_LAUNCH_CHECK();
     launch_k(in_stats_finalize_kernel, dim3(cdiv((long long)N * C, 8)), dim3(256), 0, st, partial, mean, rstd, N, C, chunks, HW, eps);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int instnorm_stats_from_sums(double* sums, float* mean, float* rstd, int N, int HW, int C, float eps, cudaStream_t st) {
+    launch_k(in_stats_from_sums_kernel, dim3(cdiv((long long)N * C, 128)), dim3(128), 0, st, sums, mean, rstd, N * C, HW, eps);
     FS_LAUNCH_CHECK();
     return 0;
 }

@@ -41,6 +41,9 @@ struct Conv3x3TcArgs {
     const float* bias; const float* addend; const float* ref;
     int relu;
     int add_crop, addH, addW;  // addend is [N,addH,addW,OC]; output pixel (y,x) reads (y-crop, x-crop)
+    double* stats; int stats_c;    // optional: accumulate per-(sample, real channel) sum / sum of squares of the raw
+                               // output into stats[N][stats_c][2] (real channel = output channel % stats_c: the
+                               // depth-to-space / paired forms carry several pixels' channels side by side)
     float* out_f32;            // [N,OH,OW,OC] fp32 (may be null)
     SplitPtr out_split;        // split planes of the same tensor (may be null)
 };

@@ -107,6 +107,10 @@ class Engine:
         False: exact-fp32 FFMA path everywhere."""
         _lib.call("fs_engine_set_tensor_path", self._h, 1 if enabled else 0)
 
+    def set_frozen_weights(self, frozen: bool):
+        """Inference with fixed parameters: prepare the transform weights once (see fs_engine_set_frozen_weights)."""
+        _lib.call("fs_engine_set_frozen_weights", self._h, 1 if frozen else 0)
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h is not None and h.value:

@@ -34,6 +34,7 @@ class FrameStylizer:
         self.swap_rb = bool(swap_rb)
         self.engine = Engine(1, self.H, self.W, transform=True, device=self.device,
                              deconv=upsample_method == "deconv")
+        self.engine.set_frozen_weights(True)       # one model per stylizer: the captured graph holds no weight prep
         self.OH, self.OW = self.engine.OH, self.engine.OW
         self.params = params_to_device(params, self.device, upsample_method)
         self.in_host = torch.empty((self.H, self.W, 3), dtype=torch.uint8).pin_memory()

@@ -66,6 +66,10 @@ int fs_engine_bind(fs_engine* e, void* workspace, size_t bytes);
  * (split-bf16 x3); 0: every convolution on the exact-fp32 FFMA path.  Also settable
  * through the environment variable FS_TENSOR_PATH=0 read at fs_engine_create. */
 int fs_engine_set_tensor_path(fs_engine* e, int enabled);
+/* frozen = 1: the transform parameters passed to fs_transform_forward do not change between calls (inference):
+ * their per-call preparation (padding, collapsing, pairing, bf16 packing: ~25 short launches) runs once and is
+ * skipped afterwards.  Call again (any value) after changing the parameter buffer. */
+int fs_engine_set_frozen_weights(fs_engine* e, int frozen);
 /* Live per-kernel timing: while enabled, the GEMM-class launches of every composite are
  * bracketed by CUDA events on the launching stream.  fs_engine_profile_read synchronises, sums
  * elapsed ms / algorithmic FLOPs / launch counts per category and resets.  Categories:
