@@ -112,24 +112,24 @@ __global__ void f32_to_u8_kernel(const float* __restrict__ in, unsigned char* __
 
 // ------------------------------------------------------------------ input pipeline: TF-1.0 bicubic resize
 // tf.image.resize_images(method=2) of TF 1.0 (reference datapipe.py:25): align_corners = False, no half-pixel
-// centres (pos = out * in/out), A = -0.75, coefficients from a 1024-entry table indexed by rint(delta * 1024),
-// border taps clamped.  Arithmetic order and roundings are those of the host restatement
-// (faststyle_b200/datapipe.py::resize_bicubic_tf1: 4 rows combined first, then the 4 columns), every operation
-// individually rounded (no FMA contraction), so the two agree bit for bit.
+// centres (pos = out * in/out), A = -0.75, coefficients from a 1024-entry table indexed by lrintf(delta * 1024)
+// (table entries evaluated in double and stored as float), border taps clamped.  Arithmetic order and roundings
+// follow TF's kernel: per 4x4 patch four horizontal interpolations, then one vertical; every operation
+// individually rounded (no FMA contraction).
 __device__ __forceinline__ void bicubic_taps(int o, float scale, int in_size, int* idx, float* w) {
     const float pos = __fmul_rn(scale, (float)o);
     const float fl = floorf(pos);
     const int loc = (int)fl;
     const float delta = __fsub_rn(pos, fl);
     const int off = (int)rintf(__fmul_rn(delta, 1024.f));
-    const float A = -0.75f;
+    const double A = -0.75;
     auto t0 = [&](int k) {          // table[2k]:   ((A+2)x - (A+3)) x x + 1
-        const float x = (float)k / 1024.f;
-        return __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(A + 2.f, x), A + 3.f), x), x), 1.f);
+        const double x = (double)((float)k / 1024.f);
+        return (float)(((A + 2.0) * x - (A + 3.0)) * x * x + 1.0);
     };
     auto t1 = [&](int k) {          // table[2k+1]: ((A x1 - 5A) x1 + 8A) x1 - 4A,  x1 = x + 1
-        const float x1 = __fadd_rn((float)k / 1024.f, 1.f);
-        return __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, x1), 5.f * A), x1), 8.f * A), x1), 4.f * A);
+        const double x1 = (double)((float)k / 1024.f) + 1.0;
+        return (float)(((A * x1 - 5.0 * A) * x1 + 8.0 * A) * x1 - 4.0 * A);
     };
     w[0] = t1(off); w[1] = t0(off); w[2] = t0(1024 - off); w[3] = t1(1024 - off);
 #pragma unroll
@@ -149,16 +149,16 @@ __global__ void resize_bicubic_tf1_kernel(const unsigned char* __restrict__ in, 
     for (int c = 0; c < 3; ++c) {
         float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float r = 0.f;           // rows[oy, ix[j], c] = sum_k img[iy[k], ix[j], c] * wy[k], k in order
+        for (int i = 0; i < 4; ++i) {
+            float r = 0.f;           // coeff[i] = sum_k img[iy[i], ix[k], c] * wx[k], k in order
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float v = (float)in[((long long)iy[k] * W + ix[j]) * 3 + c];
-                const float pr = __fmul_rn(v, wy[k]);
+                const float v = (float)in[((long long)iy[i] * W + ix[k]) * 3 + c];
+                const float pr = __fmul_rn(v, wx[k]);
                 r = k == 0 ? pr : __fadd_rn(r, pr);
             }
-            const float pr = __fmul_rn(r, wx[j]);
-            acc = j == 0 ? pr : __fadd_rn(acc, pr);
+            const float pr = __fmul_rn(r, wy[i]);
+            acc = i == 0 ? pr : __fadd_rn(acc, pr);
         }
         out[((long long)oy * OW + ox) * 3 + c] = acc;
     }

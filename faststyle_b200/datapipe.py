@@ -31,7 +31,8 @@ _A = -0.75
 
 
 def _coeff_table():
-    x = np.arange(_TABLE + 1, dtype=np.float32) / _TABLE
+    # TF evaluates the Keys polynomial in double at the float abscissa and stores floats
+    x = (np.arange(_TABLE + 1, dtype=np.float32) / _TABLE).astype(np.float64)
     t = np.empty((_TABLE + 1) * 2, np.float32)
     t[0::2] = ((_A + 2) * x - (_A + 3)) * x * x + 1
     x1 = x + 1
@@ -60,9 +61,18 @@ def resize_bicubic_tf1(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
     img = np.asarray(img, np.float32)
     wy, iy = _weights_indices(img.shape[0], out_h)
     wx, ix = _weights_indices(img.shape[1], out_w)
-    rows = (img[iy] * wy[:, :, None, None]).sum(1)                  # [out_h, W, C]
-    out = (rows[:, ix] * wx[None, :, :, None]).sum(2)               # [out_h, out_w, C]
-    return out.astype(np.float32)
+    # TF's order: per output pixel four horizontal interpolations (one per patch row), then one vertical;
+    # products summed left to right in float32
+    acc = None
+    for i in range(4):
+        rows = img[iy[:, i]]                                         # [out_h, W, C]
+        r = None
+        for k in range(4):
+            pr = rows[:, ix[:, k]] * wx[None, :, k, None]
+            r = pr if r is None else r + pr
+        pr = r * wy[:, i, None, None]
+        acc = pr if acc is None else acc + pr
+    return acc.astype(np.float32)
 
 
 # ------------------------------------------------------------------ TFRecord / tf.Example

@@ -23,5 +23,11 @@ Pinning status
 * VGG16 / Gram / losses / gradients / TF-Adam: **parity unpinned** — the
   reference holds no test, fixture or golden for them and its VGG weights file
   is absent (``.gitignore:2``).  They are restated from the source and checked
-  only for self-consistency (fp32 vs fp64, finite differences).
+  only for self-consistency: fp32 vs fp64, hand-computed loss / Adam values and central
+  finite differences of the loss path (tests/test_oracle_selfcheck.py).
+* TF-1.0 bicubic resize of the input pipeline (``oracle/bicubic.py``): **parity unpinned**
+  (restated from the published TF kernel; hand-computed known answers only).
+* ``tools/dump_tf1_goldens.py`` is the pinning kit: run under TensorFlow 1.x next to the
+  reference checkout it writes ``tests/golden/tf1/*.npz`` that ``tests/test_tf1_goldens.py``
+  consumes (skipped while the files are absent).
 """

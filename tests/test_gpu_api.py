@@ -244,21 +244,24 @@ def test_frame_stylizer_and_webcam_cli(built_lib, golden_dir, tmp_path):
 
 @pytest.mark.parametrize("shape", [((480, 640), (256, 256)), ((97, 131), (256, 256)), ((256, 256), (256, 256)),
                                    ((333, 500), (128, 192)), ((5, 7), (16, 9))])
-def test_gpu_bicubic_resize_matches_host_restatement(built_lib, shape):
-    """datapipe.preprocessing (datapipe.py:14-26) on the device.  The kernel follows the host
-    restatement of TF-1.0's legacy bicubic operation by operation (same table quantisation, same summation order,
-    no FMA contraction), so the two agree to the last bit; tolerance stated: max-abs 1e-4 on the 0..255 scale.
-    Unpinned like the host restatement itself (TensorFlow is not available to generate goldens)."""
+def test_gpu_bicubic_resize_matches_oracle(built_lib, shape):
+    """datapipe.preprocessing (datapipe.py:14-26) on the device, against the independent restatement
+    of TF-1.0's ResizeBicubic in oracle/bicubic.py (and the product's own host restatement).  The kernel follows
+    TF's arithmetic order (four horizontal interpolations, then one vertical; table entries evaluated in double;
+    no FMA contraction).  Tolerance stated: max-abs 1e-4 on the 0..255 scale (bit-exact in practice).
+    Unpinned against TensorFlow itself (tools/dump_tf1_goldens.py writes the golden for a TF-1.x owner)."""
     from faststyle_b200 import datapipe
     from faststyle_b200.ops import resize_bicubic_tf1
+    from oracle.bicubic import resize_bicubic_tf1 as oracle_bicubic
     (h, w), (oh, ow) = shape
     rng = np.random.RandomState(h * 7 + w)
     img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
-    want = datapipe.resize_bicubic_tf1(img, oh, ow)
+    want = oracle_bicubic(img, oh, ow)
     got = resize_bicubic_tf1(img, oh, ow).cpu().numpy()
     d = np.abs(got - want)
-    print("bicubic", shape, "max abs diff", d.max(), "exact", bool((got == want).all()))
+    print("bicubic", shape, "max abs diff vs oracle", d.max(), "exact", bool((got == want).all()))
     assert got.shape == (oh, ow, 3) and d.max() <= 1e-4
+    assert np.abs(got - datapipe.resize_bicubic_tf1(img, oh, ow)).max() <= 1e-4
 
 
 def test_gpu_preprocessor_batch(built_lib):
