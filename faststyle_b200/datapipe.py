@@ -142,14 +142,23 @@ def example_bytes_feature(record: bytes, key: str):
 
 
 # ------------------------------------------------------------------ batcher
-def _image_stream(train_dir, num_epochs, rng):
+def _image_stream(train_dir, num_epochs, order_rng, img_rng, shard=(0, 1)):
+    """Decoded RGB uint8 images of this rank's shard.  The stream position i counts EVERY record of the
+    multi-epoch stream (decodable or not) and only records with i % world == rank are decoded - the other ranks'
+    records cost one framing read (TFRecord) or nothing (image files), not a JPEG decode.  ``order_rng`` drives
+    only the per-epoch shard / file order and must be seeded identically on every rank (the shards of the ranks
+    are disjoint only if all ranks walk the same order); ``img_rng`` is rank-private (synthetic images)."""
     import cv2
+    rank, world = shard
+    i = 0
     if train_dir.startswith("synthetic"):
         count = int(train_dir.split(":")[1]) if ":" in train_dir else 1 << 30
-        per_epoch = count
         for _ in range(num_epochs if num_epochs else 1 << 30):
-            for _ in range(per_epoch):
-                yield rng.randint(0, 256, (256, 256, 3)).astype(np.uint8)
+            for _ in range(count):
+                mine = i % world == rank
+                i += 1
+                if mine:
+                    yield img_rng.randint(0, 256, (256, 256, 3)).astype(np.uint8)
         return
     shards = sorted(glob.glob(os.path.join(train_dir, "train-*")))
     files = [p for p in sorted(glob.glob(os.path.join(train_dir, "*")))
@@ -158,9 +167,13 @@ def _image_stream(train_dir, num_epochs, rng):
         raise IOError("no TFRecord shards (train-*) or image files found in %r" % train_dir)
     for _ in range(num_epochs if num_epochs else 1 << 30):
         if shards:
-            order = list(shards); rng.shuffle(order)               # string_input_producer(shuffle=True)
+            order = list(shards); order_rng.shuffle(order)         # string_input_producer(shuffle=True)
             for s in order:
                 for rec in iter_tfrecord(s):
+                    mine = i % world == rank
+                    i += 1
+                    if not mine:
+                        continue
                     enc = example_bytes_feature(rec, "image/encoded")
                     if enc is None:
                         continue
@@ -168,11 +181,38 @@ def _image_stream(train_dir, num_epochs, rng):
                     if img is not None:
                         yield cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
         else:
-            order = list(files); rng.shuffle(order)
+            order = list(files); order_rng.shuffle(order)
             for p in order:
+                mine = i % world == rank
+                i += 1
+                if not mine:
+                    continue
                 img = cv2.imread(p)
                 if img is not None:
                     yield cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+
+
+def next_batch_collective(batches, group=None):
+    """``next(batches)`` with a COLLECTIVE end of data: every rank of ``group`` (a torch.distributed group that
+    accepts CPU tensors, e.g. gloo) votes has-batch with an all-reduce(MIN); if any rank's pipeline is exhausted,
+    ALL ranks raise OutOfRangeError at this same step, so no rank is left waiting in the next gradient all-reduce
+    (ranks can hold different batch counts: shards differ by one image and undecodable files drop per rank).
+    ``group=None``: plain single-process behaviour."""
+    have = True
+    batch = None
+    try:
+        batch = next(batches)
+    except (OutOfRangeError, StopIteration):
+        have = False
+    if group is not None:
+        import torch
+        import torch.distributed as dist
+        vote = torch.tensor([1 if have else 0], dtype=torch.int32)
+        dist.all_reduce(vote, op=dist.ReduceOp.MIN, group=group)
+        have = bool(int(vote.item()))
+    if not have:
+        raise OutOfRangeError("input pipeline exhausted" + ("" if group is None else " on at least one rank"))
+    return batch
 
 
 class Prefetcher:
@@ -274,10 +314,14 @@ class GpuPreprocessor:
 def batcher(train_dir, batch_size, resize_shape=None, num_epochs=None, min_after_dequeue=4000, seed=0,
             shard=(0, 1), raw=False):
     """Iterator of float32 NHWC batches.  ``shard=(rank, world)`` keeps every world-th image for
-    data-parallel training.  Raises OutOfRangeError when the epochs are exhausted.
+    data-parallel training (sharded BEFORE decoding).  Raises OutOfRangeError when the epochs are exhausted;
+    ranks may reach that point one batch apart - pair with ``next_batch_collective``.
     ``raw=True`` yields lists of decoded uint8 images instead (un-resized), for GpuPreprocessor."""
-    rng = np.random.RandomState(seed)
-    stream = _image_stream(train_dir, num_epochs, rng)
+    # one RNG, seeded identically on every rank, ONLY for the epoch order; a rank-private one for everything whose
+    # consumption depends on the rank's own stream position (shuffle-buffer sampling, synthetic images)
+    order_rng = np.random.RandomState(seed)
+    rng = np.random.RandomState((seed * 9973 + 7919 * (shard[0] + 1)) % (1 << 31))
+    stream = _image_stream(train_dir, num_epochs, order_rng, rng, shard)
     buf = []
 
     def prep(img):
@@ -299,9 +343,7 @@ def batcher(train_dir, batch_size, resize_shape=None, num_epochs=None, min_after
                 except StopIteration:
                     exhausted = True
                     break
-                if i % shard[1] == shard[0]:
-                    buf.append(prep(img))
-                i += 1
+                buf.append(prep(img))
             if len(buf) < batch_size:
                 raise OutOfRangeError("input pipeline exhausted")
             out = []

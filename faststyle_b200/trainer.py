@@ -41,34 +41,101 @@ class Trainer:
                              content_layers=content_layers, style_layers=style_layers, device=self.device,
                              deconv=upsample_method == "deconv")
         self.opt = TFAdam(self.params, learn_rate)
-        self.grads = torch.empty(TRANSFORM_NPARAMS, dtype=torch.float32, device=self.device)
-        self.losses = torch.empty(4, dtype=torch.float32, device=self.device)
-        self.x_dev = torch.empty((self.batch_size, H, W, 3), dtype=torch.float32, device=self.device)
-        self.loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
+        # ONE flat exchange buffer per step: [424102 gradients | pad | content, style, tv, total].  A single
+        # all-reduce(SUM) carries the gradients and the loss scalars for logging.
+        off = (TRANSFORM_NPARAMS + 7) // 8 * 8
+        self._flat = torch.zeros(off + 8, dtype=torch.float32, device=self.device)
+        self.grads = self._flat[:TRANSFORM_NPARAMS]
+        self.losses = self._flat[off:off + 4]
+        # input double buffering: the host->device copy of batch i+1 runs on a copy stream while step i computes
+        self.x_dev = [torch.empty((self.batch_size, H, W, 3), dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.x_host = [torch.empty((self.batch_size, H, W, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._copied = [torch.cuda.Event(), torch.cuda.Event()]       # copy stream: batch landed in x_dev[slot]
+        self._consumed = [torch.cuda.Event(), torch.cuda.Event()]     # compute stream: last reader of x_dev[slot] done
+        self._slot = 0
+        self._current = self.x_dev[0]
+        self.loss_host = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self._loss_slot = 0
+        self._loss_pending = None
         self.global_step = 0
+        self.h2d_bytes_per_step = self.x_dev[0].numel() * 4
+        self.d2h_bytes_per_step = 16
 
-    def step(self, batch=None, fetch_losses=True):
-        """One optimisation step on this rank's shard ``batch`` (host NHWC float32 array / pinned
-        tensor; None re-uses the batch already on the device).  Returns [content, style, tv, total]
-        summed over ALL ranks when ``fetch_losses`` (one small device->host copy), else None."""
-        if batch is not None:
+    # ------------------------------------------------------------------ input staging
+    def _stage(self, batch):
+        """Bring ``batch`` to the device through the double buffer; returns the device tensor the step reads."""
+        if isinstance(batch, torch.Tensor) and batch.is_cuda:
+            return batch                                   # GpuPreprocessor output: already resident
+        main = torch.cuda.current_stream(self.device)
+        slot = self._slot
+        self._slot ^= 1
+        if isinstance(batch, np.ndarray) or not batch.is_pinned():
             if isinstance(batch, np.ndarray):
                 batch = torch.from_numpy(np.ascontiguousarray(batch, dtype=np.float32))
-            self.x_dev.copy_(batch, non_blocking=True)
-        self.engine.train_fwd_bwd(self.params, self.packed, self.x_dev, self.cfg, self.target_grams,
-                                  grads=self.grads, losses=self.losses)
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.pg)
-            if fetch_losses:
-                dist.all_reduce(self.losses, op=dist.ReduceOp.SUM, group=self.pg)
-        self.opt.step(self.grads)
-        self.global_step += 1
-        if not fetch_losses:
+            self._copied[slot].synchronize()               # the previous copy out of this pinned slot has finished
+            self.x_host[slot].copy_(batch)
+            batch = self.x_host[slot]
+        self.copy_stream.wait_event(self._consumed[slot])
+        with torch.cuda.stream(self.copy_stream):
+            self.x_dev[slot].copy_(batch, non_blocking=True)
+            self._copied[slot].record(self.copy_stream)
+        main.wait_event(self._copied[slot])
+        self._consumed_slot = slot
+        return self.x_dev[slot]
+
+    def step(self, batch=None, fetch_losses=True):
+        """One optimisation step on this rank's shard ``batch`` (host NHWC float32 array / pinned tensor / device
+        tensor; None re-uses the batch already on the device).
+
+        ``fetch_losses``: True - return [content, style, tv, total] summed over ALL ranks (one 16-byte
+        device->host copy + a stream synchronise); "lag" - return the losses of the PREVIOUS step that asked for
+        them (no host stall: the read of step i overlaps step i+1; ``flush_losses()`` drains the last one);
+        False - return None.
+
+        Data-parallel runs must call this the same number of times on every rank: use
+        ``datapipe.next_batch_collective`` to end the input on all ranks at the same step."""
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            self._consumed_slot = None
+            if batch is not None:
+                self._current = self._stage(batch)
+            self.engine.train_fwd_bwd(self.params, self.packed, self._current, self.cfg, self.target_grams,
+                                      grads=self.grads, losses=self.losses)
+            if self._consumed_slot is not None:
+                self._consumed[self._consumed_slot].record(main)
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.pg)
+            self.opt.step(self.grads)
+            self.global_step += 1
+            if not fetch_losses:
+                return None
+            ls = self._loss_slot
+            self._loss_slot ^= 1
+            self.loss_host[ls].copy_(self.losses, non_blocking=True)
+            self._loss_ready[ls].record(main)
+            if fetch_losses == "lag":
+                prev, self._loss_pending = self._loss_pending, ls
+                if prev is None:
+                    return None
+                self._loss_ready[prev].synchronize()
+                return self.loss_host[prev].clone().numpy()
+            self._loss_ready[ls].synchronize()
+            return self.loss_host[ls].clone().numpy()
+
+    def flush_losses(self):
+        """Losses of the last ``fetch_losses="lag"`` step (None if there is none pending)."""
+        prev, self._loss_pending = self._loss_pending, None
+        if prev is None:
             return None
-        self.loss_host.copy_(self.losses, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return self.loss_host.clone().numpy()
+        self._loss_ready[prev].synchronize()
+        return self.loss_host[prev].clone().numpy()
+
+    def param_checksum(self) -> float:
+        """fp64 sum of the flat parameter buffer: equal on every rank of a data-parallel run."""
+        return float(self.params.double().sum().item())
 
     def variables(self) -> dict:
         """Current transform-net variables as {tf_name: ndarray} (for tf.train.Saver-style saving)."""

@@ -71,3 +71,96 @@ def test_two_rank_sum_allreduce_equals_single_rank_step():
     replica_diff = q.get(timeout=10)
     assert grad_err < 1e-6 and loss_err < 1e-12      # the flat layout is float32
     assert replica_diff == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Input sharding + collective end of data (ranks with different batch counts hung in the all-reduce and
+# lost the final checkpoint).  The loop below is train.py's: next_batch_collective -> step (here a stand-in whose only
+# job is to hold the per-step gradient all-reduce) -> ... -> OutOfRangeError on every rank at the same step.
+def _loop_worker(rank, world, port, q, train_dir, local_batch, epochs):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from faststyle_b200 import datapipe
+    batches = datapipe.prefetch(datapipe.batcher(train_dir, local_batch, (256, 256), epochs, 4, seed=1234,
+                                                 shard=(rank, world)), 3)
+    steps, seen = 0, []
+    try:
+        while True:
+            batch = datapipe.next_batch_collective(batches, dist.group.WORLD)
+            g = torch.ones(8) * (rank + 1)
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)          # Trainer.step's collective: would hang on a count mismatch
+            assert float(g[0]) == world * (world + 1) / 2
+            seen += [int(round(float(im[0, 0, 0]))) for im in batch]
+            steps += 1
+    except datapipe.OutOfRangeError:
+        pass
+    finally:
+        batches.close()
+    q.put((rank, steps, seen))
+    dist.destroy_process_group()
+
+
+def _run_loop(tmp_path, world, train_dir, local_batch, epochs):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_loop_worker, args=(r, world, port, q, train_dir, local_batch, epochs)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = {}
+    for _ in range(world):
+        r, steps, seen = q.get(timeout=120)
+        out[r] = (steps, seen)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    return out
+
+
+def test_two_rank_loop_stops_together_on_uneven_input(tmp_path):
+    """synthetic:7, 2 ranks, local batch 2: rank 0 holds 4 images (2 batches), rank 1 holds 3 (1 batch) - the case
+    ADVICE simulated.  Both ranks must leave the loop after the same number of steps."""
+    out = _run_loop(tmp_path, 2, "synthetic:7", 2, 1)
+    assert out[0][0] == out[1][0] == 1
+
+
+def test_two_rank_shards_are_disjoint_across_epochs(tmp_path):
+    """23 image files, 2 epochs, 2 ranks: the epoch order comes from an RNG seeded identically on every rank and is
+    consumed ONLY by the order shuffles, so the i % world shards stay disjoint in every epoch: no image is seen
+    more often than there are epochs, and the two ranks together see (almost) every image in every epoch - only
+    the tail left in the shuffle buffers at the collective stop is missing."""
+    import cv2
+    d = tmp_path / "imgs"
+    d.mkdir()
+    n_img, epochs = 23, 2
+    for i in range(n_img):
+        cv2.imwrite(str(d / ("im%02d.png" % i)), np.full((256, 256, 3), i * 10, np.uint8))
+    out = _run_loop(tmp_path, 2, str(d), 2, epochs)
+    assert out[0][0] == out[1][0] >= 4
+    counts = np.zeros(n_img, int)
+    for r in (0, 1):
+        for v in out[r][1]:
+            assert v % 10 == 0
+            counts[v // 10] += 1
+    assert counts.max() <= epochs, counts          # with a shared RNG some images were seen 3 times (ADVICE, low)
+    assert counts.sum() == 2 * 2 * out[0][0]
+
+
+def test_image_stream_shards_before_decode(tmp_path, monkeypatch):
+    """Every rank decodes only its own records: cv2.imread is called for i % world == rank only."""
+    import cv2
+    from faststyle_b200 import datapipe
+    d = tmp_path / "imgs"
+    d.mkdir()
+    for i in range(10):
+        cv2.imwrite(str(d / ("im%02d.png" % i)), np.full((8, 8, 3), i, np.uint8))
+    calls = []
+    real = cv2.imread
+    monkeypatch.setattr(cv2, "imread", lambda p, *a: (calls.append(p), real(p, *a))[1])
+    per_rank = []
+    for rank in range(2):
+        calls.clear()
+        imgs = list(datapipe._image_stream(str(d), 1, np.random.RandomState(5), np.random.RandomState(rank), (rank, 2)))
+        assert len(imgs) == 5 and len(calls) == 5
+        per_rank.append(sorted(int(im[0, 0, 0]) for im in imgs))
+    assert sorted(per_rank[0] + per_rank[1]) == list(range(10))

@@ -9,6 +9,11 @@ Multi GPU:    python -m torch.distributed.run --nproc-per-node 8 --master-addr 1
 ``--train_dir`` may hold the reference's TFRecord shards (train-*), plain image files, or be
 the literal ``synthetic[:N]``.  VGG weights are read from libs/vgg16_weights.npz (override
 with $VGG16_WEIGHTS; ``synthetic`` selects seeded synthetic weights).
+
+Files written: ``models/<name>_final.ckpt`` holds exactly the reference's 48 variables (train.py:225,286);
+the periodic ``training/<name>.ckpt-<step>`` files hold those plus the Adam slots and an int32 ``global_step``
+under TF's names, but NOT the frozen ``vgg/*`` variables the reference's all-variables Saver also dumps
+(train.py:224,259) - no code path restores a training checkpoint.
 """
 import argparse
 import os
@@ -72,11 +77,14 @@ def main(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
-    pg = None
+    pg = vote_pg = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
         pg = dist.group.WORLD
+        # host-side group for the per-step end-of-data vote (datapipe.next_batch_collective): CPU tensors, so the
+        # vote never touches the GPU queue
+        vote_pg = dist.new_group(backend='gloo')
     if args.batch_size % world:
         raise SystemExit("--batch_size %d is not divisible by the %d ranks" % (args.batch_size, world))
     local_batch = args.batch_size // world
@@ -123,7 +131,7 @@ def main(args):
         if with_slots:
             for k, v in trainer.optimizer_slots().items():
                 V.set_variable(k, v)
-            V.set_variable('global_step', np.array(trainer.global_step, np.int64))
+            V.set_variable('global_step', np.array(trainer.global_step, np.int32))     # tf.Variable(0): int32
         return V.Saver().save(None, prefix)
 
     if rank == 0:
@@ -131,7 +139,7 @@ def main(args):
     try:
         while True:
             current_step = trainer.global_step
-            batch = next(batches)
+            batch = datapipe.next_batch_collective(batches, vote_pg)     # all ranks stop at the same step
             if prep is not None:
                 batch = prep(batch)
             want_log = (current_step % args.num_steps_ckpt == 0) or (current_step % 10 == 0)
