@@ -46,6 +46,7 @@ SIGNATURES = {
     "fs_engine_set_frozen_weights": (_I, [_P, _I]),
     "fs_engine_profile": (_I, [_P, _I]),
     "fs_engine_profile_read": (_I, [_P, _I, _P, _P, _P]),
+    "fs_engine_profile_bytes": (_I, [_P, _I, _P]),
     "fs_engine_profile_records": (_I, [_P, _I, _P, _P, _P, _P]),
     "fs_engine_workspace_bytes": (_SZ, [_P]),
     "fs_engine_bind": (_I, [_P, _P, _SZ]),

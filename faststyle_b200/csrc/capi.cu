@@ -106,6 +106,10 @@ int fs_engine_profile_read(fs_engine* e, int ncat, float* ms, double* flops, int
     FS_CHECK(e && ms && flops && launches && ncat >= 1 && ncat <= 64, "fs_engine_profile_read: bad argument");
     return e->e.prof_read(ncat, ms, flops, launches);
 }
+int fs_engine_profile_bytes(fs_engine* e, int ncat, double* bytes) {
+    FS_CHECK(e && bytes && ncat >= 1 && ncat <= 64, "fs_engine_profile_bytes: bad argument");
+    return e->e.prof_read_bytes(ncat, bytes);
+}
 int fs_engine_profile_records(fs_engine* e, int max_rec, int* cat, float* ms, double* flops, int* count) {
     FS_CHECK(e && cat && ms && flops && count && max_rec >= 0, "fs_engine_profile_records: bad argument");
     return e->e.prof_records(max_rec, cat, ms, flops, count);

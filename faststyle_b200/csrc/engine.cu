@@ -25,6 +25,7 @@ int Engine::pbegin(int cat, double flops, cudaStream_t st) {
     FS_CUDA(cudaEventCreate(&b));
     FS_CUDA(cudaEventRecord(a, st));
     prof_ev.push_back(a); prof_ev.push_back(b); prof_cat.push_back(cat); prof_flops.push_back(flops);
+    prof_bytes.push_back(next_bytes); next_bytes = 0.0;
     return 0;
 }
 int Engine::pend(cudaStream_t st) {
@@ -54,7 +55,13 @@ int Engine::prof_read(int ncat, float* ms, double* flops, int* launches) {
         if (c >= 0 && c < ncat) { ms[c] += t; flops[c] += prof_flops[i]; launches[c] += 1; }
         cudaEventDestroy(prof_ev[2 * i]); cudaEventDestroy(prof_ev[2 * i + 1]);
     }
-    prof_ev.clear(); prof_cat.clear(); prof_flops.clear();
+    prof_ev.clear(); prof_cat.clear(); prof_flops.clear(); prof_bytes.clear();
+    return 0;
+}
+int Engine::prof_read_bytes(int ncat, double* bytes) {
+    for (int i = 0; i < ncat; ++i) bytes[i] = 0.0;
+    for (size_t i = 0; i < prof_cat.size(); ++i)
+        if (prof_cat[i] >= 0 && prof_cat[i] < ncat) bytes[prof_cat[i]] += prof_bytes[i];
     return 0;
 }
 #define PROF(cat, flops, call)              \
@@ -62,6 +69,23 @@ int Engine::prof_read(int ncat, float* ms, double* flops, int* launches) {
         FS_TRY(pbegin((cat), (flops), st)); \
         FS_TRY(call);                       \
         FS_TRY(pend(st));                   \
+    } while (0)
+// algorithmic bytes of a tensor-path conv launch: every operand plane read once, every output plane written once
+static double tc_bytes(const Conv3x3TcArgs& a) {
+    const int taps = a.one_by_one ? 1 : (a.taps ? a.taps : 3);
+    double b = 4.0 * a.N * a.H * a.W * (double)a.C;                                   // hi + lo input planes
+    b += 4.0 * taps * taps * (double)a.C * a.OC * (a.one_by_one && a.per_sample_w ? a.N : 1);
+    const double out = 4.0 * a.N * a.OH * a.OW * (double)a.OC;
+    if (a.out_f32) b += out;
+    if (a.out_split.hi) b += out;
+    if (a.ref) b += out;
+    if (a.addend) b += 4.0 * a.N * a.addH * a.addW * (double)a.OC;
+    return b;
+}
+#define PROFB(cat, flops, bytes, call) \
+    do {                               \
+        next_bytes = prof_on ? (bytes) : 0.0; \
+        PROF(cat, flops, call);        \
     } while (0)
 static double igemm_flops(const IGemmArgs& a) { return 2.0 * a.N * a.OH * a.OW * (double)a.OC * a.KH * a.KW * a.C; }
 static double tc_flops(const Conv3x3TcArgs& a) { return 2.0 * a.N * a.OH * a.OW * (double)a.OC * 9.0 * a.C; }
@@ -468,12 +492,12 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
             ta.N = N; ta.H = c.inH; ta.W = c.inW; ta.C = 64; ta.OH = c.outH; ta.OW = c.outW; ta.OC = 64; ta.pad = 0;
             ta.out_f32 = tb[l].raw;
             if (in_epi) { ta.stats = in_sums; ta.stats_c = 64; }
-            PROF(PC_TC_RES_FWD, tc_flops(ta), launch_conv3x3_tc(ta, st));
+            PROFB(PC_TC_RES_FWD, tc_flops(ta), tc_bytes(ta), launch_conv3x3_tc(ta, st));
         } else if (tc2(l)) {
             Conv3x3TcArgs ta;
             FS_TRY(tc2_args(l, false, -1, tb[l].raw, ta));
             if (in_epi) { ta.stats = in_sums; ta.stats_c = c.cout; }
-            PROF(PC_TC_S2_FWD, tc2_flops(ta), launch_conv3x3_tc(ta, st));
+            PROFB(PC_TC_S2_FWD, tc2_flops(ta), tc_bytes(ta), launch_conv3x3_tc(ta, st));
         } else if (direct9(c)) {
             IGemmArgs a;
             conv_fwd_args(c, N, cur, weff[l], tb[l].raw, a);
@@ -608,7 +632,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
             ta.pad = 2;                              // VALID conv: data gradient is the "full" correlation
             if (first_of_block) { ta.addend = resid_dOut; ta.add_crop = 2; ta.addH = resid_H; ta.addW = resid_W; }
             ta.out_f32 = dPrev;
-            PROF(PC_TC_RES_DGRAD, tc_flops(ta), launch_conv3x3_tc(ta, st));
+            PROFB(PC_TC_RES_DGRAD, tc_flops(ta), tc_bytes(ta), launch_conv3x3_tc(ta, st));
             dAct = dPrev; cur = pidx;
             if (first_of_block) { held = -1; resid_dOut = nullptr; }
             continue;
@@ -616,7 +640,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         if (tc2(l)) {
             Conv3x3TcArgs ta;
             FS_TRY(tc2_args(l, true, ri, dPrev, ta));
-            PROF(PC_TC_S2_DGRAD, tc2_flops(ta), launch_conv3x3_tc(ta, st));
+            PROFB(PC_TC_S2_DGRAD, tc2_flops(ta), tc_bytes(ta), launch_conv3x3_tc(ta, st));
             dAct = dPrev; cur = pidx;
             continue;
         }
@@ -705,7 +729,7 @@ int Engine::vgg_forward(const float* packed, const float* img3, int upto, float*
             ta.out_f32 = need_f32 ? out : nullptr;
             if (l < upto && !pool_next) ta.out_split = vsplit[l + 1];     // next conv reads split planes
             else if (vtsplit[l].hi) ta.out_split = vtsplit[l];            // style tap: Gram kernels read them
-            PROF(PC_TC_VGG_FWD, tc_flops(ta), launch_conv3x3_tc(ta, st));
+            PROFB(PC_TC_VGG_FWD, tc_flops(ta), tc_bytes(ta), launch_conv3x3_tc(ta, st));
         } else if (l == 0) {             // conv1_1 (Cin = 3): direct shared-memory kernel, exact fp32
             const bool sp = use_tc && l < upto && !pool_next;
             // content-target pass: conv1_1's fp32 copy is dead unless it is a target itself (conv1_2 reads the planes)
@@ -814,7 +838,7 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
             ta.N = N; ta.H = v.H; ta.W = v.W; ta.C = v.cout; ta.OH = v.H; ta.OW = v.W; ta.OC = v.cin; ta.pad = 1;
             ta.addend = addend; ta.addH = v.H; ta.addW = v.W; ta.ref = ref;
             ta.out_f32 = out; ta.out_split = out_split;
-            PROF(PC_TC_VGG_DGRAD, tc_flops(ta), launch_conv3x3_tc(ta, st));
+            PROFB(PC_TC_VGG_DGRAD, tc_flops(ta), tc_bytes(ta), launch_conv3x3_tc(ta, st));
             return 0;
         }
         if (lsrc == 0 && !addend && !ref) {      // conv1_1 data gradient: direct kernel (64 -> 4 channels)
@@ -848,7 +872,7 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
             ta.N = N; ta.H = v.H; ta.W = v.W; ta.C = v.cout; ta.OH = v.H; ta.OW = v.W; ta.OC = v.cout; ta.pad = 0;
             ta.addend = addend; ta.addH = v.H; ta.addW = v.W; ta.ref = ref;
             ta.out_f32 = out; ta.out_split = out_split;
-            PROF(PC_GRAM_BWD, tc_flops(ta) / 9.0, launch_conv3x3_tc(ta, st));
+            PROFB(PC_GRAM_BWD, tc_flops(ta) / 9.0, tc_bytes(ta), launch_conv3x3_tc(ta, st));
             return 0;
         }
         IGemmArgs a;

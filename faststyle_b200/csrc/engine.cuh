@@ -117,10 +117,12 @@ struct Engine {
 
     // live per-kernel timing (bench.py roofline)
     bool prof_on = false;
-    std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_cat; std::vector<double> prof_flops;
+    std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_cat; std::vector<double> prof_flops, prof_bytes;
+    double next_bytes = 0.0;             // algorithmic bytes of the next bracketed launch (PROFB)
     int pbegin(int cat, double flops, cudaStream_t st);
     int pend(cudaStream_t st);
     int prof_read(int ncat, float* ms, double* flops, int* launches);
+    int prof_read_bytes(int ncat, double* bytes);
     int prof_records(int max_rec, int* cat, float* ms, double* flops, int* count);
 
     int plan();                          // fill geometry; returns 0 / error

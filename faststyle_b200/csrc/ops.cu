@@ -95,14 +95,18 @@ __global__ void u8_to_f32_kernel(const uchar4* __restrict__ in, float4* __restri
     if (i < 4 && tail < n) out1[tail] = (float)in1[tail];
 }
 
-// numpy astype(uint8) of a value in [0,255] truncates (stylize_webcam.py:89); swap_rb = cv2.COLOR_BGR2RGB (:90)
+// numpy astype(uint8) of a value in [0,255] truncates (stylize_webcam.py:89); swap_rb = cv2.COLOR_BGR2RGB (:90).
+// mode bit 0: swap channels 0/2; bit 1: round half to even first (cv2.imwrite's saturate_cast of a float image,
+// utils.py:51-52 / stylize_image.py:79-80) instead of truncating.
 __global__ void f32_to_u8_kernel(const float* __restrict__ in, unsigned char* __restrict__ out, long long npix,
-                                 int swap_rb) {
+                                 int mode) {
     FS_PDL_ENTER();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
+    const int swap_rb = mode & 1;
     const float* s = in + i * 3;
     float a = s[0], b = s[1], c = s[2];
+    if (mode & 2) { a = rintf(a); b = rintf(b); c = rintf(c); }
     unsigned char* o = out + i * 3;
     unsigned char ua = (unsigned char)fminf(fmaxf(a, 0.f), 255.f);
     unsigned char ub = (unsigned char)fminf(fmaxf(b, 0.f), 255.f);

@@ -81,6 +81,9 @@ int fs_engine_set_frozen_weights(fs_engine* e, int frozen);
 #define FS_PROF_NCAT 16
 int fs_engine_profile(fs_engine* e, int enabled);
 int fs_engine_profile_read(fs_engine* e, int ncat, float* ms, double* flops, int* launches);
+/* algorithmic bytes per category of the launches recorded so far (tensor-path convolutions: every operand plane
+ * read once + every output plane written once; 0 for categories without a byte model); call before _read */
+int fs_engine_profile_bytes(fs_engine* e, int ncat, double* bytes);
 /* per-launch records (category, ms, algorithmic FLOPs) in issue order; call before _read */
 int fs_engine_profile_records(fs_engine* e, int max_rec, int* cat, float* ms, double* flops, int* count);
 /* output dims of the transform net (== VGG input dims when both are planned) */
@@ -180,7 +183,9 @@ int fs_loss_tv(const float* Y3, int N, int H, int W, double* acc, float* out, vo
  * (reference stylize_webcam.py:82-90: the uint8 frame is fed as-is - the float cast happens inside
  * feed_dict -, the result is cast with numpy astype(uint8), i.e. truncated, and channels 0/2 are
  * swapped by cv2.cvtColor(COLOR_BGR2RGB)).  in/out are DEVICE pointers; n = number of bytes (4-byte
- * aligned input, 16-byte aligned output); npix = number of 3-channel pixels. */
+ * aligned input, 16-byte aligned output); npix = number of 3-channel pixels.  swap_rb bit 0: swap channels 0/2;
+ * bit 1: round half to even before the saturating cast (what cv2.imwrite does to a float image, reference
+ * utils.py:51-52 / stylize_image.py:79-80) instead of truncating. */
 int fs_frame_u8_to_f32(const unsigned char* in, float* out, long long n, void* stream);
 int fs_frame_f32_to_u8(const float* in, unsigned char* out, long long npix, int swap_rb, void* stream);
 

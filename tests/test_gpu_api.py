@@ -274,3 +274,34 @@ def test_gpu_preprocessor_batch(built_lib):
     assert got.shape == (3, 256, 256, 3) and np.abs(got - want).max() <= 1e-4
     got2 = prep(imgs[::-1]).cpu().numpy()           # staging buffer reuse
     assert np.abs(got2 - want[::-1]).max() <= 1e-4
+
+
+def test_batch_stylizer_pipeline(built_lib, golden_dir):
+    """BatchStylizer (pipelined uint8 -> uint8 batch inference, the e2e leg of bench.py's config-2 block): results
+    equal round-and-saturate of Engine.transform_forward, and the oracle within one grey level; two batches in
+    flight come back in order."""
+    import os
+    from faststyle_b200.engine import Engine, params_to_device
+    from faststyle_b200.stream import BatchStylizer
+    from faststyle_b200.tf_bundle import read_checkpoint
+    from oracle import restate as R
+    params = read_checkpoint(os.path.join(golden_dir, "starry_final.ckpt"))
+    rng = np.random.RandomState(5)
+    B, H, W = 3, 64, 80
+    xs = [rng.randint(0, 256, (B, H, W, 3)).astype(np.uint8) for _ in range(3)]
+    st = BatchStylizer(params, B, H, W)
+    eng = Engine(B, H, W, transform=True)
+    p = params_to_device(params, "cuda")
+    st.submit(xs[0]); st.submit(xs[1])
+    outs = [st.fetch()]
+    st.submit(xs[2])
+    outs += [st.fetch(), st.fetch()]
+    for x, got in zip(xs, outs):
+        y = eng.transform_forward(p, x.astype(np.float32)).cpu().numpy()
+        want = np.clip(np.rint(y), 0, 255).astype(np.uint8)
+        assert got.shape == want.shape and got.dtype == np.uint8
+        assert (got != want).mean() < 1e-3          # fused-statistics atomics: last-bit differences at .5 boundaries
+        assert np.abs(got.astype(int) - want.astype(int)).max() <= 1
+    with torch.no_grad():
+        yo = R.create_net(xs[2].astype(np.float32), params, "resize", torch.float64).numpy()
+    assert np.abs(outs[2].astype(float) - np.clip(yo, 0, 255)).max() <= 0.5 + 0.26      # rounding + 1e-3 of the unit scale

@@ -3,6 +3,7 @@
 
     python tools/ncu_summarize.py raw  FILE_raw.csv      # `ncu -i x.ncu-rep --page raw --csv` -> per-launch table
     python tools/ncu_summarize.py list FILE_launches.csv [period]   # launch list -> per-kernel shares
+    python tools/ncu_summarize.py traffic FILE_raw.csv REGEX OUT.json   # DRAM bytes / launch of the matched kernel
 """
 import csv
 import re
@@ -96,8 +97,40 @@ def launch_list(path, period=None):
         print("| `%s` | %d | %.1f | %.1f%% |" % (k, n, us, 100 * us / tot))
 
 
+def traffic(path, pattern, out_path):
+    """Mean dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels matching ``pattern`` in a
+    `--set full` capture -> JSON that bench.py reads for `roofline.traffic` (tagged with the hash of the CUDA
+    sources the capture was taken from)."""
+    import hashlib
+    import json
+    import os
+    rows = list(csv.reader(open(path)))
+    hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    names, units = rows[hdr], rows[hdr + 1]
+    idx = {n: i for i, n in enumerate(names)}
+    rd, wr, ki = idx["dram__bytes_read.sum"], idx["dram__bytes_write.sum"], idx["Kernel Name"]
+    tot, n, per = 0.0, 0, []
+    for r in rows[hdr + 2:]:
+        if len(r) < len(names) or not re.search(pattern, r[ki]):
+            continue
+        b = (to_unit(r[rd], units[rd], "MB") + to_unit(r[wr], units[wr], "MB")) * 1e6
+        tot += b; n += 1; per.append(round(b))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = hashlib.sha256()
+    d = os.path.join(root, "faststyle_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    out = {"kernel_regex": pattern, "launches": n, "dram_bytes_per_launch": tot / max(n, 1), "unit": "bytes/launch "
+           "(dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, mean over the captured launches)",
+           "file": os.path.basename(path), "csrc_sha16": h.hexdigest()[:16], "per_launch_bytes": per}
+    json.dump(out, open(out_path, "w"), indent=1)
+    print("%d launches of /%s/: %.1f MB per launch -> %s" % (n, pattern, out["dram_bytes_per_launch"] / 1e6, out_path))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "raw":
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    elif sys.argv[1] == "raw":
         raw(sys.argv[2])
     else:
         launch_list(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else None)

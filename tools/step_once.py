@@ -36,11 +36,15 @@ def main():
     x = bench.synthetic_batch(0).to(dev)
     grads = torch.empty_like(params)
     losses = torch.empty(4, dtype=torch.float32, device=dev)
+    from faststyle_b200 import _lib
+    lib = _lib.load()
+    n0 = lib.fs_launch_count()
     for _ in range(steps):
         eng.train_fwd_bwd(params, packed, x, cfg, tg, grads=grads, losses=losses)
         opt.step(grads)
     torch.cuda.synchronize()
     print("done", steps, "steps")
+    print("launches_per_step", (lib.fs_launch_count() - n0) // steps)
 
 
 if __name__ == "__main__":
