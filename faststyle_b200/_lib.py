@@ -43,6 +43,7 @@ SIGNATURES = {
     "fs_engine_create": (_I, [_I, _I, _I, _I, _U, _U, _PP]),
     "fs_engine_destroy": (_I, [_P]),
     "fs_engine_set_tensor_path": (_I, [_P, _I]),
+    "fs_set_tc_pair": (_I, [_I]),
     "fs_engine_set_frozen_weights": (_I, [_P, _I]),
     "fs_engine_profile": (_I, [_P, _I]),
     "fs_engine_profile_read": (_I, [_P, _I, _P, _P, _P]),

@@ -97,6 +97,7 @@ int fs_engine_set_tensor_path(fs_engine* e, int enabled) {
     e->e.weights_prepared = false;
     return 0;
 }
+int fs_set_tc_pair(int enabled) { fs::set_tc_pair(enabled); return 0; }
 int fs_engine_profile(fs_engine* e, int enabled) {
     FS_CHECK(e, "NULL engine");
     e->e.prof_on = enabled != 0;

@@ -82,6 +82,25 @@ static inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     (void)cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);   // the error is picked up by FS_LAUNCH_CHECK
 }
+// same, as clusters of two CTAs (CTA pairs for tcgen05 cta_group::2): grid.x must be even
+template <typename... KArgs, typename... Args>
+static inline void launch_k_cluster2(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    (void)cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);   // the error is picked up by FS_LAUNCH_CHECK
+}
 #endif
 
 // TF 'SAME' padding rule: out = ceil(n/s),

@@ -18,6 +18,7 @@
 // drain TMEM (tcgen05.ld), apply bias/ReLU/addend/mask and store fp32 and/or split-bf16 NHWC while the
 // next tile's MMAs run.
 #include <cuda.h>
+#include <stdlib.h>
 #include "tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -56,7 +57,7 @@ struct TcParams {
     int in_s2d, out_d2s;       // space-to-depth input view (5-D tensor map) / depth-to-space fp32 store
     int w_sample_rows;         // rows of the packed weight matrix per sample (0 = shared weights)
     int tilesX, tilesY, tilesN;
-    long long total_tiles;
+    long long total_tiles;     // work units: spatial tiles (per-sample pairs of them for the CTA-pair kernel) x tilesN
     const float* bias; const float* addend; const float* ref;
     int relu, add_crop, addH, addW;
     float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
@@ -79,14 +80,15 @@ __device__ __forceinline__ float warp_transpose_sum(float* s, int lane) {
     return s[0];
 }
 
-template <int TH, int BN>
+template <int TH, int BN, bool PAIR = false>
 struct Cfg {
     static constexpr int NACC = TH / 8;
     static constexpr int A_STAGES = (TH == 8) ? 3 : 2;             // small tiles: deeper slab ring (latency-bound)
-    static constexpr int B_STAGES = (BN == 64) ? 4 : 2;
+    static constexpr int B_ROWS = PAIR ? BN / 2 : BN;              // weight rows held by one CTA
+    static constexpr int B_STAGES = (B_ROWS <= 64) ? 4 : 2;
     static constexpr int SLAB_BYTES = (TH + 2) * TW * 128;        // one plane
     static constexpr int A_STAGE_BYTES = 2 * SLAB_BYTES;          // hi + lo
-    static constexpr int BTILE_BYTES = BN * 128;                  // one plane
+    static constexpr int BTILE_BYTES = B_ROWS * 128;              // one plane
     static constexpr int B_STAGE_BYTES = 2 * BTILE_BYTES;
     static constexpr int TMEM_COLS = 2 * NACC * BN;               // double-buffered accumulators
     static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -94,14 +96,30 @@ struct Cfg {
 
 constexpr int TC_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 epilogue (2 per TMEM lane quadrant)
 
-template <int TH, int BN, bool STATS>
+template <int BN, bool PAIR>
+__device__ __forceinline__ uint32_t make_idesc_p() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
+}
+
+// PAIR = true: two CTAs of a cluster (one TPC) work as a CTA pair on TWO spatial tiles at once.  The leader
+// (cluster rank 0) issues `tcgen05.mma.cta_group::2` with M = 256: rows 0-127 are the leader's pixels, rows
+// 128-255 the peer's, each read from the owning CTA's shared memory; the B (weight) tile of BN rows is SPLIT -
+// each CTA loads and holds BN/2 rows - so per MMA a CTA's shared memory feeds 4 KB of A + half of B instead of
+// all of it, and the weights cross L2->SMEM once per pair instead of once per CTA.  (At BN = 128 the single-CTA
+// form reads 128 B/clk of operands, the whole shared-memory bandwidth, before the TMA writes; the pair reads 96.)
+// Each CTA keeps its own 128 accumulator rows in its own TMEM and runs its own epilogue.
+// Barrier protocol: `*_full` barriers live in the leader only (both CTAs' TMA loads count their bytes there);
+// `*_empty` and `t_full` exist in both CTAs and are signalled by the leader's multicast tcgen05.commit; the
+// leader's `t_empty` collects the arrivals of both CTAs' epilogue warps (the peer's arrive remotely).
+template <int TH, int BN, bool STATS, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                   const TcParams p) {
     FS_PDL_TRIGGER();
-    using K = Cfg<TH, BN>;
+    using K = Cfg<TH, BN, PAIR>;
     constexpr int A_STAGES = K::A_STAGES;
+    constexpr int NCTA = PAIR ? 2 : 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smemA = smem;
@@ -117,6 +135,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int CB = p.C / KB;
+    const uint32_t cta = PAIR ? cluster_ctarank() : 0u;           // 0 = leader
+    const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int ustep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
@@ -124,32 +145,64 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < K::B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8 * NCTA); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, K::TMEM_COLS);
+    if (warp == 2) {
+        if (PAIR) tmem_alloc2(tmem_slot, K::TMEM_COLS);
+        else tmem_alloc(tmem_slot, K::TMEM_COLS);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();         // the peer's barriers are initialised before anything remote touches them
+    else __syncthreads();
     tc_fence_after();
     FS_PDL_WAIT();                        // everything above is CTA-local setup
     const uint32_t tmem_base = *tmem_slot;
 
+    // work unit u -> (nt, spatial tile of THIS CTA).  PAIR: unit = (nt, sample, pair of consecutive tiles of that sample):
+    // both CTAs always work on the SAME sample (per-sample weight matrices stay consistent across the split B tile);
+    // the peer of an odd tile count gets a dummy tile below the image (its TMA boxes are out of bounds = zeros, it
+    // still loads its half of the weights, nothing is stored).  Returns whether the tile is real.
+    auto decode = [&](long long u, int& nt, int& tx, int& ty, int& n) -> bool {
+        nt = (int)(u % p.tilesN);
+        long long r = u / p.tilesN;
+        if (PAIR) {
+            const int tps = p.tilesX * p.tilesY, pps = (tps + 1) >> 1;
+            n = (int)(r / pps);
+            const int s = 2 * (int)(r - (long long)n * pps) + (int)cta;
+            if (s >= tps) { tx = 0; ty = p.tilesY; return false; }
+            ty = s / p.tilesX; tx = s - ty * p.tilesX;
+            return true;
+        }
+        tx = (int)(r % p.tilesX); r /= p.tilesX;
+        ty = (int)(r % p.tilesY);
+        n = (int)(r / p.tilesY);
+        return true;
+    };
+
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
         int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            const int nt = (int)(t % p.tilesN);
-            long long r = t / p.tilesN;
-            const int tx = (int)(r % p.tilesX); r /= p.tilesX;
-            const int ty = (int)(r % p.tilesY);
-            const int n = (int)(r / p.tilesY);
-            const int y0 = ty * TH - p.pad, x0 = tx * TW - p.pad, n0 = nt * BN;
+        for (long long u = unit0; u < p.total_tiles; u += ustep) {
+            int nt, tx, ty, n;
+            decode(u, nt, tx, ty, n);
+            const int y0 = ty * TH - p.pad, x0 = tx * TW - p.pad;
+            const int n0 = nt * BN + (int)cta * K::B_ROWS;
             for (int cb = 0; cb < CB; ++cb) {
                 for (int kw = 0; kw < p.taps; ++kw) {
                     mbar_wait(&a_empty[sa], pa ^ 1);
                     uint8_t* dst = smemA + sa * K::A_STAGE_BYTES;
-                    mbar_expect_tx(&a_full[sa], K::A_STAGE_BYTES);
-                    if (p.in_s2d) {       // channel block cb = row parity p of the [2H,2W,32] source (see make_act_map_s2d)
+                    if (!PAIR || cta == 0) mbar_expect_tx(&a_full[sa], NCTA * K::A_STAGE_BYTES);
+                    if (PAIR) {
+                        const uint32_t fb = mapa_u32(&a_full[sa], 0);        // the leader's barrier counts both CTAs' bytes
+                        if (p.in_s2d) {
+                            tma2_load_5d(dst, &tmA_hi, fb, 0, x0 + kw, cb, y0, n);
+                            tma2_load_5d(dst + K::SLAB_BYTES, &tmA_lo, fb, 0, x0 + kw, cb, y0, n);
+                        } else {
+                            tma2_load_4d(dst, &tmA_hi, fb, cb * KB, x0 + kw, y0, n);
+                            tma2_load_4d(dst + K::SLAB_BYTES, &tmA_lo, fb, cb * KB, x0 + kw, y0, n);
+                        }
+                    } else if (p.in_s2d) {       // channel block cb = row parity p of the [2H,2W,32] source (see make_act_map_s2d)
                         tma_load_5d(dst, &tmA_hi, &a_full[sa], 0, x0 + kw, cb, y0, n);
                         tma_load_5d(dst + K::SLAB_BYTES, &tmA_lo, &a_full[sa], 0, x0 + kw, cb, y0, n);
                     } else {
@@ -160,25 +213,31 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     for (int kh = 0; kh < p.taps; ++kh) {
                         mbar_wait(&b_empty[sb], pb ^ 1);
                         uint8_t* bd = smemB + sb * K::B_STAGE_BYTES;
-                        mbar_expect_tx(&b_full[sb], K::B_STAGE_BYTES);
+                        if (!PAIR || cta == 0) mbar_expect_tx(&b_full[sb], NCTA * K::B_STAGE_BYTES);
                         const int row = ((kh * p.taps + kw) * CB + cb) * p.OC + n0 + n * p.w_sample_rows;
-                        tma_load_2d(bd, &tmB_hi, &b_full[sb], 0, row);
-                        tma_load_2d(bd + K::BTILE_BYTES, &tmB_lo, &b_full[sb], 0, row);
+                        if (PAIR) {
+                            const uint32_t fb = mapa_u32(&b_full[sb], 0);
+                            tma2_load_2d(bd, &tmB_hi, fb, 0, row);
+                            tma2_load_2d(bd + K::BTILE_BYTES, &tmB_lo, fb, 0, row);
+                        } else {
+                            tma_load_2d(bd, &tmB_hi, &b_full[sb], 0, row);
+                            tma_load_2d(bd + K::BTILE_BYTES, &tmB_lo, &b_full[sb], 0, row);
+                        }
                         if (++sb == K::B_STAGES) { sb = 0; pb ^= 1; }
                     }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 && (!PAIR || cta == 0)) {
+        // ===================== MMA issuer (the leader CTA of a pair) =====================
         // The whole warp runs the (warp-uniform) control flow and barrier waits; one elected lane issues.
         // Shared-memory descriptors are built once per stage; each tcgen05.mma then costs one 64-bit add per
         // operand, so the issue rate stays above the 32-64 tensor cycles an MMA takes.
-        const uint32_t idesc = make_idesc<BN>();
+        const uint32_t idesc = make_idesc_p<BN, PAIR>();
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
         int as = 0; uint32_t pt = 0;
-        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        for (long long u = unit0; u < p.total_tiles; u += ustep) {
             mbar_wait(&t_empty[as], pt ^ 1);
             tc_fence_after();
             const uint32_t acc_base = tb + (uint32_t)(as * K::NACC * BN);
@@ -204,23 +263,25 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                                     const uint64_t ad = (prod == 2 ? ad_lo : ad_hi) + aoff;
                                     const uint64_t bd = (prod == 1 ? bd_lo : bd_hi);
 #pragma unroll
-                                    for (int k4 = 0; k4 < 4; ++k4)
-                                        tc_mma_bf16(d, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc,
-                                                    (first && prod == 0 && k4 == 0) ? 0u : 1u);
+                                    for (int k4 = 0; k4 < 4; ++k4) {
+                                        const uint32_t accum = (first && prod == 0 && k4 == 0) ? 0u : 1u;
+                                        if (PAIR) tc_mma2_bf16(d, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, accum);
+                                        else tc_mma_bf16(d, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, accum);
+                                    }
                                 }
                             }
-                            tc_commit(&b_empty[sb]);
+                            if (PAIR) tc_commit2(&b_empty[sb]); else tc_commit(&b_empty[sb]);
                         }
                         __syncwarp();
                         first = false;
                         if (++sb == K::B_STAGES) { sb = 0; pb ^= 1; }
                     }
-                    if (elect_one()) tc_commit(&a_empty[sa]);
+                    if (elect_one()) { if (PAIR) tc_commit2(&a_empty[sa]); else tc_commit(&a_empty[sa]); }
                     __syncwarp();
                     if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
                 }
             }
-            if (elect_one()) tc_commit(&t_full[as]);
+            if (elect_one()) { if (PAIR) tc_commit2(&t_full[as]); else tc_commit(&t_full[as]); }
             __syncwarp();
             if (++as == 2) { as = 0; pt ^= 1; }
         }
@@ -234,20 +295,39 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         const int eg = (warp - 4) >> 2;                // 0 / 1: which half of the items
         const int row = ew * 32 + lane;                // MMA row = pixel within the 8x16 sub-tile
         const int prow = row >> 4, pcol = row & 15;
+        // fused InstanceNorm statistics (STATS): per-thread running (sum, sum of squares) over the pixels this thread
+        // has seen of the current sample; a butterfly transposition leaves lane L with the totals of channel L of
+        // the chunk, which go to the per-(sample, real channel) fp64 accumulators with one atomic each.  A CTA's
+        // tiles are sample-major, so this happens about once per sample and warp.
+        float st1[32], st2[32];
+        int stat_n = -1;
+        if (STATS) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { st1[i] = 0.f; st2[i] = 0.f; }
+        }
+        auto stats_flush = [&]() {
+            if (stat_n < 0) return;
+            const float s1 = warp_transpose_sum(st1, lane);
+            const float s2 = warp_transpose_sum(st2, lane);
+            const int cch = ((BN == 64 ? eg * 32 : 0) + lane) % p.stats_c;
+            double* sp = p.stats + ((long long)stat_n * p.stats_c + cch) * 2;
+            atomicAdd(sp, (double)s1);
+            atomicAdd(sp + 1, (double)s2);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { st1[i] = 0.f; st2[i] = 0.f; }
+        };
         int as = 0; uint32_t pt = 0;
-        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            const int nt = (int)(t % p.tilesN);
-            long long r = t / p.tilesN;
-            const int tx = (int)(r % p.tilesX); r /= p.tilesX;
-            const int ty = (int)(r % p.tilesY);
-            const int n = (int)(r / p.tilesY);
+        for (long long u = unit0; u < p.total_tiles; u += ustep) {
+            int nt, tx, ty, n;
+            const bool tile_ok = decode(u, nt, tx, ty, n);
+            if (STATS && tile_ok && n != stat_n) { stats_flush(); stat_n = n; }
             mbar_wait(&t_full[as], pt);
             tc_fence_after();
 #pragma unroll 1
             for (int item = eg; item < K::NACC * (BN / 32); item += 2) {
                 const int acc = item / (BN / 32), ch = item - acc * (BN / 32);
                 const int oy = ty * TH + acc * 8 + prow, ox = tx * TW + pcol;
-                const bool ok = oy < p.OH && ox < p.OW;
+                const bool ok = tile_ok && oy < p.OH && ox < p.OW;
                 const long long pix = ((long long)n * p.OH + oy) * p.OW + ox;
                 const float* addp = nullptr;
                 if (p.addend && ok) {
@@ -260,22 +340,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) +
                                            (uint32_t)(as * K::NACC * BN + acc * BN + ch * 32);
                     tmem_ld32(taddr, v);                // warp-collective: executed by all lanes
-                    if (STATS) {
+                    if (STATS && ok) {
                         // InstanceNorm statistics of the raw conv output, fused here so that the activation is not
-                        // read again: per 32-pixel x 32-channel block a butterfly reduction leaves lane L with the
-                        // (fp32) sums of channel c0+L, accumulated in fp64 per (sample, real channel).  All lanes
-                        // take part; pixels outside the image contribute zeros.
-                        float tsum[32];
+                        // read again: every thread keeps running sums of ITS pixels for the 32 channels of its
+                        // chunk (the chunk's real channels are the same for every item this warp handles, see
+                        // launch_conv3x3_tc); lanes are combined once per sample (stats_flush below).
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) tsum[i] = ok ? v[i] : 0.f;
-                        const float s1 = warp_transpose_sum(tsum, lane);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) tsum[i] = ok ? v[i] * v[i] : 0.f;
-                        const float s2 = warp_transpose_sum(tsum, lane);
-                        const int cch = (nt * BN + ch * 32 + lane) % p.stats_c;
-                        double* sp = p.stats + ((long long)n * p.stats_c + cch) * 2;
-                        atomicAdd(sp, (double)s1);
-                        atomicAdd(sp + 1, (double)s2);
+                        for (int i = 0; i < 32; ++i) { st1[i] += v[i]; st2[i] = fmaf(v[i], v[i], st2[i]); }
                     }
                     if (ok && p.out_d2s) {
                         const int cq = nt * (BN / 32) + ch;           // which 32-channel quarter of OC = 128
@@ -353,14 +424,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[as]);
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_cluster(mapa_u32(&t_empty[as], 0));    // the leader's barrier (its own warps too)
+                else mbar_arrive(&t_empty[as]);
+            }
             if (++as == 2) { as = 0; pt ^= 1; }
         }
+        if (STATS) stats_flush();
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, K::TMEM_COLS);
+    if (PAIR) cluster_sync_all();         // the peer's shared memory and barriers stay alive until both CTAs are done
+    else __syncthreads();
+    if (warp == 2) {
+        if (PAIR) tmem_dealloc2(tmem_base, K::TMEM_COLS);
+        else tmem_dealloc(tmem_base, K::TMEM_COLS);
+    }
 }
 
 // ------------------------------------------------------------------ helpers kernels
@@ -521,9 +600,11 @@ int num_sms() {
     return n;
 }
 
-template <int TH, int BN, bool STATS>
+int g_tc_pair = -1;     // CTA-pair (cta_group::2) kernel: -1 = read FS_TC_PAIR (default on), 0 off, 1 on
+
+template <int TH, int BN, bool STATS, bool PAIR>
 int launch_cfg_s(const Conv3x3TcArgs& a, cudaStream_t st) {
-    using K = Cfg<TH, BN>;
+    using K = Cfg<TH, BN, PAIR>;
     CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
     if (a.in_s2d) {
         FS_TRY(make_act_map_s2d(&tmA_hi, a.x.hi, a.N, a.H, a.W, TH + 2));
@@ -535,32 +616,42 @@ int launch_cfg_s(const Conv3x3TcArgs& a, cudaStream_t st) {
     const int taps = a.one_by_one ? 1 : (a.taps ? a.taps : 3);
     const long long wrows = a.one_by_one ? (long long)(a.per_sample_w ? a.N : 1) * (a.C / KB) * a.OC
                                          : (long long)taps * taps * (a.C / KB) * a.OC;
-    FS_TRY(make_w_map(&tmB_hi, a.w.hi, wrows, BN));
-    FS_TRY(make_w_map(&tmB_lo, a.w.lo, wrows, BN));
+    FS_TRY(make_w_map(&tmB_hi, a.w.hi, wrows, K::B_ROWS));
+    FS_TRY(make_w_map(&tmB_lo, a.w.lo, wrows, K::B_ROWS));
     TcParams p;
     p.N = a.N; p.H = a.H; p.W = a.W; p.C = a.C; p.OH = a.OH; p.OW = a.OW; p.OC = a.OC; p.pad = a.pad;
     p.taps = taps; p.in_s2d = a.in_s2d; p.out_d2s = a.out_d2s;
     p.w_sample_rows = a.one_by_one && a.per_sample_w ? (a.C / KB) * a.OC : 0;
     p.tilesX = cdiv(a.OW, TW); p.tilesY = cdiv(a.OH, TH); p.tilesN = a.OC / BN;
-    p.total_tiles = (long long)a.N * p.tilesX * p.tilesY * p.tilesN;
+    const long long tps = (long long)p.tilesX * p.tilesY;
+    p.total_tiles = (long long)a.N * (PAIR ? (tps + 1) / 2 : tps) * p.tilesN;
     p.bias = a.bias; p.addend = a.addend; p.ref = a.ref; p.relu = a.relu;
     p.add_crop = a.add_crop; p.addH = a.addH; p.addW = a.addW;
     p.out_f32 = a.out_f32; p.out_hi = a.out_split.hi; p.out_lo = a.out_split.lo;
     p.stats = a.stats; p.stats_c = a.stats_c;
     static bool attr_set = false;
     if (!attr_set) {
-        FS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<TH, BN, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+        FS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<TH, BN, STATS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
         attr_set = true;
     }
-    int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
-    launch_k((conv3x3_tc_kernel<TH, BN, STATS>), dim3(grid), dim3(TC_THREADS), K::SMEM_BYTES, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    const int sms = num_sms();
+    if (PAIR) {
+        const int clusters = (int)(p.total_tiles < sms / 2 ? p.total_tiles : sms / 2);
+        launch_k_cluster2((conv3x3_tc_kernel<TH, BN, STATS, PAIR>), dim3(2 * clusters), dim3(TC_THREADS), K::SMEM_BYTES, st,
+                          tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    } else {
+        const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
+        launch_k((conv3x3_tc_kernel<TH, BN, STATS, PAIR>), dim3(grid), dim3(TC_THREADS), K::SMEM_BYTES, st, tmA_hi, tmA_lo,
+                 tmB_hi, tmB_lo, p);
+    }
     FS_LAUNCH_CHECK();
     return 0;
 }
 
 template <int TH, int BN>
-int launch_cfg(const Conv3x3TcArgs& a, cudaStream_t st) {
-    return a.stats ? launch_cfg_s<TH, BN, true>(a, st) : launch_cfg_s<TH, BN, false>(a, st);
+int launch_cfg(const Conv3x3TcArgs& a, bool pair, cudaStream_t st) {
+    if (pair) return a.stats ? launch_cfg_s<TH, BN, true, true>(a, st) : launch_cfg_s<TH, BN, false, true>(a, st);
+    return a.stats ? launch_cfg_s<TH, BN, true, false>(a, st) : launch_cfg_s<TH, BN, false, false>(a, st);
 }
 
 }  // namespace
@@ -576,30 +667,41 @@ int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st) {
     FS_CHECK((a.out_split.hi == nullptr) == (a.out_split.lo == nullptr), "conv3x3_tc: split output needs both planes");
     FS_CHECK(a.OH > 0 && a.OW > 0 && a.N > 0, "conv3x3_tc: empty output");
     FS_CHECK(a.taps == 0 || a.taps == 2 || a.taps == 3, "conv3x3_tc: taps must be 2 or 3");
-    FS_CHECK(!a.stats || (a.stats_c >= 16 && a.stats_c <= 64 && (a.stats_c & (a.stats_c - 1)) == 0 && !a.bias && !a.relu &&
-                          !a.addend && !a.ref),
+    // fused statistics: the real channel (output channel % stats_c) of element i of a warp's 32-channel chunk must
+    // not depend on the chunk: stats_c divides 32, or one 64-channel tile whose two chunks go to different warps
+    FS_CHECK(!a.stats || ((a.stats_c == 16 || a.stats_c == 32 || (a.stats_c == 64 && a.OC == 64)) && a.OC <= 128 &&
+                          !a.bias && !a.relu && !a.addend && !a.ref),
              "conv3x3_tc: fused statistics are for raw transform-net conv outputs (16/32/64 real channels)");
     FS_CHECK(!a.in_s2d || (a.C == 128 && !a.one_by_one), "conv3x3_tc: the space-to-depth input view needs C == 128");
     FS_CHECK(!a.out_d2s || (a.OC == 128 && a.out_f32 && !a.out_split.hi && !a.bias && !a.addend && !a.ref && !a.relu),
              "conv3x3_tc: the depth-to-space store needs OC == 128 and a plain fp32 output");
+    if (g_tc_pair < 0) {
+        const char* e = getenv("FS_TC_PAIR");
+        g_tc_pair = (e && e[0] == '0') ? 0 : 1;
+    }
+    const bool pair = g_tc_pair != 0;
     bool tall = a.OH > 8;
     // 16-row tiles amortise the slab halo (18 rows loaded per 16) but small problems leave SMs idle or end on a
     // ragged last wave: estimate both tilings in units of one 8-row tile (x1.1 for the 10-rows-per-8 halo) and
     // take the cheaper.  E.g. the residual convs (200 vs 400 tiles on 148 SMs) and conv4_1's data gradient
-    // (64 vs 128 tiles) run faster on 8-row tiles.
+    // (64 vs 128 tiles) run faster on 8-row tiles.  The CTA-pair kernel schedules PAIRS of tiles on 74 clusters.
     if (tall) {
         const long long bn = a.OC % 128 == 0 ? 128 : 64;
-        const long long per = (long long)a.N * cdiv(a.OW, TW) * (a.OC / bn);
-        const long long t16 = per * cdiv(a.OH, 16), t8 = per * cdiv(a.OH, 8);
-        const long long sms = num_sms();
-        const double cost16 = 2.0 * (double)((t16 + sms - 1) / sms), cost8 = 1.1 * (double)((t8 + sms - 1) / sms);
+        const long long nn = a.OC / bn;
+        long long t16 = (long long)cdiv(a.OW, TW) * cdiv(a.OH, 16), t8 = (long long)cdiv(a.OW, TW) * cdiv(a.OH, 8);   // per sample
+        long long workers = num_sms();
+        if (pair) { t16 = (t16 + 1) / 2; t8 = (t8 + 1) / 2; workers /= 2; }
+        t16 *= nn * a.N; t8 *= nn * a.N;
+        const double cost16 = 2.0 * (double)((t16 + workers - 1) / workers), cost8 = 1.1 * (double)((t8 + workers - 1) / workers);
         if (cost8 < 0.85 * cost16) tall = false;
         // the small 64->64 residual convs: 8-row tiles + their 3-deep slab ring also hide the L2 latency (measured)
-        if (a.C == 64 && a.OC == 64 && !a.one_by_one && t16 * 2 < 3 * sms) tall = false;
+        if (a.C == 64 && a.OC == 64 && !a.one_by_one && t16 * 2 < 3 * workers) tall = false;
     }
-    if (a.OC % 128 == 0) return tall ? launch_cfg<16, 128>(a, st) : launch_cfg<8, 128>(a, st);
-    return tall ? launch_cfg<16, 64>(a, st) : launch_cfg<8, 64>(a, st);
+    if (a.OC % 128 == 0) return tall ? launch_cfg<16, 128>(a, pair, st) : launch_cfg<8, 128>(a, pair, st);
+    return tall ? launch_cfg<16, 64>(a, pair, st) : launch_cfg<8, 64>(a, pair, st);
 }
+
+void set_tc_pair(int on) { g_tc_pair = on ? 1 : 0; }
 
 int split_bf16(const float* x, SplitPtr out, long long n, cudaStream_t st) {
     FS_CHECK(n % 4 == 0, "split_bf16: n %% 4 != 0");

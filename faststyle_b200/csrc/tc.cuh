@@ -48,6 +48,8 @@ struct Conv3x3TcArgs {
     SplitPtr out_split;        // split planes of the same tensor (may be null)
 };
 int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st);
+// CTA-pair (tcgen05 cta_group::2) variant of the kernel on / off (default: on; FS_TC_PAIR=0 in the environment)
+void set_tc_pair(int on);
 bool conv3x3_tc_supported(int C, int OC, int W, int OW);
 
 // tcgen05 weight gradient of a 3x3 stride-1 64->64 convolution (wgrad_tc.cu):

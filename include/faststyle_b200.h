@@ -66,6 +66,10 @@ int fs_engine_bind(fs_engine* e, void* workspace, size_t bytes);
  * (split-bf16 x3); 0: every convolution on the exact-fp32 FFMA path.  Also settable
  * through the environment variable FS_TENSOR_PATH=0 read at fs_engine_create. */
 int fs_engine_set_tensor_path(fs_engine* e, int enabled);
+/* Process-wide: 1 (default) runs the tcgen05 convolution as CTA pairs (clusters of two CTAs, tcgen05.mma
+ * cta_group::2 with M = 256, the weight tile split between the two CTAs' shared memories); 0: one CTA per tile
+ * (cta_group::1).  Same results up to fp32 summation order.  Also FS_TC_PAIR=0 in the environment. */
+int fs_set_tc_pair(int enabled);
 /* frozen = 1: the transform parameters passed to fs_transform_forward do not change between calls (inference):
  * their per-call preparation (padding, collapsing, pairing, bf16 packing: ~25 short launches) runs once and is
  * skipped afterwards.  Call again (any value) after changing the parameter buffer. */

@@ -156,5 +156,21 @@ def test_config3_train_step_b4(built_lib, starry, golden_dir, weights):
           (weights, pix, ["%.2g" % e for e in lerr], 1 - cos, worst, worst_name))
     assert pix <= PIX_TOL, pix
     assert max(lerr) <= LOSS_TOL, lerr
-    assert 1 - cos <= COS_TOL, 1 - cos
-    assert worst <= GRAD_TOL, (worst_name, worst)
+    # Untrained TF-initialiser weights (unit-variance resize-conv filters) make the gradient ill-conditioned: the
+    # oracle ITSELF in fp32 vs fp64 differs by 1 - cos = 1.3e-6 / 3.4e-3 per tensor on this case (measured on the
+    # host at batch 1), against 1e-10-class numbers for the trained checkpoint.  The 16-mantissa-bit tensor path
+    # sits a few times above that floor (measured 5.9e-6 / 2.0e-2).
+    cos_tol, grad_tol = (COS_TOL, GRAD_TOL) if weights == "starry" else (2e-5, 5e-2)
+    assert 1 - cos <= cos_tol, 1 - cos
+    assert worst <= grad_tol, (worst_name, worst)
+    if weights == "tf_init":
+        # the same case on the exact-fp32 (FFMA) path must sit AT the fp32 floor: this separates operand precision
+        # from arithmetic slips in the pipeline
+        eng.set_tensor_path(False)
+        g32, _ = eng.train_fwd_bwd(params_to_device(params, "cuda"), packed, x, cfg, tgd, y=y)
+        g32 = g32.cpu().double()
+        cos32 = float((g32 @ flat_ref) / (g32.norm() * flat_ref.norm()))
+        worst32 = max(float((g32[off:off + int(np.prod(shape))].view(shape) - ref["grads"][name]).abs().max()
+                            / max(ref["grads"][name].abs().max().item(), 1e-30)) for name, (off, shape) in offs.items())
+        print("   exact-fp32 path on the same case: 1-cos %.3g, worst per-tensor %.3g" % (1 - cos32, worst32))
+        assert 1 - cos32 <= 5e-6 and worst32 <= 1e-2

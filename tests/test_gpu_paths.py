@@ -108,8 +108,10 @@ def _cos(a, b):
     return float((a @ b) / (a.norm() * b.norm()))
 
 
-# tolerances per path: (loss scalars relative, gradient max-abs relative to max, 1 - cosine)
-TOL = {False: (2e-4, 2e-3, 1e-7), True: (1e-3, 5e-2, 1e-5)}
+# tolerances per path: (loss scalars relative, gradient max-abs relative to max, 1 - cosine).  The per-tensor
+# gradient bound of the tensor path is 3x the worst value measured over these cases (5.2e-3, the deconv variant
+# with untrained weights; 1.7e-3 with the trained checkpoint; the exact-fp32 path measures 9e-4).
+TOL = {False: (2e-4, 2e-3, 1e-7), True: (1e-3, 1.5e-2, 1e-5)}
 
 
 @pytest.mark.parametrize("tensor_path", [False, True])

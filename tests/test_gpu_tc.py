@@ -33,11 +33,23 @@ CASES = [
     (2, 33, 40, 128, 256, 1, 1),     # two N tiles, two channel blocks, TH=16 path
     (1, 8, 8, 256, 512, 1, 1),       # TH=8 path, deep K
     (3, 64, 64, 64, 64, 1, 1),       # > 1 tile per CTA in flight (double-buffered TMEM)
+    (1, 24, 40, 64, 128, 1, 1),      # 3 x 3 = 9 spatial tiles (8-row): the last CTA pair has a dummy peer tile
+    (5, 40, 48, 128, 128, 0, 0),     # 45 16-row tiles: odd count, several waves of pairs
+    (8, 64, 64, 256, 256, 1, 1),     # BASELINE config 3/4 shape (conv3_2 at per-GPU batch 8): multi-wave, 4 K blocks
 ]
 
 
+@pytest.fixture(params=[1, 0], ids=["cta_pair", "single_cta"])
+def tc_pair(request):
+    """Both launch forms of the tcgen05 convolution: CTA pairs (cta_group::2, the default) and single CTAs."""
+    from faststyle_b200 import _lib
+    _lib.call("fs_set_tc_pair", request.param)
+    yield request.param
+    _lib.call("fs_set_tc_pair", 1)
+
+
 @pytest.mark.parametrize("case", CASES)
-def test_conv3x3_tc_forward_and_dgrad(built_lib, case):
+def test_conv3x3_tc_forward_and_dgrad(built_lib, case, tc_pair):
     from faststyle_b200 import _lib
     lib = _lib.load()
     N, H, W, Ci, Co, same, relu = case
