@@ -136,8 +136,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int CB = p.C / KB;
     const uint32_t cta = PAIR ? cluster_ctarank() : 0u;           // 0 = leader
-    const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int ustep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    // work distribution over the CTAs (CTA pairs): strided - at any time the chip works on a band of consecutive tiles,
+    // so neighbouring tiles' halos meet in L2 (the large VGG layers) - or, for launches with fused statistics,
+    // contiguous blocks of tiles per CTA so that a CTA stays within one or two samples (one statistics flush each).
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    long long u_begin = worker, u_end = p.total_tiles, u_stride = nworkers;
+    if (STATS) {
+        const long long per = (p.total_tiles + nworkers - 1) / nworkers;
+        u_begin = worker * per;
+        u_end = u_begin + per < p.total_tiles ? u_begin + per : p.total_tiles;
+        u_stride = 1;
+    }
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
@@ -183,7 +193,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
         int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-        for (long long u = unit0; u < p.total_tiles; u += ustep) {
+        for (long long u = u_begin; u < u_end; u += u_stride) {
             int nt, tx, ty, n;
             decode(u, nt, tx, ty, n);
             const int y0 = ty * TH - p.pad, x0 = tx * TW - p.pad;
@@ -237,7 +247,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
         int as = 0; uint32_t pt = 0;
-        for (long long u = unit0; u < p.total_tiles; u += ustep) {
+        for (long long u = u_begin; u < u_end; u += u_stride) {
             mbar_wait(&t_empty[as], pt ^ 1);
             tc_fence_after();
             const uint32_t acc_base = tb + (uint32_t)(as * K::NACC * BN);
@@ -309,15 +319,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             if (stat_n < 0) return;
             const float s1 = warp_transpose_sum(st1, lane);
             const float s2 = warp_transpose_sum(st2, lane);
+            // STATS_REPLICAS copies of the accumulators (by CTA): same-address fp64 atomics serialise in L2 at ~50 ns
+            // each, and with every CTA adding to the same N x C x 2 addresses they cost more than the pass they save
             const int cch = ((BN == 64 ? eg * 32 : 0) + lane) % p.stats_c;
-            double* sp = p.stats + ((long long)stat_n * p.stats_c + cch) * 2;
+            double* sp = p.stats + (((long long)(worker % STATS_REPLICAS) * p.N + stat_n) * p.stats_c + cch) * 2;
             atomicAdd(sp, (double)s1);
             atomicAdd(sp + 1, (double)s2);
 #pragma unroll
             for (int i = 0; i < 32; ++i) { st1[i] = 0.f; st2[i] = 0.f; }
         };
         int as = 0; uint32_t pt = 0;
-        for (long long u = unit0; u < p.total_tiles; u += ustep) {
+        for (long long u = u_begin; u < u_end; u += u_stride) {
             int nt, tx, ty, n;
             const bool tile_ok = decode(u, nt, tx, ty, n);
             if (STATS && tile_ok && n != stat_n) { stats_flush(); stat_n = n; }

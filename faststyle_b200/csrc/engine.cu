@@ -285,9 +285,18 @@ void Engine::layout(Arena& a) {
         }
         w2f = a.take<float>(4LL * 128 * 64);
         wpair = a.take<float>(4LL * 128 * 64);
+        w2f_b = a.take<float>(4LL * 128 * 64);
+        for (int i = 0; i < 4; ++i) wpair_x[i] = a.take<float>(4LL * 128 * 64);
+        for (int l = 0; l < T_NCONV; ++l) wgs[l] = nullptr;
+        if (tbw) {
+            for (int l : {0, 15}) wgs[l] = a.take<float>(81LL * 64);
+            for (int l : {1, 2, 13, 14}) wgs[l] = a.take<float>(4LL * 128 * 64);
+            wgu[0] = a.take<float>(4LL * 128 * 64);
+            wgu[1] = a.take<float>(4LL * 128 * 64);
+        }
         y3 = a.take<float>((long long)N * OH * OW * 3);
         in_partial = a.take<double>((long long)N * 64 * 64 * 2);
-        in_sums = a.take<double>((long long)N * 64 * 2);
+        in_sums = a.take<double>((long long)STATS_REPLICAS * N * 64 * 2);
         in15 = a.take<float>(8);
         wtmp15 = a.take<float>(81 * 64);
         if (tbw) {
@@ -348,14 +357,89 @@ int Engine::bind(void* ws, size_t bytes) {
     FS_CHECK(((uintptr_t)ws & 255) == 0, "engine: workspace must be 256-byte aligned");
     Arena a; a.base = (char*)ws; a.cap = bytes;
     layout(a);
-    if (in_sums) { FS_CUDA(cudaMemset(in_sums, 0, (size_t)N * 64 * 2 * sizeof(double))); FS_CUDA(cudaDeviceSynchronize()); }
+    if (in_sums) { FS_CUDA(cudaMemset(in_sums, 0, (size_t)STATS_REPLICAS * N * 64 * 2 * sizeof(double))); FS_CUDA(cudaDeviceSynchronize()); }
     bound = true;
     return 0;
 }
 
 // ---------------------------------------------------------------- transform net
+// the table-driven path covers the standard configuration: resize upsampling, tensor path on, all four stride-2 /
+// resize layers in their tcgen05 2x2 forms (even sizes); everything else keeps one launch per transform
+bool Engine::use_fast_prep() const {
+    return fast_prep && use_tc && !(flags & ENG_DECONV) && tc2(1) && tc2(2) && tc2(13) && tc2(14);
+}
+
+int Engine::prep_transform_weights_table(const float* params, bool need_bwd, cudaStream_t st) {
+    PrepPlan pl;
+    auto W = [&](int l) { return params + tc[l].offW; };
+    // ---- phase 0: everything that reads the raw parameters
+    FS_TRY(pl.add(0, pj(PJ_PAD, W(0), weff[0], 81, 3, 16, 4, 16)));
+    FS_TRY(pl.add(0, pj(PJ_PAD, W(15), weff[15], 81, 16, 3, 16, 4)));
+    FS_TRY(pl.add(0, pj(PJ_UPCONV_COLLAPSE, W(13), weff[13], tc[13].cin, tc[13].cout)));
+    FS_TRY(pl.add(0, pj(PJ_UPCONV_COLLAPSE, W(14), weff[14], tc[14].cin, tc[14].cout)));
+    {
+        PrepJob j = pj(PJ_IN15, params + tc[15].offG, in15);
+        j.src2 = params + tc[15].offB;
+        FS_TRY(pl.add(0, j));
+    }
+    for (int l = 3; l <= 12; ++l) FS_TRY(pl.add(0, pj_pack(PJ_PACK_W3X3, W(l), tw_f[l].hi, tw_f[l].lo, 64, 64, 0)));
+    if (need_bwd)
+        for (int l = 3; l <= 12; ++l) FS_TRY(pl.add(0, pj_pack(PJ_PACK_W3X3, W(l), tw_d[l].hi, tw_d[l].lo, 64, 64, 1)));
+    FS_TRY(pl.add(0, pj(PJ_S2_FWD_COLLAPSE, W(1), w2f, tc[1].cin, tc[1].cout)));          // [4][64][32]
+    FS_TRY(pl.add(0, pj(PJ_S2_FWD_COLLAPSE, W(2), w2f_b, tc[2].cin, tc[2].cout)));        // [4][128][64]
+    if (need_bwd) {
+        FS_TRY(pl.add(0, pj(PJ_S2_DGRAD_COLLAPSE, W(1), wefft[1], tc[1].cin, tc[1].cout)));
+        FS_TRY(pl.add(0, pj(PJ_S2_DGRAD_COLLAPSE, W(2), wefft[2], tc[2].cin, tc[2].cout)));
+    }
+    // ---- phase 1
+    FS_TRY(pl.add(1, pj(PJ_PAIR, w2f, wpair_x[0], 4 * tc[1].cin, tc[1].cout, 1, 0)));                       // -> [4][128][64]
+    FS_TRY(pl.add(1, pj_pack(PJ_PACK_TAPS, w2f_b, tw_f[2].hi, tw_f[2].lo, 4, 4 * tc[2].cin, tc[2].cout, 0)));
+    FS_TRY(pl.add(1, pj_pack(PJ_PACK_TAPS, weff[13], tw_f[13].hi, tw_f[13].lo, 4, tc[13].cin, 4 * tc[13].cout, 0)));
+    FS_TRY(pl.add(1, pj(PJ_PAIR, weff[14], wpair_x[1], tc[14].cin, 4 * tc[14].cout, 0, 0)));                // -> [4][64][128]
+    if (need_bwd) {
+        FS_TRY(pl.add(1, pj(PJ_FLIP_TRANSPOSE, weff[15], wefft[15], 81, tc[15].cin_s, tc[15].cout_s)));
+        FS_TRY(pl.add(1, pj(PJ_TRANSPOSE, weff[13], wefft[13], 4, tc[13].cin, 4 * tc[13].cout)));
+        FS_TRY(pl.add(1, pj(PJ_TRANSPOSE, weff[14], wefft[14], 4, tc[14].cin, 4 * tc[14].cout)));
+        FS_TRY(pl.add(1, pj(PJ_PAIR, wefft[1], wpair_x[2], tc[1].cout, 4 * tc[1].cin, 0, 1)));              // -> [4][64][128]
+        FS_TRY(pl.add(1, pj_pack(PJ_PACK_TAPS, wefft[2], tw_d[2].hi, tw_d[2].lo, 4, tc[2].cout, 4 * tc[2].cin, 1)));
+    }
+    // ---- phase 2
+    FS_TRY(pl.add(2, pj_pack(PJ_PACK_TAPS, wpair_x[0], tw_f[1].hi, tw_f[1].lo, 4, 128, 64, 0)));
+    FS_TRY(pl.add(2, pj_pack(PJ_PACK_TAPS, wpair_x[1], tw_f[14].hi, tw_f[14].lo, 4, 64, 128, 0)));
+    if (need_bwd) {
+        FS_TRY(pl.add(2, pj_pack(PJ_PACK_TAPS, wpair_x[2], tw_d[1].hi, tw_d[1].lo, 4, 64, 128, 1)));
+        FS_TRY(pl.add(2, pj_pack(PJ_PACK_TAPS, wefft[13], tw_d[13].hi, tw_d[13].lo, 4, 4 * tc[13].cout, tc[13].cin, 1)));
+        FS_TRY(pl.add(2, pj(PJ_PAIR, wefft[14], wpair_x[3], 4 * tc[14].cout, tc[14].cin, 1, 1)));           // -> [4][128][64]
+        // ---- phase 3
+        FS_TRY(pl.add(3, pj_pack(PJ_PACK_TAPS, wpair_x[3], tw_d[14].hi, tw_d[14].lo, 4, 128, 64, 1)));
+    }
+    PROF(PC_PREP, 0.0, pl.run(st));
+    return 0;
+}
+
+// weight gradients of the layers computed in a transformed layout (staged in wgs[l] by transform_backward):
+// back through the pairing / collapse / padding adjoints into the flat gradient buffer, two launches
+int Engine::finish_weight_grads_table(float* grads, cudaStream_t st) {
+    PrepPlan pl;
+    auto G = [&](int l) { return grads + tc[l].offW; };
+    FS_TRY(pl.add(0, pj(PJ_UNPAD, wgs[15], G(15), 81, 16, 3, 16, 4)));
+    FS_TRY(pl.add(0, pj(PJ_UNPAD, wgs[0], G(0), 81, 3, 16, 4, 16)));
+    FS_TRY(pl.add(0, pj(PJ_UNPAIR, wgs[14], wgu[0], tc[14].cin, 4 * tc[14].cout, 0, 1)));
+    FS_TRY(pl.add(0, pj(PJ_UPCONV_COLLAPSE_GRAD, wgs[13], G(13), tc[13].cin, tc[13].cout)));
+    FS_TRY(pl.add(0, pj(PJ_S2_FWD_COLLAPSE_GRAD, wgs[2], G(2), tc[2].cin, tc[2].cout)));
+    FS_TRY(pl.add(0, pj(PJ_UNPAIR, wgs[1], wgu[1], 4 * tc[1].cin, tc[1].cout, 1, 0)));
+    FS_TRY(pl.add(0, pj(PJ_COPY, gb_tmp, grads + tc[15].offG, 3)));
+    FS_TRY(pl.add(0, pj(PJ_COPY, gb_tmp + 4, grads + tc[15].offB, 3)));
+    FS_TRY(pl.add(1, pj(PJ_UPCONV_COLLAPSE_GRAD, wgu[0], G(14), tc[14].cin, tc[14].cout)));
+    FS_TRY(pl.add(1, pj(PJ_S2_FWD_COLLAPSE_GRAD, wgu[1], G(1), tc[1].cin, tc[1].cout)));
+    PROF(PC_PREP, 0.0, pl.run(st));
+    return 0;
+}
+
 int Engine::prep_transform_weights(const float* params, bool need_bwd, cudaStream_t st) {
     FS_CHECK(bound && (flags & ENG_TRANSFORM), "engine has no transform plan / workspace");
+    if (need_bwd) FS_CHECK(flags & ENG_TRANSFORM_BWD, "engine was not created with a backward plan");
+    if (use_fast_prep()) return prep_transform_weights_table(params, need_bwd, st);
     PROF(PC_PREP, 0.0, pad_taps(params + tc[0].offW, weff[0], 81, 3, 16, 4, 16, st));
     if (flags & ENG_DECONV) {
         // 'deconv' models (reference im_transf_net.py:57-63,158-190): W is [k,k,cout,cin] and the layer is
@@ -509,7 +593,7 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
             PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
         }
         if (in_epi && (tcl || tc2(l)))
-            PROF(PC_IN_STATS, 0.0, instnorm_stats_from_sums(in_sums, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, st));
+            PROF(PC_IN_STATS, 0.0, instnorm_stats_from_sums(in_sums, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, STATS_REPLICAS, st));
         else
             PROF(PC_IN_STATS, 0.0, instnorm_stats(tb[l].raw, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, in_partial, st));
         const float* skip = nullptr;
@@ -537,6 +621,9 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
     int cur = -1, held = -1;
     const float* resid_dOut = nullptr;
     int resid_H = 0, resid_W = 0;
+    // table-driven path: gradients computed in a transformed layout are staged per layer and mapped back by
+    // finish_weight_grads_table after the loop (2 launches instead of ~12)
+    const bool fastp = use_fast_prep();
     for (int l = T_NCONV - 1; l >= 0; --l) {
         const TConv& c = tc[l];
         const bool last = l == T_NCONV - 1;
@@ -553,7 +640,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         PROF(PC_IN_BWD, 0.0, instnorm_bwd(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw, dg, db, N,
                                 c.outH * c.outW, c.cout_s, c.act, in_partial, m12, st,
                                 tcd ? tgsplit[ri].hi : nullptr, tcd ? tgsplit[ri].lo : nullptr));
-        if (last) {
+        if (last && !fastp) {
             FS_CUDA(cudaMemcpyAsync(grads + c.offG, gb_tmp, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
             FS_CUDA(cudaMemcpyAsync(grads + c.offB, gb_tmp + 4, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
         }
@@ -587,14 +674,17 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
             const bool paired = (l == 1 || l == 14);
             const int gh = c.upconv ? c.inH : c.outH, gw = (c.upconv ? c.inW : c.outW) / (paired ? 2 : 1);
             PROF(PC_WGRAD, wgrad_flops_tc2(N, gh, gw), launch_wgrad2x2_tc(tsplit[l], c.upconv ? 0 : 1, tgsplit[ri], c.upconv ? 1 : 0,
-                                                                          wg_tmp, wg_partial, wg_partial_cap, N, gh, gw, st));
+                                                                          fastp ? wgs[l] : wg_tmp, wg_partial, wg_partial_cap, N, gh, gw, st));
             const float* wsrc = wg_tmp;
-            if (paired) {
+            if (fastp) {
+                // adjoints run after the loop
+            } else if (paired) {
                 if (c.upconv) PROF(PC_PREP, 0.0, unpair_taps(wg_tmp, wg_tmp2, c.cin, 4 * c.cout, 0, 1, st));   // dY side: paired s2d view
                 else PROF(PC_PREP, 0.0, unpair_taps(wg_tmp, wg_tmp2, 4 * c.cin, c.cout, 1, 0, st));
                 wsrc = wg_tmp2;
             }
-            if (c.upconv) PROF(PC_PREP, 0.0, upconv_collapse_grad(wsrc, grads + c.offW, c.cin, c.cout, st));
+            if (fastp) {
+            } else if (c.upconv) PROF(PC_PREP, 0.0, upconv_collapse_grad(wsrc, grads + c.offW, c.cin, c.cout, st));
             else PROF(PC_PREP, 0.0, s2_fwd_collapse_grad(wsrc, grads + c.offW, c.cin, c.cout, st));
         } else if (c.upconv) {
             wa.C = c.cin; wa.KH = wa.KW = 2; wa.stride = 1;
@@ -608,7 +698,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
             wa.OH = c.outH; wa.OW = c.outW; wa.OC = c.cout_s; wa.dy_mode = 0;
             wa.dy_bs = (long long)c.outH * c.outW * c.cout_s;
             const bool padded = (c.cin != c.cin_s) || (c.cout != c.cout_s);
-            wa.out = padded ? wg_tmp : grads + c.offW;
+            wa.out = padded ? ((fastp && wgs[l]) ? wgs[l] : wg_tmp) : grads + c.offW;
             if (tcl)
                 PROF(PC_WGRAD, wgrad_flops(wa), launch_wgrad3x3_tc(tsplit[l], tgsplit[ri], wa.out, wg_partial, wg_partial_cap,
                                                                    N, c.inH, c.inW, c.outH, c.outW, 0, st));
@@ -617,7 +707,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
                                                                 c.inH, c.inW, c.cin_s, c.cout_s, st));
             else
                 PROF(PC_WGRAD, wgrad_flops(wa), launch_wgrad(wa, st));
-            if (padded) PROF(PC_PREP, 0.0, unpad_taps(wg_tmp, grads + c.offW, c.k * c.k, c.cin, c.cout, c.cin_s, c.cout_s, st));
+            if (padded && !(fastp && wgs[l])) PROF(PC_PREP, 0.0, unpad_taps(wg_tmp, grads + c.offW, c.k * c.k, c.cin, c.cout, c.cin_s, c.cout_s, st));
         }
         if (l == 0) break;                       // no gradient w.r.t. the input image (train.py:198-204)
         // ---- data gradient -> gradient w.r.t. the previous layer's activation
@@ -695,6 +785,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         dAct = dPrev; cur = pidx;
         if (first_of_block) { held = -1; resid_dOut = nullptr; }
     }
+    if (fastp) FS_TRY(finish_weight_grads_table(grads, st));
     return 0;
 }
 

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "ops.cuh"
 #include "tc.cuh"
+#include "prep.cuh"
 #include <vector>
 
 namespace fs {
@@ -108,6 +109,16 @@ struct Engine {
     SplitPtr tw_f[T_NCONV], tw_d[T_NCONV];   // packed weights (forward / data gradient)
     float* w2f = nullptr;                // initconv_1/2 weights in the 2x2 space-to-depth form (fp32 staging)
     float* wpair = nullptr;              // pixel-paired 2x2 weights (fp32 staging, one layer at a time)
+    // table-driven preparation (prep.cu): every transform has its own staging buffer so that all transforms of a
+    // dependency phase run in ONE launch
+    float* w2f_b = nullptr;              // initconv_2's space-to-depth form (w2f holds initconv_1's)
+    float* wpair_x[4] = {nullptr, nullptr, nullptr, nullptr};   // paired forms: l=1 fwd, l=14 fwd, l=1 bwd, l=14 bwd
+    float* wgs[T_NCONV];                 // weight-gradient staging of the layers whose gradient needs a layout adjoint
+    float* wgu[2] = {nullptr, nullptr};  // un-paired weight gradients of l=14 / l=1
+    int fast_prep = 1;                   // FS_FAST_PREP=0: one launch per transform (the round-1 path)
+    bool use_fast_prep() const;
+    int prep_transform_weights_table(const float* params, bool need_bwd, cudaStream_t st);
+    int finish_weight_grads_table(float* grads, cudaStream_t st);
     // stride-2 layers on the tensor path in their collapsed 2x2 stride-1 forms: initconv_2 (3x3 s2 32->64) and
     // upsample_0 (resize-conv 64->32) have 64/128 channels on both sides as they are; initconv_1 (16->32) and
     // upsample_1 (32->16) get there by pairing horizontally adjacent pixels (pair_taps).  Forward + data gradient.

@@ -295,14 +295,19 @@ in_stats_finalize_kernel(const double* __restrict__ partial, float* __restrict__
     }
 }
 
-// mean / rstd from the (sum, sum of squares) a conv epilogue accumulated; zeroes the sums for the next launch
+// mean / rstd from the (sum, sum of squares) a conv epilogue accumulated in `reps` replicas [reps][NC][2];
+// zeroes the sums for the next launch
 __global__ void in_stats_from_sums_kernel(double* __restrict__ sums, float* __restrict__ mean, float* __restrict__ rstd,
-                                          int NC, int HW, float eps) {
+                                          int NC, int HW, float eps, int reps) {
     FS_PDL_ENTER();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NC) return;
-    const double s1 = sums[2 * i], s2 = sums[2 * i + 1];
-    sums[2 * i] = 0.0; sums[2 * i + 1] = 0.0;
+    double s1 = 0.0, s2 = 0.0;
+    for (int r = 0; r < reps; ++r) {
+        double* p = sums + ((long long)r * NC + i) * 2;
+        s1 += p[0]; s2 += p[1];
+        p[0] = 0.0; p[1] = 0.0;
+    }
     const double m = s1 / HW;
     double var = s2 / HW - m * m;
     if (var < 0) var = 0;
@@ -890,8 +895,8 @@ int instnorm_stats(const float* x, float* mean, float* rstd, int N, int HW, int 
     return 0;
 }
 
-int instnorm_stats_from_sums(double* sums, float* mean, float* rstd, int N, int HW, int C, float eps, cudaStream_t st) {
-    launch_k(in_stats_from_sums_kernel, dim3(cdiv((long long)N * C, 128)), dim3(128), 0, st, sums, mean, rstd, N * C, HW, eps);
+int instnorm_stats_from_sums(double* sums, float* mean, float* rstd, int N, int HW, int C, float eps, int reps, cudaStream_t st) {
+    launch_k(in_stats_from_sums_kernel, dim3(cdiv((long long)N * C, 128)), dim3(128), 0, st, sums, mean, rstd, N * C, HW, eps, reps);
     FS_LAUNCH_CHECK();
     return 0;
 }

@@ -23,7 +23,7 @@ int in_chunks(int N, int HW);
 int instnorm_stats(const float* x, float* mean, float* rstd, int N, int HW, int C, float eps,
                    double* partial, cudaStream_t st);
 // statistics from per-(n,c) (sum, sum of squares) accumulated by a conv epilogue; the sums are zeroed again
-int instnorm_stats_from_sums(double* sums, float* mean, float* rstd, int N, int HW, int C, float eps, cudaStream_t st);
+int instnorm_stats_from_sums(double* sums, float* mean, float* rstd, int N, int HW, int C, float eps, int reps, cudaStream_t st);
 int instnorm_apply(const float* x, const float* mean, const float* rstd, const float* scale,
                    const float* shift, const float* skip, float* out, int N, int H, int W, int C,
                    int act, int out3, cudaStream_t st, void* split_hi = nullptr, void* split_lo = nullptr);

@@ -23,6 +23,8 @@ int pack_taps_tc(const float* w, SplitPtr out, int T, int K, int Nn, int flip, c
 // same for up to 16 equally shaped weight tensors in ONE launch
 int pack_w3x3_tc_batch(const float* const* w, const SplitPtr* out, int count, int Ci, int Co, int mode, cudaStream_t st);
 
+constexpr int STATS_REPLICAS = 16;
+
 struct Conv3x3TcArgs {
     SplitPtr x;                // input  [N,H,W,C]  split bf16 planes (C % 64 == 0)
     SplitPtr w;                // packed weights (pack_w3x3_tc), reduction channels = C, outputs = OC
@@ -42,8 +44,9 @@ struct Conv3x3TcArgs {
     int relu;
     int add_crop, addH, addW;  // addend is [N,addH,addW,OC]; output pixel (y,x) reads (y-crop, x-crop)
     double* stats; int stats_c;    // optional: accumulate per-(sample, real channel) sum / sum of squares of the raw
-                               // output into stats[N][stats_c][2] (real channel = output channel % stats_c: the
-                               // depth-to-space / paired forms carry several pixels' channels side by side)
+                               // output into stats[STATS_REPLICAS][N][stats_c][2] (real channel = output channel %
+                               // stats_c: the depth-to-space / paired forms carry several pixels' channels side by
+                               // side; replica = CTA index % STATS_REPLICAS, summed by instnorm_stats_from_sums)
     float* out_f32;            // [N,OH,OW,OC] fp32 (may be null)
     SplitPtr out_split;        // split planes of the same tensor (may be null)
 };
