@@ -279,7 +279,10 @@ def test_train_step_batch_additivity_full_size(built_lib, starry):
     rel = float((g8 - (ga + gb)).abs().max() / g8.abs().max())
     print("batch additivity at 8x256x256: grad rel-to-max %.3g, losses %s vs %s" % (rel, l8.tolist(), (la + lb).tolist()))
     assert rel < 1e-4
-    assert 1 - _cos(g8, ga + gb) < 1e-9
+    # the fused InstanceNorm statistics are fp32 partial sums whose grouping follows the tile -> CTA assignment, which
+    # differs between a batch-8 and a batch-4 plan: the two sides differ by fp32 summation order in every layer
+    # (each side agrees with the fp64 oracle to 1 - cos = 6e-9 at this size, test_gpu_fullsize.py)
+    assert 1 - _cos(g8, ga + gb) < 2e-8
     for a, b in zip(l8, la + lb):
         assert abs(float(a) - float(b)) <= 1e-5 * abs(float(b)) + 1e-12
 
