@@ -269,6 +269,11 @@ void Engine::layout(Arena& a) {
         }
         for (int l = 0; l < T_NCONV; ++l) {
             tsplit[l].hi = tsplit[l].lo = nullptr; tw_f[l].hi = tw_f[l].lo = nullptr; tw_d[l].hi = tw_d[l].lo = nullptr;
+            rg[l].hi = rg[l].lo = nullptr;
+            if (tbw && l >= 3 && l <= 12) {
+                long long n = (long long)N * tc[l].outH * tc[l].outW * 64;
+                rg[l].hi = a.take<__nv_bfloat16>(n); rg[l].lo = a.take<__nv_bfloat16>(n);
+            }
             if (l >= 3 && l <= 12) {
                 long long n = (long long)N * tc[l].inH * tc[l].inW * 64;
                 tsplit[l].hi = a.take<__nv_bfloat16>(n); tsplit[l].lo = a.take<__nv_bfloat16>(n);
@@ -637,9 +642,11 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         float* dRaw = tgrad[ri];
         const bool tcl = use_tc && l >= 3 && l <= 12;
         const bool tcd = tcl || (l > 0 && tc2(l));           // the data gradient reads dRaw's split planes
+        const bool defer_wg = tcl && batch_wgrad;            // residual convs: planes kept in rg[l], weight gradient batched
+        const SplitPtr dsp = defer_wg ? rg[l] : tgsplit[ri];
         PROF(PC_IN_BWD, 0.0, instnorm_bwd(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw, dg, db, N,
                                 c.outH * c.outW, c.cout_s, c.act, in_partial, m12, st,
-                                tcd ? tgsplit[ri].hi : nullptr, tcd ? tgsplit[ri].lo : nullptr));
+                                tcd ? dsp.hi : nullptr, tcd ? dsp.lo : nullptr));
         if (last && !fastp) {
             FS_CUDA(cudaMemcpyAsync(grads + c.offG, gb_tmp, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
             FS_CUDA(cudaMemcpyAsync(grads + c.offB, gb_tmp + 4, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -699,7 +706,9 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
             wa.dy_bs = (long long)c.outH * c.outW * c.cout_s;
             const bool padded = (c.cin != c.cin_s) || (c.cout != c.cout_s);
             wa.out = padded ? ((fastp && wgs[l]) ? wgs[l] : wg_tmp) : grads + c.offW;
-            if (tcl)
+            if (defer_wg) {
+                // after the sweep (launch_wgrad3x3_tc_multi)
+            } else if (tcl)
                 PROF(PC_WGRAD, wgrad_flops(wa), launch_wgrad3x3_tc(tsplit[l], tgsplit[ri], wa.out, wg_partial, wg_partial_cap,
                                                                    N, c.inH, c.inW, c.outH, c.outW, 0, st));
             else if (c.k == 9 && c.stride == 1 && c.same && c.cin_s * c.cout_s == 64)
@@ -717,7 +726,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         if (tcl) {
             Conv3x3TcArgs ta;
             memset(&ta, 0, sizeof(ta));
-            ta.x = tgsplit[ri]; ta.w = tw_d[l];
+            ta.x = dsp; ta.w = tw_d[l];
             ta.N = N; ta.H = c.outH; ta.W = c.outW; ta.C = 64; ta.OH = c.inH; ta.OW = c.inW; ta.OC = 64;
             ta.pad = 2;                              // VALID conv: data gradient is the "full" correlation
             if (first_of_block) { ta.addend = resid_dOut; ta.add_crop = 2; ta.addH = resid_H; ta.addW = resid_W; }
@@ -784,6 +793,17 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
         dAct = dPrev; cur = pidx;
         if (first_of_block) { held = -1; resid_dOut = nullptr; }
+    }
+    if (use_tc && batch_wgrad) {
+        WgradMultiItem items[WGRAD_MULTI_MAX];
+        double fl = 0.0;
+        for (int l = 3; l <= 12; ++l) {
+            WgradMultiItem& it = items[l - 3];
+            it.x = tsplit[l]; it.dy = rg[l]; it.out = grads + tc[l].offW;
+            it.H = tc[l].inH; it.W = tc[l].inW; it.OH = tc[l].outH; it.OW = tc[l].outW; it.pad = 0;
+            fl += 2.0 * N * tc[l].outH * tc[l].outW * 9.0 * 64 * 64;
+        }
+        PROF(PC_WGRAD, fl, launch_wgrad3x3_tc_multi(items, 10, wg_partial, wg_partial_cap, N, st));
     }
     if (fastp) FS_TRY(finish_weight_grads_table(grads, st));
     return 0;

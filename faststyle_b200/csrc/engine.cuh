@@ -106,6 +106,9 @@ struct Engine {
     SplitPtr gsS[V_NCONV];               // packed per-sample Gram-space gradients S (tensor-path Gram backward)
     SplitPtr tsplit[T_NCONV];            // input planes of the tensor-path transform convs (2, 3..12, 13)
     SplitPtr tgsplit[3];                 // planes of tgrad[i] (dRaw of the tensor-path transform convs)
+    SplitPtr rg[T_NCONV];                // residual convs (3..12): planes of dRaw kept per layer, so that their ten
+                                         // weight gradients run as ONE batched launch after the backward sweep
+    int batch_wgrad = 1;                 // FS_BATCH_WGRAD=0: one weight-gradient launch per residual conv
     SplitPtr tw_f[T_NCONV], tw_d[T_NCONV];   // packed weights (forward / data gradient)
     float* w2f = nullptr;                // initconv_1/2 weights in the 2x2 space-to-depth form (fp32 staging)
     float* wpair = nullptr;              // pixel-paired 2x2 weights (fp32 staging, one layer at a time)

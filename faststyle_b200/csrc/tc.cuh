@@ -62,6 +62,12 @@ int launch_wgrad3x3_tc(SplitPtr x, SplitPtr dy, float* out, float* partial, long
                        int W, int OH, int OW, int pad, cudaStream_t st);
 
 
+// the same for up to WGRAD_MULTI_MAX convolutions (equal batch N) in one launch + one reduction
+constexpr int WGRAD_MULTI_MAX = 10;
+struct WgradMultiItem { SplitPtr x, dy; float* out; int H, W, OH, OW, pad; };
+int launch_wgrad3x3_tc_multi(const WgradMultiItem* items, int count, float* partial, long long partial_cap, int N,
+                             cudaStream_t st);
+
 // tcgen05 weight gradient of the 2x2-tap forms (wgrad_tc.cu): out [2,2,Cx,Cy], (Cx,Cy) = (64,128) | (128,64)
 long long wgrad2x2_tc_partial_floats();
 int launch_wgrad2x2_tc(SplitPtr x, int x_s2d, SplitPtr dy, int dy_s2d, float* out, float* partial, long long partial_cap,

@@ -192,6 +192,179 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Batched form: the weight gradients of SEVERAL 3x3 64->64 convolutions (the ten residual convs of the transform
+// net) in ONE launch.  Each problem owns a contiguous range of CTAs; a CTA accumulates all of its tiles in TMEM and
+// dumps one partial [9,64,64], so a problem produces ~15 partials instead of 148 and the ten launches + ten
+// reductions of the per-layer form (about 7 us of MMA work each against ~25 us of dump + reduce + launch latency)
+// become one launch + one reduction.  The body is wgrad3x3_tc_kernel's.
+struct WgProblem {
+    CUtensorMap tmX_hi, tmX_lo, tmD_hi, tmD_lo;
+    int pad, tilesX, tilesY, total_tiles;
+    int cta_begin, cta_count;
+    float* partial;            // [cta_count][9*64*64]
+    float* out;                // [3,3,64,64]
+};
+struct WgMulti { WgProblem pr[WGRAD_MULTI_MAX]; int count; };
+
+__global__ void __launch_bounds__(256, 1)
+wgrad3x3_tc_multi_kernel(const __grid_constant__ WgMulti M) {
+    FS_PDL_TRIGGER();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smemX = smem;
+    uint8_t* smemD = smem + STAGES * X_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smemD + STAGES * D_STAGE);
+    uint64_t* x_full = bars;
+    uint64_t* x_empty = x_full + STAGES;
+    uint64_t* d_full = x_empty + STAGES;
+    uint64_t* d_empty = d_full + STAGES;
+    uint64_t* done = d_empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+    int j = 0;
+    while (j + 1 < M.count && (int)blockIdx.x >= M.pr[j + 1].cta_begin) ++j;
+    const WgProblem& P = M.pr[j];
+    const int cta = (int)blockIdx.x - P.cta_begin, nctas = P.cta_count;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&P.tmX_hi); prefetch_tmap(&P.tmX_lo); prefetch_tmap(&P.tmD_hi); prefetch_tmap(&P.tmD_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1);
+            mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 1);
+        }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    FS_PDL_WAIT();                        // everything above is CTA-local setup
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        int sx = 0, sd = 0; uint32_t px = 0, pd = 0;
+        for (int t = cta; t < P.total_tiles; t += nctas) {
+            const int tx = t % P.tilesX;
+            int r = t / P.tilesX;
+            const int ty = r % P.tilesY;
+            const int n = r / P.tilesY;
+            const int y0 = ty * TH, x0 = tx * TW;
+            mbar_wait(&d_empty[sd], pd ^ 1);
+            uint8_t* dd = smemD + sd * D_STAGE;
+            mbar_expect_tx(&d_full[sd], D_STAGE);
+            tma_load_4d(dd, &P.tmD_hi, &d_full[sd], 0, x0, y0, n);
+            tma_load_4d(dd + DT_BYTES, &P.tmD_lo, &d_full[sd], 0, x0, y0, n);
+            if (++sd == STAGES) { sd = 0; pd ^= 1; }
+            for (int kw = 0; kw < 3; ++kw) {
+                mbar_wait(&x_empty[sx], px ^ 1);
+                uint8_t* xd = smemX + sx * X_STAGE;
+                mbar_expect_tx(&x_full[sx], X_STAGE);
+                tma_load_4d(xd, &P.tmX_hi, &x_full[sx], 0, x0 + kw - P.pad, y0 - P.pad, n);
+                tma_load_4d(xd + SLAB_BYTES, &P.tmX_lo, &x_full[sx], 0, x0 + kw - P.pad, y0 - P.pad, n);
+                if (++sx == STAGES) { sx = 0; px ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = make_idesc_mn();
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        int sx = 0, sd = 0; uint32_t px = 0, pd = 0;
+        bool first_tile = true;
+        for (int t = cta; t < P.total_tiles; t += nctas) {
+            mbar_wait(&d_full[sd], pd);
+            tc_fence_after();
+            const uint64_t dd_hi = make_sdesc_mn(smem_u32(smemD + sd * D_STAGE), 2048);
+            const uint64_t dd_lo = make_sdesc_mn(smem_u32(smemD + sd * D_STAGE + DT_BYTES), 2048);
+            for (int kw = 0; kw < 3; ++kw) {
+                mbar_wait(&x_full[sx], px);
+                tc_fence_after();
+                const uint64_t xd_hi = make_sdesc_mn(smem_u32(smemX + sx * X_STAGE), 2048);
+                const uint64_t xd_lo = make_sdesc_mn(smem_u32(smemX + sx * X_STAGE + SLAB_BYTES), 2048);
+                if (elect_one()) {
+#pragma unroll
+                    for (int grp = 0; grp < 2; ++grp) {
+                        const uint32_t acc = tb + (uint32_t)((kw * 2 + grp) * 64);
+#pragma unroll
+                        for (int prod = 0; prod < 3; ++prod) {
+                            const uint64_t ad = (prod == 2 ? xd_lo : xd_hi) + (uint64_t)(grp * 128);   // +2048 B
+                            const uint64_t bd = (prod == 1 ? dd_lo : dd_hi);
+#pragma unroll
+                            for (int ks = 0; ks < TH; ++ks)
+                                tc_mma_bf16(acc, ad + (uint64_t)(ks * 128), bd + (uint64_t)(ks * 128), idesc,
+                                            (first_tile && prod == 0 && ks == 0) ? 0u : 1u);
+                        }
+                    }
+                    tc_commit(&x_empty[sx]);
+                }
+                __syncwarp();
+                if (++sx == STAGES) { sx = 0; px ^= 1; }
+            }
+            if (elect_one()) tc_commit(&d_empty[sd]);
+            __syncwarp();
+            if (++sd == STAGES) { sd = 0; pd ^= 1; }
+            first_tile = false;
+        }
+        if (elect_one()) tc_commit(done);
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        const int row = ew * 32 + lane;
+        mbar_wait(done, 0);
+        tc_fence_after();
+        float* part = P.partial + (long long)cta * (9 * 64 * 64);
+        const bool has_tiles = cta < P.total_tiles;
+#pragma unroll 1
+        for (int a = 0; a < 6; ++a) {
+            const int kw = a >> 1, grp = a & 1;
+            const int kh = grp + (row >> 6);
+            const bool keep = !(grp == 1 && row < 64);
+            const int tap = kh * 3 + kw, ci = row & 63;
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ++ch) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * 64 + ch * 32), v);
+                if (keep) {
+                    float* op = part + ((long long)tap * 64 + ci) * 64 + ch * 32;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<float4*>(op + i) = has_tiles ? make_float4(v[i], v[i + 1], v[i + 2], v[i + 3])
+                                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+struct WgReduceMulti { const float* partial[WGRAD_MULTI_MAX]; float* out[WGRAD_MULTI_MAX]; int nparts[WGRAD_MULTI_MAX]; };
+
+// out[j][i] = sum_b partial[j][b][i], fixed order; blockIdx.y = problem
+__global__ void __launch_bounds__(256) reduce_cta_partials_multi_kernel(const __grid_constant__ WgReduceMulti R, int elems) {
+    FS_PDL_ENTER();
+    __shared__ float red[8][33];
+    const float* __restrict__ partial = R.partial[blockIdx.y];
+    const int nparts = R.nparts[blockIdx.y];
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lx;
+    float s = 0.f;
+    if (i < elems)
+        for (int b = ly; b < nparts; b += 8) s += partial[(long long)b * elems + i];
+    red[ly][lx] = s;
+    __syncthreads();
+    if (ly == 0 && i < elems) {
+        float r = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r += red[k][lx];
+        R.out[blockIdx.y][i] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Weight gradient of the 2x2-tap forms of the stride-2 / resize convolutions (initconv_1/2, upsample_0/1; see
 // conv3x3_tc.cu "2x2-tap mode"):  dWc[a,b,cx,cy] = sum_{n,y,x} X[n, y+a, x+b, cx] * dY[n, y, x, cy]
 // with (Cx, Cy) = (64, 128) or (128, 64); the 128-channel side is a space-to-depth view read through a 5-D tensor
@@ -931,6 +1104,64 @@ int pack_gemm_b_tc(const float* S, SplitPtr out, int N, int C, cudaStream_t st) 
     FS_CHECK(C % 64 == 0, "pack_gemm_b_tc: C must be a multiple of 64");
     long long total = (long long)N * C * C;
     launch_k(pack_gemm_b_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, S, out.hi, out.lo, N, C);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+// Batched weight gradients of `count` 3x3 64->64 convolutions (see wgrad3x3_tc_multi_kernel).  partial: workspace of
+// wgrad3x3_tc_partial_floats() floats (148 partials in total, shared out over the problems).
+int launch_wgrad3x3_tc_multi(const WgradMultiItem* items, int count, float* partial, long long partial_cap, int N,
+                             cudaStream_t st) {
+    FS_CHECK(count >= 1 && count <= WGRAD_MULTI_MAX, "wgrad3x3_tc_multi: 1..%d problems", WGRAD_MULTI_MAX);
+    int sms = 148;
+    {
+        int dev = 0; cudaGetDevice(&dev);
+        int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+        if (sms > 148) sms = 148;
+    }
+    FS_CHECK(148LL * 9 * 64 * 64 <= partial_cap, "wgrad3x3_tc_multi: partial workspace too small");
+    WgMulti M;
+    memset(&M, 0, sizeof(M));
+    M.count = count;
+    long long tiles[WGRAD_MULTI_MAX], total = 0;
+    for (int j = 0; j < count; ++j) {
+        const WgradMultiItem& it = items[j];
+        FS_CHECK(it.x.hi && it.x.lo && it.dy.hi && it.dy.lo && it.out, "wgrad3x3_tc_multi: NULL argument");
+        WgProblem& P = M.pr[j];
+        FS_TRY(make_map(&P.tmX_hi, it.x.hi, N, it.H, it.W, TH + 2));
+        FS_TRY(make_map(&P.tmX_lo, it.x.lo, N, it.H, it.W, TH + 2));
+        FS_TRY(make_map(&P.tmD_hi, it.dy.hi, N, it.OH, it.OW, TH));
+        FS_TRY(make_map(&P.tmD_lo, it.dy.lo, N, it.OH, it.OW, TH));
+        P.pad = it.pad; P.tilesX = cdiv(it.OW, TW); P.tilesY = cdiv(it.OH, TH);
+        P.total_tiles = N * P.tilesX * P.tilesY;
+        P.out = it.out;
+        tiles[j] = P.total_tiles; total += tiles[j];
+    }
+    // CTAs in proportion to the tile counts (at least one each), all SMs used
+    int begin = 0, left = sms;
+    for (int j = 0; j < count; ++j) {
+        int c = j == count - 1 ? left : (int)((tiles[j] * sms + total / 2) / total);
+        if (c < 1) c = 1;
+        const int others = count - 1 - j;
+        if (c > left - others) c = left - others;
+        if (c > M.pr[j].total_tiles) c = M.pr[j].total_tiles;
+        if (c < 1) c = 1;
+        M.pr[j].cta_begin = begin; M.pr[j].cta_count = c;
+        M.pr[j].partial = partial + (long long)begin * (9 * 64 * 64);
+        begin += c; left -= c;
+    }
+    FS_CHECK(begin <= 148 && left >= 0, "wgrad3x3_tc_multi: CTA assignment overflow");
+    static bool attr_set = false;
+    if (!attr_set) {
+        FS_CUDA(cudaFuncSetAttribute(wgrad3x3_tc_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    launch_k(wgrad3x3_tc_multi_kernel, dim3(begin), dim3(256), SMEM_BYTES, st, M);
+    FS_LAUNCH_CHECK();
+    WgReduceMulti R;
+    memset(&R, 0, sizeof(R));
+    for (int j = 0; j < count; ++j) { R.partial[j] = M.pr[j].partial; R.out[j] = M.pr[j].out; R.nparts[j] = M.pr[j].cta_count; }
+    launch_k(reduce_cta_partials_multi_kernel, dim3(cdiv(9 * 64 * 64, 32), count), dim3(256), 0, st, R, 9 * 64 * 64);
     FS_LAUNCH_CHECK();
     return 0;
 }
