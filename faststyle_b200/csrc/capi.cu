@@ -82,6 +82,8 @@ int fs_engine_create(int N, int H, int W, int flags, unsigned content_mask, unsi
     h->e.use_tc = (env && env[0] == '0') ? 0 : 1;
     env = getenv("FS_IN_EPILOGUE");
     h->e.in_epi = (env && env[0] == '0') ? 0 : 1;
+    env = getenv("FS_FOLD_POOL");
+    h->e.fold_pool = (env && env[0] == '0') ? 0 : 1;
     env = getenv("FS_BATCH_WGRAD");
     h->e.batch_wgrad = (env && env[0] == '0') ? 0 : 1;
     env = getenv("FS_FAST_PREP");

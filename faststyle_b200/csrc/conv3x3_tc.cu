@@ -59,6 +59,7 @@ struct TcParams {
     int tilesX, tilesY, tilesN;
     long long total_tiles;     // work units: spatial tiles (per-sample pairs of them for the CTA-pair kernel) x tilesN
     const float* bias; const float* addend; const float* ref;
+    const float* pool_grad; const float* ctarget; float cw2;
     int relu, add_crop, addH, addW;
     float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
     double* stats; int stats_c;       // [N][stats_c][2] running (sum, sum of squares) of the raw output per real channel
@@ -375,7 +376,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                         }
 #pragma unroll
                         for (int i = 0; i < 32; i += 8) stg256(op + i, v + i);
-                    } else if (ok) {
+                    } else if (ok || p.pool_grad) {            // (pool routing shuffles need every lane of the warp)
                         const int c0 = nt * BN + ch * 32;
                         if (p.bias) {
 #pragma unroll
@@ -398,15 +399,51 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                         }
                         if (p.ref) {
+                            // v = mask(ref > 0) * (v + route(pool_grad) + cw2 * (ref - ctarget)): the backward of
+                            // ReLU, of a following 2x2 max-pool (gradient to the FIRST maximum of the window in scan
+                            // order, as pool_bwd_combine_kernel) and of the content loss, fused.  The four pixels of a
+                            // pooling window are lanes L, L^1, L^16, L^17 of this warp (a warp covers 2 rows x 16
+                            // columns, both even-aligned); pixels outside the image count as -inf.
                             const float* rp = p.ref + pix * p.OC + c0;
+                            const float* gp = nullptr;
+                            const float* tp = p.ctarget ? p.ctarget + pix * p.OC + c0 : nullptr;
+                            if (p.pool_grad && ok)
+                                gp = p.pool_grad + (((long long)n * ((p.OH + 1) >> 1) + (oy >> 1)) * ((p.OW + 1) >> 1) + (ox >> 1)) * p.OC + c0;
+                            const int kme = ((lane >> 4) & 1) * 2 + (lane & 1);
 #pragma unroll
                             for (int i = 0; i < 32; i += 8) {
                                 float b[8];
-                                ldg256(rp + i, b);
+                                if (ok) ldg256(rp + i, b);
+                                else {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) b[j] = -INFINITY;
+                                }
+                                if (p.pool_grad) {
+                                    float g[8];
+                                    if (ok) ldg256(gp + i, g);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float o1 = __shfl_xor_sync(0xffffffffu, b[j], 1);
+                                        const float o2 = __shfl_xor_sync(0xffffffffu, b[j], 16);
+                                        const float o3 = __shfl_xor_sync(0xffffffffu, b[j], 17);
+                                        // position q = kme ^ m: earlier positions must be strictly smaller, later ones not larger
+                                        const bool w1 = (kme ^ 1) < kme ? o1 < b[j] : o1 <= b[j];
+                                        const bool w2 = (kme ^ 2) < kme ? o2 < b[j] : o2 <= b[j];
+                                        const bool w3 = (kme ^ 3) < kme ? o3 < b[j] : o3 <= b[j];
+                                        if (ok && w1 && w2 && w3) v[i + j] += g[j];
+                                    }
+                                }
+                                if (tp && ok) {
+                                    float t[8];
+                                    ldg256(tp + i, t);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) v[i + j] = fmaf(p.cw2, b[j] - t[j], v[i + j]);
+                                }
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[i + j] = b[j] > 0.f ? v[i + j] : 0.f;
                             }
                         }
+                        if (ok) {
                         if (p.out_f32) {
                             float* op = p.out_f32 + pix * p.OC + c0;
 #pragma unroll
@@ -430,6 +467,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                                 stg256_b32(hp + i, hw);
                                 stg256_b32(lp + i, lw);
                             }
+                        }
                         }
                     }
                 }
@@ -638,6 +676,7 @@ int launch_cfg_s(const Conv3x3TcArgs& a, cudaStream_t st) {
     const long long tps = (long long)p.tilesX * p.tilesY;
     p.total_tiles = (long long)a.N * (PAIR ? (tps + 1) / 2 : tps) * p.tilesN;
     p.bias = a.bias; p.addend = a.addend; p.ref = a.ref; p.relu = a.relu;
+    p.pool_grad = a.pool_grad; p.ctarget = a.ctarget; p.cw2 = a.cw2;
     p.add_crop = a.add_crop; p.addH = a.addH; p.addW = a.addW;
     p.out_f32 = a.out_f32; p.out_hi = a.out_split.hi; p.out_lo = a.out_split.lo;
     p.stats = a.stats; p.stats_c = a.stats_c;
@@ -679,6 +718,7 @@ int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st) {
     FS_CHECK((a.out_split.hi == nullptr) == (a.out_split.lo == nullptr), "conv3x3_tc: split output needs both planes");
     FS_CHECK(a.OH > 0 && a.OW > 0 && a.N > 0, "conv3x3_tc: empty output");
     FS_CHECK(a.taps == 0 || a.taps == 2 || a.taps == 3, "conv3x3_tc: taps must be 2 or 3");
+    FS_CHECK((!a.pool_grad && !a.ctarget) || (a.ref && !a.out_d2s), "conv3x3_tc: pool_grad / ctarget need the ReLU reference tensor");
     // fused statistics: the real channel (output channel % stats_c) of element i of a warp's 32-channel chunk must
     // not depend on the chunk: stats_c divides 32, or one 64-channel tile whose two chunks go to different warps
     FS_CHECK(!a.stats || ((a.stats_c == 16 || a.stats_c == 32 || (a.stats_c == 64 && a.OC == 64)) && a.OC <= 128 &&

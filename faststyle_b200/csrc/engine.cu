@@ -79,6 +79,8 @@ static double tc_bytes(const Conv3x3TcArgs& a) {
     if (a.out_f32) b += out;
     if (a.out_split.hi) b += out;
     if (a.ref) b += out;
+    if (a.ctarget) b += out;
+    if (a.pool_grad) b += out / 4.0;
     if (a.addend) b += 4.0 * a.N * a.addH * a.addW * (double)a.OC;
     return b;
 }
@@ -973,7 +975,10 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
         if (!(use_tc && l >= 1)) return 0;
         return split_bf16(vgrad[idx], vgsplit[idx], (long long)N * vc[l].H * vc[l].W * vc[l].cout, st);
     };
-    auto gram_bwd = [&](int l, const float* addend, const float* ref, float* out, SplitPtr out_split) -> int {
+    // pool_g / ct / cw2c: gradient w.r.t. the max-pool of this activation, content target and its coefficient -
+    // folded into the tensor-path epilogue (no pool_bwd_combine pass); the FFMA path takes them pre-combined in addend
+    auto gram_bwd = [&](int l, const float* addend, const float* ref, float* out, SplitPtr out_split,
+                        const float* pool_g, const float* ctt, float cw2c) -> int {
         const VConv& v = vc[l];
         const SplitPtr fp = act_planes(l, top);
         if (fp.hi) {                     // dF = F * S as a per-sample 1x1 tensor-path GEMM
@@ -982,10 +987,12 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
             ta.x = fp; ta.w = gsS[l]; ta.one_by_one = 1; ta.per_sample_w = 1;
             ta.N = N; ta.H = v.H; ta.W = v.W; ta.C = v.cout; ta.OH = v.H; ta.OW = v.W; ta.OC = v.cout; ta.pad = 0;
             ta.addend = addend; ta.addH = v.H; ta.addW = v.W; ta.ref = ref;
+            ta.pool_grad = pool_g; ta.ctarget = ctt; ta.cw2 = cw2c;
             ta.out_f32 = out; ta.out_split = out_split;
             PROFB(PC_GRAM_BWD, tc_flops(ta) / 9.0, tc_bytes(ta), launch_conv3x3_tc(ta, st));
             return 0;
         }
+        FS_CHECK(!pool_g && !ctt, "gram backward: fused pool / content terms need the tensor path");
         IGemmArgs a;
         memset(&a, 0, sizeof(a));
         a.in = vact[l]; a.w = gramS[l]; a.w_bs = (long long)v.cout * v.cout; a.out = out; a.N = N;
@@ -1011,15 +1018,17 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
             }
             if (tg[l]) {
                 int ti = -1; const float* T = nullptr;
-                if (gp || ct) {
+                const bool tcg = act_planes(l, top).hi != nullptr;
+                const bool fold = tcg && fold_pool;          // pool routing + content term inside the Gram-backward epilogue
+                if ((gp || ct) && !fold) {
                     ti = pick(gi, -1, -1);
                     PROF(PC_POINTWISE, 0.0, pool_bwd_combine(vact[l], gp, ct, cw2, 0, vgrad[ti], N, v.H, v.W, v.cout, st));
                     T = vgrad[ti];
                 }
                 int oi = pick(gi, ti, -1);
-                const bool tcg = act_planes(l, top).hi != nullptr;
                 // P_l feeds the tensor-path data gradient of conv l: only its split planes are needed
-                FS_TRY(gram_bwd(l, T, vact[l], tcg ? nullptr : vgrad[oi], tcg ? vgsplit[oi] : no_split));
+                FS_TRY(gram_bwd(l, T, vact[l], tcg ? nullptr : vgrad[oi], tcg ? vgsplit[oi] : no_split,
+                                fold ? gp : nullptr, fold ? ct : nullptr, cw2));
                 if (!tcg) PROF(PC_POINTWISE, 0.0, ensure_split(l, oi));
                 pi = oi;
             } else {
@@ -1038,7 +1047,7 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
                     T = vgrad[ti];
                 }
                 ai = pick(pi, ti, -1);
-                FS_TRY(gram_bwd(l, T, nullptr, vgrad[ai], no_split));
+                FS_TRY(gram_bwd(l, T, nullptr, vgrad[ai], no_split, nullptr, nullptr, 0.f));
                 A = vgrad[ai];
             } else if (ct) {
                 ai = pick(pi, -1, -1);

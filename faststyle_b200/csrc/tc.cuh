@@ -41,6 +41,10 @@ struct Conv3x3TcArgs {
     int per_sample_w;          // with one_by_one: weights are [N][C/64][OC][64] (one matrix per sample)
     // epilogue: v = acc + bias[c] + addend[pix,c]; relu; mask by ref[pix,c] > 0
     const float* bias; const float* addend; const float* ref;
+    // with ref: v += route(pool_grad) + cw2 * (ref - ctarget) before the mask.  pool_grad [N,ceil(OH/2),ceil(OW/2),OC]
+    // is the gradient w.r.t. the 2x2 max-pool of ref (routed to the first maximum of each window); ctarget
+    // [N,OH,OW,OC] the content target of this layer (content-loss gradient 2w/(hwc) (f - t), cw2 = 2w/(hwc))
+    const float* pool_grad; const float* ctarget; float cw2;
     int relu;
     int add_crop, addH, addW;  // addend is [N,addH,addW,OC]; output pixel (y,x) reads (y-crop, x-crop)
     double* stats; int stats_c;    // optional: accumulate per-(sample, real channel) sum / sum of squares of the raw
