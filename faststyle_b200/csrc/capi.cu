@@ -82,6 +82,10 @@ int fs_engine_create(int N, int H, int W, int flags, unsigned content_mask, unsi
     h->e.use_tc = (env && env[0] == '0') ? 0 : 1;
     env = getenv("FS_IN_EPILOGUE");
     h->e.in_epi = (env && env[0] == '0') ? 0 : 1;
+    env = getenv("FS_KEEP_ACTS");
+    h->e.keep_acts = (env && env[0] == '1') ? 1 : 0;
+    env = getenv("FS_FUSE_POOL");
+    h->e.fuse_pool = (env && env[0] == '0') ? 0 : 1;
     env = getenv("FS_FOLD_POOL");
     h->e.fold_pool = (env && env[0] == '0') ? 0 : 1;
     env = getenv("FS_BATCH_WGRAD");
@@ -101,6 +105,11 @@ int fs_engine_set_tensor_path(fs_engine* e, int enabled) {
     FS_CHECK(e, "NULL engine");
     e->e.use_tc = enabled ? 1 : 0;
     e->e.weights_prepared = false;
+    return 0;
+}
+int fs_engine_keep_activations(fs_engine* e, int keep) {
+    FS_CHECK(e, "NULL engine");
+    e->e.keep_acts = keep ? 1 : 0;
     return 0;
 }
 int fs_set_tc_pair(int enabled) { fs::set_tc_pair(enabled); return 0; }

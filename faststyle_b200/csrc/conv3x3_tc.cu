@@ -60,6 +60,7 @@ struct TcParams {
     long long total_tiles;     // work units: spatial tiles (per-sample pairs of them for the CTA-pair kernel) x tilesN
     const float* bias; const float* addend; const float* ref;
     const float* pool_grad; const float* ctarget; float cw2;
+    __nv_bfloat16* pool_hi; __nv_bfloat16* pool_lo;
     int relu, add_crop, addH, addW;
     float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
     double* stats; int stats_c;       // [N][stats_c][2] running (sum, sum of squares) of the raw output per real channel
@@ -349,6 +350,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                         addp = p.addend + (((long long)n * p.addH + ay) * p.addW + ax) * p.OC;
                 }
                 {
+                    // the ReLU reference (and the first chunk of the pooled gradient) are requested BEFORE the
+                    // accumulator is pulled out of TMEM: four independent 256-bit loads in flight per thread instead of
+                    // one load latency per 8-channel chunk (the epilogue of the memory-heavy launches was a chain of
+                    // serialised HBM round trips: Gram backward at conv1_2 ran at 2.7 TB/s)
+                    float rb[32];
+                    float gq[8];
+                    const int rc0 = nt * BN + ch * 32;
+                    const float* gp = nullptr;
+                    if (!STATS && p.ref && !p.out_d2s) {       // (launches with fused statistics never carry a reference)
+                        if (ok) {
+                            const float* rp = p.ref + pix * p.OC + rc0;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) ldg256(rp + i, rb + i);
+                            if (p.pool_grad) {
+                                gp = p.pool_grad + (((long long)n * ((p.OH + 1) >> 1) + (oy >> 1)) * ((p.OW + 1) >> 1) + (ox >> 1)) * p.OC + rc0;
+                                ldg256(gp, gq);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) rb[i] = -INFINITY;
+                        }
+                    }
                     float v[32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) +
                                            (uint32_t)(as * K::NACC * BN + acc * BN + ch * 32);
@@ -376,7 +399,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                         }
 #pragma unroll
                         for (int i = 0; i < 32; i += 8) stg256(op + i, v + i);
-                    } else if (ok || p.pool_grad) {            // (pool routing shuffles need every lane of the warp)
+                    } else if (ok || p.pool_grad || p.pool_hi) {   // (the pooling shuffles need every lane of the warp)
                         const int c0 = nt * BN + ch * 32;
                         if (p.bias) {
 #pragma unroll
@@ -398,29 +421,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                         }
-                        if (p.ref) {
+                        if (!STATS && p.ref) {
                             // v = mask(ref > 0) * (v + route(pool_grad) + cw2 * (ref - ctarget)): the backward of
                             // ReLU, of a following 2x2 max-pool (gradient to the FIRST maximum of the window in scan
                             // order, as pool_bwd_combine_kernel) and of the content loss, fused.  The four pixels of a
                             // pooling window are lanes L, L^1, L^16, L^17 of this warp (a warp covers 2 rows x 16
                             // columns, both even-aligned); pixels outside the image count as -inf.
-                            const float* rp = p.ref + pix * p.OC + c0;
-                            const float* gp = nullptr;
                             const float* tp = p.ctarget ? p.ctarget + pix * p.OC + c0 : nullptr;
-                            if (p.pool_grad && ok)
-                                gp = p.pool_grad + (((long long)n * ((p.OH + 1) >> 1) + (oy >> 1)) * ((p.OW + 1) >> 1) + (ox >> 1)) * p.OC + c0;
                             const int kme = ((lane >> 4) & 1) * 2 + (lane & 1);
 #pragma unroll
                             for (int i = 0; i < 32; i += 8) {
-                                float b[8];
-                                if (ok) ldg256(rp + i, b);
-                                else {
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) b[j] = -INFINITY;
-                                }
+                                const float* b = rb + i;
                                 if (p.pool_grad) {
                                     float g[8];
-                                    if (ok) ldg256(gp + i, g);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) g[j] = gq[j];
+                                    if (ok && i + 8 < 32) ldg256(gp + i + 8, gq);     // next chunk's gradient while this one is routed
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) {
                                         const float o1 = __shfl_xor_sync(0xffffffffu, b[j], 1);
@@ -441,6 +457,37 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                                 }
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[i + j] = b[j] > 0.f ? v[i + j] : 0.f;
+                            }
+                        }
+                        if (p.pool_hi) {
+                            // fused 2x2 stride-2 SAME max-pool of the result (libs/vgg16.py:67-71): the window's four
+                            // pixels are lanes L, L^1, L^16, L^17; the top-left lane stores the pooled split planes
+                            const bool writer = ok && (lane & 17) == 0;
+                            const long long ppix = ((long long)n * ((p.OH + 1) >> 1) + (oy >> 1)) * ((p.OW + 1) >> 1) + (ox >> 1);
+#pragma unroll
+                            for (int i = 0; i < 32; i += 16) {
+                                float m[16];
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    float x = ok ? v[i + j] : -INFINITY;
+                                    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+                                    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 16));
+                                    m[j] = x;
+                                }
+                                if (writer) {
+                                    uint32_t hw[8], lw[8];
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        __nv_bfloat16 h0 = __float2bfloat16_rn(m[2 * j]);
+                                        __nv_bfloat16 h1 = __float2bfloat16_rn(m[2 * j + 1]);
+                                        __nv_bfloat16 l0 = __float2bfloat16_rn(m[2 * j] - __bfloat162float(h0));
+                                        __nv_bfloat16 l1 = __float2bfloat16_rn(m[2 * j + 1] - __bfloat162float(h1));
+                                        hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                                        lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                                    }
+                                    stg256_b32(p.pool_hi + ppix * p.OC + c0 + i, hw);
+                                    stg256_b32(p.pool_lo + ppix * p.OC + c0 + i, lw);
+                                }
                             }
                         }
                         if (ok) {
@@ -677,6 +724,7 @@ int launch_cfg_s(const Conv3x3TcArgs& a, cudaStream_t st) {
     p.total_tiles = (long long)a.N * (PAIR ? (tps + 1) / 2 : tps) * p.tilesN;
     p.bias = a.bias; p.addend = a.addend; p.ref = a.ref; p.relu = a.relu;
     p.pool_grad = a.pool_grad; p.ctarget = a.ctarget; p.cw2 = a.cw2;
+    p.pool_hi = a.pool_split.hi; p.pool_lo = a.pool_split.lo;
     p.add_crop = a.add_crop; p.addH = a.addH; p.addW = a.addW;
     p.out_f32 = a.out_f32; p.out_hi = a.out_split.hi; p.out_lo = a.out_split.lo;
     p.stats = a.stats; p.stats_c = a.stats_c;
@@ -714,7 +762,9 @@ bool conv3x3_tc_supported(int C, int OC, int W, int OW) {
 int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st) {
     FS_CHECK(conv3x3_tc_supported(a.C, a.OC, a.W, a.OW), "conv3x3_tc: needs C%%64==0 and OC%%64==0 (C=%d OC=%d)", a.C, a.OC);
     FS_CHECK(a.x.hi && a.x.lo && a.w.hi && a.w.lo, "conv3x3_tc: NULL operand planes");
-    FS_CHECK(a.out_f32 || a.out_split.hi, "conv3x3_tc: no output requested");
+    FS_CHECK(a.out_f32 || a.out_split.hi || a.pool_split.hi, "conv3x3_tc: no output requested");
+    FS_CHECK((a.pool_split.hi == nullptr) == (a.pool_split.lo == nullptr) && !(a.pool_split.hi && a.out_d2s),
+             "conv3x3_tc: pooled split output needs both planes and a plain layout");
     FS_CHECK((a.out_split.hi == nullptr) == (a.out_split.lo == nullptr), "conv3x3_tc: split output needs both planes");
     FS_CHECK(a.OH > 0 && a.OW > 0 && a.N > 0, "conv3x3_tc: empty output");
     FS_CHECK(a.taps == 0 || a.taps == 2 || a.taps == 3, "conv3x3_tc: taps must be 2 or 3");

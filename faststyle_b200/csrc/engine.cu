@@ -81,6 +81,7 @@ static double tc_bytes(const Conv3x3TcArgs& a) {
     if (a.ref) b += out;
     if (a.ctarget) b += out;
     if (a.pool_grad) b += out / 4.0;
+    if (a.pool_split.hi) b += out / 4.0;
     if (a.addend) b += 4.0 * a.N * a.addH * a.addW * (double)a.OC;
     return b;
 }
@@ -610,6 +611,13 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
         const float* b = last ? in15 + 4 : params + c.offB;
         float* out = last ? (y3_out ? y3_out : y3) : tb[l].act;
         const bool next_tc = (use_tc && (l + 1) >= 3 && (l + 1) <= 12) || tc2(l + 1);   // next conv consumes split planes
+        // The fp32 copy of the activation is dead when its only reader is a tensor-path conv (split planes): it
+        // survives where something else reads it - the residual skip (block inputs 2,4,..,10 and the block
+        // outputs' own skip source), the FFMA 9x9 layer (input of 15) and its weight gradient, igemm fallbacks.
+        if (!last && next_tc && !keep_acts) {
+            const bool skip_src = l >= 2 && l <= 10 && (l & 1) == 0;       // read again as the next block's skip addend
+            if (!skip_src) out = nullptr;
+        }
         PROF(PC_IN_APPLY, 0.0, instnorm_apply(tb[l].raw, tb[l].mean, tb[l].rstd, g, b, skip, out, N, c.outH, c.outW,
                                   c.cout_s, c.act, last ? 1 : 0, st, next_tc ? tsplit[l + 1].hi : nullptr,
                                   next_tc ? tsplit[l + 1].lo : nullptr));
@@ -646,7 +654,10 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         const bool tcd = tcl || (l > 0 && tc2(l));           // the data gradient reads dRaw's split planes
         const bool defer_wg = tcl && batch_wgrad;            // residual convs: planes kept in rg[l], weight gradient batched
         const SplitPtr dsp = defer_wg ? rg[l] : tgsplit[ri];
-        PROF(PC_IN_BWD, 0.0, instnorm_bwd(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw, dg, db, N,
+        // dRaw in fp32 is dead when both its readers (data gradient, weight gradient) are tensor-path kernels
+        float* dRaw_f32 = dRaw;
+        if (!keep_acts && (defer_wg || (tcl && use_tc) || (l > 0 && tc2(l)))) dRaw_f32 = nullptr;
+        PROF(PC_IN_BWD, 0.0, instnorm_bwd(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw_f32, dg, db, N,
                                 c.outH * c.outW, c.cout_s, c.act, in_partial, m12, st,
                                 tcd ? dsp.hi : nullptr, tcd ? dsp.lo : nullptr));
         if (last && !fastp) {
@@ -830,6 +841,7 @@ int Engine::vgg_forward(const float* packed, const float* img3, int upto, float*
     for (int l = 0; l <= upto; ++l) {
         float* out = (act_override && act_override[l]) ? act_override[l] : vact[l];
         const bool pool_next = vc[l].pool_after && l < upto;
+        bool pooled_in_epilogue = false;
         if (use_tc && l >= 1) {
             Conv3x3TcArgs ta;
             memset(&ta, 0, sizeof(ta));
@@ -837,11 +849,15 @@ int Engine::vgg_forward(const float* packed, const float* img3, int upto, float*
             ta.N = N; ta.H = vc[l].H; ta.W = vc[l].W; ta.C = vc[l].cin;
             ta.OH = vc[l].H; ta.OW = vc[l].W; ta.OC = vc[l].cout; ta.pad = 1;
             ta.bias = packed + vc[l].offB; ta.relu = 1;
-            // content-target pass: only pooled layers, the targets and the last layer need an fp32 copy
-            const bool need_f32 = !act_override || pool_next || act_override[l] || l == upto;
+            // the following max-pool runs in this conv's epilogue (pooled split planes for the next conv)
+            const bool fpool = pool_next && fuse_pool;
+            // content-target pass: only the targets and the last layer (and un-fused pooled layers) need an fp32 copy
+            const bool need_f32 = !act_override || (pool_next && !fpool) || act_override[l] || l == upto;
             ta.out_f32 = need_f32 ? out : nullptr;
             if (l < upto && !pool_next) ta.out_split = vsplit[l + 1];     // next conv reads split planes
-            else if (vtsplit[l].hi) ta.out_split = vtsplit[l];            // style tap: Gram kernels read them
+            else if (vtsplit[l].hi && !act_override) ta.out_split = vtsplit[l];   // style tap: Gram kernels read them
+            if (fpool) ta.pool_split = vsplit[l + 1];
+            pooled_in_epilogue = fpool;
             PROFB(PC_TC_VGG_FWD, tc_flops(ta), tc_bytes(ta), launch_conv3x3_tc(ta, st));
         } else if (l == 0) {             // conv1_1 (Cin = 3): direct shared-memory kernel, exact fp32
             const bool sp = use_tc && l < upto && !pool_next;
@@ -856,7 +872,9 @@ int Engine::vgg_forward(const float* packed, const float* img3, int upto, float*
             PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
         }
         cur = out;
-        if (pool_next) {
+        if (pool_next && pooled_in_epilogue) {
+            cur = vpool[l];                  // not written on this path (the next conv reads vsplit[l + 1])
+        } else if (pool_next) {
             const bool sp = use_tc != 0;
             PROF(PC_POINTWISE, 0.0, maxpool2x2_fwd(cur, vpool[l], N, vc[l].H, vc[l].W, vc[l].cout, st,
                                   sp ? vsplit[l + 1].hi : nullptr, sp ? vsplit[l + 1].lo : nullptr));

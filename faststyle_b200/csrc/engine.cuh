@@ -108,6 +108,8 @@ struct Engine {
     SplitPtr tgsplit[3];                 // planes of tgrad[i] (dRaw of the tensor-path transform convs)
     SplitPtr rg[T_NCONV];                // residual convs (3..12): planes of dRaw kept per layer, so that their ten
                                          // weight gradients run as ONE batched launch after the backward sweep
+    int keep_acts = 0;                   // 1: write every fp32 activation / gradient even where only split planes are read (debug taps)
+    int fuse_pool = 1;                   // FS_FUSE_POOL=0: separate max-pool kernel after the VGG conv
     int fold_pool = 1;                   // FS_FOLD_POOL=0: separate pool_bwd_combine pass before the Gram backward
     int batch_wgrad = 1;                 // FS_BATCH_WGRAD=0: one weight-gradient launch per residual conv
     SplitPtr tw_f[T_NCONV], tw_d[T_NCONV];   // packed weights (forward / data gradient)

@@ -373,7 +373,7 @@ __device__ __forceinline__ void in_apply_elem(const float4 v, const float4 s, bo
         float* o = out + ((long long)n * H * W + p) * 3;
         o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
     } else {
-        st4(out + i * 4, make_float4(r[0], r[1], r[2], r[3]));
+        if (out) st4(out + i * 4, make_float4(r[0], r[1], r[2], r[3]));      // null: only the split planes are consumed
         if (shi) store_split4(shi, slo, i * 4, r);
     }
 }
@@ -418,7 +418,7 @@ __device__ __forceinline__ void in_bwd_elem(const float4 xv4, const float4 dv4, 
         }
         r[j] = g[j] * rs[j] * (dz - m1[j] - xh * m2[j]);
     }
-    st4(dx + i * 4, make_float4(r[0], r[1], r[2], r[3]));
+    if (dx) st4(dx + i * 4, make_float4(r[0], r[1], r[2], r[3]));            // null: only the split planes are consumed
     if (shi) store_split4(shi, slo, i * 4, r);
 }
 

@@ -53,6 +53,7 @@ struct Conv3x3TcArgs {
                                // side; replica = CTA index % STATS_REPLICAS, summed by instnorm_stats_from_sums)
     float* out_f32;            // [N,OH,OW,OC] fp32 (may be null)
     SplitPtr out_split;        // split planes of the same tensor (may be null)
+    SplitPtr pool_split;       // split planes of the 2x2 stride-2 SAME max-pool of the result [N,ceil(OH/2),ceil(OW/2),OC] (may be null)
 };
 int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st);
 // CTA-pair (tcgen05 cta_group::2) variant of the kernel on / off (default: on; FS_TC_PAIR=0 in the environment)

@@ -107,6 +107,11 @@ class Engine:
         False: exact-fp32 FFMA path everywhere."""
         _lib.call("fs_engine_set_tensor_path", self._h, 1 if enabled else 0)
 
+    def keep_activations(self, keep: bool = True):
+        """Also write the fp32 activations whose only consumers read split-bf16 planes (skipped by default); call
+        before a forward pass whose intermediate activations are inspected with ``transform_activation``."""
+        _lib.call("fs_engine_keep_activations", self._h, 1 if keep else 0)
+
     def set_frozen_weights(self, frozen: bool):
         """Inference with fixed parameters: prepare the transform weights once (see fs_engine_set_frozen_weights)."""
         _lib.call("fs_engine_set_frozen_weights", self._h, 1 if frozen else 0)

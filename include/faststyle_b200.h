@@ -70,6 +70,10 @@ int fs_engine_set_tensor_path(fs_engine* e, int enabled);
  * cta_group::2 with M = 256, the weight tile split between the two CTAs' shared memories); 0: one CTA per tile
  * (cta_group::1).  Same results up to fp32 summation order.  Also FS_TC_PAIR=0 in the environment. */
 int fs_set_tc_pair(int enabled);
+/* keep = 1: the composites also write the fp32 copies of activations / gradients whose only consumers are tensor-path
+ * kernels reading split-bf16 planes (they are skipped by default); needed before fs_engine_transform_activation on
+ * such layers.  Also FS_KEEP_ACTS=1 in the environment. */
+int fs_engine_keep_activations(fs_engine* e, int keep);
 /* frozen = 1: the transform parameters passed to fs_transform_forward do not change between calls (inference):
  * their per-call preparation (padding, collapsing, pairing, bf16 packing: ~25 short launches) runs once and is
  * skipped afterwards.  Call again (any value) after changing the parameter buffer. */

@@ -59,6 +59,7 @@ def test_transform_intermediates(built_lib, starry, shape):
     with torch.no_grad():
         R.create_net(x, starry, "resize", torch.float64, taps=taps)
     eng = Engine(N, H, W, transform=True)
+    eng.keep_activations(True)                  # fp32 copies of the activations only tensor-path convs read
     eng.transform_forward(params_to_device(starry, "cuda"), x)
     torch.cuda.synchronize()
     names = {0: "initconv_0", 1: "initconv_1", 2: "initconv_2", 4: "resblock_0", 12: "resblock_4",
