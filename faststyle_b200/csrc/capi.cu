@@ -82,6 +82,8 @@ int fs_engine_create(int N, int H, int W, int flags, unsigned content_mask, unsi
     h->e.use_tc = (env && env[0] == '0') ? 0 : 1;
     env = getenv("FS_IN_EPILOGUE");
     h->e.in_epi = (env && env[0] == '0') ? 0 : 1;
+    env = getenv("FS_TC9");
+    h->e.tc9_on = (env && env[0] == '0') ? 0 : 1;
     env = getenv("FS_KEEP_ACTS");
     h->e.keep_acts = (env && env[0] == '1') ? 1 : 0;
     env = getenv("FS_FUSE_POOL");

@@ -53,7 +53,9 @@ __device__ __forceinline__ uint32_t make_idesc() {
 
 struct TcParams {
     int N, H, W, C, OH, OW, OC, pad;
-    int taps;                  // 3: 3x3 convolution, 2: 2x2 (collapsed stride-2 forms), 1: 1x1 (per-sample GEMM)
+    int taps;                  // vertical taps: 3: 3x3 convolution, 2: 2x2 (collapsed stride-2 forms), 1: 1x1 (per-sample GEMM),
+                               // 9: the 9-row forms of the 9x9 layers
+    int taps_w, pad_x;         // horizontal taps / left padding (== taps / pad for the square forms)
     int in_s2d, out_d2s;       // space-to-depth input view (5-D tensor map) / depth-to-space fp32 store
     int w_sample_rows;         // rows of the packed weight matrix per sample (0 = shared weights)
     int tilesX, tilesY, tilesN;
@@ -82,13 +84,15 @@ __device__ __forceinline__ float warp_transpose_sum(float* s, int lane) {
     return s[0];
 }
 
-template <int TH, int BN, bool PAIR = false>
+// HALO = slab rows beyond the tile height = (vertical taps - 1): 2 for the 3x3 / 2x2 / 1x1 forms, 8 for the 9-row
+// forms of the 9x9 layers
+template <int TH, int BN, bool PAIR = false, int HALO = 2>
 struct Cfg {
     static constexpr int NACC = TH / 8;
-    static constexpr int A_STAGES = (TH == 8) ? 3 : 2;             // small tiles: deeper slab ring (latency-bound)
+    static constexpr int A_STAGES = (TH == 8 && HALO == 2) ? 3 : 2;   // small tiles: deeper slab ring (latency-bound)
     static constexpr int B_ROWS = PAIR ? BN / 2 : BN;              // weight rows held by one CTA
     static constexpr int B_STAGES = (B_ROWS <= 64) ? 4 : 2;
-    static constexpr int SLAB_BYTES = (TH + 2) * TW * 128;        // one plane
+    static constexpr int SLAB_BYTES = (TH + HALO) * TW * 128;     // one plane
     static constexpr int A_STAGE_BYTES = 2 * SLAB_BYTES;          // hi + lo
     static constexpr int BTILE_BYTES = B_ROWS * 128;              // one plane
     static constexpr int B_STAGE_BYTES = 2 * BTILE_BYTES;
@@ -113,13 +117,13 @@ __device__ __forceinline__ uint32_t make_idesc_p() {
 // Barrier protocol: `*_full` barriers live in the leader only (both CTAs' TMA loads count their bytes there);
 // `*_empty` and `t_full` exist in both CTAs and are signalled by the leader's multicast tcgen05.commit; the
 // leader's `t_empty` collects the arrivals of both CTAs' epilogue warps (the peer's arrive remotely).
-template <int TH, int BN, bool STATS, bool PAIR>
+template <int TH, int BN, bool STATS, bool PAIR, int HALO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                   const TcParams p) {
     FS_PDL_TRIGGER();
-    using K = Cfg<TH, BN, PAIR>;
+    using K = Cfg<TH, BN, PAIR, HALO>;
     constexpr int A_STAGES = K::A_STAGES;
     constexpr int NCTA = PAIR ? 2 : 1;
     extern __shared__ uint8_t smem_raw[];
@@ -198,10 +202,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         for (long long u = u_begin; u < u_end; u += u_stride) {
             int nt, tx, ty, n;
             decode(u, nt, tx, ty, n);
-            const int y0 = ty * TH - p.pad, x0 = tx * TW - p.pad;
+            const int y0 = ty * TH - p.pad, x0 = tx * TW - p.pad_x;
             const int n0 = nt * BN + (int)cta * K::B_ROWS;
             for (int cb = 0; cb < CB; ++cb) {
-                for (int kw = 0; kw < p.taps; ++kw) {
+                for (int kw = 0; kw < p.taps_w; ++kw) {
                     mbar_wait(&a_empty[sa], pa ^ 1);
                     uint8_t* dst = smemA + sa * K::A_STAGE_BYTES;
                     if (!PAIR || cta == 0) mbar_expect_tx(&a_full[sa], NCTA * K::A_STAGE_BYTES);
@@ -226,7 +230,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                         mbar_wait(&b_empty[sb], pb ^ 1);
                         uint8_t* bd = smemB + sb * K::B_STAGE_BYTES;
                         if (!PAIR || cta == 0) mbar_expect_tx(&b_full[sb], NCTA * K::B_STAGE_BYTES);
-                        const int row = ((kh * p.taps + kw) * CB + cb) * p.OC + n0 + n * p.w_sample_rows;
+                        const int row = ((kh * p.taps_w + kw) * CB + cb) * p.OC + n0 + n * p.w_sample_rows;
                         if (PAIR) {
                             const uint32_t fb = mapa_u32(&b_full[sb], 0);
                             tma2_load_2d(bd, &tmB_hi, fb, 0, row);
@@ -255,7 +259,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             const uint32_t acc_base = tb + (uint32_t)(as * K::NACC * BN);
             bool first = true;
             for (int cb = 0; cb < CB; ++cb) {
-                for (int kw = 0; kw < p.taps; ++kw) {
+                for (int kw = 0; kw < p.taps_w; ++kw) {
                     mbar_wait(&a_full[sa], pa);
                     tc_fence_after();
                     const uint64_t ad_hi = make_sdesc(smem_u32(smemA + sa * K::A_STAGE_BYTES));
@@ -699,25 +703,26 @@ int num_sms() {
 
 int g_tc_pair = -1;     // CTA-pair (cta_group::2) kernel: -1 = read FS_TC_PAIR (default on), 0 off, 1 on
 
-template <int TH, int BN, bool STATS, bool PAIR>
+template <int TH, int BN, bool STATS, bool PAIR, int HALO>
 int launch_cfg_s(const Conv3x3TcArgs& a, cudaStream_t st) {
-    using K = Cfg<TH, BN, PAIR>;
+    using K = Cfg<TH, BN, PAIR, HALO>;
     CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
     if (a.in_s2d) {
-        FS_TRY(make_act_map_s2d(&tmA_hi, a.x.hi, a.N, a.H, a.W, TH + 2));
-        FS_TRY(make_act_map_s2d(&tmA_lo, a.x.lo, a.N, a.H, a.W, TH + 2));
+        FS_TRY(make_act_map_s2d(&tmA_hi, a.x.hi, a.N, a.H, a.W, TH + HALO));
+        FS_TRY(make_act_map_s2d(&tmA_lo, a.x.lo, a.N, a.H, a.W, TH + HALO));
     } else {
-        FS_TRY(make_act_map(&tmA_hi, a.x.hi, a.N, a.H, a.W, a.C, TH + 2));
-        FS_TRY(make_act_map(&tmA_lo, a.x.lo, a.N, a.H, a.W, a.C, TH + 2));
+        FS_TRY(make_act_map(&tmA_hi, a.x.hi, a.N, a.H, a.W, a.C, TH + HALO));
+        FS_TRY(make_act_map(&tmA_lo, a.x.lo, a.N, a.H, a.W, a.C, TH + HALO));
     }
     const int taps = a.one_by_one ? 1 : (a.taps ? a.taps : 3);
+    const int taps_w = a.taps_w ? a.taps_w : taps;
     const long long wrows = a.one_by_one ? (long long)(a.per_sample_w ? a.N : 1) * (a.C / KB) * a.OC
-                                         : (long long)taps * taps * (a.C / KB) * a.OC;
+                                         : (long long)taps * taps_w * (a.C / KB) * a.OC;
     FS_TRY(make_w_map(&tmB_hi, a.w.hi, wrows, K::B_ROWS));
     FS_TRY(make_w_map(&tmB_lo, a.w.lo, wrows, K::B_ROWS));
     TcParams p;
     p.N = a.N; p.H = a.H; p.W = a.W; p.C = a.C; p.OH = a.OH; p.OW = a.OW; p.OC = a.OC; p.pad = a.pad;
-    p.taps = taps; p.in_s2d = a.in_s2d; p.out_d2s = a.out_d2s;
+    p.taps = taps; p.taps_w = taps_w; p.pad_x = a.taps_w ? a.pad_x : a.pad; p.in_s2d = a.in_s2d; p.out_d2s = a.out_d2s;
     p.w_sample_rows = a.one_by_one && a.per_sample_w ? (a.C / KB) * a.OC : 0;
     p.tilesX = cdiv(a.OW, TW); p.tilesY = cdiv(a.OH, TH); p.tilesN = a.OC / BN;
     const long long tps = (long long)p.tilesX * p.tilesY;
@@ -730,27 +735,27 @@ int launch_cfg_s(const Conv3x3TcArgs& a, cudaStream_t st) {
     p.stats = a.stats; p.stats_c = a.stats_c;
     static bool attr_set = false;
     if (!attr_set) {
-        FS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<TH, BN, STATS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+        FS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<TH, BN, STATS, PAIR, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
         attr_set = true;
     }
     const int sms = num_sms();
     if (PAIR) {
         const int clusters = (int)(p.total_tiles < sms / 2 ? p.total_tiles : sms / 2);
-        launch_k_cluster2((conv3x3_tc_kernel<TH, BN, STATS, PAIR>), dim3(2 * clusters), dim3(TC_THREADS), K::SMEM_BYTES, st,
+        launch_k_cluster2((conv3x3_tc_kernel<TH, BN, STATS, PAIR, HALO>), dim3(2 * clusters), dim3(TC_THREADS), K::SMEM_BYTES, st,
                           tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     } else {
         const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
-        launch_k((conv3x3_tc_kernel<TH, BN, STATS, PAIR>), dim3(grid), dim3(TC_THREADS), K::SMEM_BYTES, st, tmA_hi, tmA_lo,
+        launch_k((conv3x3_tc_kernel<TH, BN, STATS, PAIR, HALO>), dim3(grid), dim3(TC_THREADS), K::SMEM_BYTES, st, tmA_hi, tmA_lo,
                  tmB_hi, tmB_lo, p);
     }
     FS_LAUNCH_CHECK();
     return 0;
 }
 
-template <int TH, int BN>
+template <int TH, int BN, int HALO = 2>
 int launch_cfg(const Conv3x3TcArgs& a, bool pair, cudaStream_t st) {
-    if (pair) return a.stats ? launch_cfg_s<TH, BN, true, true>(a, st) : launch_cfg_s<TH, BN, false, true>(a, st);
-    return a.stats ? launch_cfg_s<TH, BN, true, false>(a, st) : launch_cfg_s<TH, BN, false, false>(a, st);
+    if (pair) return a.stats ? launch_cfg_s<TH, BN, true, true, HALO>(a, st) : launch_cfg_s<TH, BN, false, true, HALO>(a, st);
+    return a.stats ? launch_cfg_s<TH, BN, true, false, HALO>(a, st) : launch_cfg_s<TH, BN, false, false, HALO>(a, st);
 }
 
 }  // namespace
@@ -767,12 +772,14 @@ int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st) {
              "conv3x3_tc: pooled split output needs both planes and a plain layout");
     FS_CHECK((a.out_split.hi == nullptr) == (a.out_split.lo == nullptr), "conv3x3_tc: split output needs both planes");
     FS_CHECK(a.OH > 0 && a.OW > 0 && a.N > 0, "conv3x3_tc: empty output");
-    FS_CHECK(a.taps == 0 || a.taps == 2 || a.taps == 3, "conv3x3_tc: taps must be 2 or 3");
+    FS_CHECK(a.taps == 0 || a.taps == 2 || a.taps == 3 || a.taps == 9, "conv3x3_tc: taps must be 2, 3 or 9");
+    FS_CHECK(a.taps != 9 || (a.taps_w >= 1 && a.taps_w <= 3 && !a.in_s2d && !a.out_d2s && !a.one_by_one),
+             "conv3x3_tc: the 9-row form takes 1..3 horizontal taps and plain layouts");
     FS_CHECK((!a.pool_grad && !a.ctarget) || (a.ref && !a.out_d2s), "conv3x3_tc: pool_grad / ctarget need the ReLU reference tensor");
     // fused statistics: the real channel (output channel % stats_c) of element i of a warp's 32-channel chunk must
     // not depend on the chunk: stats_c divides 32, or one 64-channel tile whose two chunks go to different warps
-    FS_CHECK(!a.stats || ((a.stats_c == 16 || a.stats_c == 32 || (a.stats_c == 64 && a.OC == 64)) && a.OC <= 128 &&
-                          !a.bias && !a.relu && !a.addend && !a.ref),
+    FS_CHECK(!a.stats || ((a.stats_c == 4 || a.stats_c == 8 || a.stats_c == 16 || a.stats_c == 32 ||
+                           (a.stats_c == 64 && a.OC == 64)) && !a.bias && !a.relu && !a.addend && !a.ref),
              "conv3x3_tc: fused statistics are for raw transform-net conv outputs (16/32/64 real channels)");
     FS_CHECK(!a.in_s2d || (a.C == 128 && !a.one_by_one), "conv3x3_tc: the space-to-depth input view needs C == 128");
     FS_CHECK(!a.out_d2s || (a.OC == 128 && a.out_f32 && !a.out_split.hi && !a.bias && !a.addend && !a.ref && !a.relu),
@@ -782,6 +789,8 @@ int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st) {
         g_tc_pair = (e && e[0] == '0') ? 0 : 1;
     }
     const bool pair = g_tc_pair != 0;
+    if (a.taps == 9)         // 9-row forms (x16 space-to-depth 9x9 layers): 8-row tiles under a 16-row slab
+        return a.OC % 128 == 0 ? launch_cfg<8, 128, 8>(a, pair, st) : launch_cfg<8, 64, 8>(a, pair, st);
     bool tall = a.OH > 8;
     // 16-row tiles amortise the slab halo (18 rows loaded per 16) but small problems leave SMs idle or end on a
     // ragged last wave: estimate both tilings in units of one 8-row tile (x1.1 for the 10-rows-per-8 halo) and

@@ -293,6 +293,18 @@ void Engine::layout(Arena& a) {
         }
         w2f = a.take<float>(4LL * 128 * 64);
         wpair = a.take<float>(4LL * 128 * 64);
+        {   // 9x9 layers on the tensor path (tc9): zero-margined input planes + expanded / packed weights
+            const long long n9[3] = {(long long)N * Hp * (Wp + 16) * 4, (long long)N * OH * (OW + 16) * 16,
+                                     (long long)N * OH * (OW + 16) * 4};
+            for (int i = 0; i < 3; ++i) {
+                const bool need = i < 2 || tbw;
+                p9[i].hi = need ? a.take<__nv_bfloat16>(n9[i]) : nullptr;
+                p9[i].lo = need ? a.take<__nv_bfloat16>(n9[i]) : nullptr;
+                w9f[i] = need ? a.take<float>(18LL * 64 * 256) : nullptr;
+                tw9[i].hi = need ? a.take<__nv_bfloat16>(18LL * 64 * 256) : nullptr;
+                tw9[i].lo = need ? a.take<__nv_bfloat16>(18LL * 64 * 256) : nullptr;
+            }
+        }
         w2f_b = a.take<float>(4LL * 128 * 64);
         for (int i = 0; i < 4; ++i) wpair_x[i] = a.take<float>(4LL * 128 * 64);
         for (int l = 0; l < T_NCONV; ++l) wgs[l] = nullptr;
@@ -366,6 +378,15 @@ int Engine::bind(void* ws, size_t bytes) {
     Arena a; a.base = (char*)ws; a.cap = bytes;
     layout(a);
     if (in_sums) { FS_CUDA(cudaMemset(in_sums, 0, (size_t)STATS_REPLICAS * N * 64 * 2 * sizeof(double))); FS_CUDA(cudaDeviceSynchronize()); }
+    if (flags & ENG_TRANSFORM) {         // zero margins of the x16 planes (never written afterwards)
+        const size_t n9[3] = {(size_t)N * Hp * (Wp + 16) * 4, (size_t)N * OH * (OW + 16) * 16, (size_t)N * OH * (OW + 16) * 4};
+        for (int i = 0; i < 3; ++i)
+            if (p9[i].hi) {
+                FS_CUDA(cudaMemset(p9[i].hi, 0, n9[i] * sizeof(__nv_bfloat16)));
+                FS_CUDA(cudaMemset(p9[i].lo, 0, n9[i] * sizeof(__nv_bfloat16)));
+            }
+        FS_CUDA(cudaDeviceSynchronize());
+    }
     bound = true;
     return 0;
 }
@@ -375,6 +396,31 @@ int Engine::bind(void* ws, size_t bytes) {
 // resize layers in their tcgen05 2x2 forms (even sizes); everything else keeps one launch per transform
 bool Engine::use_fast_prep() const {
     return fast_prep && use_tc && !(flags & ENG_DECONV) && tc2(1) && tc2(2) && tc2(13) && tc2(14);
+}
+
+// 9x9 layers on the tensor path: standard (resize) model, table-driven preparation, widths in whole 16-pixel groups
+bool Engine::tc9() const {
+    return tc9_on && use_fast_prep() && Wp % 16 == 0 && OW % 16 == 0 && tc[0].outW == Wp && tc[15].inW == OW;
+}
+
+// which: 0 = initconv_0 forward (x = xpad4), 1 = upsample_2 forward (x = activation of upsample_1),
+//        2 = upsample_2 data gradient (x = gradient w.r.t. its raw output)
+int Engine::tc9_conv(int which, const float* src_f32, float* out, bool stats, cudaStream_t st) {
+    const int Hh = which == 0 ? Hp : OH, Ww = which == 0 ? Wp : OW;
+    const int cin = which == 1 ? 16 : 4;                 // channels per pixel on the K side
+    const int cout_px = which == 1 ? 4 : 16;             // channels per pixel on the N side
+    PROF(PC_POINTWISE, 0.0, split_pad_x16(src_f32, p9[which].hi, p9[which].lo, (long long)N * Hh, Ww, cin, st));
+    Conv3x3TcArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.x = p9[which]; ta.w = tw9[which];
+    ta.N = N; ta.H = Hh; ta.W = (Ww + 16) / 16; ta.C = 16 * cin;
+    ta.OH = Hh; ta.OW = Ww / 16; ta.OC = 16 * cout_px;
+    ta.taps = 9; ta.taps_w = 2; ta.pad = 4; ta.pad_x = 0;
+    ta.out_f32 = out;
+    if (stats && in_epi) { ta.stats = in_sums; ta.stats_c = cout_px; }
+    const double fl = 2.0 * N * Hh * Ww * 81.0 * (which == 1 ? 16 * 3 : 3 * 16);       // algorithmic: real channel counts
+    PROFB(which == 2 ? PC_TC9_DGRAD : PC_TC9_FWD, fl, tc_bytes(ta), launch_conv3x3_tc(ta, st));
+    return 0;
 }
 
 int Engine::prep_transform_weights_table(const float* params, bool need_bwd, cudaStream_t st) {
@@ -399,7 +445,18 @@ int Engine::prep_transform_weights_table(const float* params, bool need_bwd, cud
         FS_TRY(pl.add(0, pj(PJ_S2_DGRAD_COLLAPSE, W(1), wefft[1], tc[1].cin, tc[1].cout)));
         FS_TRY(pl.add(0, pj(PJ_S2_DGRAD_COLLAPSE, W(2), wefft[2], tc[2].cin, tc[2].cout)));
     }
+    const bool t9 = tc9();
+    if (t9) {
+        FS_TRY(pl.add(0, pj(PJ_X16, W(0), w9f[0], 3, 16, 4, 16, 0)));                    // [18][64][256]
+        FS_TRY(pl.add(0, pj(PJ_X16, W(15), w9f[1], 16, 3, 16, 4, 0)));                   // [18][256][64]
+        if (need_bwd) FS_TRY(pl.add(0, pj(PJ_X16, W(15), w9f[2], 16, 3, 4, 16, 1)));     // [18][64][256]
+    }
     // ---- phase 1
+    if (t9) {
+        FS_TRY(pl.add(1, pj_pack(PJ_PACK_TAPS, w9f[0], tw9[0].hi, tw9[0].lo, 18, 64, 256, 0)));
+        FS_TRY(pl.add(1, pj_pack(PJ_PACK_TAPS, w9f[1], tw9[1].hi, tw9[1].lo, 18, 256, 64, 0)));
+        if (need_bwd) FS_TRY(pl.add(1, pj_pack(PJ_PACK_TAPS, w9f[2], tw9[2].hi, tw9[2].lo, 18, 64, 256, 0)));
+    }
     FS_TRY(pl.add(1, pj(PJ_PAIR, w2f, wpair_x[0], 4 * tc[1].cin, tc[1].cout, 1, 0)));                       // -> [4][128][64]
     FS_TRY(pl.add(1, pj_pack(PJ_PACK_TAPS, w2f_b, tw_f[2].hi, tw_f[2].lo, 4, 4 * tc[2].cin, tc[2].cout, 0)));
     FS_TRY(pl.add(1, pj_pack(PJ_PACK_TAPS, weff[13], tw_f[13].hi, tw_f[13].lo, 4, tc[13].cin, 4 * tc[13].cout, 0)));
@@ -590,6 +647,8 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
             FS_TRY(tc2_args(l, false, -1, tb[l].raw, ta));
             if (in_epi) { ta.stats = in_sums; ta.stats_c = c.cout; }
             PROFB(PC_TC_S2_FWD, tc2_flops(ta), tc_bytes(ta), launch_conv3x3_tc(ta, st));
+        } else if (direct9(c) && tc9()) {
+            FS_TRY(tc9_conv(l == 0 ? 0 : 1, cur, tb[l].raw, true, st));
         } else if (direct9(c)) {
             IGemmArgs a;
             conv_fwd_args(c, N, cur, weff[l], tb[l].raw, a);
@@ -600,7 +659,7 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
             if (c.upconv && (flags & ENG_DECONV)) a.gather = 1;      // transposed conv: iy = oy - a
             PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
         }
-        if (in_epi && (tcl || tc2(l)))
+        if (in_epi && (tcl || tc2(l) || (direct9(c) && tc9())))
             PROF(PC_IN_STATS, 0.0, instnorm_stats_from_sums(in_sums, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, STATS_REPLICAS, st));
         else
             PROF(PC_IN_STATS, 0.0, instnorm_stats(tb[l].raw, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, in_partial, st));
@@ -769,6 +828,11 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
                 const double fl = conv9_flops(c, N);
                 PROF(PC_FFMA_CONV, fl, launch_conv9x9(dRaw, wtmp15, dPrev, N, c.inH, c.inW, c.cout_s, c.cin_s, st));
             }
+            dAct = dPrev; cur = pidx;
+            continue;
+        }
+        if (direct9(c) && tc9()) {               // upsample_2: 9x9 data gradient on the tensor path
+            FS_TRY(tc9_conv(2, dRaw, dPrev, false, st));
             dAct = dPrev; cur = pidx;
             continue;
         }

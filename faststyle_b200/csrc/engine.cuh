@@ -45,7 +45,7 @@ struct LossConfig {
 
 enum ProfCat { PC_TC_VGG_FWD = 0, PC_TC_VGG_DGRAD, PC_TC_RES_FWD, PC_TC_RES_DGRAD, PC_FFMA_CONV, PC_WGRAD,
                PC_GRAM_FWD, PC_GRAM_BWD, PC_IN_STATS, PC_IN_APPLY, PC_IN_BWD, PC_POINTWISE, PC_LOSS, PC_PREP,
-               PC_TC_S2_FWD, PC_TC_S2_DGRAD, PC_COUNT };
+               PC_TC_S2_FWD, PC_TC_S2_DGRAD, PC_TC9_FWD, PC_TC9_DGRAD, PC_COUNT };
 enum EngineFlags { ENG_TRANSFORM = 1, ENG_TRANSFORM_BWD = 2, ENG_VGG = 4, ENG_VGG_BWD = 8, ENG_DECONV = 16 };
 
 struct Arena {
@@ -108,6 +108,16 @@ struct Engine {
     SplitPtr tgsplit[3];                 // planes of tgrad[i] (dRaw of the tensor-path transform convs)
     SplitPtr rg[T_NCONV];                // residual convs (3..12): planes of dRaw kept per layer, so that their ten
                                          // weight gradients run as ONE batched launch after the backward sweep
+    // 9x9 layers on the tensor path (initconv_0 forward, upsample_2 forward + data gradient): the stride-1 SAME 9x9
+    // convolution over [H, W, c] is run as a 9x2-tap convolution over [H, W/16 (+1), 16c] - sixteen horizontally
+    // adjacent pixels form one GEMM pixel - with Toeplitz-expanded weights (PJ_X16).  The input planes carry a zero
+    // margin of 4 pixels on the left and 12 on the right (p9[.], written by split_pad_x16).
+    SplitPtr p9[3];                      // inputs: initconv_0 forward, upsample_2 forward, upsample_2 data gradient
+    float* w9f[3] = {nullptr, nullptr, nullptr};   // expanded fp32 weights [18][16 KP][16 NP]
+    SplitPtr tw9[3];                     // packed split-bf16 weights
+    int tc9_on = 1;                      // FS_TC9=0: 9x9 layers on the direct FFMA kernels
+    bool tc9() const;
+    int tc9_conv(int which, const float* src_f32, float* out, bool stats, cudaStream_t st);
     int keep_acts = 0;                   // 1: write every fp32 activation / gradient even where only split planes are read (debug taps)
     int fuse_pool = 1;                   // FS_FUSE_POOL=0: separate max-pool kernel after the VGG conv
     int fold_pool = 1;                   // FS_FOLD_POOL=0: separate pool_bwd_combine pass before the Gram backward

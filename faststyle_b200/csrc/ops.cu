@@ -824,6 +824,23 @@ __global__ void s2_fwd_collapse_grad_kernel(const float* __restrict__ dWf, float
     dW[i] = dWf[((((long long)a * 2 + b) * 4 + pq) * Ci + ci) * Co + co];
 }
 
+// fp32 [N*H, W, C] -> split-bf16 planes [N*H, W + 16, C] with the row at column offset 4: the zero-margined input of
+// the x16 space-to-depth 9x9 forms (the margins are zeroed once when the workspace is bound)
+__global__ void split_pad_x16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                     __nv_bfloat16* __restrict__ lo, long long n4, int W, int C) {
+    FS_PDL_ENTER();
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const long long e = i * 4;
+    const int c = (int)(e % C);
+    const long long pix = e / C;
+    const int xc = (int)(pix % W);
+    const long long row = pix / W;
+    const float4 v = ld4(x + e);
+    float r[4] = {v.x, v.y, v.z, v.w};
+    store_split4(hi, lo, (row * (W + 16) + xc + 4) * C + c, r);
+}
+
 inline int grid1(long long n, int bs = 256) { return (int)((n + bs - 1) / bs); }
 
 }  // namespace
@@ -1044,6 +1061,14 @@ int unpair_taps(const float* dWp, float* dW, int K0, int N0, int kmode, int n_s2
 }
 int s2_fwd_collapse_grad(const float* dWf, float* dW, int Ci, int Co, cudaStream_t st) {
     launch_k(s2_fwd_collapse_grad_kernel, dim3(grid1(9LL * Ci * Co)), dim3(256), 0, st, dWf, dW, Ci, Co);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int split_pad_x16(const float* x, void* hi, void* lo, long long rows, int W, int C, cudaStream_t st) {
+    FS_CHECK(C % 4 == 0 && W >= 1 && rows >= 1, "split_pad_x16: bad dims");
+    const long long n4 = rows * W * C / 4;
+    launch_k(split_pad_x16_kernel, dim3(grid1(n4)), dim3(256), 0, st, x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n4, W, C);
     FS_LAUNCH_CHECK();
     return 0;
 }

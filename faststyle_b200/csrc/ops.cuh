@@ -74,6 +74,8 @@ int pair_taps(const float* W, float* Wp, int K0, int N0, int kmode, int gather, 
 int unpair_taps(const float* dWp, float* dW, int K0, int N0, int kmode, int n_s2d, cudaStream_t st);
 int s2_fwd_collapse_grad(const float* dWf, float* dW, int Ci, int Co, cudaStream_t st);
 
+// fp32 [rows, W, C] -> split-bf16 planes [rows, W + 16, C], row content at column offset 4 (margins untouched)
+int split_pad_x16(const float* x, void* hi, void* lo, long long rows, int W, int C, cudaStream_t st);
 int fill_zero(void* p, size_t bytes, cudaStream_t st);
 
 }  // namespace fs

@@ -206,6 +206,28 @@ __device__ __forceinline__ void run_job(const PrepJob& j, long long i) {
         dst[i] = c < 3 ? (i < 4 ? src[c] : j.src2[c]) : 0.f;
         break;
     }
+    case PJ_X16: {            // a=A b=B (src W[9][9][A][B]) c=KP d=NP e=mode: the 9x9 stride-1 SAME conv as a 9x2-tap conv over
+                              // 16-pixel groups: dst[kh][t][dxi*KP + k][dxo*NP + n], kw = 16 t + dxi - dxo (see Engine::tc9)
+        const int A = j.a, B = j.b, KP = j.c, NP = j.d, mode = j.e;
+        int np = (int)(i % (16 * NP));
+        long long r = i / (16 * NP);
+        int kp = (int)(r % (16 * KP));
+        int tap = (int)(r / (16 * KP));
+        int kh = tap >> 1, t = tap & 1;
+        int dxo = np / NP, n = np - dxo * NP;
+        int dxi = kp / KP, k = kp - dxi * KP;
+        int kw = 16 * t + dxi - dxo;
+        float v = 0.f;
+        if (kw >= 0 && kw <= 8) {
+            if (mode == 0) {          // forward: K = input channel, N = output channel
+                if (k < A && n < B) v = src[(((long long)kh * 9 + kw) * A + k) * B + n];
+            } else {                  // data gradient: K = output channel, N = input channel, flipped taps
+                if (k < B && n < A) v = src[(((long long)(8 - kh) * 9 + (8 - kw)) * A + n) * B + k];
+            }
+        }
+        dst[i] = v;
+        break;
+    }
     case PJ_COPY:             // plain copy (a 3-float gradient slot out of its 4-channel staging)
         dst[i] = src[i];
         break;
@@ -237,6 +259,7 @@ long long prep_job_total(const PrepJob& j) {
     case PJ_PACK_W3X3: return 9LL * j.a * j.b;
     case PJ_IN15: return 8;
     case PJ_COPY: return j.a;
+    case PJ_X16: return 18LL * 16 * j.c * 16 * j.d;
     default: return 0;
     }
 }

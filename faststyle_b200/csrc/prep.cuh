@@ -9,7 +9,7 @@ namespace fs {
 enum PrepKind {
     PJ_PAD = 1, PJ_UNPAD, PJ_TRANSPOSE, PJ_FLIP_TRANSPOSE, PJ_UPCONV_COLLAPSE, PJ_UPCONV_COLLAPSE_GRAD,
     PJ_S2_DGRAD_COLLAPSE, PJ_S2_FWD_COLLAPSE, PJ_S2_FWD_COLLAPSE_GRAD, PJ_PAIR, PJ_UNPAIR, PJ_PACK_TAPS,
-    PJ_PACK_W3X3, PJ_IN15, PJ_COPY
+    PJ_PACK_W3X3, PJ_IN15, PJ_COPY, PJ_X16
 };
 
 struct PrepJob {

@@ -33,6 +33,9 @@ struct Conv3x3TcArgs {
     int pad;                   // zero padding on top/left (SAME: 1, VALID: 0, VALID data gradient: 2)
     int taps;                  // kernel extent KH = KW: 0/3 = 3x3 (default), 2 = 2x2 (the collapsed stride-2 / resize
                                // convolutions and their data gradients; weights packed by pack_taps_tc)
+    int taps_w, pad_x;         // non-square forms: horizontal taps / left padding (0 = same as taps / pad).  taps = 9 with
+                               // taps_w = 2 is the 9x9 stride-1 SAME conv of the transform net over the x16
+                               // space-to-depth view of a zero-margined input (see Engine::tc9)
     int in_s2d;                // 1: x is the space-to-depth view [N,H,W,C] of a plain [N,2H,2W,C/4] tensor (C == 128)
     int out_d2s;               // 1: the [OH,OW,OC] result is stored depth-to-space into out_f32 [N,2OH,2OW,OC/4]
                                // 2: same for pixel-paired operands, OC = (e,p,q,16) -> out_f32 [N,2OH,4OW,16]
