@@ -300,7 +300,6 @@ void Engine::layout(Arena& a) {
                 const bool need = i < 2 || tbw;
                 p9[i].hi = need ? a.take<__nv_bfloat16>(n9[i]) : nullptr;
                 p9[i].lo = need ? a.take<__nv_bfloat16>(n9[i]) : nullptr;
-                w9f[i] = need ? a.take<float>(18LL * 64 * 256) : nullptr;
                 tw9[i].hi = need ? a.take<__nv_bfloat16>(18LL * 64 * 256) : nullptr;
                 tw9[i].lo = need ? a.take<__nv_bfloat16>(18LL * 64 * 256) : nullptr;
             }
@@ -445,18 +444,17 @@ int Engine::prep_transform_weights_table(const float* params, bool need_bwd, cud
         FS_TRY(pl.add(0, pj(PJ_S2_DGRAD_COLLAPSE, W(1), wefft[1], tc[1].cin, tc[1].cout)));
         FS_TRY(pl.add(0, pj(PJ_S2_DGRAD_COLLAPSE, W(2), wefft[2], tc[2].cin, tc[2].cout)));
     }
-    const bool t9 = tc9();
-    if (t9) {
-        FS_TRY(pl.add(0, pj(PJ_X16, W(0), w9f[0], 3, 16, 4, 16, 0)));                    // [18][64][256]
-        FS_TRY(pl.add(0, pj(PJ_X16, W(15), w9f[1], 16, 3, 16, 4, 0)));                   // [18][256][64]
-        if (need_bwd) FS_TRY(pl.add(0, pj(PJ_X16, W(15), w9f[2], 16, 3, 4, 16, 1)));     // [18][64][256]
+    if (tc9()) {       // Toeplitz expansion straight into the packed split-bf16 layout: [18][K/64][N][64]
+        auto x16 = [&](int which, const float* src, int A, int B, int KP, int NP, int mode) {
+            PrepJob j = pj(PJ_X16, src, nullptr, A, B, KP, NP, mode);
+            j.hi = tw9[which].hi; j.lo = tw9[which].lo;
+            return j;
+        };
+        FS_TRY(pl.add(0, x16(0, W(0), 3, 16, 4, 16, 0)));                    // K = 64, N = 256
+        FS_TRY(pl.add(0, x16(1, W(15), 16, 3, 16, 4, 0)));                   // K = 256, N = 64
+        if (need_bwd) FS_TRY(pl.add(0, x16(2, W(15), 16, 3, 4, 16, 1)));     // K = 64, N = 256
     }
     // ---- phase 1
-    if (t9) {
-        FS_TRY(pl.add(1, pj_pack(PJ_PACK_TAPS, w9f[0], tw9[0].hi, tw9[0].lo, 18, 64, 256, 0)));
-        FS_TRY(pl.add(1, pj_pack(PJ_PACK_TAPS, w9f[1], tw9[1].hi, tw9[1].lo, 18, 256, 64, 0)));
-        if (need_bwd) FS_TRY(pl.add(1, pj_pack(PJ_PACK_TAPS, w9f[2], tw9[2].hi, tw9[2].lo, 18, 64, 256, 0)));
-    }
     FS_TRY(pl.add(1, pj(PJ_PAIR, w2f, wpair_x[0], 4 * tc[1].cin, tc[1].cout, 1, 0)));                       // -> [4][128][64]
     FS_TRY(pl.add(1, pj_pack(PJ_PACK_TAPS, w2f_b, tw_f[2].hi, tw_f[2].lo, 4, 4 * tc[2].cin, tc[2].cout, 0)));
     FS_TRY(pl.add(1, pj_pack(PJ_PACK_TAPS, weff[13], tw_f[13].hi, tw_f[13].lo, 4, tc[13].cin, 4 * tc[13].cout, 0)));

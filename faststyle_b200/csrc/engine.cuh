@@ -113,8 +113,7 @@ struct Engine {
     // adjacent pixels form one GEMM pixel - with Toeplitz-expanded weights (PJ_X16).  The input planes carry a zero
     // margin of 4 pixels on the left and 12 on the right (p9[.], written by split_pad_x16).
     SplitPtr p9[3];                      // inputs: initconv_0 forward, upsample_2 forward, upsample_2 data gradient
-    float* w9f[3] = {nullptr, nullptr, nullptr};   // expanded fp32 weights [18][16 KP][16 NP]
-    SplitPtr tw9[3];                     // packed split-bf16 weights
+    SplitPtr tw9[3];                     // Toeplitz-expanded weights, packed split-bf16 [18][16 KP / 64][16 NP][64]
     int tc9_on = 1;                      // FS_TC9=0: 9x9 layers on the direct FFMA kernels
     bool tc9() const;
     int tc9_conv(int which, const float* src_f32, float* out, bool stats, cudaStream_t st);

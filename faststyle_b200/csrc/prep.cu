@@ -209,10 +209,21 @@ __device__ __forceinline__ void run_job(const PrepJob& j, long long i) {
     case PJ_X16: {            // a=A b=B (src W[9][9][A][B]) c=KP d=NP e=mode: the 9x9 stride-1 SAME conv as a 9x2-tap conv over
                               // 16-pixel groups: dst[kh][t][dxi*KP + k][dxo*NP + n], kw = 16 t + dxi - dxo (see Engine::tc9)
         const int A = j.a, B = j.b, KP = j.c, NP = j.d, mode = j.e;
-        int np = (int)(i % (16 * NP));
-        long long r = i / (16 * NP);
-        int kp = (int)(r % (16 * KP));
-        int tap = (int)(r / (16 * KP));
+        int np, kp, tap;
+        if (j.hi) {           // straight into the packed tensor-path layout B[tap][cb][n][k] (split planes)
+            const int Nn = 16 * NP, CB = 16 * KP / 64;
+            int k = (int)(i % 64);
+            long long r = i / 64;
+            np = (int)(r % Nn); r /= Nn;
+            int cb = (int)(r % CB);
+            tap = (int)(r / CB);
+            kp = cb * 64 + k;
+        } else {
+            np = (int)(i % (16 * NP));
+            long long r = i / (16 * NP);
+            kp = (int)(r % (16 * KP));
+            tap = (int)(r / (16 * KP));
+        }
         int kh = tap >> 1, t = tap & 1;
         int dxo = np / NP, n = np - dxo * NP;
         int dxi = kp / KP, k = kp - dxi * KP;
@@ -225,7 +236,8 @@ __device__ __forceinline__ void run_job(const PrepJob& j, long long i) {
                 if (k < B && n < A) v = src[(((long long)(8 - kh) * 9 + (8 - kw)) * A + n) * B + k];
             }
         }
-        dst[i] = v;
+        if (j.hi) split_store(j.hi, j.lo, i, v);
+        else dst[i] = v;
         break;
     }
     case PJ_COPY:             // plain copy (a 3-float gradient slot out of its 4-channel staging)

@@ -21,9 +21,9 @@ struct PrepJob {
     long long total;               // elements written (filled by PrepPlan::add)
 };
 
-constexpr int PREP_MAX_JOBS = 48;
+constexpr int PREP_MAX_JOBS = 64;
 constexpr int PREP_MAX_PHASES = 8;
-struct PrepTable { PrepJob j[PREP_MAX_JOBS]; };      // 48 x 72 B = 3.4 KB: passed by value as a kernel parameter
+struct PrepTable { PrepJob j[PREP_MAX_JOBS]; };      // 64 x 72 B = 4.6 KB: passed by value as a kernel parameter
 
 struct PrepPlan {
     PrepTable t;
