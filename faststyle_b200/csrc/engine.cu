@@ -408,7 +408,8 @@ int Engine::tc9_conv(int which, const float* src_f32, float* out, bool stats, cu
     const int Hh = which == 0 ? Hp : OH, Ww = which == 0 ? Wp : OW;
     const int cin = which == 1 ? 16 : 4;                 // channels per pixel on the K side
     const int cout_px = which == 1 ? 4 : 16;             // channels per pixel on the N side
-    PROF(PC_POINTWISE, 0.0, split_pad_x16(src_f32, p9[which].hi, p9[which].lo, (long long)N * Hh, Ww, cin, st));
+    if (which != 0)      // (initconv_0's planes come straight from the reflect-pad kernel)
+        PROF(PC_POINTWISE, 0.0, split_pad_x16(src_f32, p9[which].hi, p9[which].lo, (long long)N * Hh, Ww, cin, st));
     Conv3x3TcArgs ta;
     memset(&ta, 0, sizeof(ta));
     ta.x = p9[which]; ta.w = tw9[which];
@@ -627,7 +628,8 @@ static void conv_fwd_args(const TConv& c, int N, const float* in, const float* w
 
 int Engine::transform_forward(const float* params, const float* x3, float* y3_out, cudaStream_t st) {
     FS_CHECK(bound && (flags & ENG_TRANSFORM), "engine has no transform plan / workspace");
-    PROF(PC_POINTWISE, 0.0, reflect_pad_c4(x3, xpad4, N, H, W, 40, st));
+    const bool t9 = tc9();
+    PROF(PC_POINTWISE, 0.0, reflect_pad_c4(x3, xpad4, N, H, W, 40, st, t9 ? p9[0].hi : nullptr, t9 ? p9[0].lo : nullptr));
     const float* cur = xpad4;
     for (int l = 0; l < T_NCONV; ++l) {
         const TConv& c = tc[l];

@@ -54,8 +54,11 @@ __device__ __forceinline__ float in_affine(float x, float mean, float rstd, floa
 }
 
 // ------------------------------------------------------------------ padding
+// x16hi / x16lo (optional): the same padded image as split-bf16 planes [N, OH, OW + 16, 4] at column offset 4 - the
+// zero-margined input of the x16 space-to-depth 9x9 form of initconv_0 (Engine::tc9)
 __global__ void reflect_pad_c4_kernel(const float* __restrict__ x, float* __restrict__ out, int N,
-                                      int H, int W, int pad) {
+                                      int H, int W, int pad, __nv_bfloat16* __restrict__ x16hi,
+                                      __nv_bfloat16* __restrict__ x16lo) {
     FS_PDL_ENTER();
     int OH = H + 2 * pad, OW = W + 2 * pad;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -71,6 +74,10 @@ __global__ void reflect_pad_c4_kernel(const float* __restrict__ x, float* __rest
     if (sx >= W) sx = 2 * (W - 1) - sx;
     const float* s = x + (((long long)n * H + sy) * W + sx) * 3;
     st4(out + i * 4, make_float4(s[0], s[1], s[2], 0.f));
+    if (x16hi) {
+        const float r4[4] = {s[0], s[1], s[2], 0.f};
+        store_split4(x16hi, x16lo, ((r * (OW + 16)) + ox + 4) * 4, r4);
+    }
 }
 
 __global__ void vgg_preprocess_kernel(const float* __restrict__ x, float* __restrict__ out,
@@ -846,10 +853,11 @@ inline int grid1(long long n, int bs = 256) { return (int)((n + bs - 1) / bs); }
 }  // namespace
 
 // ==================================================================== launchers
-int reflect_pad_c4(const float* x, float* out, int N, int H, int W, int pad, cudaStream_t st) {
+int reflect_pad_c4(const float* x, float* out, int N, int H, int W, int pad, cudaStream_t st, void* x16hi, void* x16lo) {
     FS_CHECK(pad < H && pad < W, "reflect_pad: pad %d must be smaller than the image (%dx%d)", pad, H, W);
     long long n = (long long)N * (H + 2 * pad) * (W + 2 * pad);
-    launch_k(reflect_pad_c4_kernel, dim3(grid1(n)), dim3(256), 0, st, x, out, N, H, W, pad);
+    launch_k(reflect_pad_c4_kernel, dim3(grid1(n)), dim3(256), 0, st, x, out, N, H, W, pad, (__nv_bfloat16*)x16hi,
+             (__nv_bfloat16*)x16lo);
     FS_LAUNCH_CHECK();
     return 0;
 }

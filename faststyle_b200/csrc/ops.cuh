@@ -7,7 +7,8 @@ namespace fs {
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH255 = 2 };
 
 // K1: tf.pad REFLECT + channel pad 3->4           (reference im_transf_net.py:78-88)
-int reflect_pad_c4(const float* x, float* out, int N, int H, int W, int pad, cudaStream_t st);
+int reflect_pad_c4(const float* x, float* out, int N, int H, int W, int pad, cudaStream_t st, void* x16hi = nullptr,
+                   void* x16lo = nullptr);
 // K9: x - VGG mean, channel pad 3->4             (reference libs/vgg16.py:41-42)
 int vgg_preprocess_c4(const float* x, float* out, long long npix, cudaStream_t st);
 
