@@ -4,7 +4,11 @@
 #include "tc.cuh"
 #include <stdarg.h>
 #include <stdlib.h>
+#include <atomic>
+#include <mutex>
 #include <new>
+#include <set>
+#include <utility>
 
 namespace fs {
 static thread_local char g_err[1024] = "";
@@ -16,6 +20,32 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 long long g_launches = 0;
+
+int ensure_dyn_smem(const void* fn, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<int, const void*>> done;
+    int dev = 0;
+    FS_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count(std::make_pair(dev, fn))) return 0;
+    FS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.insert(std::make_pair(dev, fn));
+    return 0;
+}
+
+int num_sms() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+        cache[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
 int g_pdl = -1;
 int pdl_enabled() {
     if (g_pdl < 0) {
@@ -86,6 +116,8 @@ int fs_engine_create(int N, int H, int W, int flags, unsigned content_mask, unsi
     h->e.tc9_on = (env && env[0] == '0') ? 0 : 1;
     env = getenv("FS_KEEP_ACTS");
     h->e.keep_acts = (env && env[0] == '1') ? 1 : 0;
+    env = getenv("FS_IN_FUSE");
+    h->e.fuse_in = (env && env[0] == '0') ? 0 : 1;
     env = getenv("FS_FUSE_POOL");
     h->e.fuse_pool = (env && env[0] == '0') ? 0 : 1;
     env = getenv("FS_FOLD_POOL");

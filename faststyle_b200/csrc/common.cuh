@@ -45,6 +45,13 @@ extern long long g_launches;
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Raises a kernel's dynamic shared-memory limit once per (device, kernel); thread-safe, so engines on several
+// devices / host threads of one process can launch concurrently (the attribute is per device).
+int ensure_dyn_smem(const void* fn, int bytes);
+#define FS_DYN_SMEM(kern, bytes) FS_TRY(fs::ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)(bytes)))
+// SM count of the current device (cached per device)
+int num_sms();
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // The step is a chain of ~240 short kernels (mean 30 us).  Every kernel is launched with the
 // programmatic-stream-serialization attribute and starts with FS_PDL_ENTER(): it releases its own

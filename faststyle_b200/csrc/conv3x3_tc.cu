@@ -690,17 +690,6 @@ int make_w_map(CUtensorMap* tm, const __nv_bfloat16* base, long long rows, int b
     return 0;
 }
 
-int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
-
 int g_tc_pair = -1;     // CTA-pair (cta_group::2) kernel: -1 = read FS_TC_PAIR (default on), 0 off, 1 on
 
 template <int TH, int BN, bool STATS, bool PAIR, int HALO>
@@ -733,11 +722,7 @@ int launch_cfg_s(const Conv3x3TcArgs& a, cudaStream_t st) {
     p.add_crop = a.add_crop; p.addH = a.addH; p.addW = a.addW;
     p.out_f32 = a.out_f32; p.out_hi = a.out_split.hi; p.out_lo = a.out_split.lo;
     p.stats = a.stats; p.stats_c = a.stats_c;
-    static bool attr_set = false;
-    if (!attr_set) {
-        FS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<TH, BN, STATS, PAIR, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
-        attr_set = true;
-    }
+    FS_DYN_SMEM((conv3x3_tc_kernel<TH, BN, STATS, PAIR, HALO>), K::SMEM_BYTES);
     const int sms = num_sms();
     if (PAIR) {
         const int clusters = (int)(p.total_tiles < sms / 2 ? p.total_tiles : sms / 2);

@@ -419,12 +419,10 @@ int launch_conv9x9(const float* in, const float* w, float* out, int N, int H, in
     dim3 grid(cdiv(W, TS), cdiv(H, TS), N);
     const size_t smem = (size_t)((CI / 4) * HS * PITCH + 81 * CI * (CO / 4)) * sizeof(float4);
     if (CI == 4) {
-        static bool set = false;
-        if (!set) { FS_CUDA(cudaFuncSetAttribute(conv9x9_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+        FS_DYN_SMEM((conv9x9_kernel<4, 16>), smem);
         launch_k((conv9x9_kernel<4, 16>), dim3(grid), dim3(256), smem, st, in, w, out, H, W);
     } else {
-        static bool set = false;
-        if (!set) { FS_CUDA(cudaFuncSetAttribute(conv9x9_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+        FS_DYN_SMEM((conv9x9_kernel<16, 4>), smem);
         launch_k((conv9x9_kernel<16, 4>), dim3(grid), dim3(256), smem, st, in, w, out, H, W);
     }
     FS_LAUNCH_CHECK();
@@ -443,8 +441,7 @@ int launch_conv3x3_c4_fwd(const float* in, const float* w, const float* bias, fl
 // conv1_1 data gradient: P [N,H,W,64], wf [9,64,4] (flip_transpose_taps of the forward weights) -> dx [N,H,W,4]
 int launch_dgrad3x3_c4(const float* P, const float* wf, float* dx, int N, int H, int W, cudaStream_t st) {
     const size_t smem = (size_t)(C1_QP * (C1_ROWS + 2) * C1_PITCH + 9 * 64 + 3 * 64 * 4) * sizeof(float4);
-    static bool set = false;
-    if (!set) { FS_CUDA(cudaFuncSetAttribute(dgrad3x3_c4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+    FS_DYN_SMEM((dgrad3x3_c4_kernel), smem);
     dim3 grid(cdiv(W, C1_COLS), cdiv(H, C1_ROWS), N);
     launch_k(dgrad3x3_c4_kernel, dim3(grid), dim3(256), smem, st, P, wf, dx, H, W);
     FS_LAUNCH_CHECK();
@@ -477,13 +474,11 @@ int launch_wgrad9x9(const float* in, const float* dy, float* out, float* partial
     const int nblocks = total < WG9_MAX_CTAS ? total : WG9_MAX_CTAS;
     if (CI == 16) {
         size_t smem = (size_t)(HSY * HS * 4 + TSY * TS * 1) * sizeof(float4);
-        static bool set16 = false;
-        if (!set16) { FS_CUDA(cudaFuncSetAttribute(wgrad9x9_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set16 = true; }
+        FS_DYN_SMEM((wgrad9x9_kernel<16, 4>), smem);
         launch_k((wgrad9x9_kernel<16, 4>), dim3(nblocks), dim3(NT9), smem, st, in, dy, partial, H, W, tilesX, tilesY, total);
     } else {
         size_t smem = (size_t)(HSY * HS * 1 + TSY * TS * 4) * sizeof(float4);
-        static bool set4 = false;
-        if (!set4) { FS_CUDA(cudaFuncSetAttribute(wgrad9x9_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set4 = true; }
+        FS_DYN_SMEM((wgrad9x9_kernel<4, 16>), smem);
         launch_k((wgrad9x9_kernel<4, 16>), dim3(nblocks), dim3(NT9), smem, st, in, dy, partial, H, W, tilesX, tilesY, total);
     }
     FS_LAUNCH_CHECK();

@@ -315,7 +315,9 @@ void Engine::layout(Arena& a) {
         }
         y3 = a.take<float>((long long)N * OH * OW * 3);
         in_partial = a.take<double>((long long)N * 64 * 64 * 2);
-        in_sums = a.take<double>((long long)STATS_REPLICAS * N * 64 * 2);
+        sums_n = (long long)STATS_REPLICAS * N * 64 * 2;
+        for (int i = 0; i < 2; ++i) in_sums2[i] = a.take<double>(sums_n);
+        for (int i = 0; i < 2; ++i) bw_sums2[i] = tbw ? a.take<double>(sums_n) : nullptr;
         in15 = a.take<float>(8);
         wtmp15 = a.take<float>(81 * 64);
         if (tbw) {
@@ -376,7 +378,9 @@ int Engine::bind(void* ws, size_t bytes) {
     FS_CHECK(((uintptr_t)ws & 255) == 0, "engine: workspace must be 256-byte aligned");
     Arena a; a.base = (char*)ws; a.cap = bytes;
     layout(a);
-    if (in_sums) { FS_CUDA(cudaMemset(in_sums, 0, (size_t)STATS_REPLICAS * N * 64 * 2 * sizeof(double))); FS_CUDA(cudaDeviceSynchronize()); }
+    for (double* sp : {in_sums2[0], in_sums2[1], bw_sums2[0], bw_sums2[1]})
+        if (sp) FS_CUDA(cudaMemset(sp, 0, (size_t)sums_n * sizeof(double)));
+    FS_CUDA(cudaDeviceSynchronize());
     if (flags & ENG_TRANSFORM) {         // zero margins of the x16 planes (never written afterwards)
         const size_t n9[3] = {(size_t)N * Hp * (Wp + 16) * 4, (size_t)N * OH * (OW + 16) * 16, (size_t)N * OH * (OW + 16) * 4};
         for (int i = 0; i < 3; ++i)
@@ -417,7 +421,7 @@ int Engine::tc9_conv(int which, const float* src_f32, float* out, bool stats, cu
     ta.OH = Hh; ta.OW = Ww / 16; ta.OC = 16 * cout_px;
     ta.taps = 9; ta.taps_w = 2; ta.pad = 4; ta.pad_x = 0;
     ta.out_f32 = out;
-    if (stats && in_epi) { ta.stats = in_sums; ta.stats_c = cout_px; }
+    if (stats && in_epi) { ta.stats = in_sums2[which == 0 ? 0 : 1]; ta.stats_c = cout_px; }      // layer 0 / layer 15
     const double fl = 2.0 * N * Hh * Ww * 81.0 * (which == 1 ? 16 * 3 : 3 * 16);       // algorithmic: real channel counts
     PROFB(which == 2 ? PC_TC9_DGRAD : PC_TC9_FWD, fl, tc_bytes(ta), launch_conv3x3_tc(ta, st));
     return 0;
@@ -640,12 +644,12 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
             ta.x = tsplit[l]; ta.w = tw_f[l];
             ta.N = N; ta.H = c.inH; ta.W = c.inW; ta.C = 64; ta.OH = c.outH; ta.OW = c.outW; ta.OC = 64; ta.pad = 0;
             ta.out_f32 = tb[l].raw;
-            if (in_epi) { ta.stats = in_sums; ta.stats_c = 64; }
+            if (in_epi) { ta.stats = in_sums2[l & 1]; ta.stats_c = 64; }
             PROFB(PC_TC_RES_FWD, tc_flops(ta), tc_bytes(ta), launch_conv3x3_tc(ta, st));
         } else if (tc2(l)) {
             Conv3x3TcArgs ta;
             FS_TRY(tc2_args(l, false, -1, tb[l].raw, ta));
-            if (in_epi) { ta.stats = in_sums; ta.stats_c = c.cout; }
+            if (in_epi) { ta.stats = in_sums2[l & 1]; ta.stats_c = c.cout; }
             PROFB(PC_TC_S2_FWD, tc2_flops(ta), tc_bytes(ta), launch_conv3x3_tc(ta, st));
         } else if (direct9(c) && tc9()) {
             FS_TRY(tc9_conv(l == 0 ? 0 : 1, cur, tb[l].raw, true, st));
@@ -659,10 +663,17 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
             if (c.upconv && (flags & ENG_DECONV)) a.gather = 1;      // transposed conv: iy = oy - a
             PROF(PC_FFMA_CONV, igemm_flops(a), launch_igemm(a, st));
         }
-        if (in_epi && (tcl || tc2(l) || (direct9(c) && tc9())))
-            PROF(PC_IN_STATS, 0.0, instnorm_stats_from_sums(in_sums, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, STATS_REPLICAS, st));
+        // statistics: from the conv epilogue's sums where one accumulated them (finalised inside the fused apply
+        // below, or by a separate launch with FS_IN_FUSE=0), else a reduction pass over the raw output
+        const bool from_sums = in_epi && (tcl || tc2(l) || (direct9(c) && tc9()));
+        const bool fused_apply = from_sums && fuse_in;
+        if (fused_apply) {
+        } else if (from_sums)
+            PROF(PC_IN_STATS, 0.0, instnorm_stats_from_sums(in_sums2[l & 1], tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, STATS_REPLICAS, st));
         else
             PROF(PC_IN_STATS, 0.0, instnorm_stats(tb[l].raw, tb[l].mean, tb[l].rstd, N, c.outH * c.outW, c.cout_s, IN_EPS, in_partial, st));
+        // the other accumulator set is zeroed by every fused apply; a layer off that path does it here
+        if (in_epi && fuse_in && !fused_apply) FS_TRY(fill_zero(in_sums2[(l + 1) & 1], (size_t)sums_n * sizeof(double), st));
         const float* skip = nullptr;
         if (l >= 4 && l <= 12 && (l & 1) == 0) skip = tb[l - 2].act;       // residual: block input
         const bool last = l == T_NCONV - 1;
@@ -677,6 +688,12 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
             const bool skip_src = l >= 2 && l <= 10 && (l & 1) == 0;       // read again as the next block's skip addend
             if (!skip_src) out = nullptr;
         }
+        if (fused_apply)
+            PROF(PC_IN_APPLY, 0.0, instnorm_apply_from_sums(tb[l].raw, in_sums2[l & 1], STATS_REPLICAS, IN_EPS, tb[l].mean, tb[l].rstd,
+                                      in_sums2[(l + 1) & 1], sums_n, g, b, skip, out, N, c.outH, c.outW, c.cout_s, c.act,
+                                      last ? 1 : 0, st, next_tc ? tsplit[l + 1].hi : nullptr,
+                                      next_tc ? tsplit[l + 1].lo : nullptr));
+        else
         PROF(PC_IN_APPLY, 0.0, instnorm_apply(tb[l].raw, tb[l].mean, tb[l].rstd, g, b, skip, out, N, c.outH, c.outW,
                                   c.cout_s, c.act, last ? 1 : 0, st, next_tc ? tsplit[l + 1].hi : nullptr,
                                   next_tc ? tsplit[l + 1].lo : nullptr));
@@ -716,6 +733,11 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         // dRaw in fp32 is dead when both its readers (data gradient, weight gradient) are tensor-path kernels
         float* dRaw_f32 = dRaw;
         if (!keep_acts && (defer_wg || (tcl && use_tc) || (l > 0 && tc2(l)))) dRaw_f32 = nullptr;
+        if (fuse_in)
+            PROF(PC_IN_BWD, 0.0, instnorm_bwd_sums(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw_f32, dg, db, N,
+                                    c.outH * c.outW, c.cout_s, c.act, bw_sums2[l & 1], STATS_REPLICAS, bw_sums2[(l + 1) & 1],
+                                    sums_n, st, tcd ? dsp.hi : nullptr, tcd ? dsp.lo : nullptr));
+        else
         PROF(PC_IN_BWD, 0.0, instnorm_bwd(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw_f32, dg, db, N,
                                 c.outH * c.outW, c.cout_s, c.act, in_partial, m12, st,
                                 tcd ? dsp.hi : nullptr, tcd ? dsp.lo : nullptr));

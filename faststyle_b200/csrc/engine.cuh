@@ -77,7 +77,13 @@ struct Engine {
     float* wefft[T_NCONV];               // transposed weights for the data gradient
     float* y3 = nullptr;                 // [N,OH,OW,3] when the caller does not supply an output
     double* in_partial = nullptr;
-    double* in_sums = nullptr;           // [N][64][2] (sum, sum sq) accumulated by the tensor-path conv epilogues; zero between uses
+    // [STATS_REPLICAS][N][64][2] fp64 accumulators in two ping-pong sets.  Forward: layer l's conv epilogue adds
+    // (sum, sum sq) of its raw output to in_sums2[l & 1]; the fused apply of layer l reads them and zeroes set (l+1)&1
+    // (last read one layer earlier).  Backward: the same scheme on bw_sums2 with (sum dz, sum dz*xhat).
+    double* in_sums2[2] = {nullptr, nullptr};
+    double* bw_sums2[2] = {nullptr, nullptr};
+    long long sums_n = 0;                // doubles per set
+    int fuse_in = 1;                     // FS_IN_FUSE=0: separate finalize launches (stats -> finalize -> apply chains)
     int in_epi = 1;                      // FS_IN_EPILOGUE=0: separate statistics pass for every layer
     float* in15 = nullptr;               // 4-channel staging of the last layer's IN scale/shift
     float* gb_tmp = nullptr;

@@ -406,6 +406,75 @@ __global__ void in_apply_kernel(const float* __restrict__ x, const float* __rest
                   out, i, n, p, H, W, act, out3, shi, slo);
 }
 
+// (sum0, sum1) of channel t of sample n over the `reps` replicas [reps][N*C][2], for threads t < C of a 256-thread CTA.
+// The 256 threads split the replicas (256 / C' groups, C' = C rounded up to a power of two <= 128) so that every
+// thread's loads are independent and issued together: one L2 round trip instead of `reps` dependent ones.
+__device__ __forceinline__ double2 sum_replicas(const double* __restrict__ sums, int reps, int N, int n, int C,
+                                               double2* s_part) {
+    const int t = threadIdx.x;
+    int Cp = 4;
+    while (Cp < C) Cp <<= 1;
+    const int groups = 256 / Cp, c = t % Cp, grp = t / Cp;
+    double2 acc = make_double2(0.0, 0.0);
+    if (c < C) {
+#pragma unroll 4
+        for (int r = grp; r < reps; r += groups) {
+            const double2 v = *reinterpret_cast<const double2*>(sums + (((long long)r * N + n) * C + c) * 2);
+            acc.x += v.x; acc.y += v.y;
+        }
+    }
+    s_part[t] = acc;
+    __syncthreads();
+    double2 tot = make_double2(0.0, 0.0);
+    if (t < C)
+        for (int g = 0; g < groups; ++g) { tot.x += s_part[g * Cp + t].x; tot.y += s_part[g * Cp + t].y; }
+    __syncthreads();
+    return tot;
+}
+
+// Fused form of stats-finalize + apply for the layers whose conv epilogue accumulated (sum, sum of squares) in
+// `reps` replicas [reps][N*C][2]: every CTA (chunk, n) derives its sample's mean / rstd itself (C x reps fp64 loads,
+// the same arithmetic as in_stats_from_sums_kernel), chunk 0 publishes them for the backward pass, and the CTAs
+// jointly zero `zero_buf` - the OTHER ping-pong set of accumulators, last read one layer ago - for the next conv.
+__global__ void __launch_bounds__(256)
+in_apply_sums_kernel(const float* __restrict__ x, const double* __restrict__ sums, int reps, float eps,
+                     float* __restrict__ mean, float* __restrict__ rstd, double* __restrict__ zero_buf, long long zero_n,
+                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ skip,
+                     float* __restrict__ out, int N, int H, int W, int C, int act, int out3,
+                     __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo, int chunks) {
+    FS_PDL_ENTER();
+    __shared__ __align__(16) float s_mu[128], s_rs[128];
+    __shared__ double2 s_part[256];
+    const int n = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x, HW = H * W;
+    {
+        const double2 s = sum_replicas(sums, reps, N, n, C, s_part);      // valid for t < C
+        if (t < C) {
+            const double m = s.x / HW;
+            double var = s.y / HW - m * m;
+            if (var < 0) var = 0;
+            const float mf = (float)m, rf = (float)(1.0 / sqrt(var + (double)eps));
+            s_mu[t] = mf; s_rs[t] = rf;
+            if (chunk == 0) { mean[(long long)n * C + t] = mf; rstd[(long long)n * C + t] = rf; }
+        }
+    }
+    if (zero_buf) {
+        const long long cta = (long long)blockIdx.y * gridDim.x + blockIdx.x, nct = (long long)gridDim.x * gridDim.y;
+        const long long per = (zero_n + nct - 1) / nct, zb = cta * per, ze = zb + per < zero_n ? zb + per : zero_n;
+        for (long long i = zb + t; i < ze; i += 256) zero_buf[i] = 0.0;
+    }
+    __syncthreads();
+    const int C4 = C >> 2, lane = t % C4, rows = 256 / C4, row = t / C4, c = lane * 4;
+    const float4 mu = ld4(s_mu + c), rs = ld4(s_rs + c), g = ld4(scale + c), b = ld4(shift + c);
+    const int per = (HW + chunks - 1) / chunks, beg = chunk * per, end = min(beg + per, HW);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int p = beg + row; p < end; p += rows) {
+        const long long i = ((long long)n * HW + p) * C4 + lane;
+        in_apply_elem(ld4(x + i * 4), skip ? ld4(in_skip_ptr(skip, n, p, c, H, W, C)) : z4, skip != nullptr,
+                      mu, rs, g, b, out, i, n, p, H, W, act, out3, shi, slo);
+    }
+}
+
 // one float4 of the InstanceNorm backward: dx = g*rstd*(dz - mean(dz) - xhat*mean(dz*xhat))
 __device__ __forceinline__ void in_bwd_elem(const float4 xv4, const float4 dv4, const float* mu,
                                             const float* rs, const float* g, const float* b, const float* m1,
@@ -451,6 +520,73 @@ __global__ void in_bwd_apply_kernel(const float* __restrict__ dY, const float* _
     float g[4] = {g4.x, g4.y, g4.z, g4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
     float m1[4] = {ma.x, ma.z, mb.x, mb.z}, m2[4] = {ma.y, ma.w, mb.y, mb.w};
     in_bwd_elem(ld4(x + i * 4), ld4(dY + i * 4), mu, rs, g, b, m1, m2, dx, i, act, shi, slo);
+}
+
+// Two-launch InstanceNorm backward.  in_bwd_reduce_kernel: per-CTA (sum dz, sum dz*xhat) added to the replicated fp64
+// accumulators bs[rep][N*C][2] (rep = chunk % reps; one atomic per CTA, channel and quantity).  in_bwd_apply_sums_kernel:
+// every CTA (chunk, n) derives m1 / m2 of its sample from the replicas, applies dx, zeroes the other ping-pong set for the
+// next layer; the first ceil(C/8) CTAs also reduce dgamma / dbeta over (replica, sample) - a warp per channel.
+__global__ void __launch_bounds__(256)
+in_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dY, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
+                     double* __restrict__ bs, int reps, int N, int HW, int C, int chunks, int act) {
+    FS_PDL_ENTER();
+    extern __shared__ double sm[];            // [C][2]
+    const int t = threadIdx.x, n = blockIdx.y, chunk = blockIdx.x;
+    const int per = (HW + chunks - 1) / chunks;
+    const int beg = chunk * per, end = min(beg + per, HW);
+    in_reduce_chunk<1>(x, dY, mean, rstd, scale, shift, sm, n, beg, end, HW, C, act);
+    double* dst = bs + (((long long)(chunk % reps) * N + n) * C) * 2;
+    for (int i = t; i < 2 * C; i += 256) atomicAdd(dst + i, sm[i]);
+}
+
+__global__ void __launch_bounds__(256)
+in_bwd_apply_sums_kernel(const float* __restrict__ dY, const float* __restrict__ x, const float* __restrict__ mean,
+                         const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
+                         const double* __restrict__ bs, int reps, double* __restrict__ zero_buf, long long zero_n,
+                         float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx, int N, int HW,
+                         int C, int act, __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo, int chunks) {
+    FS_PDL_ENTER();
+    __shared__ __align__(16) float s_m1[128], s_m2[128];
+    __shared__ double2 s_part[256];
+    const int n = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
+    {
+        const double2 s = sum_replicas(bs, reps, N, n, C, s_part);        // valid for t < C
+        if (t < C) { s_m1[t] = (float)(s.x / HW); s_m2[t] = (float)(s.y / HW); }
+    }
+    const long long cta = (long long)blockIdx.y * gridDim.x + blockIdx.x, nct = (long long)gridDim.x * gridDim.y;
+    if (zero_buf) {
+        const long long per = (zero_n + nct - 1) / nct, zb = cta * per, ze = zb + per < zero_n ? zb + per : zero_n;
+        for (long long i = zb + t; i < ze; i += 256) zero_buf[i] = 0.0;
+    }
+    // dgamma[c] = sum over (replica, sample) of sum dz*xhat, dbeta[c] likewise of sum dz: CTA j takes channels 8j..8j+7
+    for (long long j = cta; j * 8 < C; j += nct) {
+        const int cc = (int)j * 8 + (t >> 5), lane = t & 31;
+        double gb = 0.0, gg = 0.0;
+        if (cc < C)
+            for (int k = lane; k < reps * N; k += 32) {
+                const double* p = bs + ((long long)k * C + cc) * 2;
+                gb += p[0]; gg += p[1];
+            }
+        gb = warp_sum(gb); gg = warp_sum(gg);
+        if (lane == 0 && cc < C) {
+            if (dgamma) dgamma[cc] = (float)gg;
+            if (dbeta) dbeta[cc] = (float)gb;
+        }
+    }
+    __syncthreads();
+    const int C4 = C >> 2, lane = t % C4, rows = 256 / C4, row = t / C4, c = lane * 4;
+    const float4 mu4 = ld4(mean + (long long)n * C + c), rs4 = ld4(rstd + (long long)n * C + c);
+    const float4 g4 = ld4(scale + c), b4 = ld4(shift + c), ma = ld4(s_m1 + c), mb = ld4(s_m2 + c);
+    const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
+    const float g[4] = {g4.x, g4.y, g4.z, g4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+    const float m1[4] = {ma.x, ma.y, ma.z, ma.w}, m2[4] = {mb.x, mb.y, mb.z, mb.w};
+    const int per = (HW + chunks - 1) / chunks, beg = chunk * per, end = min(beg + per, HW);
+#pragma unroll 4
+    for (int p = beg + row; p < end; p += rows) {
+        const long long i = ((long long)n * HW + p) * C4 + lane;
+        in_bwd_elem(ld4(x + i * 4), ld4(dY + i * 4), mu, rs, g, b, m1, m2, dx, i, act, shi, slo);
+    }
 }
 
 // ------------------------------------------------------------------ pooling
@@ -953,6 +1089,49 @@ int instnorm_bwd(const float* dY, const float* x, const float* mean, const float
     long long n = (long long)N * HW * (C / 4);
     launch_k(in_bwd_apply_kernel, dim3(grid1(n)), dim3(256), 0, st, dY, x, mean, rstd, scale, shift, m12, dx, N, HW, C, act,
                                                   (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+// grid of the fused apply kernels: about eight CTAs per SM (one resident wave), at least 64 pixels each
+static int apply_chunks(int N, int HW) {
+    int c = (num_sms() * 8 + N - 1) / N;
+    int maxc = HW / 64;
+    if (maxc < 1) maxc = 1;
+    if (c > maxc) c = maxc;
+    if (c < 1) c = 1;
+    return c;
+}
+
+int instnorm_apply_from_sums(const float* x, const double* sums, int reps, float eps, float* mean, float* rstd,
+                             double* zero_buf, long long zero_n, const float* scale, const float* shift,
+                             const float* skip, float* out, int N, int H, int W, int C, int act, int out3,
+                             cudaStream_t st, void* split_hi, void* split_lo) {
+    FS_TRY(check_in_c(C));
+    FS_CHECK(C <= 128, "instnorm_apply_from_sums: C <= 128");
+    FS_CHECK(!(split_hi && out3), "instnorm_apply_from_sums: split output not available with out3");
+    FS_CHECK(!out3 || C == 4, "instnorm_apply_from_sums: out3 needs C==4");
+    const int chunks = apply_chunks(N, H * W);
+    launch_k(in_apply_sums_kernel, dim3(chunks, N), dim3(256), 0, st, x, sums, reps, eps, mean, rstd, zero_buf, zero_n,
+             scale, shift, skip, out, N, H, W, C, act, out3, (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo, chunks);
+    FS_LAUNCH_CHECK();
+    return 0;
+}
+
+int instnorm_bwd_sums(const float* dY, const float* x, const float* mean, const float* rstd, const float* scale,
+                      const float* shift, float* dx, float* dgamma, float* dbeta, int N, int HW, int C, int act,
+                      double* bs, int reps, double* zero_buf, long long zero_n, cudaStream_t st, void* split_hi,
+                      void* split_lo) {
+    FS_TRY(check_in_c(C));
+    FS_CHECK(C <= 128, "instnorm_bwd_sums: C <= 128");
+    const int rchunks = in_chunks(N, HW);
+    launch_k(in_bwd_reduce_kernel, dim3(rchunks, N), dim3(256), 2 * C * sizeof(double), st, x, dY, mean, rstd, scale, shift,
+             bs, reps, N, HW, C, rchunks, act);
+    FS_LAUNCH_CHECK();
+    const int chunks = apply_chunks(N, HW);
+    launch_k(in_bwd_apply_sums_kernel, dim3(chunks, N), dim3(256), 0, st, dY, x, mean, rstd, scale, shift,
+             (const double*)bs, reps, zero_buf, zero_n, dgamma, dbeta, dx, N, HW, C, act, (__nv_bfloat16*)split_hi,
+             (__nv_bfloat16*)split_lo, chunks);
     FS_LAUNCH_CHECK();
     return 0;
 }

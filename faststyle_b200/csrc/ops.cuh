@@ -35,6 +35,18 @@ int instnorm_bwd(const float* dY, const float* x, const float* mean, const float
                  int N, int HW, int C, int act, double* partial, float* m12 /*[N][C][2]*/,
                  cudaStream_t st, void* split_hi = nullptr, void* split_lo = nullptr);
 
+// fused forms (one / two launches per site instead of two / three).  `sums` / `bs`: [reps][N*C][2] fp64 accumulators
+// (filled by a conv epilogue / by the reduction launch); `zero_buf` (zero_n doubles): the other ping-pong set, zeroed
+// for the next site.  instnorm_apply_from_sums also publishes mean / rstd for the backward pass.
+int instnorm_apply_from_sums(const float* x, const double* sums, int reps, float eps, float* mean, float* rstd,
+                             double* zero_buf, long long zero_n, const float* scale, const float* shift,
+                             const float* skip, float* out, int N, int H, int W, int C, int act, int out3,
+                             cudaStream_t st, void* split_hi = nullptr, void* split_lo = nullptr);
+int instnorm_bwd_sums(const float* dY, const float* x, const float* mean, const float* rstd, const float* scale,
+                      const float* shift, float* dx, float* dgamma, float* dbeta, int N, int HW, int C, int act,
+                      double* bs, int reps, double* zero_buf, long long zero_n, cudaStream_t st,
+                      void* split_hi = nullptr, void* split_lo = nullptr);
+
 // K8: 2x2 s2 SAME max-pool                        (reference libs/vgg16.py:67-71)
 int maxpool2x2_fwd(const float* x, float* out, int N, int H, int W, int C, cudaStream_t st,
                    void* split_hi = nullptr, void* split_lo = nullptr);

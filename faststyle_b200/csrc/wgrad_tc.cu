@@ -602,11 +602,7 @@ int launch_wgrad3x3_tc(SplitPtr x, SplitPtr dy, float* out, float* partial, long
     int grid = p.total_tiles < sms ? p.total_tiles : sms;
     FS_CHECK(grid >= 1, "wgrad3x3_tc: empty problem");
     FS_CHECK((long long)grid * 9 * 64 * 64 <= partial_cap, "wgrad3x3_tc: partial workspace too small");
-    static bool attr_set = false;
-    if (!attr_set) {
-        FS_CUDA(cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
+    FS_DYN_SMEM(wgrad3x3_tc_kernel, SMEM_BYTES);
     launch_k(wgrad3x3_tc_kernel, dim3(grid), dim3(256), SMEM_BYTES, st, tmX_hi, tmX_lo, tmD_hi, tmD_lo, p);
     FS_LAUNCH_CHECK();
     launch_k(reduce_cta_partials_kernel, dim3(cdiv(9 * 64 * 64, 32)), dim3(256), 0, st, partial, out, 9 * 64 * 64, grid);
@@ -675,11 +671,7 @@ int launch_wgrad2x2_tc(SplitPtr x, int x_s2d, SplitPtr dy, int dy_s2d, float* ou
     FS_CHECK(grid >= 1, "wgrad2x2_tc: empty problem");
     const int elems = 4 * 64 * 128;
     FS_CHECK((long long)grid * elems <= partial_cap, "wgrad2x2_tc: partial workspace too small");
-    static bool attr_set = false;
-    if (!attr_set) {
-        FS_CUDA(cudaFuncSetAttribute(wgrad2x2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM));
-        attr_set = true;
-    }
+    FS_DYN_SMEM(wgrad2x2_tc_kernel, W2_SMEM);
     launch_k(wgrad2x2_tc_kernel, dim3(grid), dim3(256), W2_SMEM, st, tmX_hi, tmX_lo, tmD_hi, tmD_lo, p);
     FS_LAUNCH_CHECK();
     launch_k(reduce_cta_partials_kernel, dim3(cdiv(elems, 32)), dim3(256), 0, st, partial, out, elems, grid);
@@ -1056,11 +1048,7 @@ static int launch_gram_tc2(SplitPtr f, float* G, float* partial, long long parti
     FS_TRY(make_map3(&tm_hi, f.hi, N, HW, C, p.gp));
     FS_TRY(make_map3(&tm_lo, f.lo, N, HW, C, p.gp));
     const int smem = p.stages * p.stage_bytes + 1024 + 256;
-    static bool attr_set = false;
-    if (!attr_set) {
-        FS_CUDA(cudaFuncSetAttribute(gram_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608 + 1024 + 256));
-        attr_set = true;
-    }
+    FS_DYN_SMEM(gram_tc2_kernel, 196608 + 1024 + 256);
     int grid = N * p.mtiles * p.ksplit;
     launch_k(gram_tc2_kernel, dim3(grid), dim3(256), smem, st, tm_hi, tm_lo, p);
     FS_LAUNCH_CHECK();
@@ -1086,11 +1074,7 @@ int launch_gram_tc(SplitPtr f, float* G, float* partial, long long partial_cap, 
     CUtensorMap tm_hi, tm_lo;
     FS_TRY(make_map3(&tm_hi, f.hi, N, HW, C));
     FS_TRY(make_map3(&tm_lo, f.lo, N, HW, C));
-    static bool attr_set = false;
-    if (!attr_set) {
-        FS_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
-        attr_set = true;
-    }
+    FS_DYN_SMEM(gram_tc_kernel, G_SMEM);
     int grid = N * p.mtiles * p.ntiles * p.ksplit;
     launch_k(gram_tc_kernel, dim3(grid), dim3(256), G_SMEM, st, tm_hi, tm_lo, p);
     FS_LAUNCH_CHECK();
@@ -1151,11 +1135,7 @@ int launch_wgrad3x3_tc_multi(const WgradMultiItem* items, int count, float* part
         begin += c; left -= c;
     }
     FS_CHECK(begin <= 148 && left >= 0, "wgrad3x3_tc_multi: CTA assignment overflow");
-    static bool attr_set = false;
-    if (!attr_set) {
-        FS_CUDA(cudaFuncSetAttribute(wgrad3x3_tc_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
+    FS_DYN_SMEM(wgrad3x3_tc_multi_kernel, SMEM_BYTES);
     launch_k(wgrad3x3_tc_multi_kernel, dim3(begin), dim3(256), SMEM_BYTES, st, M);
     FS_LAUNCH_CHECK();
     WgReduceMulti R;

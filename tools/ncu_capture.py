@@ -29,6 +29,13 @@ def run(cmd, log=None):
     return r
 
 
+def drop_report(path):
+    """gpurun copies back at most 64 MiB of gpurun_out/: the raw CSV pages are the evidence, the binary report goes
+    (keep it with FS_KEEP_NCU_REP=1 when the source page is wanted and the capture is small)."""
+    if os.environ.get("FS_KEEP_NCU_REP") != "1" and os.path.exists(path):
+        os.remove(path)
+
+
 def kernel_names(path):
     rows = list(csv.reader(open(path)))
     hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
@@ -78,6 +85,7 @@ def main():
         "# %s: `ncu --set full` of every tcgen05 conv launch of one train step (%d launches)\n\n" % (tag, tc_step)
         + run([PY, SUMM, "raw", raw]).stdout)
     print(run([PY, SUMM, "traffic", raw, "conv3x3_tc", os.path.join(OUT, "ncu_traffic.json")]).stdout)
+    drop_report(rep + ".ncu-rep")
     extra = []
     if "--gram" in sys.argv:
         extra.append(("gram", "regex:gram_tc", 4, 4))
@@ -91,6 +99,7 @@ def main():
         raw = rep + "_raw.csv"
         open(raw, "w").write(run(["ncu", "-i", rep + ".ncu-rep", "--page", "raw", "--csv"]).stdout)
         open(os.path.join(OUT, "%s_ncu_%s.md" % (tag, name)), "w").write(run([PY, SUMM, "raw", raw]).stdout)
+        drop_report(rep + ".ncu-rep")
 
 
 if __name__ == "__main__":
