@@ -168,7 +168,7 @@ long long wgrad9x9_partial_floats(int N, int H, int W);
 int launch_conv9x9(const float* in, const float* w, float* out, int N, int H, int W, int CI, int CO, cudaStream_t st);
 int flip_transpose_taps(const float* W, float* Wf, int T, int Ci, int Co, cudaStream_t st);
 int launch_conv3x3_c4_fwd(const float* in, const float* w, const float* bias, float* out, void* split_hi, void* split_lo,
-                          int N, int H, int W, cudaStream_t st);
+                          int N, int H, int W, cudaStream_t st, unsigned char* code = nullptr);
 int launch_dgrad3x3_c4(const float* P, const float* wf, float* dx, int N, int H, int W, cudaStream_t st);
 int launch_wgrad9x9(const float* in, const float* dy, float* out, float* partial, long long partial_cap, int N,
                     int H, int W, int CI, int CO, cudaStream_t st);

@@ -62,6 +62,7 @@ struct TcParams {
     long long total_tiles;     // work units: spatial tiles (per-sample pairs of them for the CTA-pair kernel) x tilesN
     const float* bias; const float* addend; const float* ref;
     const float* pool_grad; const float* ctarget; float cw2;
+    const unsigned char* ref8; unsigned char* out_code;
     __nv_bfloat16* pool_hi; __nv_bfloat16* pool_lo;
     int relu, add_crop, addH, addW;
     float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
@@ -360,8 +361,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     // serialised HBM round trips: Gram backward at conv1_2 ran at 2.7 TB/s)
                     float rb[32];
                     float gq[8];
+                    uint32_t cw8[8];
                     const int rc0 = nt * BN + ch * 32;
                     const float* gp = nullptr;
+                    if (!STATS && p.ref8) {                    // one code byte per element instead of the fp32 reference
+                        if (ok) {
+                            ldg256_b32(p.ref8 + pix * p.OC + rc0, cw8);
+                            if (p.pool_grad) {
+                                gp = p.pool_grad + (((long long)n * ((p.OH + 1) >> 1) + (oy >> 1)) * ((p.OW + 1) >> 1) + (ox >> 1)) * p.OC + rc0;
+                                ldg256(gp, gq);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) cw8[i] = 0u;
+                        }
+                    } else
                     if (!STATS && p.ref && !p.out_d2s) {       // (launches with fused statistics never carry a reference)
                         if (ok) {
                             const float* rp = p.ref + pix * p.OC + rc0;
@@ -425,6 +439,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                         }
+                        if (!STATS && p.ref8) {
+                            // v = bit0 * (v + bit1 * pool_grad): ReLU mask and max-pool routing from the code bytes
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                float g[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) g[j] = p.pool_grad ? gq[j] : 0.f;
+                                if (p.pool_grad && ok && i + 8 < 32) ldg256(gp + i + 8, gq);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const uint32_t code = cw8[(i + j) >> 2] >> (8 * ((i + j) & 3));
+                                    const float a = v[i + j] + ((code & 2u) ? g[j] : 0.f);
+                                    v[i + j] = (code & 1u) ? a : 0.f;
+                                }
+                            }
+                        } else
                         if (!STATS && p.ref) {
                             // v = mask(ref > 0) * (v + route(pool_grad) + cw2 * (ref - ctarget)): the backward of
                             // ReLU, of a following 2x2 max-pool (gradient to the FIRST maximum of the window in scan
@@ -463,6 +493,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                                 for (int j = 0; j < 8; ++j) v[i + j] = b[j] > 0.f ? v[i + j] : 0.f;
                             }
                         }
+                        uint32_t ismax = 0u;          // bit c: channel c of this pixel equals its window's maximum
                         if (p.pool_hi) {
                             // fused 2x2 stride-2 SAME max-pool of the result (libs/vgg16.py:67-71): the window's four
                             // pixels are lanes L, L^1, L^16, L^17; the top-left lane stores the pooled split planes
@@ -477,6 +508,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                                     x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
                                     x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 16));
                                     m[j] = x;
+                                    if (ok && v[i + j] == x) ismax |= 1u << (i + j);
                                 }
                                 if (writer) {
                                     uint32_t hw[8], lw[8];
@@ -492,6 +524,37 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                                     stg256_b32(p.pool_hi + ppix * p.OC + c0 + i, hw);
                                     stg256_b32(p.pool_lo + ppix * p.OC + c0 + i, lw);
                                 }
+                            }
+                        }
+                        if (p.out_code) {
+                            // ReLU / arg-max codes for the backward pass (Conv3x3TcArgs::ref_code).  The first maximum in
+                            // scan order: the earlier positions of the window (lanes L^1, L^16, L^17 by position) do not
+                            // hold the maximum.  (Warp-collective: shuffles before the `ok` test.)
+                            uint32_t first = 0u;
+                            if (p.pool_hi) {
+                                const int kme = ((lane >> 4) & 1) * 2 + (lane & 1);
+                                const uint32_t e1 = __shfl_xor_sync(0xffffffffu, ismax, 1);
+                                const uint32_t e2 = __shfl_xor_sync(0xffffffffu, ismax, 16);
+                                const uint32_t e3 = __shfl_xor_sync(0xffffffffu, ismax, 17);
+                                uint32_t earlier = 0u;
+                                if ((kme ^ 1) < kme) earlier |= e1;
+                                if ((kme ^ 2) < kme) earlier |= e2;
+                                if ((kme ^ 3) < kme) earlier |= e3;
+                                first = ismax & ~earlier;
+                            }
+                            if (ok) {
+                                uint32_t pos = 0u;
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) pos |= (v[i] > 0.f ? 1u : 0u) << i;
+                                uint32_t words[8];
+#pragma unroll
+                                for (int w = 0; w < 8; ++w) {
+                                    const uint32_t pb = (pos >> (4 * w)) & 0xFu, fb = (first >> (4 * w)) & 0xFu;
+                                    const uint32_t ps = (pb & 1u) | ((pb & 2u) << 7) | ((pb & 4u) << 14) | ((pb & 8u) << 21);
+                                    const uint32_t fs4 = (fb & 1u) | ((fb & 2u) << 7) | ((fb & 4u) << 14) | ((fb & 8u) << 21);
+                                    words[w] = ps | (fs4 << 1);
+                                }
+                                stg256_b32(p.out_code + pix * p.OC + c0, words);
                             }
                         }
                         if (ok) {
@@ -719,6 +782,7 @@ int launch_cfg_s(const Conv3x3TcArgs& a, cudaStream_t st) {
     p.bias = a.bias; p.addend = a.addend; p.ref = a.ref; p.relu = a.relu;
     p.pool_grad = a.pool_grad; p.ctarget = a.ctarget; p.cw2 = a.cw2;
     p.pool_hi = a.pool_split.hi; p.pool_lo = a.pool_split.lo;
+    p.ref8 = a.ref_code; p.out_code = a.out_code;
     p.add_crop = a.add_crop; p.addH = a.addH; p.addW = a.addW;
     p.out_f32 = a.out_f32; p.out_hi = a.out_split.hi; p.out_lo = a.out_split.lo;
     p.stats = a.stats; p.stats_c = a.stats_c;
@@ -753,6 +817,8 @@ int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st) {
     FS_CHECK(conv3x3_tc_supported(a.C, a.OC, a.W, a.OW), "conv3x3_tc: needs C%%64==0 and OC%%64==0 (C=%d OC=%d)", a.C, a.OC);
     FS_CHECK(a.x.hi && a.x.lo && a.w.hi && a.w.lo, "conv3x3_tc: NULL operand planes");
     FS_CHECK(a.out_f32 || a.out_split.hi || a.pool_split.hi, "conv3x3_tc: no output requested");
+    FS_CHECK(!a.ref_code || (!a.ref && !a.ctarget && !a.out_d2s && !a.stats), "conv3x3_tc: ref_code excludes ref / ctarget / d2s / stats");
+    FS_CHECK(!a.out_code || (!a.out_d2s && !a.stats && a.relu), "conv3x3_tc: out_code is for plain ReLU outputs");
     FS_CHECK((a.pool_split.hi == nullptr) == (a.pool_split.lo == nullptr) && !(a.pool_split.hi && a.out_d2s),
              "conv3x3_tc: pooled split output needs both planes and a plain layout");
     FS_CHECK((a.out_split.hi == nullptr) == (a.out_split.lo == nullptr), "conv3x3_tc: split output needs both planes");
@@ -760,7 +826,8 @@ int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st) {
     FS_CHECK(a.taps == 0 || a.taps == 2 || a.taps == 3 || a.taps == 9, "conv3x3_tc: taps must be 2, 3 or 9");
     FS_CHECK(a.taps != 9 || (a.taps_w >= 1 && a.taps_w <= 3 && !a.in_s2d && !a.out_d2s && !a.one_by_one),
              "conv3x3_tc: the 9-row form takes 1..3 horizontal taps and plain layouts");
-    FS_CHECK((!a.pool_grad && !a.ctarget) || (a.ref && !a.out_d2s), "conv3x3_tc: pool_grad / ctarget need the ReLU reference tensor");
+    FS_CHECK((!a.pool_grad && !a.ctarget) || ((a.ref || (a.ref_code && !a.ctarget)) && !a.out_d2s),
+             "conv3x3_tc: pool_grad / ctarget need the ReLU reference tensor");
     // fused statistics: the real channel (output channel % stats_c) of element i of a warp's 32-channel chunk must
     // not depend on the chunk: stats_c divides 32, or one 64-channel tile whose two chunks go to different warps
     FS_CHECK(!a.stats || ((a.stats_c == 4 || a.stats_c == 8 || a.stats_c == 16 || a.stats_c == 32 ||

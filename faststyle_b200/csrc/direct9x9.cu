@@ -209,7 +209,7 @@ constexpr int C1_ROWS = 32, C1_COLS = 8, C1_PITCH = 11;   // pitch 11 float4: th
 __global__ void __launch_bounds__(256) conv3x3_c4_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ out,
                                                              __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo,
-                                                             int H, int W) {
+                                                             unsigned char* __restrict__ code, int H, int W) {
     FS_PDL_ENTER();
     __shared__ float4 in_s[(C1_ROWS + 2) * C1_PITCH];
     __shared__ float4 w_s[9 * 4 * 16];
@@ -290,6 +290,14 @@ __global__ void __launch_bounds__(256) conv3x3_c4_fwd_kernel(const float* __rest
             }
             tcptx::stg256_b32(shi + o, hw);
             tcptx::stg256_b32(slo + o, lw);
+        }
+        if (code) {          // ReLU codes for the backward pass (Conv3x3TcArgs::ref_code): bit 0 = value > 0
+            uint32_t cw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                cw[j] = (r[4 * j] > 0.f ? 1u : 0u) | (r[4 * j + 1] > 0.f ? 0x100u : 0u) |
+                        (r[4 * j + 2] > 0.f ? 0x10000u : 0u) | (r[4 * j + 3] > 0.f ? 0x1000000u : 0u);
+            *reinterpret_cast<uint4*>(code + o) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
         }
     }
 }
@@ -431,9 +439,10 @@ int launch_conv9x9(const float* in, const float* w, float* out, int N, int H, in
 
 // conv1_1 forward: in [N,H,W,4], w [9,4,64], bias [64] -> out [N,H,W,64] fp32 (+ optional split planes)
 int launch_conv3x3_c4_fwd(const float* in, const float* w, const float* bias, float* out, void* split_hi, void* split_lo,
-                          int N, int H, int W, cudaStream_t st) {
+                          int N, int H, int W, cudaStream_t st, unsigned char* code) {
+    FS_CHECK(out || split_hi || code, "conv3x3_c4_fwd: no output requested");
     dim3 grid(cdiv(W, C1_COLS), cdiv(H, C1_ROWS), N);
-    launch_k(conv3x3_c4_fwd_kernel, dim3(grid), dim3(256), 0, st, in, w, bias, out, (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo, H, W);
+    launch_k(conv3x3_c4_fwd_kernel, dim3(grid), dim3(256), 0, st, in, w, bias, out, (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo, code, H, W);
     FS_LAUNCH_CHECK();
     return 0;
 }

@@ -79,6 +79,8 @@ static double tc_bytes(const Conv3x3TcArgs& a) {
     if (a.out_f32) b += out;
     if (a.out_split.hi) b += out;
     if (a.ref) b += out;
+    if (a.ref_code) b += out / 4.0;
+    if (a.out_code) b += out / 4.0;
     if (a.ctarget) b += out;
     if (a.pool_grad) b += out / 4.0;
     if (a.pool_split.hi) b += out / 4.0;
@@ -360,6 +362,8 @@ void Engine::layout(Arena& a) {
             }
         }
         loss_acc = a.take<double>(4);
+        for (int l = 0; l < V_NCONV; ++l)
+            vcode[l] = vgb ? a.take<unsigned char>((long long)N * vc[l].H * vc[l].W * vc[l].cout) : nullptr;
         if (vgb) {
             vgrad_floats = maxact;
             for (int i = 0; i < 4; ++i) {
@@ -919,7 +923,7 @@ static void vgg_conv_args(const VConv& v, int N, const float* packed, const floa
 }
 
 int Engine::vgg_forward(const float* packed, const float* img3, int upto, float* const* act_override,
-                        cudaStream_t st) {
+                        cudaStream_t st, unsigned code_mask) {
     FS_CHECK(bound && (flags & ENG_VGG), "engine has no VGG plan / workspace");
     FS_CHECK(upto >= 0 && upto < V_NCONV, "vgg_forward: bad layer %d", upto);
     PROF(PC_POINTWISE, 0.0, vgg_preprocess_c4(img3, v_in4, (long long)N * VH * VW, st));
@@ -938,8 +942,10 @@ int Engine::vgg_forward(const float* packed, const float* img3, int upto, float*
             // the following max-pool runs in this conv's epilogue (pooled split planes for the next conv)
             const bool fpool = pool_next && fuse_pool;
             // content-target pass: only the targets and the last layer (and un-fused pooled layers) need an fp32 copy
-            const bool need_f32 = !act_override || (pool_next && !fpool) || act_override[l] || l == upto;
+            const bool coded = !act_override && ((code_mask >> l) & 1u) && vcode[l] && (!pool_next || fpool);
+            const bool need_f32 = (!act_override && !coded) || (pool_next && !fpool) || (act_override && (act_override[l] || l == upto));
             ta.out_f32 = need_f32 ? out : nullptr;
+            if (coded) ta.out_code = vcode[l];
             if (l < upto && !pool_next) ta.out_split = vsplit[l + 1];     // next conv reads split planes
             else if (vtsplit[l].hi && !act_override) ta.out_split = vtsplit[l];   // style tap: Gram kernels read them
             if (fpool) ta.pool_split = vsplit[l + 1];
@@ -948,10 +954,11 @@ int Engine::vgg_forward(const float* packed, const float* img3, int upto, float*
         } else if (l == 0) {             // conv1_1 (Cin = 3): direct shared-memory kernel, exact fp32
             const bool sp = use_tc && l < upto && !pool_next;
             // content-target pass: conv1_1's fp32 copy is dead unless it is a target itself (conv1_2 reads the planes)
-            float* out0 = (sp && act_override && !act_override[0]) ? nullptr : out;
+            const bool coded0 = sp && !act_override && (code_mask & 1u) && vcode[0];
+            float* out0 = ((sp && act_override && !act_override[0]) || coded0) ? nullptr : out;
             PROF(PC_FFMA_CONV, 2.0 * N * vc[0].H * vc[0].W * 9.0 * 3 * 64,
                  launch_conv3x3_c4_fwd(cur, packed + vc[0].offW, packed + vc[0].offB, out0, sp ? vsplit[1].hi : nullptr,
-                                       sp ? vsplit[1].lo : nullptr, N, vc[0].H, vc[0].W, st));
+                                       sp ? vsplit[1].lo : nullptr, N, vc[0].H, vc[0].W, st, coded0 ? vcode[0] : nullptr));
         } else {
             IGemmArgs a;
             vgg_conv_args(vc[l], N, packed, cur, out, a);
@@ -1004,7 +1011,19 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
         cw[l] = lc.content_w[i]; has_c[l] = true; top = std::max(top, l);
     }
     FS_CHECK(top >= 0, "no loss layers configured");
-    FS_TRY(vgg_forward(packed, img3, top, nullptr, st));
+    // Layers whose fp32 activation nobody reads in this pass store ReLU / arg-max code bytes instead: every tensor-path
+    // layer (and conv1_1 feeding one) that is no content target; a layer followed by a pool must be a style tap on
+    // the tensor path (its pooling gradient is routed inside the Gram-backward epilogue).
+    unsigned code_mask = 0;
+    if (need_grad && relu_codes && use_tc && !keep_acts && fuse_pool && fold_pool && top >= 1)
+        for (int l = 0; l <= top; ++l) {
+            const bool pool_follow = vc[l].pool_after && l < top;
+            if (has_c[l]) continue;
+            if (l == 0 && (tg[0] || pool_follow)) continue;
+            if (pool_follow && !tg[l]) continue;
+            code_mask |= 1u << l;
+        }
+    FS_TRY(vgg_forward(packed, img3, top, nullptr, st, code_mask));
 
     // split-bf16 planes of activation l after vgg_forward(top): the next conv's input planes, or the
     // dedicated planes of a style tap that is followed by a pool / is the top layer
@@ -1045,7 +1064,11 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
     // ---- backward: P_l = dLoss/d(pre-activation of conv l), top-down
     auto pick = [](int a, int b, int c) { for (int i = 0; i < 4; ++i) if (i != a && i != b && i != c) return i; return -1; };
     // data gradient of VGG conv lsrc applied to the masked gradient held in vgrad[pidx]
-    auto dgrad = [&](int lsrc, int pidx, float* out, SplitPtr out_split, const float* addend, const float* ref) -> int {
+    // the ReLU reference of layer l: its code bytes when it stored them, else its fp32 activation
+    auto refc = [&](int l) -> const unsigned char* { return ((code_mask >> l) & 1u) ? vcode[l] : nullptr; };
+    auto reff = [&](int l) -> const float* { return ((code_mask >> l) & 1u) ? nullptr : vact[l]; };
+    auto dgrad = [&](int lsrc, int pidx, float* out, SplitPtr out_split, const float* addend, const float* ref,
+                     const unsigned char* ref_code) -> int {
         const VConv& v = vc[lsrc];
         const float* P = vgrad[pidx];
         if (use_tc && lsrc >= 1) {
@@ -1053,7 +1076,7 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
             memset(&ta, 0, sizeof(ta));
             ta.x = vgsplit[pidx]; ta.w = vgg_tc_w(packed, v, 1);
             ta.N = N; ta.H = v.H; ta.W = v.W; ta.C = v.cout; ta.OH = v.H; ta.OW = v.W; ta.OC = v.cin; ta.pad = 1;
-            ta.addend = addend; ta.addH = v.H; ta.addW = v.W; ta.ref = ref;
+            ta.addend = addend; ta.addH = v.H; ta.addW = v.W; ta.ref = ref; ta.ref_code = ref_code;
             ta.out_f32 = out; ta.out_split = out_split;
             PROFB(PC_TC_VGG_DGRAD, tc_flops(ta), tc_bytes(ta), launch_conv3x3_tc(ta, st));
             return 0;
@@ -1063,6 +1086,7 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
             return 0;
         }
         FS_CHECK(lsrc != 0, "conv1_1 data gradient with an epilogue is not supported");
+        FS_CHECK(!ref_code, "code-byte references need the tensor path");
         IGemmArgs a;
         memset(&a, 0, sizeof(a));
         a.in = P; a.w = packed + v.offWT; a.out = out; a.N = N; a.gather = 1;
@@ -1081,8 +1105,8 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
     };
     // pool_g / ct / cw2c: gradient w.r.t. the max-pool of this activation, content target and its coefficient -
     // folded into the tensor-path epilogue (no pool_bwd_combine pass); the FFMA path takes them pre-combined in addend
-    auto gram_bwd = [&](int l, const float* addend, const float* ref, float* out, SplitPtr out_split,
-                        const float* pool_g, const float* ctt, float cw2c) -> int {
+    auto gram_bwd = [&](int l, const float* addend, const float* ref, const unsigned char* ref_code, float* out,
+                        SplitPtr out_split, const float* pool_g, const float* ctt, float cw2c) -> int {
         const VConv& v = vc[l];
         const SplitPtr fp = act_planes(l, top);
         if (fp.hi) {                     // dF = F * S as a per-sample 1x1 tensor-path GEMM
@@ -1090,13 +1114,13 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
             memset(&ta, 0, sizeof(ta));
             ta.x = fp; ta.w = gsS[l]; ta.one_by_one = 1; ta.per_sample_w = 1;
             ta.N = N; ta.H = v.H; ta.W = v.W; ta.C = v.cout; ta.OH = v.H; ta.OW = v.W; ta.OC = v.cout; ta.pad = 0;
-            ta.addend = addend; ta.addH = v.H; ta.addW = v.W; ta.ref = ref;
+            ta.addend = addend; ta.addH = v.H; ta.addW = v.W; ta.ref = ref; ta.ref_code = ref_code;
             ta.pool_grad = pool_g; ta.ctarget = ctt; ta.cw2 = cw2c;
             ta.out_f32 = out; ta.out_split = out_split;
             PROFB(PC_GRAM_BWD, tc_flops(ta) / 9.0, tc_bytes(ta), launch_conv3x3_tc(ta, st));
             return 0;
         }
-        FS_CHECK(!pool_g && !ctt, "gram backward: fused pool / content terms need the tensor path");
+        FS_CHECK(!pool_g && !ctt && !ref_code, "gram backward: fused pool / content terms need the tensor path");
         IGemmArgs a;
         memset(&a, 0, sizeof(a));
         a.in = vact[l]; a.w = gramS[l]; a.w_bs = (long long)v.cout * v.cout; a.out = out; a.N = N;
@@ -1117,7 +1141,7 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
             int gi = -1; const float* gp = nullptr;
             if (pool_follow) {
                 gi = pick(pi, -1, -1);
-                FS_TRY(dgrad(l + 1, pi, vgrad[gi], no_split, nullptr, nullptr));
+                FS_TRY(dgrad(l + 1, pi, vgrad[gi], no_split, nullptr, nullptr, nullptr));
                 gp = vgrad[gi];
             }
             if (tg[l]) {
@@ -1131,7 +1155,7 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
                 }
                 int oi = pick(gi, ti, -1);
                 // P_l feeds the tensor-path data gradient of conv l: only its split planes are needed
-                FS_TRY(gram_bwd(l, T, vact[l], tcg ? nullptr : vgrad[oi], tcg ? vgsplit[oi] : no_split,
+                FS_TRY(gram_bwd(l, T, reff(l), refc(l), tcg ? nullptr : vgrad[oi], tcg ? vgsplit[oi] : no_split,
                                 fold ? gp : nullptr, fold ? ct : nullptr, cw2));
                 if (!tcg) PROF(PC_POINTWISE, 0.0, ensure_split(l, oi));
                 pi = oi;
@@ -1151,7 +1175,7 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
                     T = vgrad[ti];
                 }
                 ai = pick(pi, ti, -1);
-                FS_TRY(gram_bwd(l, T, nullptr, vgrad[ai], no_split, nullptr, nullptr, 0.f));
+                FS_TRY(gram_bwd(l, T, nullptr, nullptr, vgrad[ai], no_split, nullptr, nullptr, 0.f));
                 A = vgrad[ai];
             } else if (ct) {
                 ai = pick(pi, -1, -1);
@@ -1159,11 +1183,12 @@ int Engine::vgg_loss_backward(const float* packed, const float* img3, const Loss
                 A = vgrad[ai];
             }
             int oi = pick(pi, ai, -1);
-            FS_TRY(dgrad(l + 1, pi, (use_tc && l >= 1) ? nullptr : vgrad[oi], (use_tc && l >= 1) ? vgsplit[oi] : no_split, A, vact[l]));
+            FS_TRY(dgrad(l + 1, pi, (use_tc && l >= 1) ? nullptr : vgrad[oi], (use_tc && l >= 1) ? vgsplit[oi] : no_split, A,
+                         reff(l), refc(l)));
             pi = oi;
         }
     }
-    FS_TRY(dgrad(0, pi, dY4, no_split, nullptr, nullptr));
+    FS_TRY(dgrad(0, pi, dY4, no_split, nullptr, nullptr, nullptr));
     return 0;
 }
 

@@ -126,6 +126,11 @@ struct Engine {
     int keep_acts = 0;                   // 1: write every fp32 activation / gradient even where only split planes are read (debug taps)
     int fuse_pool = 1;                   // FS_FUSE_POOL=0: separate max-pool kernel after the VGG conv
     int fold_pool = 1;                   // FS_FOLD_POOL=0: separate pool_bwd_combine pass before the Gram backward
+    // ReLU / arg-max code bytes (Conv3x3TcArgs::ref_code) instead of fp32 copies of the VGG activations in the
+    // training pass: the backward epilogues need only "value > 0" and "first maximum of its pooling window" of a
+    // layer that is no content target.  FS_RELU_CODES=0: fp32 references as before.
+    int relu_codes = 1;
+    unsigned char* vcode[V_NCONV];
     int batch_wgrad = 1;                 // FS_BATCH_WGRAD=0: one weight-gradient launch per residual conv
     SplitPtr tw_f[T_NCONV], tw_d[T_NCONV];   // packed weights (forward / data gradient)
     float* w2f = nullptr;                // initconv_1/2 weights in the 2x2 space-to-depth form (fp32 staging)
@@ -165,8 +170,9 @@ struct Engine {
     int prep_transform_weights(const float* params, bool need_bwd, cudaStream_t st);
     int transform_forward(const float* params, const float* x3, float* y3_out, cudaStream_t st);
     int transform_backward(const float* params, const float* dY4_in, float* grads, cudaStream_t st);
+    // code_mask: bit l set = layer l stores code bytes (vcode[l]) instead of its fp32 activation
     int vgg_forward(const float* packed, const float* img3, int upto, float* const* act_override,
-                    cudaStream_t st);
+                    cudaStream_t st, unsigned code_mask = 0);
     int vgg_content_targets(const float* packed, const float* img3, const LossConfig& lc, cudaStream_t st);
     int vgg_loss_backward(const float* packed, const float* img3, const LossConfig& lc,
                           const float* const* target_grams, bool need_grad, cudaStream_t st);

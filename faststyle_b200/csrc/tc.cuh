@@ -48,6 +48,11 @@ struct Conv3x3TcArgs {
     // is the gradient w.r.t. the 2x2 max-pool of ref (routed to the first maximum of each window); ctarget
     // [N,OH,OW,OC] the content target of this layer (content-loss gradient 2w/(hwc) (f - t), cw2 = 2w/(hwc))
     const float* pool_grad; const float* ctarget; float cw2;
+    // ref_code: the same reference as one byte per element instead of fp32 (written by a forward launch through
+    // out_code): bit 0 = value > 0 (the ReLU mask), bit 1 = this element is the FIRST maximum of its 2x2 pooling window
+    // (scan order) - the max-pool gradient goes to it.  Excludes ref / ctarget.  A quarter of the reference traffic and
+    // no window shuffles in the backward epilogue; the forward launch stores 1 byte instead of 4 per element.
+    const unsigned char* ref_code;
     int relu;
     int add_crop, addH, addW;  // addend is [N,addH,addW,OC]; output pixel (y,x) reads (y-crop, x-crop)
     double* stats; int stats_c;    // optional: accumulate per-(sample, real channel) sum / sum of squares of the raw
@@ -57,6 +62,7 @@ struct Conv3x3TcArgs {
     float* out_f32;            // [N,OH,OW,OC] fp32 (may be null)
     SplitPtr out_split;        // split planes of the same tensor (may be null)
     SplitPtr pool_split;       // split planes of the 2x2 stride-2 SAME max-pool of the result [N,ceil(OH/2),ceil(OW/2),OC] (may be null)
+    unsigned char* out_code;   // [N,OH,OW,OC] ReLU / arg-max codes of the result (see ref_code; bit 1 only with pool_split)
 };
 int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st);
 // CTA-pair (tcgen05 cta_group::2) variant of the kernel on / off (default: on; FS_TC_PAIR=0 in the environment)
