@@ -394,7 +394,7 @@ def run_ours(args, rank, local_rank, world):
 PROF_CATS = ["tc_vgg_conv_fwd", "tc_vgg_conv_dgrad", "tc_res_conv_fwd", "tc_res_conv_dgrad",
              "ffma_conv", "wgrad", "gram_fwd", "gram_bwd", "instnorm_stats", "instnorm_apply", "instnorm_bwd",
              "pointwise", "losses", "weight_prep", "tc_s2_conv_fwd", "tc_s2_conv_dgrad", "tc_9x9_conv_fwd",
-             "tc_9x9_conv_dgrad"]
+             "tc_9x9_conv_dgrad", "tc_conv1_1_fwd"]
 TC_CONV_CATS = ("tc_vgg_conv_fwd", "tc_vgg_conv_dgrad", "tc_res_conv_fwd", "tc_res_conv_dgrad",
                 "tc_s2_conv_fwd", "tc_s2_conv_dgrad", "tc_9x9_conv_fwd", "tc_9x9_conv_dgrad")
 

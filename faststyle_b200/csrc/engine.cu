@@ -956,6 +956,11 @@ int Engine::vgg_forward(const float* packed, const float* img3, int upto, float*
             // content-target pass: conv1_1's fp32 copy is dead unless it is a target itself (conv1_2 reads the planes)
             const bool coded0 = sp && !act_override && (code_mask & 1u) && vcode[0];
             float* out0 = ((sp && act_override && !act_override[0]) || coded0) ? nullptr : out;
+            if (use_tc && conv11_tc)
+                PROF(PC_TC_C11_FWD, 2.0 * N * vc[0].H * vc[0].W * 9.0 * 3 * 64,
+                     launch_conv1_1_tc(cur, packed + vc[0].offW, packed + vc[0].offB, out0, sp ? vsplit[1].hi : nullptr,
+                                       sp ? vsplit[1].lo : nullptr, coded0 ? vcode[0] : nullptr, N, vc[0].H, vc[0].W, st));
+            else
             PROF(PC_FFMA_CONV, 2.0 * N * vc[0].H * vc[0].W * 9.0 * 3 * 64,
                  launch_conv3x3_c4_fwd(cur, packed + vc[0].offW, packed + vc[0].offB, out0, sp ? vsplit[1].hi : nullptr,
                                        sp ? vsplit[1].lo : nullptr, N, vc[0].H, vc[0].W, st, coded0 ? vcode[0] : nullptr));

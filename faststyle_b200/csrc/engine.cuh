@@ -45,7 +45,7 @@ struct LossConfig {
 
 enum ProfCat { PC_TC_VGG_FWD = 0, PC_TC_VGG_DGRAD, PC_TC_RES_FWD, PC_TC_RES_DGRAD, PC_FFMA_CONV, PC_WGRAD,
                PC_GRAM_FWD, PC_GRAM_BWD, PC_IN_STATS, PC_IN_APPLY, PC_IN_BWD, PC_POINTWISE, PC_LOSS, PC_PREP,
-               PC_TC_S2_FWD, PC_TC_S2_DGRAD, PC_TC9_FWD, PC_TC9_DGRAD, PC_COUNT };
+               PC_TC_S2_FWD, PC_TC_S2_DGRAD, PC_TC9_FWD, PC_TC9_DGRAD, PC_TC_C11_FWD, PC_COUNT };
 enum EngineFlags { ENG_TRANSFORM = 1, ENG_TRANSFORM_BWD = 2, ENG_VGG = 4, ENG_VGG_BWD = 8, ENG_DECONV = 16 };
 
 struct Arena {
@@ -130,6 +130,7 @@ struct Engine {
     // training pass: the backward epilogues need only "value > 0" and "first maximum of its pooling window" of a
     // layer that is no content target.  FS_RELU_CODES=0: fp32 references as before.
     int relu_codes = 1;
+    int conv11_tc = 1;                   // FS_CONV11_TC=0: VGG conv1_1 on the exact-fp32 direct kernel
     unsigned char* vcode[V_NCONV];
     int batch_wgrad = 1;                 // FS_BATCH_WGRAD=0: one weight-gradient launch per residual conv
     SplitPtr tw_f[T_NCONV], tw_d[T_NCONV];   // packed weights (forward / data gradient)

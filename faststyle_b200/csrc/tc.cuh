@@ -69,6 +69,11 @@ int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st);
 void set_tc_pair(int on);
 bool conv3x3_tc_supported(int C, int OC, int W, int OW);
 
+// VGG conv1_1 (3(4) -> 64, 3x3 SAME, bias + ReLU) with the im2col tile built in shared memory (conv1_1_tc.cu):
+// in [N,H,W,4] fp32, w [9,4,64] fp32 -> any of fp32 out / split planes / ReLU code bytes
+int launch_conv1_1_tc(const float* in, const float* w, const float* bias, float* out, void* split_hi, void* split_lo,
+                      unsigned char* code, int N, int H, int W, cudaStream_t st);
+
 // tcgen05 weight gradient of a 3x3 stride-1 64->64 convolution (wgrad_tc.cu):
 // x [N,H,W,64], dy [N,OH,OW,64] split planes -> out [3,3,64,64] fp32 (HWIO)
 long long wgrad3x3_tc_partial_floats();

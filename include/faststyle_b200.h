@@ -86,8 +86,8 @@ int fs_engine_set_frozen_weights(fs_engine* e, int frozen);
  * 8 InstanceNorm statistics, 9 InstanceNorm apply, 10 InstanceNorm backward, 11 pooling / padding /
  * split / other element-wise, 12 losses, 13 per-step weight preparation, 14 tc stride-2 / resize conv fwd
  * (collapsed 2x2 forms), 15 their data gradients, 16 tc 9x9 conv fwd (x16 space-to-depth forms), 17 its data
- * gradient. */
-#define FS_PROF_NCAT 18
+ * gradient, 18 tc VGG conv1_1 fwd (im2col tile built in shared memory). */
+#define FS_PROF_NCAT 19
 int fs_engine_profile(fs_engine* e, int enabled);
 int fs_engine_profile_read(fs_engine* e, int ncat, float* ms, double* flops, int* launches);
 /* algorithmic bytes per category of the launches recorded so far (tensor-path convolutions: every operand plane
