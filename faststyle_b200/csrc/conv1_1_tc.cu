@@ -27,7 +27,8 @@ constexpr int C11_THREADS = 288;          // warps 0-3 epilogue (TMEM lane quadr
 constexpr int C11_PLANE = 128 * 64;       // one operand plane of the A tile: 128 rows x 64 B
 constexpr int C11_A_STAGE = 3 * C11_PLANE;
 constexpr int C11_B_PLANE = 64 * 64;
-constexpr int C11_SMEM = 2 * C11_A_STAGE + 3 * C11_B_PLANE + 1024 /*align*/ + 256 /*bias*/ + 128 /*barriers*/;
+constexpr int C11_STG_WARP = 4096 + 4096 + 2048;      // per epilogue warp: hi / lo planes (32 px x 128 B), codes (32 px x 64 B)
+constexpr int C11_SMEM = 2 * C11_A_STAGE + 3 * C11_B_PLANE + 4 * C11_STG_WARP + 1024 /*align*/ + 256 /*bias*/ + 128 /*barriers*/;
 
 __device__ __forceinline__ uint64_t sdesc64(uint32_t saddr) {      // K-major, SWIZZLE_64B: 64-byte rows, 8-row atoms of 512 B
     uint64_t d = 0;
@@ -42,33 +43,36 @@ __device__ __forceinline__ uint64_t sdesc64(uint32_t saddr) {      // K-major, S
 // byte offset of 16-byte chunk `c` (0..3) of row `r` in a 64B-swizzled tile of 64-byte rows (address bits 4-5 ^= bits 7-8)
 __device__ __forceinline__ uint32_t swz64(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
 
-__device__ __forceinline__ void split2(float a, float b, uint32_t& h, uint32_t& l) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0)), l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
-    h = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-}
+__device__ __forceinline__ void split2(float a, float b, uint32_t& h, uint32_t& l) { split_pair(a, b, h, l); }
 // three-way split of a pair: a = h + m + l exactly (fp32 has 24 mantissa bits, each part carries 8)
 __device__ __forceinline__ void split3(float a, float b, uint32_t& h, uint32_t& m, uint32_t& l) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
-    const float ra = a - __bfloat162float(h0), rb = b - __bfloat162float(h1);
-    const __nv_bfloat16 m0 = __float2bfloat16_rn(ra), m1 = __float2bfloat16_rn(rb);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(ra - __bfloat162float(m0)), l1 = __float2bfloat16_rn(rb - __bfloat162float(m1));
-    h = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    m = (uint32_t)__bfloat16_as_ushort(m0) | ((uint32_t)__bfloat16_as_ushort(m1) << 16);
-    l = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(hh);
+    const float ra = a - hf.x, rb = b - hf.y;
+    const __nv_bfloat162 mm = __floats2bfloat162_rn(ra, rb);
+    const float2 mf = __bfloat1622float2(mm);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(ra - mf.x, rb - mf.y);
+    h = *reinterpret_cast<const uint32_t*>(&hh);
+    m = *reinterpret_cast<const uint32_t*>(&mm);
+    l = *reinterpret_cast<const uint32_t*>(&ll);
 }
 
-__global__ void __launch_bounds__(C11_THREADS, 3)
-conv1_1_tc_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-                  float* __restrict__ out, __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo,
-                  unsigned char* __restrict__ code, int N, int H, int W, int tilesX, int tilesY) {
+// Output path: every epilogue warp owns two image rows x 16 pixels of the tile.  Its lanes write their pixel's 64
+// channels into a 128B-swizzled (codes: 64B-swizzled) staging box in shared memory - conflict-free 16-byte stores -
+// and one lane hands the box to the TMA engine (cp.async.bulk.tensor store, clipped at the image border).  Scattered
+// 32-byte global stores (one 128-byte line per lane and instruction) kept the LSU data pipe at 67 % of its peak.
+__global__ void __launch_bounds__(C11_THREADS, 2)
+conv1_1_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                  const __grid_constant__ CUtensorMap tm_code, const float* __restrict__ in, const float* __restrict__ w,
+                  const float* __restrict__ bias, float* __restrict__ out, int has_split, int has_code, int N, int H, int W,
+                  int tilesX, int tilesY) {
     FS_PDL_TRIGGER();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smA = smem;                                   // [2 stages][h | m | l][128 rows x 64 B]
     uint8_t* smB = smem + 2 * C11_A_STAGE;                 // [h | m | l][64 rows x 64 B]
-    float* s_bias = reinterpret_cast<float*>(smB + 3 * C11_B_PLANE);
+    uint8_t* smS = smB + 3 * C11_B_PLANE;                  // [4 epilogue warps][hi 4 KB | lo 4 KB | codes 2 KB]
+    float* s_bias = reinterpret_cast<float*>(smS + 4 * C11_STG_WARP);
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 64);
     uint64_t* a_full = bars;            // [2] 128 builder arrivals
     uint64_t* a_empty = bars + 2;       // [2] tcgen05.commit
@@ -82,6 +86,7 @@ conv1_1_tc_kernel(const float* __restrict__ in, const float* __restrict__ w, con
         fence_barrier_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, 128);             // 2 accumulators x 64 fp32 columns
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tm_hi); prefetch_tmap(&tm_lo); prefetch_tmap(&tm_code); }
     FS_PDL_WAIT();
     // weights: B[n][k] = w[tap][c][n] for k = tap * 3 + c < 27 (fp32 [9][4][64]), zero up to k = 31; bias
     for (int i = t; i < 64 * 4; i += C11_THREADS) {        // one 16-byte chunk (8 k values) of one output-channel row
@@ -179,6 +184,9 @@ conv1_1_tc_kernel(const float* __restrict__ in, const float* __restrict__ w, con
     } else if (warp < 4) {
         // ===================== epilogue: thread = pixel, 2 x 32 channels =====================
         const int r = warp * 32 + lane, prow = r >> 4, pcol = r & 15;
+        uint8_t* stg_hi = smS + warp * C11_STG_WARP;       // row = lane (y-major over the warp's 2 x 16 pixels)
+        uint8_t* stg_lo = stg_hi + 4096;
+        uint8_t* stg_cd = stg_hi + 8192;
         int s = 0; uint32_t ph = 0;
         for (long long u = blockIdx.x; u < total; u += gridDim.x) {
             const int tx = (int)(u % tilesX); const long long q = u / tilesX;
@@ -188,41 +196,59 @@ conv1_1_tc_kernel(const float* __restrict__ in, const float* __restrict__ w, con
             const long long o = (((long long)n * H + y) * W + x) * 64;
             mbar_wait(&t_full[s], ph);
             tc_fence_after();
+            if (lane == 0) bulk_wait_read0();              // the previous tile's boxes have left the staging buffers
+            __syncwarp();
 #pragma unroll 1
             for (int ch = 0; ch < 2; ++ch) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * 64 + ch * 32), v);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + s_bias[ch * 32 + i], 0.f);
-                if (!ok) continue;
-                if (out) {
+                if (out && ok) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 8) stg256(out + o + ch * 32 + i, v + i);
                 }
-                if (shi) {
+                if (has_split) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 16) {
-                        uint32_t hw[8], lw[8];
+                    for (int jj = 0; jj < 4; ++jj) {       // 16-byte chunk ch * 4 + jj of this pixel's 128-byte row
+                        uint32_t hw[4], lw[4];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) split2(v[i + 2 * j], v[i + 2 * j + 1], hw[j], lw[j]);
-                        stg256_b32(shi + o + ch * 32 + i, hw);
-                        stg256_b32(slo + o + ch * 32 + i, lw);
+                        for (int j = 0; j < 4; ++j) split2(v[jj * 8 + 2 * j], v[jj * 8 + 2 * j + 1], hw[j], lw[j]);
+                        const uint32_t off = (uint32_t)(lane * 128 + (((ch * 4 + jj) ^ (lane & 7)) << 4));
+                        *reinterpret_cast<uint4*>(stg_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        *reinterpret_cast<uint4*>(stg_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                     }
                 }
-                if (code) {                                // ReLU codes (Conv3x3TcArgs::ref_code): bit 0 = value > 0
-                    uint32_t cw[8];
+                if (has_code) {                            // ReLU codes (Conv3x3TcArgs::ref_code): bit 0 = value > 0
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        cw[j] = (v[4 * j] > 0.f ? 1u : 0u) | (v[4 * j + 1] > 0.f ? 0x100u : 0u) |
-                                (v[4 * j + 2] > 0.f ? 0x10000u : 0u) | (v[4 * j + 3] > 0.f ? 0x1000000u : 0u);
-                    stg256_b32(code + o + ch * 32, cw);
+                    for (int jj = 0; jj < 2; ++jj) {       // 16-byte chunk ch * 2 + jj of this pixel's 64-byte row
+                        uint32_t cw[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int b = jj * 16 + 4 * j;
+                            cw[j] = (v[b] > 0.f ? 1u : 0u) | (v[b + 1] > 0.f ? 0x100u : 0u) |
+                                    (v[b + 2] > 0.f ? 0x10000u : 0u) | (v[b + 3] > 0.f ? 0x1000000u : 0u);
+                        }
+                        const uint32_t off = (uint32_t)(lane * 64 + (((ch * 2 + jj) ^ ((lane >> 1) & 3)) << 4));
+                        *reinterpret_cast<uint4*>(stg_cd + off) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+                    }
                 }
             }
             tc_fence_before();
+            fence_proxy_async();                           // staging writes -> visible to the TMA engine
             __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[s]);
+            if (lane == 0) {
+                mbar_arrive(&t_empty[s]);
+                const int y0 = ty * 8 + warp * 2, x0 = tx * 16;
+                if (y0 < H) {
+                    if (has_split) { tma_store_4d(&tm_hi, stg_hi, 0, x0, y0, n); tma_store_4d(&tm_lo, stg_lo, 0, x0, y0, n); }
+                    if (has_code) tma_store_4d(&tm_code, stg_cd, 0, x0, y0, n);
+                }
+                bulk_commit();
+            }
             if (++s == 2) { s = 0; ph ^= 1; }
         }
+        if (lane == 0) bulk_wait0();                       // all boxes written before the CTA retires
     }
     tc_fence_before();
     __syncthreads();
@@ -239,11 +265,17 @@ int launch_conv1_1_tc(const float* in, const float* w, const float* bias, float*
     FS_CHECK((split_hi == nullptr) == (split_lo == nullptr), "conv1_1_tc: split output needs both planes");
     const int tilesX = cdiv(W, 16), tilesY = cdiv(H, 8);
     const long long total = (long long)N * tilesX * tilesY;
+    // store maps: box = 2 rows x 16 pixels x 64 channels (an absent output gets a map over a present one; never used)
+    CUtensorMap tm_hi, tm_lo, tm_code;
+    const void* any2 = split_hi ? split_hi : (const void*)in;
+    FS_TRY(tc_make_map_nhwc(&tm_hi, any2, 2, N, H, W, 64, 64, 16, 2, 128));
+    FS_TRY(tc_make_map_nhwc(&tm_lo, split_lo ? split_lo : any2, 2, N, H, W, 64, 64, 16, 2, 128));
+    FS_TRY(tc_make_map_nhwc(&tm_code, code ? (const void*)code : any2, 1, N, H, W, 64, 64, 16, 2, 64));
     FS_DYN_SMEM(conv1_1_tc_kernel, C11_SMEM);
-    const long long cap = 3LL * num_sms();
+    const long long cap = 2LL * num_sms();
     const int grid = (int)(total < cap ? total : cap);
-    launch_k(conv1_1_tc_kernel, dim3(grid), dim3(C11_THREADS), C11_SMEM, st, in, w, bias, out, (__nv_bfloat16*)split_hi,
-             (__nv_bfloat16*)split_lo, code, N, H, W, tilesX, tilesY);
+    launch_k(conv1_1_tc_kernel, dim3(grid), dim3(C11_THREADS), C11_SMEM, st, tm_hi, tm_lo, tm_code, in, w, bias, out,
+             split_hi ? 1 : 0, code ? 1 : 0, N, H, W, tilesX, tilesY);
     FS_LAUNCH_CHECK();
     return 0;
 }

@@ -514,12 +514,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                                     uint32_t hw[8], lw[8];
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) {
-                                        __nv_bfloat16 h0 = __float2bfloat16_rn(m[2 * j]);
-                                        __nv_bfloat16 h1 = __float2bfloat16_rn(m[2 * j + 1]);
-                                        __nv_bfloat16 l0 = __float2bfloat16_rn(m[2 * j] - __bfloat162float(h0));
-                                        __nv_bfloat16 l1 = __float2bfloat16_rn(m[2 * j + 1] - __bfloat162float(h1));
-                                        hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                                        lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                                        split_pair(m[2 * j], m[2 * j + 1], hw[j], lw[j]);
                                     }
                                     stg256_b32(p.pool_hi + ppix * p.OC + c0 + i, hw);
                                     stg256_b32(p.pool_lo + ppix * p.OC + c0 + i, lw);
@@ -571,12 +566,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                                 uint32_t hw[8], lw[8];
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
-                                    __nv_bfloat16 h0 = __float2bfloat16_rn(v[i + 2 * j]);
-                                    __nv_bfloat16 h1 = __float2bfloat16_rn(v[i + 2 * j + 1]);
-                                    __nv_bfloat16 l0 = __float2bfloat16_rn(v[i + 2 * j] - __bfloat162float(h0));
-                                    __nv_bfloat16 l1 = __float2bfloat16_rn(v[i + 2 * j + 1] - __bfloat162float(h1));
-                                    hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                                    lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                                    split_pair(v[i + 2 * j], v[i + 2 * j + 1], hw[j], lw[j]);
                                 }
                                 stg256_b32(hp + i, hw);
                                 stg256_b32(lp + i, lw);
@@ -809,6 +799,25 @@ int launch_cfg(const Conv3x3TcArgs& a, bool pair, cudaStream_t st) {
 
 }  // namespace
 
+int tc_make_map_nhwc(CUtensorMap* tm, const void* base, int elem_bytes, int N, int H, int W, int C, int boxC, int boxW,
+                     int boxH, int swizzle_bytes) {
+    EncodeTiledFn enc = get_encode_fn();
+    FS_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    FS_CHECK(boxC * elem_bytes == swizzle_bytes && (swizzle_bytes == 64 || swizzle_bytes == 128), "tc_make_map_nhwc: bad box");
+    const CUtensorMapDataType dt = elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                 : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const cuuint64_t e = (cuuint64_t)elem_bytes;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * e, (cuuint64_t)W * C * e, (cuuint64_t)H * W * C * e};
+    cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)boxW, (cuuint32_t)boxH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, dt, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(store map %dx%dx%dx%d, %d B) failed: %d", N, H, W, C, elem_bytes, (int)r);
+    return 0;
+}
+
 bool conv3x3_tc_supported(int C, int OC, int W, int OW) {
     return C % 64 == 0 && OC % 64 == 0 && C >= 64 && OC >= 64 && W >= 1 && OW >= 1;
 }
@@ -859,6 +868,14 @@ int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st) {
         if (cost8 < 0.85 * cost16) tall = false;
         // the small 64->64 residual convs: 8-row tiles + their 3-deep slab ring also hide the L2 latency (measured)
         if (a.C == 64 && a.OC == 64 && !a.one_by_one && t16 * 2 < 3 * workers) tall = false;
+        // MMA-bound layers (>= 256 channels) on small planes: 8-row tiles.  With 16-row tiles a CTA pair gets one or
+        // two work units (conv4_x: 64 units on 74 pairs, conv3_x: 128), so the first load latency and the whole last
+        // epilogue stay un-overlapped; twice as many half-size units hide them (measured: 4.390 -> 4.339 ms per step).
+        // FS_TC_TH8 (bit mask, default 3): 1 = planes of <= 32 rows, 2 = planes of 33..64 rows, 4 = 65..128 rows.
+        static int th8 = -1;
+        if (th8 < 0) { const char* e = getenv("FS_TC_TH8"); th8 = e ? atoi(e) : 3; }
+        if (!a.one_by_one && a.C >= 256 && (((th8 & 1) && a.OH <= 32) || ((th8 & 2) && a.OH > 32 && a.OH <= 64))) tall = false;
+        if (!a.one_by_one && a.C >= 128 && (th8 & 4) && a.OH > 64 && a.OH <= 128) tall = false;
     }
     if (a.OC % 128 == 0) return tall ? launch_cfg<16, 128>(a, pair, st) : launch_cfg<8, 128>(a, pair, st);
     return tall ? launch_cfg<16, 64>(a, pair, st) : launch_cfg<8, 64>(a, pair, st);

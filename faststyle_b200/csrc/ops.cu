@@ -38,12 +38,12 @@ __device__ __forceinline__ double block_sum(double v) {
 __device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, long long idx, const float* r) {
     uint32_t h[2], l[2];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        __nv_bfloat16 h0 = __float2bfloat16_rn(r[2 * j]), h1 = __float2bfloat16_rn(r[2 * j + 1]);
-        __nv_bfloat16 l0 = __float2bfloat16_rn(r[2 * j] - __bfloat162float(h0));
-        __nv_bfloat16 l1 = __float2bfloat16_rn(r[2 * j + 1] - __bfloat162float(h1));
-        h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    for (int j = 0; j < 2; ++j) {           // packed conversions: one cvt.rn.bf16x2.f32 per two values
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(r[2 * j], r[2 * j + 1]);
+        const float2 hf = __bfloat1622float2(hh);
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(r[2 * j] - hf.x, r[2 * j + 1] - hf.y);
+        h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[j] = *reinterpret_cast<const uint32_t*>(&ll);
     }
     *reinterpret_cast<uint2*>(hi + idx) = make_uint2(h[0], h[1]);
     *reinterpret_cast<uint2*>(lo + idx) = make_uint2(l[0], l[1]);

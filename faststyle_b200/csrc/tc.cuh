@@ -1,6 +1,7 @@
 // Tensor-core (tcgen05 / TMEM / TMA) path: 3x3 stride-1 implicit-GEMM convolution with
 // split-bf16 operands.  sm_100a only.
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -68,6 +69,11 @@ int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st);
 // CTA-pair (tcgen05 cta_group::2) variant of the kernel on / off (default: on; FS_TC_PAIR=0 in the environment)
 void set_tc_pair(int on);
 bool conv3x3_tc_supported(int C, int OC, int W, int OW);
+
+// Tiled tensor map over an NHWC tensor [N,H,W,C] of 1- / 2- / 4-byte elements with box {boxC, boxW, boxH, 1}; the box's
+// inner extent (boxC * elem bytes) must equal swizzle_bytes (64 or 128).  Used for TMA stores of epilogue tiles.
+int tc_make_map_nhwc(CUtensorMap* tm, const void* base, int elem_bytes, int N, int H, int W, int C, int boxC, int boxW,
+                     int boxH, int swizzle_bytes);
 
 // VGG conv1_1 (3(4) -> 64, 3x3 SAME, bias + ReLU) with the im2col tile built in shared memory (conv1_1_tc.cu):
 // in [N,H,W,4] fp32, w [9,4,64] fp32 -> any of fp32 out / split planes / ReLU code bytes

@@ -66,6 +66,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, ui
         " [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// TMA store of a shared-memory box (written by generic stores + fence_proxy_async) to the tensor; bulk-group completion
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's bulk groups have finished READING shared memory (the staging buffer may be rewritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed (their global writes are done)
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
@@ -175,6 +185,17 @@ __device__ __forceinline__ void tc_mma2_bf16(uint32_t d_tmem, uint64_t adesc, ui
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// split-bf16 of a PAIR of floats with packed conversions (cvt.rn.bf16x2.f32: one conversion instruction per two
+// values - the single-value F2F runs on the 16-lane XU pipe and showed up at 50 % of it in the store-heavy epilogues):
+// h = (bf16(a), bf16(b)), l = (bf16(a - hi_a), bf16(b - hi_b)), a in the low half
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& h, uint32_t& l) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(hh);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    h = *reinterpret_cast<const uint32_t*>(&hh);
+    l = *reinterpret_cast<const uint32_t*>(&ll);
 }
 
 // 256-bit global accesses (LDG/STG.E.256, sm_100+): a thread that owns a contiguous 128-byte run of one

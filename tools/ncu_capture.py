@@ -47,6 +47,8 @@ def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r02x"
     os.makedirs(OUT, exist_ok=True)
     steps = 3
+    if "--only-extra" in sys.argv:          # just the --extra / --gram captures (no launch list, no full conv capture)
+        return extras(tag)
     lst = os.path.join(OUT, tag + "_launches.csv")
     r = run(["ncu", "--metrics", "gpu__time_duration.sum", "--clock-control", "none", "-c", "4000", "--csv",
              "--log-file", lst, PY, STEP, str(steps)], os.path.join(OUT, tag + "_launches.log"))
@@ -86,12 +88,16 @@ def main():
         + run([PY, SUMM, "raw", raw]).stdout)
     print(run([PY, SUMM, "traffic", raw, "conv3x3_tc", os.path.join(OUT, "ncu_traffic.json")]).stdout)
     drop_report(rep + ".ncu-rep")
+    extras(tag)
+
+
+def extras(tag):
     extra = []
     if "--gram" in sys.argv:
         extra.append(("gram", "regex:gram_tc", 4, 4))
     for i, a in enumerate(sys.argv):
         if a == "--extra" and i + 1 < len(sys.argv):
-            extra.append((re.sub(r"\W+", "_", sys.argv[i + 1]), "regex:" + sys.argv[i + 1], 0, 40))
+            extra.append((re.sub(r"\W+", "_", sys.argv[i + 1])[:40], "regex:" + sys.argv[i + 1], 0, 40))
     for name, kreg, skip, count in extra:
         rep = os.path.join(OUT, "%s_%s" % (tag, name))
         run(["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on", "-k", kreg, "-s", str(skip),
