@@ -368,9 +368,14 @@ def run_ours(args, rank, local_rank, world):
                        "global_batch": PER_GPU_BATCH * world, "parallelism": "dp%d" % world,
                        "l2": "per-step working set ~1.3 GB >> 126 MB L2, no explicit flush",
                        "precision": "fp32 storage; VGG conv1_2..conv4_3, the residual convs, the four stride-2 / "
-                                    "resize convs (2x2 forms) incl. data + weight gradients, Gram fwd/bwd: split-bf16 x3 "
-                                    "on tcgen05 (fp32-class, 16 mantissa bits), fp32 accumulate; 9x9 convs, conv1_1, "
-                                    "InstanceNorm, pooling, losses, Adam: exact fp32 on CUDA cores",
+                                    "resize convs (2x2 forms) incl. data + weight gradients, the 9x9 convs (fwd + data "
+                                    "gradient), Gram fwd/bwd: split-bf16 x3 on tcgen05 (fp32-class, 16 mantissa bits), "
+                                    "fp32 accumulate; conv1_1 fwd: three-way bf16 split, six products on tcgen05 "
+                                    "(24 mantissa bits); 9x9 weight gradients, conv1_1 data gradient, InstanceNorm, "
+                                    "losses, Adam: exact fp32 on CUDA cores",
+                       "dp_exchange": (None if world == 1 else
+                                       "fs_dp_allreduce_adam: one kernel, gradient all-reduce over NVLink peer loads + Adam"
+                                       if trainer.peer is not None else "NCCL all_reduce + Adam kernel"),
                        "api": "faststyle_b200.trainer.Trainer.step (the call train.py makes)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s",

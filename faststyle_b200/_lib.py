@@ -62,6 +62,12 @@ SIGNATURES = {
     "fs_perceptual_loss": (_I, [_P, _P, _P, C.POINTER(LossConfigC), _PP, _P, _P, _P]),
     "fs_train_fwd_bwd": (_I, [_P, _P, _P, _P, C.POINTER(LossConfigC), _PP, _P, _P, _P, _P]),
     "fs_adam_step": (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _P, _P]),
+    "fs_enable_peer_access": (_I, [_I]),
+    "fs_peer_buffer_create": (_I, [_SZ, _PP, _P]),
+    "fs_peer_buffer_open": (_I, [_P, _PP]),
+    "fs_peer_buffer_close": (_I, [_P]),
+    "fs_peer_buffer_free": (_I, [_P]),
+    "fs_dp_allreduce_adam": (_I, [_PP, _I, _I, _LL, _LL, _LL, _I, _LL, _U, _P, _P, _P, _F, _F, _F, _F, _P, _P, _P, _P]),
     "fs_conv2d_forward": (_I, [_P, _P, _P, _P] + [_I] * 10 + [_P]),
     "fs_conv2d_dgrad": (_I, [_P, _P, _P, _P] + [_I] * 9 + [_P]),
     "fs_conv2d_wgrad_scratch_floats": (_LL, [_I, _I, _I, _I]),

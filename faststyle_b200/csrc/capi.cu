@@ -280,6 +280,62 @@ int fs_adam_step(float* params, const float* grads, float* m, float* v, long lon
     return adam_step(params, grads, m, v, n, lr, beta1, beta2, eps, step_counter, S(stream));
 }
 
+int fs_enable_peer_access(int peer_device) {
+    int cur = 0;
+    FS_CUDA(cudaGetDevice(&cur));
+    if (cur == peer_device) return 0;
+    int can = 0;
+    FS_CUDA(cudaDeviceCanAccessPeer(&can, cur, peer_device));
+    FS_CHECK(can, "fs_enable_peer_access: device %d cannot access device %d (no NVLink / PCIe peer path)", cur, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); return 0; }
+    FS_CUDA(e);
+    return 0;
+}
+
+// Exchange buffers of the data-parallel step: plain cudaMalloc allocations (exact base pointers, not sub-allocations of
+// a caching allocator) exported / imported through CUDA IPC under the CONSUMER's device, so the driver maps the peer's
+// memory into this device's address space and enables peer access (NVLink) as part of the open.
+int fs_peer_buffer_create(size_t bytes, void** dev_ptr, unsigned char* handle64) {
+    FS_CHECK(dev_ptr && handle64 && bytes > 0, "fs_peer_buffer_create: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    FS_CUDA(cudaMalloc(&p, bytes));
+    FS_CUDA(cudaMemset(p, 0, bytes));
+    FS_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); FS_CUDA(e); }
+    memcpy(handle64, &h, 64);
+    *dev_ptr = p;
+    return 0;
+}
+int fs_peer_buffer_open(const unsigned char* handle64, void** dev_ptr) {
+    FS_CHECK(dev_ptr && handle64, "fs_peer_buffer_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    FS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr = p;
+    return 0;
+}
+int fs_peer_buffer_close(void* dev_ptr) {
+    if (dev_ptr) FS_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+int fs_peer_buffer_free(void* dev_ptr) {
+    if (dev_ptr) FS_CUDA(cudaFree(dev_ptr));
+    return 0;
+}
+
+int fs_dp_allreduce_adam(const void* const* peer_bufs, int rank, int world, long long grad_off_floats, long long n,
+                         long long extra_off_floats, int n_extra, long long flag_off_bytes, unsigned tag, float* params,
+                         float* m, float* v, float lr, float beta1, float beta2, float eps, int* step_counter,
+                         float* extra_out, int* err_flag, void* stream) {
+    return dp_allreduce_adam(peer_bufs, rank, world, grad_off_floats, n, extra_off_floats, n_extra, flag_off_bytes, tag,
+                             params, m, v, lr, beta1, beta2, eps, step_counter, extra_out, err_flag, S(stream));
+}
+
 // ------------------------------------------------------------------ single ops
 static int conv_geom(int H, int W, int KH, int KW, int stride, int same, int* OH, int* OW, int* pt, int* pl) {
     FS_CHECK(stride >= 1 && KH >= 1 && KW >= 1, "conv: bad geometry");

@@ -47,6 +47,15 @@ int instnorm_bwd_sums(const float* dY, const float* x, const float* mean, const 
                       double* bs, int reps, double* zero_buf, long long zero_n, cudaStream_t st,
                       void* split_hi = nullptr, void* split_lo = nullptr);
 
+// data-parallel step: all-reduce(SUM) of the ranks' flat gradient buffers over peer memory fused with TF-Adam
+// (dp_adam.cu).  peer_bufs[r]: rank r's exchange buffer as addressable from THIS device; gradients of this step at
+// float offset grad_off, n_extra scalars (summed into extra_out) at grad_off + extra_off, the flag array
+// (unsigned[world]) at byte offset flag_off_bytes; tag: step number, strictly increasing.
+int dp_allreduce_adam(const void* const* peer_bufs, int rank, int world, long long grad_off, long long n,
+                      long long extra_off, int n_extra, long long flag_off_bytes, unsigned tag, float* params, float* m,
+                      float* v, float lr, float b1, float b2, float eps, int* step_counter, float* extra_out, int* err,
+                      cudaStream_t st);
+
 // K8: 2x2 s2 SAME max-pool                        (reference libs/vgg16.py:67-71)
 int maxpool2x2_fwd(const float* x, float* out, int N, int H, int W, int C, cudaStream_t st,
                    void* split_hi = nullptr, void* split_lo = nullptr);

@@ -47,6 +47,10 @@ class Trainer:
         self._flat = torch.zeros(off + 8, dtype=torch.float32, device=self.device)
         self.grads = self._flat[:TRANSFORM_NPARAMS]
         self.losses = self._flat[off:off + 4]
+        # Multi-GPU on one node: the all-reduce and Adam run as ONE kernel over NVLink peer memory
+        # (fs_dp_allreduce_adam, faststyle_b200/peer.py) when every rank can map its peers' exchange buffers;
+        # otherwise (FS_DP_FUSED=0, gloo / CPU harness, IPC unavailable) one NCCL all-reduce + the Adam kernel.
+        self.peer = self._setup_peer_exchange() if self.world > 1 else None
         # input double buffering: the host->device copy of batch i+1 runs on a copy stream while step i computes
         self.x_dev = [torch.empty((self.batch_size, H, W, 3), dtype=torch.float32, device=self.device) for _ in range(2)]
         self.x_host = [torch.empty((self.batch_size, H, W, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -62,6 +66,23 @@ class Trainer:
         self.global_step = 0
         self.h2d_bytes_per_step = self.x_dev[0].numel() * 4
         self.d2h_bytes_per_step = 16
+
+    def _setup_peer_exchange(self):
+        import os
+        import torch.distributed as dist
+        ok, px = 1, None
+        if os.environ.get("FS_DP_FUSED", "1") == "0" or dist.get_backend(self.pg) != "nccl":
+            ok = 0
+        else:
+            try:
+                from .peer import PeerExchange
+                px = PeerExchange(TRANSFORM_NPARAMS, 4, self.device, self.pg)
+            except Exception as e:                       # noqa: BLE001 - any failure means "use NCCL", on ALL ranks
+                print("faststyle_b200: peer-memory exchange unavailable (%s); using NCCL all-reduce" % (e,), flush=True)
+                ok, px = 0, None
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pg)      # the choice must be the same on every rank
+        return px if int(flag.item()) == 1 else None
 
     # ------------------------------------------------------------------ input staging
     def _stage(self, batch):
@@ -101,14 +122,24 @@ class Trainer:
             self._consumed_slot = None
             if batch is not None:
                 self._current = self._stage(batch)
-            self.engine.train_fwd_bwd(self.params, self.packed, self._current, self.cfg, self.target_grams,
-                                      grads=self.grads, losses=self.losses)
-            if self._consumed_slot is not None:
-                self._consumed[self._consumed_slot].record(main)
-            if self.world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.pg)
-            self.opt.step(self.grads)
+            if self.peer is not None:
+                par = self.global_step & 1
+                self.grads, local_losses = self.peer.grads(par), self.peer.extra(par)
+                self.engine.train_fwd_bwd(self.params, self.packed, self._current, self.cfg, self.target_grams,
+                                          grads=self.grads, losses=local_losses)
+                if self._consumed_slot is not None:
+                    self._consumed[self._consumed_slot].record(main)
+                self.peer.allreduce_adam(self.opt, par, self.global_step + 1)
+                self.losses = self.peer.extra_sum
+            else:
+                self.engine.train_fwd_bwd(self.params, self.packed, self._current, self.cfg, self.target_grams,
+                                          grads=self.grads, losses=self.losses)
+                if self._consumed_slot is not None:
+                    self._consumed[self._consumed_slot].record(main)
+                if self.world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.pg)
+                self.opt.step(self.grads)
             self.global_step += 1
             if not fetch_losses:
                 return None

@@ -150,6 +150,31 @@ int fs_train_fwd_bwd(fs_engine* e, const float* params, const float* packed, con
 int fs_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr,
                  float beta1, float beta2, float eps, int* step_counter, void* stream);
 
+/* Data-parallel optimiser step in ONE kernel over NVLink peer memory (reference: train.py:198-204 on a batch sharded
+ * over the GPUs of a node): all-reduce(SUM) of every rank's flat gradient buffer + the TF-Adam update of this rank's
+ * replica.  peer_bufs: HOST array of `world` device pointers - rank r's exchange buffer as addressable from this
+ * device (CUDA IPC mapping / peer access; entry [rank] is the local buffer).  Layout of every exchange buffer:
+ * this step's n gradients at float offset grad_off_floats (double-buffer by step parity), n_extra scalars to be
+ * summed into extra_out (loss terms; may be 0 / NULL) at grad_off_floats + extra_off_floats, an unsigned[world] flag
+ * array (zero-initialised, then owned by the kernel) at byte offset flag_off_bytes.  tag: the step number
+ * (1, 2, 3, ... strictly increasing; the same on all ranks).  Sums are formed in rank order on every rank, so the
+ * replicas stay bit-identical.  err_flag (device int, may be NULL) is set to 1 when a peer's flag did not arrive
+ * within ~10 s.  Every rank must make the call once per step. */
+/* Let kernels of the CURRENT device dereference memory of `peer_device` (cudaDeviceEnablePeerAccess; a no-op when it
+ * is already enabled or peer_device is the current device).  Needed once per peer before fs_dp_allreduce_adam. */
+int fs_enable_peer_access(int peer_device);
+/* Exchange buffers for fs_dp_allreduce_adam.  create: a zero-filled device allocation on the current device + its
+ * 64-byte CUDA IPC handle (send it to the peer processes of the node); open: map a peer's buffer into the CURRENT
+ * device's address space (peer access over NVLink is enabled by the open); close / free release them. */
+int fs_peer_buffer_create(size_t bytes, void** dev_ptr, unsigned char* handle64);
+int fs_peer_buffer_open(const unsigned char* handle64, void** dev_ptr);
+int fs_peer_buffer_close(void* dev_ptr);
+int fs_peer_buffer_free(void* dev_ptr);
+int fs_dp_allreduce_adam(const void* const* peer_bufs, int rank, int world, long long grad_off_floats, long long n,
+                         long long extra_off_floats, int n_extra, long long flag_off_bytes, unsigned tag, float* params,
+                         float* m, float* v, float lr, float beta1, float beta2, float eps, int* step_counter,
+                         float* extra_out, int* err_flag, void* stream);
+
 /* ------------------------------------------------------------------ single ops
  * (exported for op-level parity tests and the Python op mirror) */
 /* tf.nn.conv2d NHWC/HWIO; padding_same: 1 = TF 'SAME', 0 = 'VALID'; C and OC must be
