@@ -44,6 +44,7 @@ SIGNATURES = {
     "fs_engine_destroy": (_I, [_P]),
     "fs_engine_set_tensor_path": (_I, [_P, _I]),
     "fs_set_tc_pair": (_I, [_I]),
+    "fs_set_tc_epilogue_warps": (_I, [_I]),
     "fs_engine_keep_activations": (_I, [_P, _I]),
     "fs_engine_set_frozen_weights": (_I, [_P, _I]),
     "fs_engine_profile": (_I, [_P, _I]),

@@ -151,6 +151,11 @@ int fs_engine_keep_activations(fs_engine* e, int keep) {
     return 0;
 }
 int fs_set_tc_pair(int enabled) { fs::set_tc_pair(enabled); return 0; }
+int fs_set_tc_epilogue_warps(int warps) {
+    FS_CHECK(warps == 8 || warps == 16, "fs_set_tc_epilogue_warps: 8 or 16");
+    fs::set_tc_epi_warps(warps);
+    return 0;
+}
 int fs_engine_profile(fs_engine* e, int enabled) {
     FS_CHECK(e, "NULL engine");
     e->e.prof_on = enabled != 0;

@@ -101,7 +101,17 @@ struct Cfg {
     static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-constexpr int TC_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 epilogue (2 per TMEM lane quadrant)
+// warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4.. epilogue (EW / 4 warps per TMEM lane quadrant).
+// The epilogues of the memory-heavy launches (64-channel VGG layers, Gram backward) are chains of dependent TMEM loads,
+// shuffles, conversions and scattered stores: with 8 warps they are instruction-latency-bound (ncu: tensor pipe 45 % and
+// no memory pipe above 55 % on conv1_2).  Launches without fused statistics therefore run SIXTEEN epilogue warps; the
+// CTA's registers (640 threads x 96 at launch: setmaxnreg moves registers only WITHIN the CTA's own allocation) are
+// re-divided: producer / MMA warpgroup down to 64, the four epilogue warpgroups up to 104 (128 x 64 + 512 x 104 =
+// 640 x 96).  The statistics variant keeps 64 running sums per thread and stays at 8 warps x 168 registers.
+// EPI: 0 = lean epilogue (16 warps), 1 = fused InstanceNorm statistics (8 warps), 2 = fp32 reference tensor (ReLU mask /
+// pooling / content term from the fp32 activation: 32 more live registers; 8 warps)
+__host__ __device__ constexpr int tc_epi_warps(int epi) { return epi == 0 ? 16 : 8; }
+__host__ __device__ constexpr int tc_threads(int epi) { return 128 + 32 * tc_epi_warps(epi); }
 
 template <int BN, bool PAIR>
 __device__ __forceinline__ uint32_t make_idesc_p() {
@@ -118,8 +128,8 @@ __device__ __forceinline__ uint32_t make_idesc_p() {
 // Barrier protocol: `*_full` barriers live in the leader only (both CTAs' TMA loads count their bytes there);
 // `*_empty` and `t_full` exist in both CTAs and are signalled by the leader's multicast tcgen05.commit; the
 // leader's `t_empty` collects the arrivals of both CTAs' epilogue warps (the peer's arrive remotely).
-template <int TH, int BN, bool STATS, bool PAIR, int HALO>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int TH, int BN, int EPI, bool PAIR, int HALO>
+__global__ void __launch_bounds__(tc_threads(EPI), 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                   const TcParams p) {
@@ -127,6 +137,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     using K = Cfg<TH, BN, PAIR, HALO>;
     constexpr int A_STAGES = K::A_STAGES;
     constexpr int NCTA = PAIR ? 2 : 1;
+    constexpr bool STATS = EPI == 1, F32REF = EPI == 2;
+    constexpr int EW = tc_epi_warps(EPI);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smemA = smem;
@@ -162,7 +174,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < K::B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8 * NCTA); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], EW * NCTA); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -197,6 +209,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         return true;
     };
 
+    if (warp < 4) {
+    if (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");     // (warpgroup-uniform) registers for the epilogue
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
         int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
@@ -302,14 +316,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             __syncwarp();
             if (++as == 2) { as = 0; pt ^= 1; }
         }
-    } else if (warp >= 4) {
-        // ===================== epilogue (8 warps: 2 per 32-lane TMEM quadrant) =====================
+    }
+    } else {
+        if (EW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        // ===================== epilogue (EW warps: EW / 4 per 32-lane TMEM quadrant) =====================
         // The two warps of a quadrant take alternate (accumulator, 32-channel chunk) items: the epilogue is a
         // chain of dependent global loads (addend / ReLU-mask reference) and stores per item, so a second warp
         // per quadrant doubles the memory-level parallelism of the memory-heavy launches (1x1 Gram backward,
         // 64-channel layers at 256^2).
         const int ew = (warp - 4) & 3;                 // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
-        const int eg = (warp - 4) >> 2;                // 0 / 1: which half of the items
+        const int eg = (warp - 4) >> 2;                // 0 .. EW/4-1: which share of the items
         const int row = ew * 32 + lane;                // MMA row = pixel within the 8x16 sub-tile
         const int prow = row >> 4, pcol = row & 15;
         // fused InstanceNorm statistics (STATS): per-thread running (sum, sum of squares) over the pixels this thread
@@ -343,7 +359,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             mbar_wait(&t_full[as], pt);
             tc_fence_after();
 #pragma unroll 1
-            for (int item = eg; item < K::NACC * (BN / 32); item += 2) {
+            for (int item = eg; item < K::NACC * (BN / 32); item += EW / 4) {
                 const int acc = item / (BN / 32), ch = item - acc * (BN / 32);
                 const int oy = ty * TH + acc * 8 + prow, ox = tx * TW + pcol;
                 const bool ok = tile_ok && oy < p.OH && ox < p.OW;
@@ -376,7 +392,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                             for (int i = 0; i < 8; ++i) cw8[i] = 0u;
                         }
                     } else
-                    if (!STATS && p.ref && !p.out_d2s) {       // (launches with fused statistics never carry a reference)
+                    if (F32REF && p.ref && !p.out_d2s) {
                         if (ok) {
                             const float* rp = p.ref + pix * p.OC + rc0;
 #pragma unroll
@@ -455,7 +471,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                                 }
                             }
                         } else
-                        if (!STATS && p.ref) {
+                        if (F32REF && p.ref) {
                             // v = mask(ref > 0) * (v + route(pool_grad) + cw2 * (ref - ctarget)): the backward of
                             // ReLU, of a following 2x2 max-pool (gradient to the FIRST maximum of the window in scan
                             // order, as pool_bwd_combine_kernel) and of the content loss, fused.  The four pixels of a
@@ -744,8 +760,9 @@ int make_w_map(CUtensorMap* tm, const __nv_bfloat16* base, long long rows, int b
 }
 
 int g_tc_pair = -1;     // CTA-pair (cta_group::2) kernel: -1 = read FS_TC_PAIR (default on), 0 off, 1 on
+int g_tc_epi_warps = -1;   // lean launches: 16 epilogue warps (default) or 8 (FS_TC_EPI_WARPS=8 / set_tc_epi_warps: A/B switch)
 
-template <int TH, int BN, bool STATS, bool PAIR, int HALO>
+template <int TH, int BN, int EPI, bool PAIR, int HALO>
 int launch_cfg_s(const Conv3x3TcArgs& a, cudaStream_t st) {
     using K = Cfg<TH, BN, PAIR, HALO>;
     CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
@@ -776,15 +793,15 @@ int launch_cfg_s(const Conv3x3TcArgs& a, cudaStream_t st) {
     p.add_crop = a.add_crop; p.addH = a.addH; p.addW = a.addW;
     p.out_f32 = a.out_f32; p.out_hi = a.out_split.hi; p.out_lo = a.out_split.lo;
     p.stats = a.stats; p.stats_c = a.stats_c;
-    FS_DYN_SMEM((conv3x3_tc_kernel<TH, BN, STATS, PAIR, HALO>), K::SMEM_BYTES);
+    FS_DYN_SMEM((conv3x3_tc_kernel<TH, BN, EPI, PAIR, HALO>), K::SMEM_BYTES);
     const int sms = num_sms();
     if (PAIR) {
         const int clusters = (int)(p.total_tiles < sms / 2 ? p.total_tiles : sms / 2);
-        launch_k_cluster2((conv3x3_tc_kernel<TH, BN, STATS, PAIR, HALO>), dim3(2 * clusters), dim3(TC_THREADS), K::SMEM_BYTES, st,
+        launch_k_cluster2((conv3x3_tc_kernel<TH, BN, EPI, PAIR, HALO>), dim3(2 * clusters), dim3(tc_threads(EPI)), K::SMEM_BYTES, st,
                           tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     } else {
         const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
-        launch_k((conv3x3_tc_kernel<TH, BN, STATS, PAIR, HALO>), dim3(grid), dim3(TC_THREADS), K::SMEM_BYTES, st, tmA_hi, tmA_lo,
+        launch_k((conv3x3_tc_kernel<TH, BN, EPI, PAIR, HALO>), dim3(grid), dim3(tc_threads(EPI)), K::SMEM_BYTES, st, tmA_hi, tmA_lo,
                  tmB_hi, tmB_lo, p);
     }
     FS_LAUNCH_CHECK();
@@ -793,8 +810,18 @@ int launch_cfg_s(const Conv3x3TcArgs& a, cudaStream_t st) {
 
 template <int TH, int BN, int HALO = 2>
 int launch_cfg(const Conv3x3TcArgs& a, bool pair, cudaStream_t st) {
-    if (pair) return a.stats ? launch_cfg_s<TH, BN, true, true, HALO>(a, st) : launch_cfg_s<TH, BN, false, true, HALO>(a, st);
-    return a.stats ? launch_cfg_s<TH, BN, true, false, HALO>(a, st) : launch_cfg_s<TH, BN, false, false, HALO>(a, st);
+    if (g_tc_epi_warps < 0) {
+        const char* e = getenv("FS_TC_EPI_WARPS");
+        g_tc_epi_warps = (e && atoi(e) == 8) ? 8 : 16;
+    }
+    // (the fp32-reference variant with no reference tensor is exactly the lean epilogue on 8 warps.)  Measured: the 16-warp
+    // epilogue pays on the 1x1 per-sample GEMMs of the Gram backward (all epilogue, 0.256 -> 0.240 ms per step) and costs
+    // ~1 % on the 3x3 layers (fewer registers for the same work), so only the 1x1 launches take it.
+    const int epi = a.stats ? 1 : ((a.ref || g_tc_epi_warps == 8 || !a.one_by_one) ? 2 : 0);
+    if (pair) return epi == 1 ? launch_cfg_s<TH, BN, 1, true, HALO>(a, st)
+                   : epi == 2 ? launch_cfg_s<TH, BN, 2, true, HALO>(a, st) : launch_cfg_s<TH, BN, 0, true, HALO>(a, st);
+    return epi == 1 ? launch_cfg_s<TH, BN, 1, false, HALO>(a, st)
+         : epi == 2 ? launch_cfg_s<TH, BN, 2, false, HALO>(a, st) : launch_cfg_s<TH, BN, 0, false, HALO>(a, st);
 }
 
 }  // namespace
@@ -882,6 +909,7 @@ int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st) {
 }
 
 void set_tc_pair(int on) { g_tc_pair = on ? 1 : 0; }
+void set_tc_epi_warps(int warps) { g_tc_epi_warps = warps == 8 ? 8 : 16; }
 
 int split_bf16(const float* x, SplitPtr out, long long n, cudaStream_t st) {
     FS_CHECK(n % 4 == 0, "split_bf16: n %% 4 != 0");

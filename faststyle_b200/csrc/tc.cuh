@@ -68,6 +68,8 @@ struct Conv3x3TcArgs {
 int launch_conv3x3_tc(const Conv3x3TcArgs& a, cudaStream_t st);
 // CTA-pair (tcgen05 cta_group::2) variant of the kernel on / off (default: on; FS_TC_PAIR=0 in the environment)
 void set_tc_pair(int on);
+// epilogue warps of the launches without fused statistics / fp32 reference: 16 (default) or 8 (FS_TC_EPI_WARPS=8)
+void set_tc_epi_warps(int warps);
 bool conv3x3_tc_supported(int C, int OC, int W, int OW);
 
 // Tiled tensor map over an NHWC tensor [N,H,W,C] of 1- / 2- / 4-byte elements with box {boxC, boxW, boxH, 1}; the box's

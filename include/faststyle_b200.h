@@ -70,6 +70,9 @@ int fs_engine_set_tensor_path(fs_engine* e, int enabled);
  * cta_group::2 with M = 256, the weight tile split between the two CTAs' shared memories); 0: one CTA per tile
  * (cta_group::1).  Same results up to fp32 summation order.  Also FS_TC_PAIR=0 in the environment. */
 int fs_set_tc_pair(int enabled);
+/* Process-wide: epilogue warps of the tcgen05 conv launches without fused statistics / fp32 reference tensor - 16
+ * (default; registers re-divided with setmaxnreg) or 8 (the previous shape; an A/B switch).  Also FS_TC_EPI_WARPS=8. */
+int fs_set_tc_epilogue_warps(int warps);
 /* keep = 1: the composites also write the fp32 copies of activations / gradients whose only consumers are tensor-path
  * kernels reading split-bf16 planes (they are skipped by default); needed before fs_engine_transform_activation on
  * such layers.  Also FS_KEEP_ACTS=1 in the environment. */

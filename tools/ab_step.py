@@ -59,19 +59,22 @@ def main():
         grads = torch.empty_like(params)
         losses = torch.empty(4, dtype=torch.float32, device=dev)
         pair = int(env.get("FS_TC_PAIR", "1"))
+        ew = int(env.get("FS_TC_EPI_WARPS", "16"))
 
         def step(eng=eng, params=params, opt=opt, grads=grads, losses=losses):
             eng.train_fwd_bwd(params, packed, x, cfg, tg, grads=grads, losses=losses)
             opt.step(grads)
-        runs.append(dict(name=name, env=env, eng=eng, step=step, pair=pair, ms=[]))
+        runs.append(dict(name=name, env=env, eng=eng, step=step, pair=pair, ew=ew, ms=[]))
     for r in runs:
         _lib.call("fs_set_tc_pair", r["pair"])
+        _lib.call("fs_set_tc_epilogue_warps", r["ew"])
         for _ in range(5):
             r["step"]()
     torch.cuda.synchronize()
     for _ in range(ROUNDS):
         for r in runs:
             _lib.call("fs_set_tc_pair", r["pair"])
+            _lib.call("fs_set_tc_epilogue_warps", r["ew"])
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             r["step"]()
             e0.record()
@@ -83,10 +86,12 @@ def main():
     out = {}
     for r in runs:
         _lib.call("fs_set_tc_pair", r["pair"])
+        _lib.call("fs_set_tc_epilogue_warps", r["ew"])
         prof = bench.live_kernel_profile(r["eng"], r["step"])
         out[r["name"]] = dict(env=r["env"], ms_per_step=r["ms"], best=min(r["ms"]), by_kernel_class=prof,
                               launches=sum(v["launches_per_step"] for v in prof.values()))
     _lib.call("fs_set_tc_pair", 1)
+    _lib.call("fs_set_tc_epilogue_warps", 16)
     names = [r["name"] for r in runs]
     print("%-22s" % "" + "".join("%12s" % n for n in names))
     print("%-22s" % "ms/step (best)" + "".join("%12.3f" % out[n]["best"] for n in names))
