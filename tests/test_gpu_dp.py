@@ -24,4 +24,5 @@ def test_fused_dp_step_matches_nccl(built_lib):
     out = json.loads(line)
     print(out)
     assert out["fused_available"], "peer-memory exchange could not be set up on this box"
-    assert out["replicas_identical"] and out["param_maxdiff_rel"] <= 1e-6 and out["loss_maxdiff_rel"] <= 1e-6
+    assert out["replicas_identical"] and out["kernel_maxdiff_rel"] <= 1e-6
+    assert out["param_maxdiff_rel"] <= 1e-5 and out["loss_maxdiff_rel"] <= 1e-6
