@@ -296,8 +296,9 @@ void Engine::layout(Arena& a) {
         w2f = a.take<float>(4LL * 128 * 64);
         wpair = a.take<float>(4LL * 128 * 64);
         {   // 9x9 layers on the tensor path (tc9): zero-margined input planes + expanded / packed weights
-            const long long n9[3] = {(long long)N * Hp * (Wp + 16) * 4, (long long)N * OH * (OW + 16) * 16,
-                                     (long long)N * OH * (OW + 16) * 4};
+            // (the 4-channel planes hold either form: x16 [H, W + 16, 4] or x8 [H, W / 8, 64])
+            const long long n9[3] = {(long long)N * Hp * maxll((Wp + 16) * 4, Wp * 8), (long long)N * OH * (OW + 16) * 16,
+                                     (long long)N * OH * maxll((OW + 16) * 4, OW * 8)};
             for (int i = 0; i < 3; ++i) {
                 const bool need = i < 2 || tbw;
                 p9[i].hi = need ? a.take<__nv_bfloat16>(n9[i]) : nullptr;
@@ -386,7 +387,8 @@ int Engine::bind(void* ws, size_t bytes) {
         if (sp) FS_CUDA(cudaMemset(sp, 0, (size_t)sums_n * sizeof(double)));
     FS_CUDA(cudaDeviceSynchronize());
     if (flags & ENG_TRANSFORM) {         // zero margins of the x16 planes (never written afterwards)
-        const size_t n9[3] = {(size_t)N * Hp * (Wp + 16) * 4, (size_t)N * OH * (OW + 16) * 16, (size_t)N * OH * (OW + 16) * 4};
+        const size_t n9[3] = {(size_t)N * Hp * (size_t)maxll((Wp + 16) * 4, Wp * 8), (size_t)N * OH * (OW + 16) * 16,
+                              (size_t)N * OH * (size_t)maxll((OW + 16) * 4, OW * 8)};
         for (int i = 0; i < 3; ++i)
             if (p9[i].hi) {
                 FS_CUDA(cudaMemset(p9[i].hi, 0, n9[i] * sizeof(__nv_bfloat16)));
@@ -416,14 +418,15 @@ int Engine::tc9_conv(int which, const float* src_f32, float* out, bool stats, cu
     const int Hh = which == 0 ? Hp : OH, Ww = which == 0 ? Wp : OW;
     const int cin = which == 1 ? 16 : 4;                 // channels per pixel on the K side
     const int cout_px = which == 1 ? 4 : 16;             // channels per pixel on the N side
+    const bool x8 = tc9_x8 && which != 1;                // 4-channel input side: 8-pixel output groups, one horizontal tap
     if (which != 0)      // (initconv_0's planes come straight from the reflect-pad kernel)
-        PROF(PC_POINTWISE, 0.0, split_pad_x16(src_f32, p9[which].hi, p9[which].lo, (long long)N * Hh, Ww, cin, st));
+        PROF(PC_POINTWISE, 0.0, split_pad_x16(src_f32, p9[which].hi, p9[which].lo, (long long)N * Hh, Ww, cin, st, x8 ? 1 : 0));
     Conv3x3TcArgs ta;
     memset(&ta, 0, sizeof(ta));
     ta.x = p9[which]; ta.w = tw9[which];
-    ta.N = N; ta.H = Hh; ta.W = (Ww + 16) / 16; ta.C = 16 * cin;
-    ta.OH = Hh; ta.OW = Ww / 16; ta.OC = 16 * cout_px;
-    ta.taps = 9; ta.taps_w = 2; ta.pad = 4; ta.pad_x = 0;
+    ta.N = N; ta.H = Hh; ta.W = x8 ? Ww / 8 : (Ww + 16) / 16; ta.C = 16 * cin;
+    ta.OH = Hh; ta.OW = x8 ? Ww / 8 : Ww / 16; ta.OC = (x8 ? 8 : 16) * cout_px;
+    ta.taps = 9; ta.taps_w = x8 ? 1 : 2; ta.pad = 4; ta.pad_x = 0;
     ta.out_f32 = out;
     if (stats && in_epi) { ta.stats = in_sums2[which == 0 ? 0 : 1]; ta.stats_c = cout_px; }      // layer 0 / layer 15
     const double fl = 2.0 * N * Hh * Ww * 81.0 * (which == 1 ? 16 * 3 : 3 * 16);       // algorithmic: real channel counts
@@ -459,9 +462,10 @@ int Engine::prep_transform_weights_table(const float* params, bool need_bwd, cud
             j.hi = tw9[which].hi; j.lo = tw9[which].lo;
             return j;
         };
-        FS_TRY(pl.add(0, x16(0, W(0), 3, 16, 4, 16, 0)));                    // K = 64, N = 256
+        const int x8 = tc9_x8 ? 2 : 0;                                       // (bit 1 of the mode word: the x8 form)
+        FS_TRY(pl.add(0, x16(0, W(0), 3, 16, 4, 16, 0 | x8)));               // K = 64, N = 256 (x8: 128)
         FS_TRY(pl.add(0, x16(1, W(15), 16, 3, 16, 4, 0)));                   // K = 256, N = 64
-        if (need_bwd) FS_TRY(pl.add(0, x16(2, W(15), 16, 3, 4, 16, 1)));     // K = 64, N = 256
+        if (need_bwd) FS_TRY(pl.add(0, x16(2, W(15), 16, 3, 4, 16, 1 | x8)));   // K = 64, N = 256 (x8: 128)
     }
     // ---- phase 1
     FS_TRY(pl.add(1, pj(PJ_PAIR, w2f, wpair_x[0], 4 * tc[1].cin, tc[1].cout, 1, 0)));                       // -> [4][128][64]
@@ -637,7 +641,8 @@ static void conv_fwd_args(const TConv& c, int N, const float* in, const float* w
 int Engine::transform_forward(const float* params, const float* x3, float* y3_out, cudaStream_t st) {
     FS_CHECK(bound && (flags & ENG_TRANSFORM), "engine has no transform plan / workspace");
     const bool t9 = tc9();
-    PROF(PC_POINTWISE, 0.0, reflect_pad_c4(x3, xpad4, N, H, W, 40, st, t9 ? p9[0].hi : nullptr, t9 ? p9[0].lo : nullptr));
+    PROF(PC_POINTWISE, 0.0, reflect_pad_c4(x3, xpad4, N, H, W, 40, st, t9 ? p9[0].hi : nullptr, t9 ? p9[0].lo : nullptr,
+                                            (t9 && tc9_x8) ? 1 : 0));
     const float* cur = xpad4;
     for (int l = 0; l < T_NCONV; ++l) {
         const TConv& c = tc[l];

@@ -121,6 +121,10 @@ struct Engine {
     SplitPtr p9[3];                      // inputs: initconv_0 forward, upsample_2 forward, upsample_2 data gradient
     SplitPtr tw9[3];                     // Toeplitz-expanded weights, packed split-bf16 [18][16 KP / 64][16 NP][64]
     int tc9_on = 1;                      // FS_TC9=0: 9x9 layers on the direct FFMA kernels
+    // The two forms with a 4-channel input side (initconv_0 forward, upsample_2 data gradient) use 8-pixel output groups
+    // over 16-pixel input windows instead (planes [H, W/8, 16 px x 4]: every pixel stored into the two windows that
+    // overlap it): ONE horizontal tap, K = 64, N = 8 x 16 = 128 - half the MMA work of the x16 form.  FS_TC9_X8=0: x16.
+    int tc9_x8 = 1;
     bool tc9() const;
     int tc9_conv(int which, const float* src_f32, float* out, bool stats, cudaStream_t st);
     int keep_acts = 0;                   // 1: write every fp32 activation / gradient even where only split planes are read (debug taps)

@@ -56,9 +56,17 @@ __device__ __forceinline__ float in_affine(float x, float mean, float rstd, floa
 // ------------------------------------------------------------------ padding
 // x16hi / x16lo (optional): the same padded image as split-bf16 planes [N, OH, OW + 16, 4] at column offset 4 - the
 // zero-margined input of the x16 space-to-depth 9x9 form of initconv_0 (Engine::tc9)
+// x8 != 0: the planes of the x8 form instead, [N, OH, OW / 8, 16 px x 4]: group X holds the padded-row columns
+// 8X .. 8X+15 (pixels 8X-4 .. 8X+11), so every pixel is stored into the two groups that overlap it
+__device__ __forceinline__ void store_x8(__nv_bfloat16* hi, __nv_bfloat16* lo, long long row, int col, int G, const float* r4) {
+    const int X = col >> 3;
+    if (X < G) store_split4(hi, lo, ((row * G + X) * 16 + (col - 8 * X)) * 4, r4);
+    if (X >= 1 && X - 1 < G) store_split4(hi, lo, ((row * G + X - 1) * 16 + (col - 8 * (X - 1))) * 4, r4);
+}
+
 __global__ void reflect_pad_c4_kernel(const float* __restrict__ x, float* __restrict__ out, int N,
                                       int H, int W, int pad, __nv_bfloat16* __restrict__ x16hi,
-                                      __nv_bfloat16* __restrict__ x16lo) {
+                                      __nv_bfloat16* __restrict__ x16lo, int x8) {
     FS_PDL_ENTER();
     int OH = H + 2 * pad, OW = W + 2 * pad;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -76,7 +84,8 @@ __global__ void reflect_pad_c4_kernel(const float* __restrict__ x, float* __rest
     st4(out + i * 4, make_float4(s[0], s[1], s[2], 0.f));
     if (x16hi) {
         const float r4[4] = {s[0], s[1], s[2], 0.f};
-        store_split4(x16hi, x16lo, ((r * (OW + 16)) + ox + 4) * 4, r4);
+        if (x8) store_x8(x16hi, x16lo, r, ox + 4, OW >> 3, r4);
+        else store_split4(x16hi, x16lo, ((r * (OW + 16)) + ox + 4) * 4, r4);
     }
 }
 
@@ -970,7 +979,7 @@ __global__ void s2_fwd_collapse_grad_kernel(const float* __restrict__ dWf, float
 // fp32 [N*H, W, C] -> split-bf16 planes [N*H, W + 16, C] with the row at column offset 4: the zero-margined input of
 // the x16 space-to-depth 9x9 forms (the margins are zeroed once when the workspace is bound)
 __global__ void split_pad_x16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
-                                     __nv_bfloat16* __restrict__ lo, long long n4, int W, int C) {
+                                     __nv_bfloat16* __restrict__ lo, long long n4, int W, int C, int x8) {
     FS_PDL_ENTER();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
@@ -981,7 +990,8 @@ __global__ void split_pad_x16_kernel(const float* __restrict__ x, __nv_bfloat16*
     const long long row = pix / W;
     const float4 v = ld4(x + e);
     float r[4] = {v.x, v.y, v.z, v.w};
-    store_split4(hi, lo, (row * (W + 16) + xc + 4) * C + c, r);
+    if (x8) store_x8(hi, lo, row, xc + 4, W >> 3, r);          // (C == 4: one pixel per thread)
+    else store_split4(hi, lo, (row * (W + 16) + xc + 4) * C + c, r);
 }
 
 inline int grid1(long long n, int bs = 256) { return (int)((n + bs - 1) / bs); }
@@ -989,11 +999,12 @@ inline int grid1(long long n, int bs = 256) { return (int)((n + bs - 1) / bs); }
 }  // namespace
 
 // ==================================================================== launchers
-int reflect_pad_c4(const float* x, float* out, int N, int H, int W, int pad, cudaStream_t st, void* x16hi, void* x16lo) {
+int reflect_pad_c4(const float* x, float* out, int N, int H, int W, int pad, cudaStream_t st, void* x16hi, void* x16lo, int x8) {
     FS_CHECK(pad < H && pad < W, "reflect_pad: pad %d must be smaller than the image (%dx%d)", pad, H, W);
     long long n = (long long)N * (H + 2 * pad) * (W + 2 * pad);
+    FS_CHECK(!x8 || (W + 2 * pad) % 8 == 0, "reflect_pad: the x8 planes need a padded width in whole 8-pixel groups");
     launch_k(reflect_pad_c4_kernel, dim3(grid1(n)), dim3(256), 0, st, x, out, N, H, W, pad, (__nv_bfloat16*)x16hi,
-             (__nv_bfloat16*)x16lo);
+             (__nv_bfloat16*)x16lo, x8);
     FS_LAUNCH_CHECK();
     return 0;
 }
@@ -1252,10 +1263,11 @@ int s2_fwd_collapse_grad(const float* dWf, float* dW, int Ci, int Co, cudaStream
     return 0;
 }
 
-int split_pad_x16(const float* x, void* hi, void* lo, long long rows, int W, int C, cudaStream_t st) {
+int split_pad_x16(const float* x, void* hi, void* lo, long long rows, int W, int C, cudaStream_t st, int x8) {
     FS_CHECK(C % 4 == 0 && W >= 1 && rows >= 1, "split_pad_x16: bad dims");
+    FS_CHECK(!x8 || (C == 4 && W % 8 == 0), "split_pad_x16: the x8 form needs 4 channels and W %% 8 == 0");
     const long long n4 = rows * W * C / 4;
-    launch_k(split_pad_x16_kernel, dim3(grid1(n4)), dim3(256), 0, st, x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n4, W, C);
+    launch_k(split_pad_x16_kernel, dim3(grid1(n4)), dim3(256), 0, st, x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n4, W, C, x8);
     FS_LAUNCH_CHECK();
     return 0;
 }

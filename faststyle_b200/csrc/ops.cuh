@@ -8,7 +8,7 @@ enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH255 = 2 };
 
 // K1: tf.pad REFLECT + channel pad 3->4           (reference im_transf_net.py:78-88)
 int reflect_pad_c4(const float* x, float* out, int N, int H, int W, int pad, cudaStream_t st, void* x16hi = nullptr,
-                   void* x16lo = nullptr);
+                   void* x16lo = nullptr, int x8 = 0);
 // K9: x - VGG mean, channel pad 3->4             (reference libs/vgg16.py:41-42)
 int vgg_preprocess_c4(const float* x, float* out, long long npix, cudaStream_t st);
 
@@ -97,7 +97,7 @@ int unpair_taps(const float* dWp, float* dW, int K0, int N0, int kmode, int n_s2
 int s2_fwd_collapse_grad(const float* dWf, float* dW, int Ci, int Co, cudaStream_t st);
 
 // fp32 [rows, W, C] -> split-bf16 planes [rows, W + 16, C], row content at column offset 4 (margins untouched)
-int split_pad_x16(const float* x, void* hi, void* lo, long long rows, int W, int C, cudaStream_t st);
+int split_pad_x16(const float* x, void* hi, void* lo, long long rows, int W, int C, cudaStream_t st, int x8 = 0);
 int fill_zero(void* p, size_t bytes, cudaStream_t st);
 
 }  // namespace fs

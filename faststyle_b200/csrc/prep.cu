@@ -208,10 +208,13 @@ __device__ __forceinline__ void run_job(const PrepJob& j, long long i) {
     }
     case PJ_X16: {            // a=A b=B (src W[9][9][A][B]) c=KP d=NP e=mode: the 9x9 stride-1 SAME conv as a 9x2-tap conv over
                               // 16-pixel groups: dst[kh][t][dxi*KP + k][dxo*NP + n], kw = 16 t + dxi - dxo (see Engine::tc9)
-        const int A = j.a, B = j.b, KP = j.c, NP = j.d, mode = j.e;
+        // e bit 1: the x8 form - 8-pixel output groups over 16-pixel input windows (one horizontal tap, N = 8 * NP):
+        // half the MMA work of the x16 form when the input side has 4 channels (16 px x 4 ch = one 64-channel K block)
+        const int A = j.a, B = j.b, KP = j.c, NP = j.d, mode = j.e & 1, x8 = (j.e >> 1) & 1;
+        const int PXO = x8 ? 8 : 16, TWn = x8 ? 1 : 2;
         int np, kp, tap;
         if (j.hi) {           // straight into the packed tensor-path layout B[tap][cb][n][k] (split planes)
-            const int Nn = 16 * NP, CB = 16 * KP / 64;
+            const int Nn = PXO * NP, CB = 16 * KP / 64;
             int k = (int)(i % 64);
             long long r = i / 64;
             np = (int)(r % Nn); r /= Nn;
@@ -219,12 +222,12 @@ __device__ __forceinline__ void run_job(const PrepJob& j, long long i) {
             tap = (int)(r / CB);
             kp = cb * 64 + k;
         } else {
-            np = (int)(i % (16 * NP));
-            long long r = i / (16 * NP);
+            np = (int)(i % (PXO * NP));
+            long long r = i / (PXO * NP);
             kp = (int)(r % (16 * KP));
             tap = (int)(r / (16 * KP));
         }
-        int kh = tap >> 1, t = tap & 1;
+        int kh = tap / TWn, t = tap - kh * TWn;
         int dxo = np / NP, n = np - dxo * NP;
         int dxi = kp / KP, k = kp - dxi * KP;
         int kw = 16 * t + dxi - dxo;
@@ -271,7 +274,7 @@ long long prep_job_total(const PrepJob& j) {
     case PJ_PACK_W3X3: return 9LL * j.a * j.b;
     case PJ_IN15: return 8;
     case PJ_COPY: return j.a;
-    case PJ_X16: return 18LL * 16 * j.c * 16 * j.d;
+    case PJ_X16: return ((j.e >> 1) & 1) ? 9LL * 16 * j.c * 8 * j.d : 18LL * 16 * j.c * 16 * j.d;
     default: return 0;
     }
 }
