@@ -116,6 +116,8 @@ int fs_engine_create(int N, int H, int W, int flags, unsigned content_mask, unsi
     h->e.tc9_on = (env && env[0] == '0') ? 0 : 1;
     env = getenv("FS_KEEP_ACTS");
     h->e.keep_acts = (env && env[0] == '1') ? 1 : 0;
+    env = getenv("FS_WGRAD9_TC");
+    h->e.wgrad9_tc = (env && env[0] == '0') ? 0 : 1;
     env = getenv("FS_TC9_X8");
     h->e.tc9_x8 = (env && env[0] == '0') ? 0 : 1;
     env = getenv("FS_CONV11_TC");

@@ -266,7 +266,7 @@ void Engine::layout(Arena& a) {
                 int K = c.upconv ? 4 * c.cin : c.k * c.k * c.cin_s;
                 int OC = c.upconv ? 4 * c.cout : c.cout_s;
                 wgcap = maxll(wgcap, wgrad_partial_floats(K, OC, 1));
-                if (c.k == 9) wgcap = maxll(wgcap, wgrad9x9_partial_floats(N, c.inH, c.inW));
+                if (c.k == 9) wgcap = maxll(wgcap, maxll(wgrad9x9_partial_floats(N, c.inH, c.inW), wgrad9_x8_partial_floats()));
                 if ((flags & ENG_DECONV) && c.upconv) wgcap = maxll(wgcap, wgrad_partial_floats(9 * c.cout, c.cin, 1));
                 if (l >= 3 && l <= 12) wgcap = maxll(wgcap, wgrad3x3_tc_partial_floats());
                 if (tc2_layout(l)) wgcap = maxll(wgcap, wgrad2x2_tc_partial_floats());
@@ -306,6 +306,11 @@ void Engine::layout(Arena& a) {
                 tw9[i].hi = need ? a.take<__nv_bfloat16>(18LL * 64 * 256) : nullptr;
                 tw9[i].lo = need ? a.take<__nv_bfloat16>(18LL * 64 * 256) : nullptr;
             }
+        }
+        if (tbw) {         // plain split planes for the tensor-path 9x9 weight gradients (Engine::wg9)
+            const long long n0 = (long long)N * Hp * Wp * 16, n14 = (long long)N * OH * OW * 16;
+            g0split.hi = a.take<__nv_bfloat16>(n0); g0split.lo = a.take<__nv_bfloat16>(n0);
+            a14split.hi = a.take<__nv_bfloat16>(n14); a14split.lo = a.take<__nv_bfloat16>(n14);
         }
         w2f_b = a.take<float>(4LL * 128 * 64);
         for (int i = 0; i < 4; ++i) wpair_x[i] = a.take<float>(4LL * 128 * 64);
@@ -414,12 +419,12 @@ bool Engine::tc9() const {
 
 // which: 0 = initconv_0 forward (x = xpad4), 1 = upsample_2 forward (x = activation of upsample_1),
 //        2 = upsample_2 data gradient (x = gradient w.r.t. its raw output)
-int Engine::tc9_conv(int which, const float* src_f32, float* out, bool stats, cudaStream_t st) {
+int Engine::tc9_conv(int which, const float* src_f32, float* out, bool stats, cudaStream_t st, bool planes_ready) {
     const int Hh = which == 0 ? Hp : OH, Ww = which == 0 ? Wp : OW;
     const int cin = which == 1 ? 16 : 4;                 // channels per pixel on the K side
     const int cout_px = which == 1 ? 4 : 16;             // channels per pixel on the N side
     const bool x8 = tc9_x8 && which != 1;                // 4-channel input side: 8-pixel output groups, one horizontal tap
-    if (which != 0)      // (initconv_0's planes come straight from the reflect-pad kernel)
+    if (which != 0 && !planes_ready)      // (initconv_0's planes come straight from the reflect-pad kernel)
         PROF(PC_POINTWISE, 0.0, split_pad_x16(src_f32, p9[which].hi, p9[which].lo, (long long)N * Hh, Ww, cin, st, x8 ? 1 : 0));
     Conv3x3TcArgs ta;
     memset(&ta, 0, sizeof(ta));
@@ -498,8 +503,10 @@ int Engine::prep_transform_weights_table(const float* params, bool need_bwd, cud
 int Engine::finish_weight_grads_table(float* grads, cudaStream_t st) {
     PrepPlan pl;
     auto G = [&](int l) { return grads + tc[l].offW; };
-    FS_TRY(pl.add(0, pj(PJ_UNPAD, wgs[15], G(15), 81, 16, 3, 16, 4)));
-    FS_TRY(pl.add(0, pj(PJ_UNPAD, wgs[0], G(0), 81, 3, 16, 4, 16)));
+    if (!wg9()) {      // (the tensor-path 9x9 weight gradients write their [9,9,3|16,16|3] slots directly)
+        FS_TRY(pl.add(0, pj(PJ_UNPAD, wgs[15], G(15), 81, 16, 3, 16, 4)));
+        FS_TRY(pl.add(0, pj(PJ_UNPAD, wgs[0], G(0), 81, 3, 16, 4, 16)));
+    }
     FS_TRY(pl.add(0, pj(PJ_UNPAIR, wgs[14], wgu[0], tc[14].cin, 4 * tc[14].cout, 0, 1)));
     FS_TRY(pl.add(0, pj(PJ_UPCONV_COLLAPSE_GRAD, wgs[13], G(13), tc[13].cin, tc[13].cout)));
     FS_TRY(pl.add(0, pj(PJ_S2_FWD_COLLAPSE_GRAD, wgs[2], G(2), tc[2].cin, tc[2].cout)));
@@ -690,6 +697,10 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
         const float* b = last ? in15 + 4 : params + c.offB;
         float* out = last ? (y3_out ? y3_out : y3) : tb[l].act;
         const bool next_tc = (use_tc && (l + 1) >= 3 && (l + 1) <= 12) || tc2(l + 1);   // next conv consumes split planes
+        // training: the input of upsample_2 also as plain split planes for its tensor-path weight gradient
+        const bool planes14 = l == 14 && (flags & ENG_TRANSFORM_BWD) && wg9() && a14split.hi;
+        __nv_bfloat16* const sp_hi = next_tc ? tsplit[l + 1].hi : (planes14 ? a14split.hi : nullptr);
+        __nv_bfloat16* const sp_lo = next_tc ? tsplit[l + 1].lo : (planes14 ? a14split.lo : nullptr);
         // The fp32 copy of the activation is dead when its only reader is a tensor-path conv (split planes): it
         // survives where something else reads it - the residual skip (block inputs 2,4,..,10 and the block
         // outputs' own skip source), the FFMA 9x9 layer (input of 15) and its weight gradient, igemm fallbacks.
@@ -700,12 +711,10 @@ int Engine::transform_forward(const float* params, const float* x3, float* y3_ou
         if (fused_apply)
             PROF(PC_IN_APPLY, 0.0, instnorm_apply_from_sums(tb[l].raw, in_sums2[l & 1], STATS_REPLICAS, IN_EPS, tb[l].mean, tb[l].rstd,
                                       in_sums2[(l + 1) & 1], sums_n, g, b, skip, out, N, c.outH, c.outW, c.cout_s, c.act,
-                                      last ? 1 : 0, st, next_tc ? tsplit[l + 1].hi : nullptr,
-                                      next_tc ? tsplit[l + 1].lo : nullptr));
+                                      last ? 1 : 0, st, sp_hi, sp_lo));
         else
         PROF(PC_IN_APPLY, 0.0, instnorm_apply(tb[l].raw, tb[l].mean, tb[l].rstd, g, b, skip, out, N, c.outH, c.outW,
-                                  c.cout_s, c.act, last ? 1 : 0, st, next_tc ? tsplit[l + 1].hi : nullptr,
-                                  next_tc ? tsplit[l + 1].lo : nullptr));
+                                  c.cout_s, c.act, last ? 1 : 0, st, sp_hi, sp_lo));
         cur = tb[l].act;
     }
     return 0;
@@ -738,18 +747,20 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         const bool tcl = use_tc && l >= 3 && l <= 12;
         const bool tcd = tcl || (l > 0 && tc2(l));           // the data gradient reads dRaw's split planes
         const bool defer_wg = tcl && batch_wgrad;            // residual convs: planes kept in rg[l], weight gradient batched
-        const SplitPtr dsp = defer_wg ? rg[l] : tgsplit[ri];
+        const bool wg9_l = direct9(c) && wg9() && !(flags & ENG_DECONV);    // this layer's weight gradient on tcgen05 (x8 form)
+        const SplitPtr dsp = defer_wg ? rg[l] : ((wg9_l && l == 0) ? g0split : tgsplit[ri]);
         // dRaw in fp32 is dead when both its readers (data gradient, weight gradient) are tensor-path kernels
         float* dRaw_f32 = dRaw;
-        if (!keep_acts && (defer_wg || (tcl && use_tc) || (l > 0 && tc2(l)))) dRaw_f32 = nullptr;
+        if (!keep_acts && (defer_wg || (tcl && use_tc) || (l > 0 && tc2(l)) || (wg9_l && l == 0))) dRaw_f32 = nullptr;
+        const bool tcd_planes = tcd || (wg9_l && l == 0);
         if (fuse_in)
             PROF(PC_IN_BWD, 0.0, instnorm_bwd_sums(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw_f32, dg, db, N,
                                     c.outH * c.outW, c.cout_s, c.act, bw_sums2[l & 1], STATS_REPLICAS, bw_sums2[(l + 1) & 1],
-                                    sums_n, st, tcd ? dsp.hi : nullptr, tcd ? dsp.lo : nullptr));
+                                    sums_n, st, tcd_planes ? dsp.hi : nullptr, tcd_planes ? dsp.lo : nullptr));
         else
         PROF(PC_IN_BWD, 0.0, instnorm_bwd(dAct, tb[l].raw, tb[l].mean, tb[l].rstd, g, b, dRaw_f32, dg, db, N,
                                 c.outH * c.outW, c.cout_s, c.act, in_partial, m12, st,
-                                tcd ? dsp.hi : nullptr, tcd ? dsp.lo : nullptr));
+                                tcd_planes ? dsp.hi : nullptr, tcd_planes ? dsp.lo : nullptr));
         if (last && !fastp) {
             FS_CUDA(cudaMemcpyAsync(grads + c.offG, gb_tmp, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
             FS_CUDA(cudaMemcpyAsync(grads + c.offB, gb_tmp + 4, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -762,6 +773,19 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
         wa.H = c.inH; wa.W = c.inW; wa.in_bs = (long long)c.inH * c.inW * c.cin_s;
         wa.N = N; wa.per_sample = 0; wa.scale = 1.f;
         const bool dcv = (flags & ENG_DECONV) && l >= 13;     // conv2d_transpose layers (im_transf_net.py:57-63)
+        bool planes15_ready = false;
+        if (wg9_l) {
+            const double fl9 = conv9_flops(c, N);
+            if (l == 0) {            // windowed planes of the padded input (forward pass) x plain planes of dRaw
+                PROF(PC_WGRAD, fl9, launch_wgrad9_x8_tc(p9[0], g0split, grads + c.offW, wg_partial, wg_partial_cap, N, Hp, Wp / 8,
+                                                        3, 0, st));
+            } else {                 // windowed planes of dRaw (also the data gradient's input) x plain planes of the layer input
+                PROF(PC_POINTWISE, 0.0, split_pad_x16(dRaw, p9[2].hi, p9[2].lo, (long long)N * OH, OW, 4, st, 1));
+                planes15_ready = true;
+                PROF(PC_WGRAD, fl9, launch_wgrad9_x8_tc(p9[2], a14split, grads + c.offW, wg_partial, wg_partial_cap, N, OH, OW / 8,
+                                                        3, 1, st));
+            }
+        } else
         if (dcv && c.upconv) {
             // y = conv2d_transpose(x, W[3,3,cout,cin], s2 SAME) is the data gradient of the SAME conv
             // C: [2H,2W,cout] -> [H,W,cin] with HWIO filter W.  Hence dW = weight gradient of C with
@@ -863,7 +887,7 @@ int Engine::transform_backward(const float* params, const float* dY4_in, float* 
             continue;
         }
         if (direct9(c) && tc9()) {               // upsample_2: 9x9 data gradient on the tensor path
-            FS_TRY(tc9_conv(2, dRaw, dPrev, false, st));
+            FS_TRY(tc9_conv(2, dRaw, dPrev, false, st, planes15_ready));
             dAct = dPrev; cur = pidx;
             continue;
         }

@@ -126,7 +126,13 @@ struct Engine {
     // overlap it): ONE horizontal tap, K = 64, N = 8 x 16 = 128 - half the MMA work of the x16 form.  FS_TC9_X8=0: x16.
     int tc9_x8 = 1;
     bool tc9() const;
-    int tc9_conv(int which, const float* src_f32, float* out, bool stats, cudaStream_t st);
+    int tc9_conv(int which, const float* src_f32, float* out, bool stats, cudaStream_t st, bool planes_ready = false);
+    // weight gradients of the two 9x9 layers on tcgen05 in their x8 forms (wgrad9_tc.cu): the windowed planes p9[0] /
+    // p9[2] against the plain planes of layer 0's raw-output gradient (g0split) / of layer 15's input (a14split).
+    // FS_WGRAD9_TC=0: the direct CUDA-core kernels.
+    int wgrad9_tc = 1;
+    SplitPtr g0split = {nullptr, nullptr}, a14split = {nullptr, nullptr};
+    bool wg9() const { return wgrad9_tc && tc9_x8 && tc9(); }
     int keep_acts = 0;                   // 1: write every fp32 activation / gradient even where only split planes are read (debug taps)
     int fuse_pool = 1;                   // FS_FUSE_POOL=0: separate max-pool kernel after the VGG conv
     int fold_pool = 1;                   // FS_FOLD_POOL=0: separate pool_bwd_combine pass before the Gram backward

@@ -95,6 +95,13 @@ struct WgradMultiItem { SplitPtr x, dy; float* out; int H, W, OH, OW, pad; };
 int launch_wgrad3x3_tc_multi(const WgradMultiItem* items, int count, float* partial, long long partial_cap, int N,
                              cudaStream_t st);
 
+// tcgen05 weight gradient of the 9x9 layers in their x8 forms (wgrad9_tc.cu): xw = windowed planes [N,H,G,64] of the
+// 4-channel side, dg = plain planes [N,H,8G,16] of the 16-channel side; out [9,9,A,16] (mode 0: the 4-channel side is the
+// conv input) or [9,9,16,A] (mode 1: it is the output gradient), A = real channels of that side (3)
+long long wgrad9_x8_partial_floats();
+int launch_wgrad9_x8_tc(SplitPtr xw, SplitPtr dg, float* out, float* partial, long long partial_cap, int N, int H, int G,
+                        int A, int mode, cudaStream_t st);
+
 // tcgen05 weight gradient of the 2x2-tap forms (wgrad_tc.cu): out [2,2,Cx,Cy], (Cx,Cy) = (64,128) | (128,64)
 long long wgrad2x2_tc_partial_floats();
 int launch_wgrad2x2_tc(SplitPtr x, int x_s2d, SplitPtr dy, int dy_s2d, float* out, float* partial, long long partial_cap,
