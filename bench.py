@@ -267,7 +267,9 @@ def run_ours(args, rank, local_rank, world):
                 fn()
             barrier()
             sampler.start()
-        n0 = lib.fs_launch_count()
+        def launches():      # kernels issued through the library + kernels executed by the step-graph replays
+            return lib.fs_launch_count() + trainer.replayed_launches
+        n0 = launches()
         e0.record()
         for _ in range(steps):
             fn()
@@ -275,7 +277,7 @@ def run_ours(args, rank, local_rank, world):
             finish()
         e1.record()
         barrier()
-        n1 = lib.fs_launch_count()
+        n1 = launches()
         clocks = sampler.stop() if sampler else None
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
@@ -376,7 +378,9 @@ def run_ours(args, rank, local_rank, world):
                        "dp_exchange": (None if world == 1 else
                                        "fs_dp_allreduce_adam: one kernel, gradient all-reduce over NVLink peer loads + Adam"
                                        if trainer.peer is not None else "NCCL all_reduce + Adam kernel"),
-                       "api": "faststyle_b200.trainer.Trainer.step (the call train.py makes)"},
+                       "api": "faststyle_b200.trainer.Trainer.step (the call train.py makes)",
+                       "step_issue": ("CUDA-graph replay of the step's launches (captured once per input buffer)"
+                                      if trainer._use_graph and trainer._graphs else "one launch per kernel")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s",
                     "h2d_bytes_per_step": int(trainer.h2d_bytes_per_step), "d2h_bytes_per_step": int(trainer.d2h_bytes_per_step),

@@ -48,6 +48,7 @@ dp_allreduce_adam_kernel(const DpPeers peers, int rank, int world, unsigned tag,
     FS_PDL_ENTER();                      // this rank's backward pass (previous kernels of the stream) is complete
     __shared__ float lr_t_s;
     const int t = threadIdx.x;
+    if (tag == 0u) tag = (unsigned)(*step + 1);      // graph replay: the step number lives on the device
     if (blockIdx.x == 0 && t < world) {
         __threadfence_system();
         st_release_sys(peers.flags[t] + rank, tag);

@@ -86,7 +86,8 @@ class PeerExchange:
 
     def allreduce_adam(self, opt, parity: int, tag: int):
         """All-reduce(SUM) of every rank's gradients of this step + TF-Adam on ``opt``'s buffers; the summed extra
-        scalars land in ``self.extra_sum``.  One kernel launch on the current stream."""
+        scalars land in ``self.extra_sum``.  One kernel launch on the current stream.  ``tag`` = the step number
+        (1, 2, ...), or 0 to let the kernel take ``opt.step_counter + 1`` on the device (CUDA-graph replay)."""
         from .engine import ptr, stream_ptr
         with torch.cuda.device(self.device):
             self._lib.call("fs_dp_allreduce_adam", C.cast(self.ptr_array, C.POINTER(C.c_void_p)), self.rank, self.world,

@@ -160,7 +160,8 @@ int fs_adam_step(float* params, const float* grads, float* m, float* v, long lon
  * this step's n gradients at float offset grad_off_floats (double-buffer by step parity), n_extra scalars to be
  * summed into extra_out (loss terms; may be 0 / NULL) at grad_off_floats + extra_off_floats, an unsigned[world] flag
  * array (zero-initialised, then owned by the kernel) at byte offset flag_off_bytes.  tag: the step number
- * (1, 2, 3, ... strictly increasing; the same on all ranks).  Sums are formed in rank order on every rank, so the
+ * (1, 2, 3, ... strictly increasing; the same on all ranks); 0 = take *step_counter + 1 on the device (for CUDA-graph
+ * replay, where host arguments are frozen).  Sums are formed in rank order on every rank, so the
  * replicas stay bit-identical.  err_flag (device int, may be NULL) is set to 1 when a peer's flag did not arrive
  * within ~10 s.  Every rank must make the call once per step. */
 /* Let kernels of the CURRENT device dereference memory of `peer_device` (cudaDeviceEnablePeerAccess; a no-op when it
