@@ -164,7 +164,7 @@ wgrad9_x8_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_con
     if (warp == 2) tmem_dealloc(tmem_base, W9_TMEM);
 }
 
-// Fold the Toeplitz-space partials back and sum them over the CTAs: one warp per output element.
+// Fold the Toeplitz-space partials back and sum them over the CTAs.
 //   mode 0 (windowed side = the conv INPUT, c4 = ci; grouped side = dY, c16 = co):  out[kh][kw][ci < A][co < 16]
 //       = sum_dxo Wt[kh][(dxo + kw) * 4 + ci][dxo * 16 + co]
 //   mode 1 (windowed side = dY, c4 = co; grouped side = the conv input, c16 = ci):  out[kh][kw][ci < 16][co < A]
@@ -173,26 +173,34 @@ wgrad9_x8_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_con
 __global__ void __launch_bounds__(256) wgrad9_x8_fold_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                                              int nparts, int A, int mode) {
     FS_PDL_ENTER();
-    const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    const int total = 81 * 16 * A;
-    if (o >= total) return;
-    int kh, kw, ci, co;
-    if (mode == 0) { co = o % 16; int r = o / 16; ci = r % A; r /= A; kw = r % 9; kh = r / 9; }
-    else { co = o % A; int r = o / A; ci = r % 16; r /= 16; kw = r % 9; kh = r / 9; }
+    // one CTA per (kh, kw, c4); lane = (half of the dxo range, c16) reads 16 contiguous floats of a partial row; the
+    // eight warps split the CTA pairs (fixed assignment and order -> deterministic)
+    __shared__ float red[8][16];
+    const int wid = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c4 = wid % A, kw = (wid / A) % 9, kh = wid / (9 * A);
     const int tkh = mode == 0 ? kh : 8 - kh, tkw = mode == 0 ? kw : 8 - kw;
-    const int c4 = mode == 0 ? ci : co, c16 = mode == 0 ? co : ci;
-    float s = 0.f;
-    // 8 dxo terms x the CTAs holding that column half; lanes stride over (dxo, cta pair)
+    const int c16 = lane & 15, half = lane >> 4;
     const int pairs = nparts >> 1;
-    for (int i = lane; i < 8 * pairs; i += 32) {
-        const int dxo = i / pairs, cp = i - dxo * pairs;
-        const int n = dxo * 16 + c16, nbh = n >> 6;
-        const int k = (dxo + tkw) * 4 + c4;
-        s += partial[((long long)(2 * cp + nbh) * 9 + tkh) * 4096 + k * 64 + (n & 63)];
-    }
+    float s = 0.f;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (lane == 0) out[o] = s;
+    for (int d = 0; d < 4; ++d) {
+        const int dxo = 4 * half + d;
+        const int n = dxo * 16 + c16, nbh = n >> 6;          // column half = dxo / 4 = `half`
+        const int k = (dxo + tkw) * 4 + c4;
+        const float* pp = partial + ((long long)nbh * 9 + tkh) * 4096 + k * 64 + (n & 63);
+        for (int cp = warp; cp < pairs; cp += 8) s += pp[(long long)cp * (2 * 9 * 4096)];
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    if (half == 0) red[warp][c16] = s;
+    __syncthreads();
+    if (warp == 0 && half == 0) {
+        float r = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) r += red[w][c16];
+        const int ci = mode == 0 ? c4 : c16, co = mode == 0 ? c16 : c4;
+        const int Ci = mode == 0 ? A : 16, Co = mode == 0 ? 16 : A;
+        out[((kh * 9 + kw) * Ci + ci) * Co + co] = r;
+    }
 }
 
 }  // namespace
@@ -223,7 +231,7 @@ int launch_wgrad9_x8_tc(SplitPtr xw, SplitPtr dg, float* out, float* partial, lo
     FS_DYN_SMEM(wgrad9_x8_tc_kernel, W9_SMEM);
     launch_k(wgrad9_x8_tc_kernel, dim3(grid), dim3(256), W9_SMEM, st, tmX_hi, tmX_lo, tmD_hi, tmD_lo, p);
     FS_LAUNCH_CHECK();
-    launch_k(wgrad9_x8_fold_kernel, dim3(cdiv(81 * 16 * A, 8)), dim3(256), 0, st, (const float*)partial, out, grid, A, mode);
+    launch_k(wgrad9_x8_fold_kernel, dim3(81 * A), dim3(256), 0, st, (const float*)partial, out, grid, A, mode);
     FS_LAUNCH_CHECK();
     return 0;
 }
