@@ -62,6 +62,20 @@ def csrc_sha16():
     return h.hexdigest()[:16]
 
 
+KERNEL_SOURCES = ("conv3x3_tc.cu", "tc.cuh", "tc_ptx.cuh", "common.cuh")
+
+
+def kernel_sha16():
+    """Hash of the dominant kernel's own sources (conv3x3_tc_kernel and the headers it includes): an ncu capture of
+    that kernel stays valid while other kernels of the library change."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "faststyle_b200", "csrc")
+    for f in KERNEL_SOURCES:
+        h.update(f.encode())
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 class ClockSampler:
     """SM clock / throttle reasons sampled through NVML every ~5 ms DURING the timed region (a thread of this
     process: nvidia-smi's own loop delivers 2-3 samples in a 0.1-0.3 s region)."""
@@ -443,7 +457,8 @@ def load_ncu_traffic():
         d = json.load(open(TRAFFIC_FILE))
     except Exception:
         return None
-    d["build_matches"] = d.get("csrc_sha16") == csrc_sha16()
+    d["build_matches"] = d.get("csrc_sha16") == csrc_sha16()                 # every CUDA source identical
+    d["kernel_source_matches"] = d.get("kernel_sha16") == kernel_sha16()     # the captured kernel's sources identical
     return d
 
 
@@ -479,7 +494,8 @@ def dominant_kernel_roofline(prof, peaks, step_ms, clocks):
                           (peaks["source"], "burst" if burst else "sustained",
                            "max SM clock, no power cap" if burst else "power-capped clocks"),
            "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
-           "traffic_source": ({k: traffic.get(k) for k in ("file", "launches", "build_matches", "csrc_sha16", "unit")}
+           "traffic_source": ({k: traffic.get(k) for k in ("file", "launches", "build_matches", "kernel_source_matches",
+                                                             "csrc_sha16", "kernel_sha16", "unit")}
                               if traffic else "no ncu capture of this build committed (profiles/ncu_traffic.json absent)"),
            "algorithmic_bytes_per_launch": mb * 1e6 / launches if launches and mb else None,
            "kernel": kernel, "precision": precision, "kernel_ms_per_step": ms, "launches_per_step": launches,

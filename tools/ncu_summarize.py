@@ -120,9 +120,13 @@ def traffic(path, pattern, out_path):
     d = os.path.join(root, "faststyle_b200", "csrc")
     for f in sorted(os.listdir(d)):
         h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    hk = hashlib.sha256()
+    for f in ("conv3x3_tc.cu", "tc.cuh", "tc_ptx.cuh", "common.cuh"):        # bench.KERNEL_SOURCES
+        hk.update(f.encode()); hk.update(open(os.path.join(d, f), "rb").read())
     out = {"kernel_regex": pattern, "launches": n, "dram_bytes_per_launch": tot / max(n, 1), "unit": "bytes/launch "
            "(dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, mean over the captured launches)",
-           "file": os.path.basename(path), "csrc_sha16": h.hexdigest()[:16], "per_launch_bytes": per}
+           "file": os.path.basename(path), "csrc_sha16": h.hexdigest()[:16], "kernel_sha16": hk.hexdigest()[:16],
+           "per_launch_bytes": per}
     json.dump(out, open(out_path, "w"), indent=1)
     print("%d launches of /%s/: %.1f MB per launch -> %s" % (n, pattern, out["dram_bytes_per_launch"] / 1e6, out_path))
 
