@@ -317,6 +317,16 @@ def run_ours(args, rank, local_rank, world):
         replicas_identical = all(float(c.item()) == float(allcs[0].item()) for c in allcs)
         assert replicas_identical, "data-parallel replicas diverged: parameter checksums %s" % [float(c) for c in allcs]
 
+    # ---- live per-kernel-class profile (rank 0), taken directly after the timed legs - in the same clock / thermal
+    # state - and before the heavier legs below.  Forward/backward only and no optimiser step: the replicas (and the
+    # device-side step counter the fused exchange tags its flags with) must stay in lock-step for the next leg.
+    prof = None
+    if rank == 0:
+        eng0 = trainer.engine
+        prof = live_kernel_profile(eng0, lambda: eng0.train_fwd_bwd(
+            trainer.params, trainer.packed, trainer._current, trainer.cfg, trainer.target_grams,
+            grads=trainer.grads, losses=trainer.losses))
+
     # ---- strong-scaling leg (every rank takes part): global batch 64 split over the ranks
     strong = None
     try:
@@ -346,11 +356,6 @@ def run_ours(args, rank, local_rank, world):
         step_ms = ms / args.steps
         eng = trainer.engine
 
-        def step_local():           # rank-local (no collective)
-            eng.train_fwd_bwd(trainer.params, trainer.packed, trainer._current, trainer.cfg, trainer.target_grams,
-                              grads=trainer.grads, losses=trainer.losses)
-            trainer.opt.step(trainer.grads)
-        prof = live_kernel_profile(eng, step_local)
         roof = dominant_kernel_roofline(prof, peaks, step_ms, clocks)
         step_tflops = GFLOP_PER_IMAGE_TRAIN * PER_GPU_BATCH / (step_ms / 1e3) / 1e3
         roof["whole_step"] = {"tflops_algorithmic": step_tflops, "frac_of_burst": step_tflops / peaks["bf16_tflops"],
